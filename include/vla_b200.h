@@ -1,0 +1,175 @@
+/* libvla_b200 -- C ABI of the B200 (sm_100a) implementation of the vae-los-angeles hot path.
+ *
+ * The reference (marcin119a/vae-los-angeles) is pure Python on top of PyTorch; it has no FFI of its
+ * own.  The boundary this library sits behind is therefore the reference's Python import surface
+ * (SURVEY.md section 8b); each entry point below names the reference interface whose arithmetic it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ * all work is enqueued on `stream` (a cudaStream_t passed as void*) with no host synchronisation;
+ * functions return 0 on success and a negative code on failure, with the message available from
+ * vla_last_error() (thread-local).  fp32 tensors are dense row-major, `site` is int64.
+ * There is no CPU fallback.
+ */
+#ifndef VLA_B200_H
+#define VLA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vla_stream_t;
+typedef struct vla_model vla_model_t;
+
+enum { VLA_KIND_MULTIMODAL = 0, VLA_KIND_RNA2DNA = 1, VLA_KIND_DNA2RNA = 2 };
+enum { VLA_OK = 0, VLA_ERR_INVALID = -1, VLA_ERR_CUDA = -2, VLA_ERR_STATE = -3 };
+enum { VLA_TENSOR_PARAM = 0, VLA_TENSOR_BUFFER = 1, VLA_TENSOR_COUNTER = 2 };
+
+/* Model geometry.  kind selects the encoder / decoder stacks:
+ *   MULTIMODAL: MultiModalVAE.__init__ (src/models/vae.py:27-35)
+ *   RNA2DNA / DNA2RNA: RNA2DNAVAE / DNA2RNAVAE.__init__ (src/models/directional_vae.py:19-23, 70-74) */
+typedef struct {
+  int kind;
+  int dim_a;     /* RNA features   (input_dim_a / rna_dim) */
+  int dim_b;     /* DNA features   (input_dim_b / dna_dim) */
+  int n_sites;
+  int latent;
+  int embed;     /* embed_dim, 32 by default in the reference */
+} vla_config_t;
+
+/* One state_dict entry.  PARAM offsets index the fp32 parameter arena,
+ * BUFFER offsets the fp32 running-statistics arena, COUNTER offsets the int64 num_batches_tracked array. */
+typedef struct {
+  char name[96];
+  int kind;
+  long long offset;
+  int ndim;
+  int shape[2];
+} vla_tensor_info_t;
+
+const char* vla_last_error(void);
+int vla_abi_version(void);
+
+int vla_model_create(const vla_config_t* cfg, vla_model_t** out);
+void vla_model_destroy(vla_model_t* m);
+/* Makes sure workspace for `batch` rows exists (also done lazily by the calls below). */
+int vla_model_reserve(vla_model_t* m, int batch);
+
+long long vla_param_count(const vla_model_t* m);    /* fp32 elements in the parameter arena */
+long long vla_buffer_count(const vla_model_t* m);   /* fp32 elements in the running-statistics arena */
+int vla_counter_count(const vla_model_t* m);        /* number of BatchNorm layers */
+int vla_num_tensors(const vla_model_t* m);
+int vla_tensor_info(const vla_model_t* m, int index, vla_tensor_info_t* out);
+
+/* Forward pass.  Replaces MultiModalVAE.forward (src/models/vae.py:37-79), RNA2DNAVAE.forward /
+ * DNA2RNAVAE.forward (src/models/directional_vae.py:25-60, 76-111) including EncoderA/B/C.forward
+ * (src/models/encoders.py:21-23, 43-46, 57-61), reparameterize (src/models/vae.py:11-15) and
+ * DecoderA/B/C.forward (src/models/decoders.py:18-19, 35-36, 49-50).
+ * A null x_a / x_b / site means "modality absent"; at least one encoder input must be present.
+ * train != 0: BatchNorm uses batch statistics and updates the running statistics, dropout is active, and
+ * activations are kept for vla_backward.  eps == NULL draws epsilon from Philox(seed, offset).
+ * keep_masks: optional array with one entry per dropout layer (model order), each NULL or a uint8 keep
+ * mask [batch, width]; used by the parity tests to replay the reference's dropout decisions. */
+typedef struct {
+  const float* params;
+  float* buffers;
+  long long* counters;
+  const float* x_a;
+  const float* x_b;
+  const long long* site;
+  int batch;
+  int train;
+  int refresh_shadows;          /* != 0: re-derive the bf16 MMA copies of the weights from `params` first */
+  const float* eps;
+  const unsigned char* const* keep_masks;
+  unsigned long long seed;
+  unsigned long long offset;
+  float* recon_a;               /* [batch, dim_a]   (kinds with a type-A decoder) */
+  float* recon_b;               /* [batch, dim_b]   (type-B decoder, sigmoid output) */
+  float* recon_c;               /* [batch, n_sites] (type-C decoder, logits) */
+  float* mu;                    /* [batch, latent] */
+  float* logvar;                /* [batch, latent] */
+} vla_forward_args_t;
+int vla_forward(vla_model_t* m, const vla_forward_args_t* a, vla_stream_t stream);
+
+/* Re-derives the bf16 tensor-core copies of the weights from the fp32 parameter arena (needed after the
+ * parameters were changed by anything other than vla_adamw / vla_train_step). */
+int vla_refresh_shadows(vla_model_t* m, const float* params, vla_stream_t stream);
+
+/* Backward of the last train-mode vla_forward on this handle: what autograd does for the reference
+ * after loss.backward() (train_rna2dna.py:95).  g_* are dL/d(output) (NULL = zero); `recon_b` must be the
+ * sigmoid output returned by that forward when g_recon_b is given.  Writes every parameter gradient into
+ * grads[param_count] (gradients of absent stacks are left zero). */
+typedef struct {
+  const float* params;
+  const float* g_recon_a;
+  const float* g_recon_b;
+  const float* g_recon_c;
+  const float* g_mu;
+  const float* g_logvar;
+  const float* recon_b;
+  float* grads;
+} vla_backward_args_t;
+int vla_backward(vla_model_t* m, const vla_backward_args_t* a, vla_stream_t stream);
+
+/* Loss values and gradients w.r.t. the model outputs.  Replaces vae_loss (src/utils/losses.py:8-46),
+ * rna2dna_loss / dna2rna_loss (src/utils/directional_losses.py:8-30, 33-55): any term whose recon pointer
+ * is NULL is skipped.  out[4] = {total, recon, class, kld}.  Gradient outputs are optional.
+ * workspace: vla_loss_workspace_bytes() bytes, zero-initialised once by the caller. */
+typedef struct {
+  const float* recon_a; const float* a; int dim_a;
+  const float* recon_b; const float* b; int dim_b;
+  const float* recon_c; const long long* site; const float* class_weights; int n_sites;
+  const float* mu; const float* logvar; int latent;
+  int batch;
+  float beta, gamma;
+  float* g_recon_a; float* g_recon_b; float* g_recon_c; float* g_mu; float* g_logvar;
+  float* out;
+  void* workspace;
+} vla_loss_args_t;
+long long vla_loss_workspace_bytes(int batch, int dim_a, int dim_b, int n_sites, int latent);
+int vla_loss(const vla_loss_args_t* a, vla_stream_t stream);
+
+/* One fused multi-tensor AdamW step over the flat arena (torch.optim.AdamW semantics, the optimizer built at
+ * train_rna2dna.py:185-189 and stepped at :94-96); also refreshes the bf16 weight copies. */
+typedef struct {
+  float* params; const float* grads; float* exp_avg; float* exp_avg_sq;
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;                     /* 1-based */
+} vla_adamw_args_t;
+int vla_adamw(vla_model_t* m, const vla_adamw_args_t* a, vla_stream_t stream);
+
+/* Whole training step: forward + loss + backward + AdamW, the loop body at train_rna2dna.py:82-99 /
+ * optimize_hyperparameters.py:104-113, with the learning rate, weight decay, KL weight, gamma and the step
+ * count held on the device (vla_set_hyper) so that a captured CUDA graph of this call can be replayed.
+ * Targets are the same tensors as the inputs (a, b, site): x_a, x_b and site are all required (inputs and/or
+ * targets of every kind).  loss_out[4] = {total, recon, class, kld}. */
+typedef struct {
+  float* params; float* grads; float* exp_avg; float* exp_avg_sq;
+  float* buffers; long long* counters;
+  const float* x_a; const float* x_b; const long long* site;
+  const float* class_weights;
+  int batch;
+  long long dataset_rows;       /* rows behind x_a / x_b / site; > batch: step t trains on rows
+                                   [(i mod n) * batch, +batch), i = device-side batch index, n = dataset_rows / batch */
+  const float* eps;
+  const unsigned char* const* keep_masks;
+  unsigned long long seed;
+  float beta1, beta2, adam_eps;
+  float* recon_a; float* recon_b; float* recon_c; float* mu; float* logvar;   /* optional outputs */
+  float* loss_out;
+} vla_train_args_t;
+int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream);
+int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, float gamma, vla_stream_t stream);
+int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, vla_stream_t stream);
+
+/* Test hook: C[M,N] = A[M,K] * B[N,K]^T (mode 0) or C[M,N] = A[K,M]^T * B[K,N] (mode 1) on the tcgen05 path.
+ * A, B bf16 (uint16 storage) with element pitches lda / ldb (multiples of 8), C fp32 dense, zero-filled by
+ * the caller in mode 1 (split-K accumulation).  bias_grad (mode 1, optional) receives sum_k A[k, m]. */
+int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K,
+                  int bn, int k_splits, float* bias_grad, vla_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

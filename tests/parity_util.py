@@ -1,0 +1,92 @@
+"""Shared helpers of the GPU parity tests: build the CUDA module from an oracle state, run the oracle,
+compare with the tolerances BASELINE.json states."""
+import re
+
+import numpy as np
+import torch
+
+from oracle import vae_oracle as vo
+
+# BASELINE.json north_star: fp32 kernels 1e-5 relative; bf16 tensor-core kernels 2e-2 relative on losses and
+# gradients; argmax site predictions exact.  "relative" is measured as ||x - ref||_2 / ||ref||_2 per tensor.
+TOL_FP32 = 1e-5
+TOL_BF16 = 2e-2
+
+
+def rel_l2(x, ref):
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def is_pre_bn_bias(name):
+    m = re.fullmatch(r"encoder_\w+\.fc\.(\d+)\.bias", name)
+    return bool(m) and int(m.group(1)) % 4 == 0
+
+
+def module_class(kind):
+    from src.models import DNA2RNAVAE, MultiModalVAE, RNA2DNAVAE
+    return {"multimodal": MultiModalVAE, "rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE}[kind]
+
+
+def make_module(kind, dims, state, device="cuda"):
+    cls = module_class(kind)
+    m = cls(dims["A"], dims["B"], dims["S"], dims["L"], embed_dim=dims.get("E", 32))
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in state.items()}
+    m.load_state_dict(sd, strict=True)
+    return m.to(device)
+
+
+def call_module(m, kind, a=None, b=None, site=None):
+    """Uniform call -> dict(recon={decoder prefix: tensor}, mu, logvar)."""
+    if kind == "multimodal":
+        ra, rb, rc, mu, lv = m(a=a, b=b, site=site)
+        recon = {"decoder_a": ra, "decoder_b": rb, "decoder_c": rc}
+    elif kind == "rna2dna":
+        rb, mu, lv = m(rna=a, site=site)
+        recon = {"decoder_dna": rb}
+    else:
+        ra, mu, lv = m(dna=b, site=site)
+        recon = {"decoder_rna": ra}
+    return dict(recon=recon, mu=mu, logvar=lv)
+
+
+def loss_for(kind, out, batch_t, beta, gamma, cw):
+    from src.utils.directional_losses import dna2rna_loss, rna2dna_loss
+    from src.utils.losses import vae_loss
+    if kind == "multimodal":
+        total, recon, cls, kld = vae_loss(out["recon"]["decoder_a"], batch_t["a"], out["recon"]["decoder_b"], batch_t["b"],
+                                          out["recon"]["decoder_c"], batch_t["site"], out["mu"], out["logvar"],
+                                          beta=beta, gamma=gamma, class_weights=cw)
+    elif kind == "rna2dna":
+        total, recon, kld = rna2dna_loss(out["recon"]["decoder_dna"], batch_t["b"], out["mu"], out["logvar"], beta=beta)
+        cls = 0.0
+    else:
+        total, recon, kld = dna2rna_loss(out["recon"]["decoder_rna"], batch_t["a"], out["mu"], out["logvar"], beta=beta)
+        cls = 0.0
+    return total, (recon, cls, kld)
+
+
+def to_t(x, device="cuda"):
+    return None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(device)
+
+
+def oracle_step(kind, dims, state, batch, present, eps, masks, beta, gamma, cw, train=True, dtype=np.float64):
+    """Oracle forward + loss + backward on a private fp64 copy of `state`."""
+    st = {k: (v.astype(dtype) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
+    bt = {k: (v.astype(dtype) if v.dtype.kind == "f" else v) for k, v in batch.items()}
+    inputs = {k: (bt[k] if k in present else None) for k in ("a", "b", "site")}
+    out, cache = vo.forward(kind, dims, st, inputs, eps.astype(dtype), masks, train=train)
+    scalars, og = vo.loss_and_output_grads(kind, out, bt, beta, gamma, None if cw is None else cw.astype(dtype))
+    grads = vo.backward(kind, dims, st, cache, og, train=train)
+    return out, scalars, grads, st
+
+
+def assert_close(name, got, ref, tol, atol=0.0):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    err = np.linalg.norm(got - ref)
+    bound = tol * np.linalg.norm(ref) + atol
+    assert np.isfinite(got).all(), name
+    assert err <= bound, f"{name}: |err|={err:.4g} > {bound:.4g} (rel {err / max(np.linalg.norm(ref), 1e-30):.3g})"

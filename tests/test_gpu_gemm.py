@@ -1,0 +1,60 @@
+"""tcgen05 GEMM kernel in isolation (through the C ABI test hook) against torch.matmul on the same
+bf16-rounded operands.  Tolerance 2e-3 relative: identical products, only the fp32 accumulation order differs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, A, B, M, N, K, bn, splits, want_bias=False):
+    from vla_b200 import _lib
+    L = _lib.lib()
+    Cout = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    bias = torch.zeros(M, dtype=torch.float32, device="cuda") if want_bias else None
+    rc = L.vla_test_gemm(mode, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cout.data_ptr(), M, N, K, bn, splits,
+                         None if bias is None else bias.data_ptr(), None)
+    _lib.check(rc, "vla_test_gemm")
+    torch.cuda.synchronize()
+    return Cout, bias
+
+
+def _padded(rows, cols, seed):
+    ld = (cols + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    buf = torch.randn(rows, ld, device="cuda", generator=g).to(torch.bfloat16)
+    return buf, buf[:, :cols]
+
+
+NT_CASES = [(128, 128, 64, 128), (256, 64, 782, 32), (4096, 572, 512, 144), (33, 40, 128, 16), (4096, 128, 782, 32),
+            (100, 448, 20, 64), (4096, 20, 448, 32), (515, 160, 200, 160), (4096, 782, 128, 112)]
+
+
+@pytest.mark.parametrize("M,N,K,bn", NT_CASES)
+def test_gemm_nt(M, N, K, bn):
+    Ab, A = _padded(M, K, 1)
+    Bb, B = _padded(N, K, 2)
+    out, _ = _run(0, Ab, Bb, M, N, K, bn, 1)
+    ref = A.float() @ B.float().t()
+    err = (out - ref).norm() / ref.norm()
+    assert err < 2e-3, float(err)
+    assert (out - ref).abs().max() < 2e-3 * ref.abs().max() + 1e-3
+
+
+TN_CASES = [(128, 128, 64, 128, 1), (572, 512, 4096, 192, 8), (40, 128, 4096, 128, 4), (448, 20, 4096, 64, 8),
+            (24, 32, 100, 64, 1), (128, 782, 4096, 128, 7), (512, 257, 1000, 128, 3)]
+
+
+@pytest.mark.parametrize("M,N,Kb,bn,splits", TN_CASES)
+def test_gemm_tn_with_bias_grad(M, N, Kb, bn, splits):
+    Gb, G = _padded(Kb, M, 3)
+    Xb, X = _padded(Kb, N, 4)
+    out, bias = _run(1, Gb, Xb, M, N, Kb, bn, splits, want_bias=True)
+    ref = G.float().t() @ X.float()
+    err = (out - ref).norm() / ref.norm()
+    assert err < 2e-3, float(err)
+    bref = G.float().sum(0)
+    berr = (bias - bref).norm() / bref.norm()
+    assert berr < 2e-3, float(berr)

@@ -1,0 +1,597 @@
+// HBM / L2-bound element-wise and reduction kernels of the VAE step: input ingest (fp32 -> bf16 MMA
+// operands, embedding gather), BatchNorm apply + ReLU + dropout, the fused latent kernel
+// (modality mean, reparameterisation, per-sample KL), the fused loss (MSE + BCE + weighted CE + KL
+// with their gradients), BatchNorm backward, the latent backward and the fused multi-tensor AdamW.
+// All arithmetic is fp32; reductions are deterministic (fixed-order partials, no float atomics).
+#include "vla_internal.h"
+
+#include <cfloat>
+
+namespace vla {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }   // [0,1)
+__device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);               // (0,1]
+  const float u2 = u01(b);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = (l < (blockDim.x >> 5)) ? sh[l] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ingest: fp32 inputs -> bf16 padded operands; embedding gather; one-hot; step counter
+// ---------------------------------------------------------------------------------------------
+__global__ void ingest_kernel(IngestArgs a) {
+  if (a.bump_step && blockIdx.x == 0 && threadIdx.x == 0) a.dyn->step += 1;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
+  for (int e = 0; e < a.n; ++e) {
+    const int half_ld = a.ld_dst[e] >> 1;
+    const long long total = static_cast<long long>(a.rows) * half_ld;
+    const float* __restrict__ src = a.src[e];
+    __nv_bfloat162* __restrict__ dst = reinterpret_cast<__nv_bfloat162*>(a.dst[e]);
+    const int w = a.width[e];
+    for (long long i = tid; i < total; i += nthr) {
+      const int r = static_cast<int>(i / half_ld);
+      const int c = static_cast<int>(i - static_cast<long long>(r) * half_ld) * 2;
+      const float* s = src + (row0 + r) * w + c;
+      const float x0 = (c < w) ? __ldg(s) : 0.f;
+      const float x1 = (c + 1 < w) ? __ldg(s + 1) : 0.f;
+      dst[i] = __floats2bfloat162_rn(x0, x1);
+    }
+  }
+  if (a.site != nullptr) {
+    const long long tot_h = static_cast<long long>(a.rows) * a.ld_hsite;
+    for (long long i = tid; i < tot_h; i += nthr) {
+      const int r = static_cast<int>(i / a.ld_hsite);
+      const int c = static_cast<int>(i - static_cast<long long>(r) * a.ld_hsite);
+      const long long s = a.site[row0 + r];
+      a.h_site[i] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
+    }
+    const long long tot_o = static_cast<long long>(a.rows) * a.ld_onehot;
+    for (long long i = tid; i < tot_o; i += nthr) {
+      const int r = static_cast<int>(i / a.ld_onehot);
+      const int c = static_cast<int>(i - static_cast<long long>(r) * a.ld_onehot);
+      a.onehot[i] = __float2bfloat16(a.site[row0 + r] == c ? 1.f : 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm apply (+ReLU +dropout) and BatchNorm backward.  Tile: 64 columns x ROWS rows per CTA,
+// 256 threads = 32 column pairs x 8 row lanes.
+// ---------------------------------------------------------------------------------------------
+constexpr int BN_COLS = 64;
+
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ stats, int m_tiles, int n, int col,
+                                                bool col_ok, double (*sh)[BN_COLS][2], double* out) {
+  // out[0..3] = (sum0[col], sum0[col+1], sum1[col], sum1[col+1]); valid for threads with ty == 0
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+  if (col_ok) {
+    for (int t = ty; t < m_tiles; t += 8) {
+      const float2 s0 = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(t) * 2 + 0) * n + col);
+      const float2 s1 = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(t) * 2 + 1) * n + col);
+      a0 += s0.x; a1 += s0.y; b0 += s1.x; b1 += s1.y;
+    }
+  }
+  sh[ty][lane * 2][0] = a0; sh[ty][lane * 2 + 1][0] = a1;
+  sh[ty][lane * 2][1] = b0; sh[ty][lane * 2 + 1][1] = b1;
+  __syncthreads();
+  if (ty == 0) {
+    double r[4] = {0, 0, 0, 0};
+    for (int t = 0; t < 8; ++t) {
+      r[0] += sh[t][lane * 2][0]; r[1] += sh[t][lane * 2 + 1][0];
+      r[2] += sh[t][lane * 2][1]; r[3] += sh[t][lane * 2 + 1][1];
+    }
+    out[0] = r[0]; out[1] = r[1]; out[2] = r[2]; out[3] = r[3];
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_block) {
+  __shared__ double sh[8][BN_COLS][2];
+  __shared__ float s_mean[BN_COLS], s_rstd[BN_COLS];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * BN_COLS + lane * 2;
+  const bool col_ok = col < a.n;     // n is even
+  if (a.train) {
+    double r[4];
+    reduce_partials(a.stats, a.m_tiles, a.n, col, col_ok, sh, r);
+    if (ty == 0 && col_ok) {
+      for (int j = 0; j < 2; ++j) {
+        const double mean = r[j] / a.rows;
+        double var = r[2 + j] / a.rows - mean * mean;
+        var = var < 0 ? 0 : var;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+        s_mean[lane * 2 + j] = static_cast<float>(mean);
+        s_rstd[lane * 2 + j] = rstd;
+        if (blockIdx.y == 0) {
+          a.save_mean[col + j] = static_cast<float>(mean);
+          a.save_rstd[col + j] = rstd;
+          if (a.update_running) {
+            const double unbiased = a.rows > 1 ? var * a.rows / (a.rows - 1) : var;
+            a.running_mean[col + j] = 0.9f * a.running_mean[col + j] + 0.1f * static_cast<float>(mean);
+            a.running_var[col + j] = 0.9f * a.running_var[col + j] + 0.1f * static_cast<float>(unbiased);
+          }
+        }
+      }
+    }
+    if (a.update_running && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && a.num_batches_tracked)
+      *a.num_batches_tracked += 1;
+  } else if (ty == 0 && col_ok) {
+    for (int j = 0; j < 2; ++j) {
+      const float rstd = 1.0f / sqrtf(a.running_var[col + j] + 1e-5f);
+      s_mean[lane * 2 + j] = a.running_mean[col + j];
+      s_rstd[lane * 2 + j] = rstd;
+      if (blockIdx.y == 0) { a.save_mean[col + j] = a.running_mean[col + j]; a.save_rstd[col + j] = rstd; }
+    }
+  }
+  __syncthreads();
+  if (!col_ok) return;
+  const float m0 = s_mean[lane * 2], m1 = s_mean[lane * 2 + 1];
+  const float r0 = s_rstd[lane * 2] * a.gamma[col], r1 = s_rstd[lane * 2 + 1] * a.gamma[col + 1];
+  const float b0 = a.beta[col], b1 = a.beta[col + 1];
+  const bool drop = a.train && a.p_drop > 0.f;
+  const float keep_scale = drop ? 1.0f / (1.0f - a.p_drop) : 1.0f;
+  unsigned long long offset = a.offset;
+  if (a.dyn) offset += static_cast<unsigned long long>(a.dyn->step) << 20;
+  const int row_end = min(a.rows, static_cast<int>(blockIdx.y + 1) * rows_per_block);
+  for (int row = blockIdx.y * rows_per_block + ty; row < row_end; row += 8) {
+    const float2 x = *reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col);
+    float y0 = fmaxf((x.x - m0) * r0 + b0, 0.f);
+    float y1 = fmaxf((x.y - m1) * r1 + b1, 0.f);
+    if (drop) {
+      bool k0, k1;
+      if (a.keep_mask) {
+        const uchar2 k = *reinterpret_cast<const uchar2*>(a.keep_mask + static_cast<size_t>(row) * a.n + col);
+        k0 = k.x != 0; k1 = k.y != 0;
+      } else {
+        const unsigned long long idx = (static_cast<unsigned long long>(row) * a.n + col) >> 1;
+        const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32),
+                                                   static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32)),
+                                        make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
+        k0 = u01(rnd.x) >= a.p_drop; k1 = u01(rnd.y) >= a.p_drop;
+      }
+      y0 = k0 ? y0 * keep_scale : 0.f;
+      y1 = k1 ? y1 * keep_scale : 0.f;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(a.out + static_cast<size_t>(row) * a.ld_out + col) = __floats2bfloat162_rn(y0, y1);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdArgs a, int rows_per_block) {
+  __shared__ double sh[8][BN_COLS][2];
+  __shared__ float s_s1[BN_COLS], s_s2[BN_COLS];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * BN_COLS + lane * 2;
+  const bool col_ok = col < a.n;
+  {
+    double r[4];
+    reduce_partials(a.stats, a.m_tiles, a.n, col, col_ok, sh, r);
+    if (ty == 0 && col_ok) {
+      for (int j = 0; j < 2; ++j) {
+        s_s1[lane * 2 + j] = static_cast<float>(r[j]);
+        s_s2[lane * 2 + j] = static_cast<float>(r[2 + j]);
+        if (blockIdx.y == 0) {
+          a.dbeta[col + j] = static_cast<float>(r[j]);
+          a.dgamma[col + j] = static_cast<float>(r[2 + j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!col_ok) return;
+  const float inv_n = 1.0f / a.rows;
+  const float m0 = a.mean[col], m1 = a.mean[col + 1];
+  const float rs0 = a.rstd[col], rs1 = a.rstd[col + 1];
+  const float g0 = a.gamma[col] * rs0, g1 = a.gamma[col + 1] * rs1;
+  const float c10 = a.train ? s_s1[lane * 2] * inv_n : 0.f, c11 = a.train ? s_s1[lane * 2 + 1] * inv_n : 0.f;
+  const float c20 = a.train ? s_s2[lane * 2] * inv_n : 0.f, c21 = a.train ? s_s2[lane * 2 + 1] * inv_n : 0.f;
+  const int row_end = min(a.rows, static_cast<int>(blockIdx.y + 1) * rows_per_block);
+  for (int row = blockIdx.y * rows_per_block + ty; row < row_end; row += 8) {
+    const float2 gy = __bfloat1622float2(
+        *reinterpret_cast<const __nv_bfloat162*>(a.gy + static_cast<size_t>(row) * a.ld_gy + col));
+    const float2 x = *reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col);
+    const float xh0 = (x.x - m0) * rs0, xh1 = (x.y - m1) * rs1;
+    const float o0 = g0 * (gy.x - c10 - xh0 * c20);
+    const float o1 = g1 * (gy.y - c11 - xh1 * c21);
+    *reinterpret_cast<__nv_bfloat162*>(a.gpre + static_cast<size_t>(row) * a.ld_gpre + col) = __floats2bfloat162_rn(o0, o1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Latent: mean over present encoders' (mu | logvar) heads, z = mu + eps * exp(logvar / 2), KL partials
+// (vae.py:11-15, 64-73; losses.py:42)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) latent_fwd_kernel(LatentFwdArgs a) {
+  __shared__ float sh[32];
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(a.rows) * a.L;
+  float kl = 0.f;
+  if (idx < total) {
+    const int r = static_cast<int>(idx / a.L);
+    const int j = static_cast<int>(idx - static_cast<long long>(r) * a.L);
+    float mu = 0.f, lv = 0.f;
+    for (int e = 0; e < a.n_enc; ++e) {
+      const float* p = a.ml[e] + static_cast<size_t>(r) * a.ld_ml[e];
+      mu += p[j];
+      lv += p[a.L + j];
+    }
+    if (a.n_enc > 1) { mu /= a.n_enc; lv /= a.n_enc; }
+    float eps;
+    if (a.eps_in) {
+      eps = a.eps_in[idx];
+    } else {
+      unsigned long long offset = a.offset;
+      if (a.dyn) offset += static_cast<unsigned long long>(a.dyn->step) << 20;
+      const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32),
+                                                 static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32) ^ 0x5EEDu),
+                                      make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
+      eps = normal_from(rnd.x, rnd.y);
+    }
+    const float sd = expf(0.5f * lv);
+    const float z = mu + eps * sd;
+    a.mu[idx] = mu;
+    a.logvar[idx] = lv;
+    a.eps_save[idx] = eps;
+    a.z[static_cast<size_t>(r) * a.ld_z + j] = __float2bfloat16(z);
+    kl = 1.0f + lv - mu * mu - expf(lv);
+  }
+  const float t = block_sum(kl, sh);
+  if (threadIdx.x == 0) a.kl_partials[blockIdx.x] = -0.5f * t;
+}
+
+__global__ void __launch_bounds__(256) latent_bwd_kernel(LatentBwdArgs a) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(a.rows) * a.L;
+  if (idx >= total) return;
+  const int r = static_cast<int>(idx / a.L);
+  const int j = static_cast<int>(idx - static_cast<long long>(r) * a.L);
+  const float beta = a.dyn ? a.dyn->beta_kl : a.beta;
+  const float gz = a.gz ? a.gz[static_cast<size_t>(r) * a.ld_gz + j] : 0.f;
+  const float mu = a.mu[idx], lv = a.logvar[idx], eps = a.eps[idx];
+  float gmu = gz + beta * mu;
+  float glv = gz * eps * 0.5f * expf(0.5f * lv) + beta * 0.5f * (expf(lv) - 1.0f);
+  if (a.gmu_in) gmu += a.gmu_in[idx];
+  if (a.glv_in) glv += a.glv_in[idx];
+  if (a.n_modalities > 1) { gmu /= a.n_modalities; glv /= a.n_modalities; }
+  a.gml[static_cast<size_t>(r) * a.ld_gml + j] = __float2bfloat16(gmu);
+  a.gml[static_cast<size_t>(r) * a.ld_gml + a.L + j] = __float2bfloat16(glv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused loss: MSE-sum + BCE-sum (ATen clamps) + weighted CE-sum + KL-sum, values and gradients
+// (losses.py:27-46; directional_losses.py:23-30, 48-55).  Block roles by blockIdx range.
+// ---------------------------------------------------------------------------------------------
+constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_PER_THREAD = 16;
+constexpr int LOSS_PER_BLOCK = LOSS_THREADS * LOSS_PER_THREAD;
+
+__host__ __device__ inline int ceil_div_ll(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+struct LossGrid { int nb_a, nb_b, nb_c, nb_k; };
+__host__ __device__ inline LossGrid loss_grid(const LossArgs& a) {
+  LossGrid g;
+  g.nb_a = a.recon_a ? ceil_div_ll(static_cast<long long>(a.rows) * a.width_a, LOSS_PER_BLOCK) : 0;
+  g.nb_b = a.recon_b ? ceil_div_ll(static_cast<long long>(a.rows) * a.width_b, LOSS_PER_BLOCK) : 0;
+  g.nb_c = a.logits ? ceil_div_ll(a.rows, LOSS_THREADS) : 0;
+  g.nb_k = (a.mu && !a.kl_partials) ? ceil_div_ll(static_cast<long long>(a.rows) * a.L, LOSS_PER_BLOCK) : 0;
+  return g;
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(LossArgs a) {
+  __shared__ float sh[32];
+  __shared__ bool s_last;
+  const LossGrid G = loss_grid(a);
+  const float beta = a.dyn ? a.dyn->beta_kl : a.beta;
+  const float gamma = a.dyn ? a.dyn->gamma : a.gamma;
+  const float gs = a.grad_scale;
+  const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
+  int b = blockIdx.x;
+  float acc = 0.f;
+  if (b < G.nb_a) {
+    // ---- MSE ----
+    const long long total = static_cast<long long>(a.rows) * a.width_a;
+    const long long base = static_cast<long long>(b) * LOSS_PER_BLOCK;
+#pragma unroll 4
+    for (int i = 0; i < LOSS_PER_THREAD; ++i) {
+      const long long idx = base + static_cast<long long>(i) * LOSS_THREADS + threadIdx.x;
+      if (idx < total) {
+        const float d = a.recon_a[idx] - __ldg(a.a + row0 * a.width_a + idx);
+        acc += d * d;
+        const float g = 2.0f * d * gs;
+        if (a.ga_f32) a.ga_f32[idx] = g;
+        if (a.ga_bf16) {
+          const int r = static_cast<int>(idx / a.width_a);
+          const int c = static_cast<int>(idx - static_cast<long long>(r) * a.width_a);
+          a.ga_bf16[static_cast<size_t>(r) * a.ld_ga + c] = __float2bfloat16(g);
+        }
+      }
+    }
+  } else if ((b -= G.nb_a) < G.nb_b) {
+    // ---- BCE ----
+    const long long total = static_cast<long long>(a.rows) * a.width_b;
+    const long long base = static_cast<long long>(b) * LOSS_PER_BLOCK;
+#pragma unroll 4
+    for (int i = 0; i < LOSS_PER_THREAD; ++i) {
+      const long long idx = base + static_cast<long long>(i) * LOSS_THREADS + threadIdx.x;
+      if (idx < total) {
+        const float y = a.recon_b[idx];
+        const float t = __ldg(a.b + row0 * a.width_b + idx);
+        const float ly = fmaxf(logf(y), -100.0f);
+        const float l1 = fmaxf(log1pf(-y), -100.0f);
+        acc -= t * ly + (1.0f - t) * l1;
+        const float yy = y * (1.0f - y);
+        const float gy = (y - t) / fmaxf(yy, 1e-12f) * gs;
+        if (a.gb_f32) a.gb_f32[idx] = gy;
+        if (a.gb_bf16) {
+          const int r = static_cast<int>(idx / a.width_b);
+          const int c = static_cast<int>(idx - static_cast<long long>(r) * a.width_b);
+          a.gb_bf16[static_cast<size_t>(r) * a.ld_gb + c] = __float2bfloat16(gy * yy);   // w.r.t. the logit
+        }
+      }
+    }
+  } else if ((b -= G.nb_b) < G.nb_c) {
+    // ---- weighted cross-entropy, one thread per sample ----
+    const int r = b * LOSS_THREADS + threadIdx.x;
+    if (r < a.rows) {
+      const float* x = a.logits + static_cast<size_t>(r) * a.n_sites;
+      const int t = static_cast<int>(a.site[row0 + r]);
+      float mx = -FLT_MAX;
+      for (int j = 0; j < a.n_sites; ++j) mx = fmaxf(mx, x[j]);
+      float se = 0.f;
+      for (int j = 0; j < a.n_sites; ++j) se += expf(x[j] - mx);
+      const float lse = logf(se) + mx;
+      const float w = a.class_w ? a.class_w[t] : 1.0f;
+      acc = -w * (x[t] - lse);
+      if (a.gc_f32 || a.gc_bf16) {
+        const float sc = w * gamma * gs;
+        for (int j = 0; j < a.n_sites; ++j) {
+          const float g = (expf(x[j] - lse) - (j == t ? 1.0f : 0.0f)) * sc;
+          if (a.gc_f32) a.gc_f32[static_cast<size_t>(r) * a.n_sites + j] = g;
+          if (a.gc_bf16) a.gc_bf16[static_cast<size_t>(r) * a.ld_gc + j] = __float2bfloat16(g);
+        }
+      }
+    }
+  } else if ((b -= G.nb_c) < G.nb_k) {
+    // ---- KL directly from mu / logvar (functional loss API) ----
+    const long long total = static_cast<long long>(a.rows) * a.L;
+    const long long base = static_cast<long long>(b) * LOSS_PER_BLOCK;
+    for (int i = 0; i < LOSS_PER_THREAD; ++i) {
+      const long long idx = base + static_cast<long long>(i) * LOSS_THREADS + threadIdx.x;
+      if (idx < total) {
+        const float mu = a.mu[idx], lv = a.logvar[idx];
+        const float e = expf(lv);
+        acc += -0.5f * (1.0f + lv - mu * mu - e);
+        if (a.gmu_f32) a.gmu_f32[idx] = beta * mu * gs;
+        if (a.glv_f32) a.glv_f32[idx] = beta * 0.5f * (e - 1.0f) * gs;
+      }
+    }
+  }
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    a.partials[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(a.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: fixed-order reduction of every role's partials ----
+  double sums[4] = {0, 0, 0, 0};   // mse, bce, ce, kl
+  const int starts[5] = {0, G.nb_a, G.nb_a + G.nb_b, G.nb_a + G.nb_b + G.nb_c, G.nb_a + G.nb_b + G.nb_c + G.nb_k};
+  __shared__ double dsh[LOSS_THREADS];
+  for (int role = 0; role < 4; ++role) {
+    double s = 0;
+    for (int i = starts[role] + threadIdx.x; i < starts[role + 1]; i += LOSS_THREADS) s += a.partials[i];
+    if (role == 3 && a.kl_partials)
+      for (int i = threadIdx.x; i < a.n_kl_partials; i += LOSS_THREADS) s += a.kl_partials[i];
+    dsh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = LOSS_THREADS / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) dsh[threadIdx.x] += dsh[threadIdx.x + o];
+      __syncthreads();
+    }
+    sums[role] = dsh[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double recon = sums[0] + sums[1];
+    a.out[0] = static_cast<float>(recon + static_cast<double>(gamma) * sums[2] + static_cast<double>(beta) * sums[3]);
+    a.out[1] = static_cast<float>(recon);
+    a.out[2] = static_cast<float>(sums[2]);
+    a.out[3] = static_cast<float>(sums[3]);
+    *a.counter = 0;   // re-arm for the next launch (graph replays)
+    if (a.dyn_bump) a.dyn_bump->batch_index += 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Autograd path: upstream fp32 dL/d(recon) -> bf16 operands of the backward GEMMs
+// ---------------------------------------------------------------------------------------------
+struct OutGradPack { OutGradArgs e[3]; int n; };
+__global__ void out_grad_kernel(OutGradPack p) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int e = 0; e < p.n; ++e) {
+    const OutGradArgs& a = p.e[e];
+    const long long total = static_cast<long long>(a.rows) * a.width;
+    for (long long i = tid; i < total; i += nthr) {
+      float g = a.g[i];
+      if (a.y) { const float y = a.y[i]; g *= y * (1.0f - y); }
+      const int r = static_cast<int>(i / a.width);
+      const int c = static_cast<int>(i - static_cast<long long>(r) * a.width);
+      a.dst[static_cast<size_t>(r) * a.ld_dst + c] = __float2bfloat16(g);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused multi-tensor AdamW over the flat arena + refresh of the bf16 MMA shadows (both orientations)
+// (torch.optim.AdamW semantics; call sites train_rna2dna.py:94-96, 185-189)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
+  const AdamChunk ch = a.chunks[blockIdx.x];
+  const AdamSegment sg = a.segs[ch.seg];
+  const long long seg_n = static_cast<long long>(sg.rows) * sg.cols;
+  float lr = a.lr, wd = a.weight_decay;
+  int step = a.step;
+  if (a.dyn) { lr = a.dyn->lr; wd = a.dyn->weight_decay; step = a.dyn->step; }
+  float bc1 = 1.f, bc2s = 1.f;
+  if (a.update) {
+    bc1 = 1.0f - powf(a.beta1, static_cast<float>(step));
+    bc2s = sqrtf(1.0f - powf(a.beta2, static_cast<float>(step)));
+  }
+  const float step_size = lr / bc1;
+#pragma unroll 4
+  for (int i = 0; i < ADAM_CHUNK / 256; ++i) {
+    const long long e = static_cast<long long>(ch.start) + i * 256 + threadIdx.x;
+    if (e >= seg_n) break;
+    const long long gi = sg.offset + e;
+    float p = a.p[gi];
+    if (a.update) {
+      const float g = a.g[gi];
+      float m = a.m[gi], v = a.v[gi];
+      p *= (1.0f - lr * wd);
+      m = a.beta1 * m + (1.0f - a.beta1) * g;
+      v = a.beta2 * v + (1.0f - a.beta2) * g * g;
+      const float denom = sqrtf(v) / bc2s + a.eps;
+      p -= step_size * (m / denom);
+      a.p[gi] = p; a.m[gi] = m; a.v[gi] = v;
+      if (a.zero_grad) a.g[gi] = 0.f;
+    }
+    if (sg.shadow_off >= 0 || sg.shadow_t_off >= 0) {
+      const int r = static_cast<int>(e / sg.cols);
+      const int c = static_cast<int>(e - static_cast<long long>(r) * sg.cols);
+      const bf16 pb = __float2bfloat16(p);
+      if (sg.shadow_off >= 0) a.shadow[sg.shadow_off + static_cast<long long>(r) * sg.ld_shadow + c] = pb;
+      if (sg.shadow_t_off >= 0) a.shadow[sg.shadow_t_off + static_cast<long long>(c) * sg.ld_shadow_t + r] = pb;
+    }
+  }
+}
+
+inline int grid_for(long long work_items, int threads, int max_blocks) {
+  long long b = (work_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+cudaError_t launch_ingest(const IngestArgs& a, cudaStream_t s) {
+  long long work = 0;
+  for (int e = 0; e < a.n; ++e) work = std::max(work, static_cast<long long>(a.rows) * (a.ld_dst[e] / 2));
+  if (a.site) work = std::max(work, static_cast<long long>(a.rows) * std::max(a.ld_hsite, a.ld_onehot));
+  ingest_kernel<<<grid_for(work, 256, 148 * 8), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+static int bn_rows_per_block(int rows, int m_tiles) {
+  int rpb = 64;
+  if (m_tiles * 2 > rpb) rpb = m_tiles * 2;
+  return rpb;
+}
+
+cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s) {
+  if (a.n % 2) return cudaErrorInvalidValue;
+  const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0);
+  dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
+  bn_act_kernel<<<grid, 256, 0, s>>>(a, rpb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {
+  if (a.n % 2) return cudaErrorInvalidValue;
+  const int rpb = bn_rows_per_block(a.rows, a.m_tiles);
+  dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
+  bn_bwd_kernel<<<grid, 256, 0, s>>>(a, rpb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_t s) {
+  const long long total = static_cast<long long>(a.rows) * a.L;
+  const int grid = static_cast<int>((total + 255) / 256);
+  if (grid_out) *grid_out = grid;
+  latent_fwd_kernel<<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
+  const long long total = static_cast<long long>(a.rows) * a.L;
+  latent_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+int loss_grid_size(int rows, int width_a, int width_b, int n_sites) {
+  LossArgs a{};
+  a.rows = rows;
+  a.recon_a = width_a ? reinterpret_cast<const float*>(1) : nullptr; a.width_a = width_a;
+  a.recon_b = width_b ? reinterpret_cast<const float*>(1) : nullptr; a.width_b = width_b;
+  a.logits = n_sites ? reinterpret_cast<const float*>(1) : nullptr; a.n_sites = n_sites;
+  a.mu = reinterpret_cast<const float*>(1); a.L = 128;
+  const LossGrid g = loss_grid(a);
+  return g.nb_a + g.nb_b + g.nb_c + g.nb_k + 1;
+}
+
+cudaError_t launch_loss(const LossArgs& a, cudaStream_t s) {
+  const LossGrid g = loss_grid(a);
+  int grid = g.nb_a + g.nb_b + g.nb_c + g.nb_k;
+  if (grid == 0) grid = 1;   // KL-from-partials only: one block does the final reduction
+  loss_kernel<<<grid, LOSS_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  OutGradPack p{};
+  p.n = n;
+  long long work = 0;
+  for (int i = 0; i < n; ++i) { p.e[i] = a[i]; work = std::max(work, static_cast<long long>(a[i].rows) * a[i].width); }
+  out_grad_kernel<<<grid_for(work, 256, 148 * 8), 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s) {
+  if (a.n_chunks <= 0) return cudaSuccess;
+  adamw_kernel<<<a.n_chunks, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace vla

@@ -1,0 +1,969 @@
+// Host side of libvla_b200: parameter-arena layout, workspace, launch sequencing of the forward,
+// backward and fused train step, and the extern "C" boundary declared in include/vla_b200.h.
+#include "../../include/vla_b200.h"
+#include "vla_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace vla;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(expr)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(VLA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+  } while (0)
+
+inline int pad8(int x) { return (x + 7) & ~7; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+struct Lin {
+  int out = 0, in = 0;
+  long long w_off = -1, b_off = -1;
+  long long sh_off = -1; int sh_ld = 0;      // bf16 [out, sh_ld]   (K-major B operand of forward GEMMs)
+  long long sht_off = -1; int sht_ld = 0;    // bf16 [in, sht_ld]   (K-major B operand of data-gradient GEMMs)
+};
+struct Bn { int n = 0; long long g_off = -1, b_off = -1, rm_off = -1, rv_off = -1; int counter = -1; };
+struct Enc {
+  char type; std::string prefix; int in_dim; int slot;   // slot: 0 = a, 1 = b, 2 = site
+  std::vector<Lin> fc; std::vector<Bn> bn; Lin heads; long long emb_off = -1;
+  int first_drop = 0;                                     // index of this encoder's first dropout layer
+};
+struct Dec {
+  char type; std::string prefix; int out_dim;
+  int cat_off = 0, cat_w = 0;                             // slice of the fused first layer
+  std::vector<Lin> rest;
+};
+
+struct EncWS {
+  bf16* x = nullptr; int ldx = 0;                         // bf16 input (dense) / gathered embedding (site)
+  bf16* onehot = nullptr; int ld_onehot = 0;
+  bf16* g_x = nullptr;                                    // site: gradient w.r.t. the gathered embedding
+  std::vector<float*> pre, stats, bstats, mean, rstd;
+  std::vector<bf16*> act, gy, gpre;
+  float* ml = nullptr;
+};
+struct DecWS {
+  std::vector<bf16*> act, gact;                           // hidden activations after the fused first layer
+  bf16* g_out = nullptr; int ld_gout = 0;                 // bf16 gradient w.r.t. the last layer's pre-activation
+  float* recon = nullptr;                                 // fp32 output when the caller passes none
+};
+
+struct TmapKey {
+  uintptr_t base; uint64_t inner, outer, pitch; uint32_t box_outer;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(base, inner, outer, pitch, box_outer) < std::tie(o.base, o.inner, o.outer, o.pitch, o.box_outer);
+  }
+};
+
+}  // namespace
+
+struct vla_model {
+  vla_config_t cfg{};
+  int L = 0, E = 0, S = 0;
+  std::vector<Enc> encs;
+  std::vector<Dec> decs;
+  Lin cat;
+  int n_drop = 0;
+  long long n_params = 0, n_buffers = 0, n_shadow = 0;
+  int n_bn = 0;
+  std::vector<vla_tensor_info_t> infos;
+  std::vector<AdamSegment> segs_h;
+  std::vector<AdamChunk> chunks_h;
+  // device-resident, batch independent
+  bf16* shadow = nullptr;
+  AdamSegment* segs_d = nullptr;
+  AdamChunk* chunks_d = nullptr;
+  DynParams* dyn = nullptr;
+  float* loss_partials = nullptr; unsigned int* loss_counter = nullptr; float* loss_out = nullptr;
+  // workspace sized for `cap` rows
+  int cap = 0;
+  char* ws = nullptr;
+  std::vector<EncWS> ews;
+  std::vector<DecWS> dws;
+  float *mu = nullptr, *logvar = nullptr, *eps = nullptr, *kl_partials = nullptr, *gz = nullptr;
+  bf16 *z = nullptr, *gml = nullptr, *d0 = nullptr, *g_d0 = nullptr;
+  int ldz = 0, ldgml = 0;
+  std::map<TmapKey, CUtensorMap> tmaps;
+  // what the last forward left in the workspace
+  bool saved = false; int saved_batch = 0, saved_present = 0, saved_train = 0, kl_grid = 0;
+  unsigned long long generation = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Layout
+// ---------------------------------------------------------------------------------------------
+struct ArenaBuilder {
+  vla_model* m;
+  long long p = 0, b = 0, sh = 0;
+  long long take_p(long long n) { long long o = p; p += (n + 3) & ~3LL; return o; }
+  long long take_b(long long n) { long long o = b; b += (n + 3) & ~3LL; return o; }
+  long long take_sh(long long n) { long long o = sh; sh += (n + 63) & ~63LL; return o; }   // 128-byte aligned
+  void info(const std::string& name, int kind, long long off, int d0, int d1 = -1) {
+    vla_tensor_info_t t{};
+    snprintf(t.name, sizeof(t.name), "%s", name.c_str());
+    t.kind = kind; t.offset = off;
+    t.ndim = d0 < 0 ? 0 : (d1 < 0 ? 1 : 2);
+    t.shape[0] = d0 < 0 ? 0 : d0; t.shape[1] = d1 < 0 ? 0 : d1;
+    m->infos.push_back(t);
+  }
+  void seg(long long off, int rows, int cols, long long sh_off, int sh_ld, long long sht_off, int sht_ld) {
+    AdamSegment s{off, rows, cols, sh_off, sh_ld, sht_off, sht_ld};
+    const int idx = static_cast<int>(m->segs_h.size());
+    m->segs_h.push_back(s);
+    const long long n = static_cast<long long>(rows) * cols;
+    for (long long st = 0; st < n; st += ADAM_CHUNK) m->chunks_h.push_back(AdamChunk{idx, static_cast<int>(st)});
+  }
+  // A Linear whose weight rows may be exposed under several state_dict names (fused groups).
+  Lin linear(int out, int in, bool need_t) {
+    Lin l; l.out = out; l.in = in;
+    l.w_off = take_p(static_cast<long long>(out) * in);
+    l.b_off = take_p(out);
+    l.sh_ld = pad8(in);
+    l.sh_off = take_sh(static_cast<long long>(out) * l.sh_ld);
+    if (need_t) { l.sht_ld = pad8(out); l.sht_off = take_sh(static_cast<long long>(in) * l.sht_ld); }
+    seg(l.w_off, out, in, l.sh_off, l.sh_ld, l.sht_off, l.sht_ld);
+    seg(l.b_off, out, 1, -1, 0, -1, 0);
+    return l;
+  }
+};
+
+int build_layout(vla_model* m) {
+  const vla_config_t& c = m->cfg;
+  m->L = c.latent; m->E = c.embed; m->S = c.n_sites;
+  struct StackSpec { const char* prefix; char type; };
+  std::vector<StackSpec> es, ds;
+  if (c.kind == VLA_KIND_MULTIMODAL) {
+    es = {{"encoder_a", 'A'}, {"encoder_b", 'B'}, {"encoder_c", 'C'}};
+    ds = {{"decoder_a", 'A'}, {"decoder_b", 'B'}, {"decoder_c", 'C'}};
+  } else if (c.kind == VLA_KIND_RNA2DNA) {
+    es = {{"encoder_rna", 'A'}, {"encoder_site", 'C'}};
+    ds = {{"decoder_dna", 'B'}};
+  } else if (c.kind == VLA_KIND_DNA2RNA) {
+    es = {{"encoder_dna", 'B'}, {"encoder_site", 'C'}};
+    ds = {{"decoder_rna", 'A'}};
+  } else {
+    return fail(VLA_ERR_INVALID, "unknown model kind");
+  }
+  ArenaBuilder ab{m};
+  const int L = m->L;
+  for (const auto& s : es) {
+    Enc e; e.type = s.type; e.prefix = s.prefix;
+    e.slot = s.type == 'A' ? 0 : (s.type == 'B' ? 1 : 2);
+    e.first_drop = m->n_drop;
+    int last;
+    if (s.type == 'C') {
+      e.in_dim = c.n_sites;
+      e.emb_off = ab.take_p(static_cast<long long>(c.n_sites) * c.embed);
+      ab.seg(e.emb_off, c.n_sites, c.embed, -1, 0, -1, 0);
+      ab.info(e.prefix + ".embedding.weight", VLA_TENSOR_PARAM, e.emb_off, c.n_sites, c.embed);
+      last = c.embed;
+    } else {
+      e.in_dim = s.type == 'A' ? c.dim_a : c.dim_b;
+      std::vector<int> hidden = s.type == 'A' ? std::vector<int>{128} : std::vector<int>{512, 256};
+      last = e.in_dim;
+      for (size_t i = 0; i < hidden.size(); ++i) {
+        const int h = hidden[i];
+        Lin l = ab.linear(h, last, /*need_t=*/i > 0);   // no data gradient for the input layer
+        Bn bn; bn.n = h;
+        bn.g_off = ab.take_p(h); ab.seg(bn.g_off, h, 1, -1, 0, -1, 0);
+        bn.b_off = ab.take_p(h); ab.seg(bn.b_off, h, 1, -1, 0, -1, 0);
+        bn.rm_off = ab.take_b(h); bn.rv_off = ab.take_b(h);
+        bn.counter = m->n_bn++;
+        const std::string fc = e.prefix + ".fc." + std::to_string(4 * i);
+        const std::string nb = e.prefix + ".fc." + std::to_string(4 * i + 1);
+        ab.info(fc + ".weight", VLA_TENSOR_PARAM, l.w_off, h, last);
+        ab.info(fc + ".bias", VLA_TENSOR_PARAM, l.b_off, h);
+        ab.info(nb + ".weight", VLA_TENSOR_PARAM, bn.g_off, h);
+        ab.info(nb + ".bias", VLA_TENSOR_PARAM, bn.b_off, h);
+        ab.info(nb + ".running_mean", VLA_TENSOR_BUFFER, bn.rm_off, h);
+        ab.info(nb + ".running_var", VLA_TENSOR_BUFFER, bn.rv_off, h);
+        ab.info(nb + ".num_batches_tracked", VLA_TENSOR_COUNTER, bn.counter, -1);
+        e.fc.push_back(l); e.bn.push_back(bn);
+        last = h;
+        m->n_drop++;
+      }
+    }
+    // fused heads: rows [0, L) = fc_mu, rows [L, 2L) = fc_logvar
+    e.heads = ab.linear(2 * L, last, /*need_t=*/true);
+    ab.info(e.prefix + ".fc_mu.weight", VLA_TENSOR_PARAM, e.heads.w_off, L, last);
+    ab.info(e.prefix + ".fc_mu.bias", VLA_TENSOR_PARAM, e.heads.b_off, L);
+    ab.info(e.prefix + ".fc_logvar.weight", VLA_TENSOR_PARAM, e.heads.w_off + static_cast<long long>(L) * last, L, last);
+    ab.info(e.prefix + ".fc_logvar.bias", VLA_TENSOR_PARAM, e.heads.b_off + L, L);
+    m->encs.push_back(e);
+  }
+  // fused first decoder layers: one [sum of first hidden widths, L] matrix
+  int cat_w = 0;
+  for (const auto& s : ds) cat_w += s.type == 'A' ? 128 : (s.type == 'B' ? 256 : 64);
+  m->cat = ab.linear(cat_w, L, /*need_t=*/true);
+  int off = 0;
+  for (const auto& s : ds) {
+    Dec d; d.type = s.type; d.prefix = s.prefix;
+    d.out_dim = s.type == 'A' ? c.dim_a : (s.type == 'B' ? c.dim_b : c.n_sites);
+    d.cat_w = s.type == 'A' ? 128 : (s.type == 'B' ? 256 : 64);
+    d.cat_off = off; off += d.cat_w;
+    ab.info(d.prefix + ".fc.0.weight", VLA_TENSOR_PARAM, m->cat.w_off + static_cast<long long>(d.cat_off) * L, d.cat_w, L);
+    ab.info(d.prefix + ".fc.0.bias", VLA_TENSOR_PARAM, m->cat.b_off + d.cat_off, d.cat_w);
+    std::vector<int> widths = s.type == 'B' ? std::vector<int>{512, d.out_dim} : std::vector<int>{d.out_dim};
+    int last = d.cat_w;
+    for (size_t i = 0; i < widths.size(); ++i) {
+      Lin l = ab.linear(widths[i], last, true);
+      const std::string fc = d.prefix + ".fc." + std::to_string(2 * (i + 1));
+      ab.info(fc + ".weight", VLA_TENSOR_PARAM, l.w_off, widths[i], last);
+      ab.info(fc + ".bias", VLA_TENSOR_PARAM, l.b_off, widths[i]);
+      d.rest.push_back(l);
+      last = widths[i];
+    }
+    m->decs.push_back(d);
+  }
+  m->n_params = ab.p; m->n_buffers = ab.b; m->n_shadow = ab.sh;
+  return VLA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Workspace
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+  size_t off = 0; char* base = nullptr;
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+void carve(vla_model* m, Bump& b, int cap) {
+  const int L = m->L;
+  const int mt = ceil_div(cap, GEMM_BM);
+  m->ews.assign(m->encs.size(), EncWS{});
+  for (size_t i = 0; i < m->encs.size(); ++i) {
+    const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+    if (e.type == 'C') {
+      w.ldx = pad8(m->E); w.x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
+      w.g_x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
+      w.ld_onehot = pad8(m->S); w.onehot = b.take<bf16>(static_cast<size_t>(cap) * w.ld_onehot);
+    } else {
+      w.ldx = pad8(e.in_dim); w.x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
+      for (const Lin& l : e.fc) {
+        w.pre.push_back(b.take<float>(static_cast<size_t>(cap) * l.out));
+        w.stats.push_back(b.take<float>(static_cast<size_t>(mt) * 2 * l.out));
+        w.bstats.push_back(b.take<float>(static_cast<size_t>(mt) * 2 * l.out));
+        w.mean.push_back(b.take<float>(l.out));
+        w.rstd.push_back(b.take<float>(l.out));
+        w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
+        w.gy.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
+        w.gpre.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
+      }
+    }
+    w.ml = b.take<float>(static_cast<size_t>(cap) * 2 * L);
+  }
+  m->mu = b.take<float>(static_cast<size_t>(cap) * L);
+  m->logvar = b.take<float>(static_cast<size_t>(cap) * L);
+  m->eps = b.take<float>(static_cast<size_t>(cap) * L);
+  m->gz = b.take<float>(static_cast<size_t>(cap) * L);
+  m->kl_partials = b.take<float>(ceil_div(cap * L, 256) + 1);
+  m->ldz = pad8(L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
+  m->ldgml = pad8(2 * L); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
+  m->d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
+  m->g_d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
+  m->dws.assign(m->decs.size(), DecWS{});
+  for (size_t i = 0; i < m->decs.size(); ++i) {
+    const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+    for (size_t r = 0; r + 1 < d.rest.size(); ++r) {
+      w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * d.rest[r].out));
+      w.gact.push_back(b.take<bf16>(static_cast<size_t>(cap) * d.rest[r].out));
+    }
+    w.ld_gout = pad8(d.out_dim);
+    w.g_out = b.take<bf16>(static_cast<size_t>(cap) * w.ld_gout);
+    w.recon = b.take<float>(static_cast<size_t>(cap) * d.out_dim);
+  }
+  const int lg = loss_grid_size(cap, m->cfg.dim_a, m->cfg.dim_b, m->S);
+  m->loss_partials = b.take<float>(lg);
+}
+
+int reserve(vla_model* m, int batch) {
+  if (batch <= m->cap) return VLA_OK;
+  int cap = std::max(batch, 32);
+  if (m->ws) { CK(cudaDeviceSynchronize()); CK(cudaFree(m->ws)); m->ws = nullptr; m->cap = 0; }
+  m->tmaps.clear();
+  m->saved = false;
+  Bump dry; carve(m, dry, cap);
+  const size_t bytes = dry.off + 256;
+  CK(cudaMalloc(&m->ws, bytes));
+  CK(cudaMemset(m->ws, 0, bytes));
+  Bump real; real.base = m->ws; carve(m, real, cap);
+  m->cap = cap;
+  return VLA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM problem builders
+// ---------------------------------------------------------------------------------------------
+int get_tmap(vla_model* m, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+             uint32_t box_outer) {
+  TmapKey k{reinterpret_cast<uintptr_t>(base), inner, outer, pitch_bytes, box_outer};
+  auto it = m->tmaps.find(k);
+  if (it == m->tmaps.end()) {
+    CUtensorMap t;
+    std::string err;
+    if (!make_tmap_bf16(&t, base, inner, outer, pitch_bytes, 64, box_outer, &err)) return fail(VLA_ERR_CUDA, err);
+    if (m->tmaps.size() > 4096) m->tmaps.clear();
+    it = m->tmaps.emplace(k, t).first;
+  }
+  *out = it->second;
+  return VLA_OK;
+}
+
+int choose_bn_nt(int M, int N) {
+  const int mt = ceil_div(M, GEMM_BM);
+  int best = 16; double best_cost = 1e30;
+  for (int bn = 16; bn <= GEMM_BN_MAX_NT; bn += 16) {
+    const int tiles = mt * ceil_div(N, bn);
+    const double cost = static_cast<double>(ceil_div(tiles, 148)) * (bn + 24);
+    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+int choose_bn_tn(int N) {
+  int best = 64; int best_cost = 1 << 30;
+  for (int bn = 64; bn <= GEMM_BN_MAX_TN; bn += 64) {
+    const int cost = ceil_div(N, bn) * bn;
+    if (cost < best_cost || (cost == best_cost && bn > best)) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+// C[M,N] = A[M,K] * W[N,K]^T ; A bf16 [M, lda], W bf16 [N, ldw]
+int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int flags,
+           GemmProblem** out, int force_bn = 0) {
+  if (g.nprob >= GEMM_MAX_PROBLEMS) return fail(VLA_ERR_STATE, "too many problems in one GEMM group");
+  GemmProblem& p = g.p[g.nprob];
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.BN = force_bn ? force_bn : choose_bn_nt(M, N);
+  p.m_tiles = ceil_div(M, GEMM_BM); p.n_tiles = ceil_div(N, p.BN);
+  p.k_splits = 1; p.kb_per_split = ceil_div(K, GEMM_BK);
+  p.flags = flags;
+  int rc;
+  if ((rc = get_tmap(m, &p.tmA, A, K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
+  if ((rc = get_tmap(m, &p.tmB, W, K, N, static_cast<uint64_t>(ldw) * 2, p.BN))) return rc;
+  p.tile_begin = g.total_tiles;
+  g.total_tiles += p.m_tiles * p.n_tiles;
+  g.nprob++;
+  *out = &p;
+  return VLA_OK;
+}
+
+// dW[M,N] += G[Kb,M]^T * X[Kb,N] ; G bf16 [Kb, ldg], X bf16 [Kb, ldx]; tiling is fixed up by finalize_tn
+int add_tn(vla_model* m, GemmGroup& g, const bf16* G, int ldg, const bf16* X, int ldx, int M, int N, int Kb, float* dW,
+           int ld_dw, float* dbias, int force_bn = 0) {
+  if (g.nprob >= GEMM_MAX_PROBLEMS) return fail(VLA_ERR_STATE, "too many problems in one GEMM group");
+  GemmProblem& p = g.p[g.nprob];
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = Kb;
+  p.BN = force_bn ? force_bn : choose_bn_tn(N);
+  p.m_tiles = ceil_div(M, GEMM_BM); p.n_tiles = ceil_div(N, p.BN);
+  p.flags = GF_RED | (dbias ? GF_BIASGRAD : 0);
+  p.out_f32 = dW; p.ld_f32 = ld_dw; p.bias_grad = dbias;
+  int rc;
+  if ((rc = get_tmap(m, &p.tmA, G, M, Kb, static_cast<uint64_t>(ldg) * 2, 64))) return rc;
+  if ((rc = get_tmap(m, &p.tmB, X, N, Kb, static_cast<uint64_t>(ldx) * 2, 64))) return rc;
+  g.nprob++;
+  return VLA_OK;
+}
+void finalize_tn(GemmGroup& g, int Kb, int force_splits = 0) {
+  int base = 0;
+  for (int i = 0; i < g.nprob; ++i) base += g.p[i].m_tiles * g.p[i].n_tiles;
+  const int kb_total = ceil_div(Kb, GEMM_BK);
+  int splits = force_splits ? force_splits : std::max(1, (2 * 148 + base / 2) / std::max(base, 1));
+  splits = std::min(splits, kb_total);
+  const int per = ceil_div(kb_total, splits);
+  splits = ceil_div(kb_total, per);
+  g.total_tiles = 0;
+  for (int i = 0; i < g.nprob; ++i) {
+    GemmProblem& p = g.p[i];
+    p.k_splits = splits; p.kb_per_split = per;
+    p.tile_begin = g.total_tiles;
+    g.total_tiles += p.m_tiles * p.n_tiles * splits;
+  }
+}
+
+void init_group(GemmGroup& g) { g.nprob = 0; g.total_tiles = 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Sequencing
+// ---------------------------------------------------------------------------------------------
+struct FwdIO {
+  const float* params; float* buffers; long long* counters;
+  const float* x[2]; const long long* site;
+  int batch, train;
+  const float* eps; const unsigned char* const* keep_masks;
+  unsigned long long seed, offset;
+  float* recon[3];   // by decoder type A, B, C
+  float* mu; float* logvar;
+  bool engine;       // train step: dyn-driven Philox offsets / step bump
+  int n_batches;     // train step over a resident dataset
+};
+
+int present_mask(const vla_model* m, const FwdIO& io) {
+  int mask = 0;
+  for (size_t i = 0; i < m->encs.size(); ++i) {
+    const Enc& e = m->encs[i];
+    const bool here = e.slot == 2 ? io.site != nullptr : io.x[e.slot] != nullptr;
+    if (here) mask |= 1 << i;
+  }
+  return mask;
+}
+
+int run_shadow_refresh(vla_model* m, const float* params, cudaStream_t st) {
+  AdamArgs a{};
+  a.p = const_cast<float*>(params); a.shadow = m->shadow;
+  a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
+  a.update = 0;
+  CK(launch_adamw(a, st));
+  return VLA_OK;
+}
+
+int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
+  const int B = io.batch, L = m->L;
+  if (B <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
+  const int present = present_mask(m, io);
+  if (!present) return fail(VLA_ERR_INVALID, "no encoder input present");
+  int rc;
+  if ((rc = reserve(m, B))) return rc;
+  if (io.train && B < 2)
+    for (size_t i = 0; i < m->encs.size(); ++i)
+      if ((present >> i & 1) && m->encs[i].type != 'C')
+        return fail(VLA_ERR_INVALID, "Expected more than 1 value per channel when training (BatchNorm1d)");
+  const float* P = io.params;
+  const bf16* SH = m->shadow;
+
+  // ---- ingest ----
+  {
+    IngestArgs a{};
+    a.rows = B;
+    for (size_t i = 0; i < m->encs.size(); ++i) {
+      if (!(present >> i & 1)) continue;
+      const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+      if (e.type == 'C') {
+        a.site = io.site; a.emb = P + e.emb_off; a.h_site = w.x; a.ld_hsite = w.ldx;
+        a.onehot = w.onehot; a.ld_onehot = w.ld_onehot; a.n_sites = m->S; a.embed = m->E;
+      } else {
+        a.src[a.n] = io.x[e.slot]; a.dst[a.n] = w.x; a.width[a.n] = e.in_dim; a.ld_dst[a.n] = w.ldx; a.n++;
+      }
+    }
+    a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches;
+    CK(launch_ingest(a, st));
+  }
+  const int mt = ceil_div(B, GEMM_BM);
+  // ---- encoders, round by round ----
+  size_t max_depth = 0;
+  for (size_t i = 0; i < m->encs.size(); ++i) if (present >> i & 1) max_depth = std::max(max_depth, m->encs[i].fc.size());
+  for (size_t r = 0; r <= max_depth; ++r) {
+    GemmGroup g; init_group(g);
+    for (size_t i = 0; i < m->encs.size(); ++i) {
+      if (!(present >> i & 1)) continue;
+      const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+      GemmProblem* p;
+      if (r < e.fc.size()) {
+        const Lin& l = e.fc[r];
+        const bf16* A = r == 0 ? w.x : w.act[r - 1];
+        const int lda = r == 0 ? w.ldx : e.fc[r - 1].out;
+        const int flags = GF_BIAS | GF_OUT_F32 | (io.train ? GF_COLSTATS : 0);
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+        p->bias = P + l.b_off; p->out_f32 = w.pre[r]; p->ld_f32 = l.out; p->stats = w.stats[r];
+      } else if (r == e.fc.size()) {
+        const Lin& l = e.heads;
+        const bf16* A = r == 0 ? w.x : w.act[r - 1];
+        const int lda = r == 0 ? w.ldx : e.fc[r - 1].out;
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_OUT_F32, &p))) return rc;
+        p->bias = P + l.b_off; p->out_f32 = w.ml; p->ld_f32 = 2 * L;
+      }
+    }
+    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+    for (size_t i = 0; i < m->encs.size(); ++i) {
+      if (!(present >> i & 1)) continue;
+      const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+      if (r >= e.fc.size()) continue;
+      const Bn& bn = e.bn[r];
+      BnActArgs a{};
+      a.pre = w.pre[r]; a.ld_pre = bn.n; a.stats = w.stats[r]; a.m_tiles = mt;
+      a.gamma = P + bn.g_off; a.beta = P + bn.b_off;
+      a.running_mean = io.buffers + bn.rm_off; a.running_var = io.buffers + bn.rv_off;
+      a.num_batches_tracked = io.counters ? io.counters + bn.counter : nullptr;
+      a.save_mean = w.mean[r]; a.save_rstd = w.rstd[r];
+      a.out = w.act[r]; a.ld_out = bn.n;
+      a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
+      a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
+      a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
+      CK(launch_bn_act(a, st));
+    }
+  }
+  // ---- latent ----
+  {
+    LatentFwdArgs a{};
+    for (size_t i = 0; i < m->encs.size(); ++i)
+      if (present >> i & 1) { a.ml[a.n_enc] = m->ews[i].ml; a.ld_ml[a.n_enc] = 2 * L; a.n_enc++; }
+    a.eps_in = io.eps; a.seed = io.seed; a.offset = io.offset * 16; a.dyn = io.engine ? m->dyn : nullptr;
+    a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz;
+    a.kl_partials = m->kl_partials; a.rows = B; a.L = L;
+    CK(launch_latent_fwd(a, &m->kl_grid, st));
+    if (io.mu) CK(cudaMemcpyAsync(io.mu, m->mu, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+    if (io.logvar) CK(cudaMemcpyAsync(io.logvar, m->logvar, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+  }
+  // ---- decoders ----
+  {
+    GemmGroup g; init_group(g); GemmProblem* p;
+    const Lin& l = m->cat;
+    if ((rc = add_nt(m, g, m->z, m->ldz, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p))) return rc;
+    p->bias = P + l.b_off; p->out_bf16 = m->d0; p->ld_bf16 = l.out;
+    CK(launch_gemm_group(g, 0, st));
+  }
+  size_t max_rest = 0;
+  for (const Dec& d : m->decs) max_rest = std::max(max_rest, d.rest.size());
+  for (size_t r = 0; r < max_rest; ++r) {
+    GemmGroup g; init_group(g);
+    for (size_t i = 0; i < m->decs.size(); ++i) {
+      const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+      if (r >= d.rest.size()) continue;
+      const Lin& l = d.rest[r];
+      const bf16* A = r == 0 ? m->d0 + d.cat_off : w.act[r - 1];
+      const int lda = r == 0 ? m->cat.out : d.rest[r - 1].out;
+      GemmProblem* p;
+      const bool last = r + 1 == d.rest.size();
+      if (last) {
+        const int slot = d.type == 'A' ? 0 : (d.type == 'B' ? 1 : 2);
+        float* dst = io.recon[slot] ? io.recon[slot] : w.recon;
+        const int flags = GF_BIAS | GF_OUT_F32 | (d.type == 'B' ? GF_SIGMOID : 0);
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+        p->bias = P + l.b_off; p->out_f32 = dst; p->ld_f32 = l.out;
+      } else {
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p))) return rc;
+        p->bias = P + l.b_off; p->out_bf16 = w.act[r]; p->ld_bf16 = l.out;
+      }
+    }
+    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+  }
+  m->saved = true; m->saved_batch = B; m->saved_present = present; m->saved_train = io.train;
+  m->generation++;
+  return VLA_OK;
+}
+
+struct BwdIO {
+  const float* params;
+  const float* g_recon[3]; const float* recon_b;   // fp32 upstream gradients (autograd path), may be null
+  const float* g_mu; const float* g_logvar;
+  float* grads;
+  bool engine;                                     // bf16 output gradients already written by the loss kernel
+  bool zero_grads;
+};
+
+int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
+  if (!m->saved) return fail(VLA_ERR_STATE, "vla_backward without a preceding vla_forward on this handle");
+  const int B = m->saved_batch, L = m->L, present = m->saved_present, train = m->saved_train;
+  const float* P = io.params; const bf16* SH = m->shadow; float* G = io.grads;
+  int rc;
+  if (io.zero_grads) CK(cudaMemsetAsync(G, 0, sizeof(float) * m->n_params, st));
+  // which decoders carry a gradient
+  std::vector<bool> active(m->decs.size(), false);
+  if (!io.engine) {
+    OutGradArgs og[3]; int n = 0;
+    for (size_t i = 0; i < m->decs.size(); ++i) {
+      const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+      const int slot = d.type == 'A' ? 0 : (d.type == 'B' ? 1 : 2);
+      if (!io.g_recon[slot]) continue;
+      if (d.type == 'B' && !io.recon_b) return fail(VLA_ERR_INVALID, "g_recon_b given without recon_b");
+      og[n].g = io.g_recon[slot]; og[n].width = d.out_dim; og[n].y = d.type == 'B' ? io.recon_b : nullptr;
+      og[n].dst = w.g_out; og[n].ld_dst = w.ld_gout; og[n].rows = B; n++;
+      active[i] = true;
+    }
+    CK(launch_out_grad(og, n, st));
+  } else {
+    for (size_t i = 0; i < m->decs.size(); ++i) active[i] = true;
+  }
+  bool any_dec = false;
+  for (bool a : active) any_dec = any_dec || a;
+  // ---- decoder data gradients, last layer first ----
+  size_t max_rest = 0;
+  for (const Dec& d : m->decs) max_rest = std::max(max_rest, d.rest.size());
+  for (size_t rr = max_rest; rr-- > 0;) {
+    GemmGroup g; init_group(g);
+    for (size_t i = 0; i < m->decs.size(); ++i) {
+      const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+      if (!active[i] || rr >= d.rest.size()) continue;
+      const Lin& l = d.rest[rr];
+      const bool last = rr + 1 == d.rest.size();
+      const bf16* A = last ? w.g_out : w.gact[rr];
+      const int lda = last ? w.ld_gout : l.out;
+      GemmProblem* p;
+      // dX[B, in] = dY[B, out] * W[out, in]  ->  NT with the transposed shadow [in, out]
+      if ((rc = add_nt(m, g, A, lda, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_MASK | GF_OUT_BF16, &p))) return rc;
+      if (rr == 0) {
+        p->mask_src = m->d0 + d.cat_off; p->ld_mask = m->cat.out;
+        p->out_bf16 = m->g_d0 + d.cat_off; p->ld_bf16 = m->cat.out;
+      } else {
+        p->mask_src = w.act[rr - 1]; p->ld_mask = l.in;
+        p->out_bf16 = w.gact[rr - 1]; p->ld_bf16 = l.in;
+      }
+      p->mask_scale = 1.0f;
+    }
+    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+  }
+  // inactive decoders contribute zero to dL/dz: clear their slice of g_d0
+  if (any_dec)
+    for (size_t i = 0; i < m->decs.size(); ++i)
+      if (!active[i])
+        CK(cudaMemset2DAsync(m->g_d0 + m->decs[i].cat_off, sizeof(bf16) * m->cat.out, 0, sizeof(bf16) * m->decs[i].cat_w, B, st));
+  if (any_dec) {
+    GemmGroup g; init_group(g); GemmProblem* p;
+    const Lin& l = m->cat;
+    if ((rc = add_nt(m, g, m->g_d0, l.out, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
+    p->out_f32 = m->gz; p->ld_f32 = L;
+    CK(launch_gemm_group(g, 0, st));
+  }
+  // ---- latent ----
+  int n_present = 0;
+  for (size_t i = 0; i < m->encs.size(); ++i) n_present += present >> i & 1;
+  {
+    LatentBwdArgs a{};
+    a.gz = any_dec ? m->gz : nullptr; a.ld_gz = L;
+    a.gmu_in = io.g_mu; a.glv_in = io.g_logvar;
+    a.mu = m->mu; a.logvar = m->logvar; a.eps = m->eps;
+    a.beta = 0.f; a.dyn = io.engine ? m->dyn : nullptr;
+    a.n_modalities = n_present; a.gml = m->gml; a.ld_gml = m->ldgml; a.rows = B; a.L = L;
+    CK(launch_latent_bwd(a, st));
+  }
+  const int mt = ceil_div(B, GEMM_BM);
+  // ---- encoder data gradients ----
+  size_t max_depth = 0;
+  for (size_t i = 0; i < m->encs.size(); ++i) if (present >> i & 1) max_depth = std::max(max_depth, m->encs[i].fc.size());
+  bool site_done = false;
+  for (size_t r = max_depth; r >= 1; --r) {
+    GemmGroup g; init_group(g);
+    std::vector<std::pair<size_t, size_t>> bn_todo;   // (encoder, layer) whose gy this round produces
+    for (size_t i = 0; i < m->encs.size(); ++i) {
+      if (!(present >> i & 1)) continue;
+      const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+      GemmProblem* p;
+      if (e.type == 'C') {
+        if (site_done) continue;
+        const Lin& l = e.heads;
+        if ((rc = add_nt(m, g, m->gml, m->ldgml, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
+        p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
+        site_done = true;
+        continue;
+      }
+      const size_t depth = e.fc.size();
+      if (r > depth) continue;
+      const Lin& l = r == depth ? e.heads : e.fc[r];
+      const bf16* A = r == depth ? m->gml : w.gpre[r];
+      const int lda = r == depth ? m->ldgml : l.out;
+      const size_t tgt = r - 1;                       // gradient w.r.t. act[tgt]
+      if ((rc = add_nt(m, g, A, lda, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_MASK | GF_BNSTATS | GF_OUT_BF16, &p))) return rc;
+      p->mask_src = w.act[tgt]; p->ld_mask = l.in; p->mask_scale = train ? 1.0f / 0.9f : 1.0f;
+      p->pre = w.pre[tgt]; p->ld_pre = l.in; p->mean = w.mean[tgt]; p->rstd = w.rstd[tgt];
+      p->stats = w.bstats[tgt];
+      p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;
+      bn_todo.emplace_back(i, tgt);
+    }
+    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+    for (auto& it : bn_todo) {
+      const Enc& e = m->encs[it.first]; EncWS& w = m->ews[it.first]; const Bn& bn = e.bn[it.second];
+      BnBwdArgs a{};
+      a.gy = w.gy[it.second]; a.ld_gy = bn.n; a.pre = w.pre[it.second]; a.ld_pre = bn.n;
+      a.stats = w.bstats[it.second]; a.m_tiles = mt;
+      a.mean = w.mean[it.second]; a.rstd = w.rstd[it.second]; a.gamma = P + bn.g_off;
+      a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
+      a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
+      CK(launch_bn_bwd(a, st));
+    }
+  }
+  if (!site_done) {
+    for (size_t i = 0; i < m->encs.size(); ++i) {
+      if (!(present >> i & 1) || m->encs[i].type != 'C') continue;
+      GemmGroup g; init_group(g); GemmProblem* p;
+      const Lin& l = m->encs[i].heads; EncWS& w = m->ews[i];
+      if ((rc = add_nt(m, g, m->gml, m->ldgml, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
+      p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
+      CK(launch_gemm_group(g, 0, st));
+    }
+  }
+  // ---- every weight (and bias) gradient in one grouped split-K launch ----
+  {
+    GemmGroup g; init_group(g);
+    for (size_t i = 0; i < m->encs.size(); ++i) {
+      if (!(present >> i & 1)) continue;
+      const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+      for (size_t r = 0; r < e.fc.size(); ++r) {
+        const Lin& l = e.fc[r];
+        const bf16* X = r == 0 ? w.x : w.act[r - 1];
+        const int ldx = r == 0 ? w.ldx : e.fc[r - 1].out;
+        if ((rc = add_tn(m, g, w.gpre[r], l.out, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc;
+      }
+      const Lin& h = e.heads;
+      const bf16* X = e.fc.empty() ? w.x : w.act.back();
+      const int ldx = e.fc.empty() ? w.ldx : e.fc.back().out;
+      if ((rc = add_tn(m, g, m->gml, m->ldgml, X, ldx, h.out, h.in, B, G + h.w_off, h.in, G + h.b_off))) return rc;
+      if (e.type == 'C')
+        if ((rc = add_tn(m, g, w.onehot, w.ld_onehot, w.g_x, w.ldx, m->S, m->E, B, G + e.emb_off, m->E, nullptr))) return rc;
+    }
+    if (any_dec) {
+      // fused first decoder layer: rows of inactive decoders receive zeros (their g_d0 slice was cleared)
+      const Lin& c = m->cat;
+      if ((rc = add_tn(m, g, m->g_d0, c.out, m->z, m->ldz, c.out, c.in, B, G + c.w_off, c.in, G + c.b_off))) return rc;
+      for (size_t i = 0; i < m->decs.size(); ++i) {
+        if (!active[i]) continue;
+        const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+        for (size_t r = 0; r < d.rest.size(); ++r) {
+          const Lin& l = d.rest[r];
+          const bool last = r + 1 == d.rest.size();
+          const bf16* Gr = last ? w.g_out : w.gact[r];
+          const int ldg = last ? w.ld_gout : l.out;
+          const bf16* X = r == 0 ? m->d0 + d.cat_off : w.act[r - 1];
+          const int ldx = r == 0 ? m->cat.out : d.rest[r - 1].out;
+          if ((rc = add_tn(m, g, Gr, ldg, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc;
+        }
+      }
+    }
+    finalize_tn(g, B);
+    CK(launch_gemm_group(g, 1, st));
+  }
+  return VLA_OK;
+}
+
+cudaStream_t as_stream(vla_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+const char* vla_last_error(void) { return g_err.c_str(); }
+int vla_abi_version(void) { return 1; }
+
+int vla_model_create(const vla_config_t* cfg, vla_model_t** out) {
+  if (!cfg || !out) return fail(VLA_ERR_INVALID, "null argument");
+  if (cfg->dim_a < 1 || cfg->dim_b < 1 || cfg->n_sites < 1 || cfg->latent < 1 || cfg->embed < 1)
+    return fail(VLA_ERR_INVALID, "dimensions must be positive");
+  if (2 * cfg->latent > 256) return fail(VLA_ERR_INVALID, "latent_dim > 128 is not supported");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(VLA_ERR_CUDA, std::string("libvla_b200 is built for sm_100a only; device is sm_") +
+                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  vla_model* m = new vla_model();
+  m->cfg = *cfg;
+  int rc = build_layout(m);
+  if (rc) { delete m; return rc; }
+  auto bail = [&](cudaError_t e, const char* what) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    vla_model_destroy(m);
+    return fail(VLA_ERR_CUDA, msg);
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&m->shadow, sizeof(bf16) * m->n_shadow)) != cudaSuccess) return bail(e, "cudaMalloc shadow");
+  if ((e = cudaMemset(m->shadow, 0, sizeof(bf16) * m->n_shadow)) != cudaSuccess) return bail(e, "cudaMemset shadow");
+  if ((e = cudaMalloc(&m->segs_d, sizeof(AdamSegment) * m->segs_h.size())) != cudaSuccess) return bail(e, "cudaMalloc segs");
+  if ((e = cudaMalloc(&m->chunks_d, sizeof(AdamChunk) * m->chunks_h.size())) != cudaSuccess) return bail(e, "cudaMalloc chunks");
+  if ((e = cudaMemcpy(m->segs_d, m->segs_h.data(), sizeof(AdamSegment) * m->segs_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy segs");
+  if ((e = cudaMemcpy(m->chunks_d, m->chunks_h.data(), sizeof(AdamChunk) * m->chunks_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy chunks");
+  if ((e = cudaMalloc(&m->dyn, sizeof(DynParams))) != cudaSuccess) return bail(e, "cudaMalloc dyn");
+  DynParams d{5e-4f, 1e-5f, 1e-3f, 1.0f, 0, 0, {0, 0}};
+  if ((e = cudaMemcpy(m->dyn, &d, sizeof(d), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy dyn");
+  if ((e = cudaMalloc(&m->loss_counter, 64)) != cudaSuccess) return bail(e, "cudaMalloc counter");
+  if ((e = cudaMemset(m->loss_counter, 0, 64)) != cudaSuccess) return bail(e, "memset counter");
+  m->loss_out = reinterpret_cast<float*>(m->loss_counter) + 4;
+  *out = m;
+  return VLA_OK;
+}
+
+void vla_model_destroy(vla_model_t* m) {
+  if (!m) return;
+  cudaFree(m->shadow); cudaFree(m->segs_d); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
+  cudaFree(m->ws);
+  delete m;
+}
+
+int vla_model_reserve(vla_model_t* m, int batch) { return m ? reserve(m, batch) : fail(VLA_ERR_INVALID, "null model"); }
+long long vla_param_count(const vla_model_t* m) { return m->n_params; }
+long long vla_buffer_count(const vla_model_t* m) { return m->n_buffers; }
+int vla_counter_count(const vla_model_t* m) { return m->n_bn; }
+int vla_num_tensors(const vla_model_t* m) { return static_cast<int>(m->infos.size()); }
+int vla_tensor_info(const vla_model_t* m, int index, vla_tensor_info_t* out) {
+  if (!m || !out || index < 0 || index >= static_cast<int>(m->infos.size())) return fail(VLA_ERR_INVALID, "bad tensor index");
+  *out = m->infos[index];
+  return VLA_OK;
+}
+
+int vla_forward(vla_model_t* m, const vla_forward_args_t* a, vla_stream_t stream) {
+  if (!m || !a || !a->params || !a->buffers) return fail(VLA_ERR_INVALID, "null argument");
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (a->refresh_shadows && (rc = run_shadow_refresh(m, a->params, st))) return rc;
+  FwdIO io{};
+  io.params = a->params; io.buffers = a->buffers; io.counters = a->counters;
+  io.x[0] = a->x_a; io.x[1] = a->x_b; io.site = a->site;
+  io.batch = a->batch; io.train = a->train ? 1 : 0;
+  io.eps = a->eps; io.keep_masks = a->keep_masks; io.seed = a->seed; io.offset = a->offset;
+  io.recon[0] = a->recon_a; io.recon[1] = a->recon_b; io.recon[2] = a->recon_c;
+  io.mu = a->mu; io.logvar = a->logvar; io.engine = false;
+  return run_forward(m, io, st);
+}
+
+int vla_refresh_shadows(vla_model_t* m, const float* params, vla_stream_t stream) {
+  if (!m || !params) return fail(VLA_ERR_INVALID, "null argument");
+  return run_shadow_refresh(m, params, as_stream(stream));
+}
+
+int vla_backward(vla_model_t* m, const vla_backward_args_t* a, vla_stream_t stream) {
+  if (!m || !a || !a->params || !a->grads) return fail(VLA_ERR_INVALID, "null argument");
+  BwdIO io{};
+  io.params = a->params;
+  io.g_recon[0] = a->g_recon_a; io.g_recon[1] = a->g_recon_b; io.g_recon[2] = a->g_recon_c;
+  io.recon_b = a->recon_b; io.g_mu = a->g_mu; io.g_logvar = a->g_logvar;
+  io.grads = a->grads; io.engine = false; io.zero_grads = true;
+  return run_backward(m, io, as_stream(stream));
+}
+
+long long vla_loss_workspace_bytes(int batch, int dim_a, int dim_b, int n_sites, int latent) {
+  (void)latent;
+  return 256 + 4LL * loss_grid_size(batch, dim_a, dim_b, n_sites);
+}
+
+int vla_loss(const vla_loss_args_t* a, vla_stream_t stream) {
+  if (!a || !a->out || !a->workspace) return fail(VLA_ERR_INVALID, "null argument");
+  if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
+  LossArgs l{};
+  l.recon_a = a->recon_a; l.a = a->a; l.width_a = a->dim_a;
+  l.recon_b = a->recon_b; l.b = a->b; l.width_b = a->dim_b;
+  l.logits = a->recon_c; l.site = a->site; l.class_w = a->class_weights; l.n_sites = a->n_sites;
+  if ((l.recon_a && !l.a) || (l.recon_b && !l.b) || (l.logits && !l.site)) return fail(VLA_ERR_INVALID, "recon without target");
+  l.mu = a->mu; l.logvar = a->logvar; l.L = a->latent;
+  l.beta = a->beta; l.gamma = a->gamma; l.rows = a->batch;
+  l.ga_f32 = a->g_recon_a; l.gb_f32 = a->g_recon_b; l.gc_f32 = a->g_recon_c; l.gmu_f32 = a->g_mu; l.glv_f32 = a->g_logvar;
+  l.grad_scale = 1.0f;
+  l.counter = reinterpret_cast<unsigned int*>(a->workspace);
+  l.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + 256);
+  l.out = a->out;
+  CK(launch_loss(l, as_stream(stream)));
+  return VLA_OK;
+}
+
+static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float* eas, float lr, float b1, float b2,
+                     float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st) {
+  AdamArgs a{};
+  a.p = p; a.g = const_cast<float*>(g); a.m = ea; a.v = eas; a.shadow = m->shadow;
+  a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
+  a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd; a.step = step;
+  a.dyn = dyn ? m->dyn : nullptr; a.update = 1; a.zero_grad = zero_grad ? 1 : 0;
+  CK(launch_adamw(a, st));
+  return VLA_OK;
+}
+
+int vla_adamw(vla_model_t* m, const vla_adamw_args_t* a, vla_stream_t stream) {
+  if (!m || !a || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq) return fail(VLA_ERR_INVALID, "null argument");
+  if (a->step < 1) return fail(VLA_ERR_INVALID, "step is 1-based");
+  return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->lr, a->beta1, a->beta2, a->eps, a->weight_decay,
+                   a->step, false, false, as_stream(stream));
+}
+
+int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, float gamma, vla_stream_t stream) {
+  if (!m) return fail(VLA_ERR_INVALID, "null model");
+  const float h[4] = {lr, weight_decay, beta_kl, gamma};
+  CK(cudaMemcpyAsync(m->dyn, h, sizeof(h), cudaMemcpyHostToDevice, as_stream(stream)));
+  return VLA_OK;
+}
+int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, vla_stream_t stream) {
+  if (!m) return fail(VLA_ERR_INVALID, "null model");
+  const int v[2] = {completed_steps, batch_index};
+  CK(cudaMemcpyAsync(&m->dyn->step, v, sizeof(v), cudaMemcpyHostToDevice, as_stream(stream)));
+  return VLA_OK;
+}
+
+int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream) {
+  if (!m || !a || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->buffers || !a->loss_out)
+    return fail(VLA_ERR_INVALID, "null argument");
+  cudaStream_t st = as_stream(stream);
+  FwdIO io{};
+  io.params = a->params; io.buffers = a->buffers; io.counters = a->counters;
+  // encoder inputs per kind (train_rna2dna.py:86, train_dna2rna.py:86, optimize_hyperparameters.py:106)
+  for (const Enc& e : m->encs) {
+    if (e.slot == 0) io.x[0] = a->x_a;
+    if (e.slot == 1) io.x[1] = a->x_b;
+    if (e.slot == 2) io.site = a->site;
+  }
+  io.batch = a->batch; io.train = 1; io.eps = a->eps; io.keep_masks = a->keep_masks;
+  io.seed = a->seed; io.offset = 0;
+  io.recon[0] = a->recon_a; io.recon[1] = a->recon_b; io.recon[2] = a->recon_c;
+  io.mu = a->mu; io.logvar = a->logvar; io.engine = true;
+  if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
+  io.n_batches = a->dataset_rows > a->batch ? static_cast<int>(a->dataset_rows / a->batch) : 1;
+  int rc;
+  if ((rc = run_forward(m, io, st))) return rc;
+  // ---- loss: values + bf16 gradients for the backward GEMMs ----
+  {
+    LossArgs l{};
+    l.rows = a->batch; l.dyn = m->dyn; l.grad_scale = 1.0f; l.dyn_bump = m->dyn; l.n_batches = io.n_batches;
+    for (size_t i = 0; i < m->decs.size(); ++i) {
+      const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+      const int slot = d.type == 'A' ? 0 : (d.type == 'B' ? 1 : 2);
+      const float* recon = io.recon[slot] ? io.recon[slot] : w.recon;
+      if (d.type == 'A') {
+        if (!a->x_a) return fail(VLA_ERR_INVALID, "x_a (target) missing");
+        l.recon_a = recon; l.a = a->x_a; l.width_a = d.out_dim; l.ga_bf16 = w.g_out; l.ld_ga = w.ld_gout;
+      } else if (d.type == 'B') {
+        if (!a->x_b) return fail(VLA_ERR_INVALID, "x_b (target) missing");
+        l.recon_b = recon; l.b = a->x_b; l.width_b = d.out_dim; l.gb_bf16 = w.g_out; l.ld_gb = w.ld_gout;
+      } else {
+        if (!a->site) return fail(VLA_ERR_INVALID, "site (target) missing");
+        l.logits = recon; l.site = a->site; l.class_w = a->class_weights; l.n_sites = m->S;
+        l.gc_bf16 = w.g_out; l.ld_gc = w.ld_gout;
+      }
+    }
+    l.kl_partials = m->kl_partials; l.n_kl_partials = m->kl_grid; l.mu = m->mu; l.logvar = m->logvar; l.L = m->L;
+    l.partials = m->loss_partials; l.counter = m->loss_counter; l.out = a->loss_out;
+    CK(launch_loss(l, st));
+  }
+  BwdIO bo{};
+  bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
+  if ((rc = run_backward(m, bo, st))) return rc;
+  return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
+                   true, st);
+}
+
+int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K, int bn,
+                  int k_splits, float* bias_grad, vla_stream_t stream) {
+  static vla_model scratch;   // only its tensor-map cache is used
+  GemmGroup g; init_group(g);
+  int rc;
+  if (mode == 0) {
+    GemmProblem* p;
+    if ((rc = add_nt(&scratch, g, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, M, N, K, GF_OUT_F32, &p, bn))) return rc;
+    p->out_f32 = C; p->ld_f32 = N;
+  } else {
+    if ((rc = add_tn(&scratch, g, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, M, N, K, C, N, bias_grad, bn))) return rc;
+    finalize_tn(g, K, k_splits);
+  }
+  CK(launch_gemm_group(g, mode, as_stream(stream)));
+  scratch.tmaps.clear();
+  return VLA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+// Internal declarations shared by the kernels and the host-side plan builder.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+namespace vla {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// Grouped tcgen05 GEMM
+// ---------------------------------------------------------------------------------------------
+enum GemmFlags : int {
+  GF_BIAS = 1 << 0,       // v += bias[col]
+  GF_RELU = 1 << 1,       // v = max(v, 0)
+  GF_SIGMOID = 1 << 2,    // v = 1 / (1 + exp(-v))
+  GF_COLSTATS = 1 << 3,   // per-tile column sum / sum of squares of v (after bias, before activation)
+  GF_MASK = 1 << 4,       // v = mask_src[row, col] > 0 ? v * mask_scale : 0  (ReLU / dropout backward)
+  GF_BNSTATS = 1 << 5,    // per-tile column sums of v and v * xhat, xhat = (pre - mean) * rstd
+  GF_OUT_F32 = 1 << 6,    // store fp32
+  GF_OUT_BF16 = 1 << 7,   // store bf16
+  GF_RED = 1 << 8,        // accumulate into out_f32 with red.global.add (split-K weight gradients)
+  GF_BIASGRAD = 1 << 9,   // TN mode: also produce sum_k A[m, k] into bias_grad[m] (ones-MMA)
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_BN_MAX_NT = 160;   // multiple of 16
+constexpr int GEMM_BN_MAX_TN = 192;   // multiple of 64
+constexpr int GEMM_MAX_PROBLEMS = 16;
+constexpr int GEMM_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int GEMM_TMEM_COLS = 256;
+constexpr int GEMM_BIAS_TMEM_COL = 224;
+
+struct alignas(64) GemmProblem {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int M, N, K;
+  int BN;
+  int m_tiles, n_tiles, k_splits, kb_per_split;
+  int tile_begin;
+  int flags;
+  int ld_f32, ld_bf16, ld_mask, ld_pre;
+  float mask_scale;
+  int pad0;
+  const float* bias;
+  float* out_f32;
+  bf16* out_bf16;
+  const bf16* mask_src;
+  const float* pre;
+  const float* mean;
+  const float* rstd;
+  float* stats;
+  float* bias_grad;
+};
+
+struct GemmGroup {
+  int nprob;
+  int total_tiles;
+  int pad[14];
+  GemmProblem p[GEMM_MAX_PROBLEMS];
+};
+
+// mode 0: NT (both operands K-major; forward and data gradients); mode 1: TN (both MN-major; weight gradients)
+cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream);
+size_t gemm_smem_bytes();
+
+// Builds a 2-D bf16 tensor map with 128-byte swizzle.  inner/outer are extents in elements,
+// pitch_bytes the outer stride; box_inner must be 64 (=128 B).  Returns false on failure.
+bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                    uint32_t box_inner, uint32_t box_outer, std::string* err);
+
+// ---------------------------------------------------------------------------------------------
+// Element-wise / reduction kernels (elementwise.cu)
+// ---------------------------------------------------------------------------------------------
+// Per-step scalars that live on the device so that a captured CUDA graph can be replayed while the
+// learning rate, the KL weight (beta warm-up, train_rna2dna.py:80) and the step count change.
+struct DynParams {
+  float lr, weight_decay, beta_kl, gamma;
+  int step;          // number of the optimizer step in flight (1-based); bumped by the ingest kernel
+  int batch_index;   // which resident batch the step in flight trains on; bumped by the loss kernel's last block
+  int pad[2];
+};
+
+struct IngestArgs {           // fp32 [rows, width] (dense) -> bf16 [rows, ld_dst]
+  const float* src[2];
+  bf16* dst[2];
+  int width[2];
+  int ld_dst[2];
+  int n;                      // number of active entries (0..2)
+  int rows;
+  // site encoder input: h_site[r, :] = bf16(emb[site[r], :]) and onehot[r, s] = (site[r] == s)
+  const long long* site; const float* emb; bf16* h_site; int ld_hsite; bf16* onehot; int ld_onehot;
+  int n_sites, embed;
+  // train step bookkeeping: dyn->step += 1 (first kernel of a train step)
+  struct DynParams* dyn; int bump_step;
+  int n_batches;              // > 1: rows are read at offset (dyn->batch_index % n_batches) * rows
+};
+cudaError_t launch_ingest(const IngestArgs& a, cudaStream_t s);
+
+struct BnActArgs {
+  const float* pre; int ld_pre;         // [rows, n]
+  const float* stats; int m_tiles;      // [m_tiles][2][n] (train)
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float* save_mean; float* save_rstd;   // [n]
+  bf16* out; int ld_out;
+  const unsigned char* keep_mask;       // optional injected keep mask [rows, n]
+  int rows, n;
+  int train;                            // batch statistics + dropout
+  int update_running;
+  float p_drop;
+  unsigned long long seed, offset;      // Philox stream for dropout when keep_mask == nullptr
+  const struct DynParams* dyn;          // if set, the Philox offset also mixes in dyn->step
+};
+cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s);
+
+struct BnBwdArgs {
+  const bf16* gy; int ld_gy;            // dL/dy (already through dropout and ReLU), [rows, n]
+  const float* pre; int ld_pre;
+  const float* stats; int m_tiles;      // [m_tiles][2][n]: sum gy, sum gy * xhat
+  const float* mean; const float* rstd; const float* gamma;
+  float* dgamma; float* dbeta;
+  bf16* gpre; int ld_gpre;
+  int rows, n, train;
+};
+cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s);
+
+struct LatentFwdArgs {
+  const float* ml[3]; int ld_ml[3]; int n_enc;    // present encoders' heads output [rows, 2L]
+  const float* eps_in;                            // injected eps [rows, L] or nullptr -> Philox
+  unsigned long long seed, offset; const struct DynParams* dyn;
+  float* mu; float* logvar;                       // outputs [rows, L] dense
+  float* eps_save;                                // [rows, L]
+  bf16* z; int ld_z;                              // [rows, ld_z]
+  float* kl_partials;                             // [grid]
+  int rows, L;
+};
+cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_t s);
+
+struct LatentBwdArgs {
+  const float* gz; int ld_gz;                     // [rows, L] (may be nullptr -> 0)
+  const float* gmu_in; const float* glv_in;       // autograd-supplied dL/dmu, dL/dlogvar (optional)
+  const float* mu; const float* logvar; const float* eps;
+  float beta;                                     // engine mode: adds beta * dKL/d(mu, logvar)
+  int n_modalities;
+  bf16* gml; int ld_gml;                          // [rows, >= 2L]
+  const struct DynParams* dyn;                    // if set, beta is read from dyn->beta_kl
+  int rows, L;
+};
+cudaError_t launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
+
+struct LossArgs {
+  // MSE term
+  const float* recon_a; const float* a; int width_a;
+  // BCE term
+  const float* recon_b; const float* b; int width_b;
+  // CE term
+  const float* logits; const long long* site; const float* class_w; int n_sites;
+  // KL term: either from kl_partials (engine) or directly from mu / logvar
+  const float* kl_partials; int n_kl_partials;
+  const float* mu; const float* logvar; int L;
+  float beta, gamma;
+  const struct DynParams* dyn;   // if set, beta / gamma are read from it
+  struct DynParams* dyn_bump;    // if set, the last block advances dyn_bump->batch_index
+  int n_batches;                 // > 1: targets are read at row offset (dyn->batch_index % n_batches) * rows
+  int rows;
+  // gradient outputs (all optional).  bf16 outputs are what the backward GEMMs consume:
+  bf16* ga_bf16; int ld_ga;      // 2 (recon_a - a)
+  bf16* gb_bf16; int ld_gb;      // dL/dlogit_b = (y - t) * y(1-y) / max(y(1-y), 1e-12)
+  bf16* gc_bf16; int ld_gc;      // gamma * w * (softmax - onehot)
+  float* ga_f32; float* gb_f32; float* gc_f32;   // dense fp32 dL/d(recon) for the autograd path
+  float* gmu_f32; float* glv_f32;
+  float grad_scale;              // upstream dL/dtotal (autograd path), 1 for the engine
+  float* partials;               // workspace [grid * 4]
+  unsigned int* counter;         // zero-initialised ticket for the last-block reduction
+  float* out;                    // [4]: total, recon, class, kld
+};
+cudaError_t launch_loss(const LossArgs& a, cudaStream_t s);
+int loss_grid_size(int rows, int width_a, int width_b, int n_sites);
+
+struct OutGradArgs {  // autograd path: fp32 upstream dL/d(recon) -> bf16 GEMM operands
+  const float* g; int width;           // dense [rows, width]
+  const float* y;                      // sigmoid output (multiply by y (1 - y)) or nullptr
+  bf16* dst; int ld_dst;
+  int rows;
+};
+cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s);
+
+struct AdamSegment {          // one parameter tensor of the flat arena
+  long long offset;           // element offset in the arena
+  int rows, cols;             // matrix shape (vectors: rows = numel, cols = 1)
+  long long shadow_off;       // bf16 shadow [rows, ld_shadow] offset, -1 = none
+  int ld_shadow;
+  long long shadow_t_off;     // bf16 transposed shadow [cols, ld_shadow_t], -1 = none
+  int ld_shadow_t;
+};
+struct AdamChunk { int seg; int start; };   // start = element offset inside the segment
+constexpr int ADAM_CHUNK = 4096;
+struct AdamArgs {
+  float* p; float* g; float* m; float* v;
+  bf16* shadow;
+  const AdamSegment* segs; const AdamChunk* chunks; int n_chunks;
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;                   // 1-based step count for the bias corrections
+  const struct DynParams* dyn;// if set, lr / weight_decay / step are read from it
+  int update;                 // 0: only refresh the bf16 shadows from p
+  int zero_grad;              // 1: clear g after use
+};
+cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s);
+
+}  // namespace vla

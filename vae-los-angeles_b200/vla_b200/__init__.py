@@ -1,0 +1,10 @@
+"""vla_b200: B200 (sm_100a) implementation of the vae-los-angeles hot path behind the reference's Python surface.
+
+Everything numeric runs in libvla_b200.so (hand-written CUDA, C ABI in include/vla_b200.h); PyTorch provides
+device memory, streams, autograd plumbing and torch.distributed.  There is no CPU fallback.
+"""
+from .core import VaeModule, Stack, KINDS
+from .engine import DeviceDataset, FusedAdamW, Trainer
+from .losses import fused_vae_loss
+
+__all__ = ["VaeModule", "Stack", "KINDS", "DeviceDataset", "FusedAdamW", "Trainer", "fused_vae_loss"]

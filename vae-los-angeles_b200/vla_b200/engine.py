@@ -1,0 +1,195 @@
+"""Fused training engine: whole step (forward + loss + backward + AdamW) as one C-ABI call,
+captured into a CUDA graph, over a device-resident dataset.
+
+`FusedAdamW` is the drop-in optimizer for scripts that want the fused multi-tensor kernel while keeping
+the per-call autograd path; `Trainer` is the throughput path used by bench.py and the DP launcher:
+it restates the loop body at train_rna2dna.py:82-99 / optimize_hyperparameters.py:104-113 with zero
+host synchronisation per step.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .core import _ptr, _stream
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled decay, bias correction) in one launch over the flat arena.
+
+    Construct with the module, not a parameter list: `FusedAdamW(model, lr=5e-4, weight_decay=1e-5)`.
+    LR schedulers work as usual (the learning rate is read from `param_groups[0]['lr']` every step)."""
+
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.module = module
+        core = module._ensure_core()
+        super().__init__(list(core.order), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.exp_avg = torch.zeros_like(core.arena)
+        self.exp_avg_sq = torch.zeros_like(core.arena)
+        self.steps = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        core = self.module._ensure_core()
+        grads = core.last_grads
+        if grads is None or any(p.grad is None for p in core.order):
+            raise RuntimeError("FusedAdamW.step(): every parameter needs a gradient from the fused backward "
+                               "(use torch.optim.AdamW when training a subset of the stacks)")
+        base = grads.data_ptr()
+        for p, (offset, _) in zip(core.order, core.param_offsets):
+            if p.grad.data_ptr() != base + 4 * offset:
+                raise RuntimeError("FusedAdamW.step(): .grad tensors are not views of the fused gradient arena "
+                                   "(gradient accumulation / clipping copies are not supported here)")
+        g = self.param_groups[0]
+        self.steps += 1
+        args = _lib.AdamWArgs(params=_ptr(core.arena), grads=_ptr(grads), exp_avg=_ptr(self.exp_avg),
+                              exp_avg_sq=_ptr(self.exp_avg_sq), lr=float(g["lr"]), beta1=float(g["betas"][0]),
+                              beta2=float(g["betas"][1]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]),
+                              step=self.steps)
+        with torch.cuda.device(core.device):
+            _lib.check(_lib.lib().vla_adamw(core.handle, C.byref(args), _stream()), "vla_adamw")
+        for p in core.order:              # the kernel wrote through the arena: keep version counters honest
+            p._version  # noqa: B018  (views share storage; shadows were refreshed by the kernel itself)
+        core.shadow_version = core.param_version()
+        return loss
+
+
+class DeviceDataset:
+    """Device-resident dataset with the reference's schema (src/data/dataset.py:19-30):
+    tpm fp32 [N, A], beta fp32 [N, B], site int64 [N]."""
+
+    def __init__(self, tpm, beta, site, device):
+        self.tpm = torch.as_tensor(tpm, dtype=torch.float32).to(device).contiguous()
+        self.beta = torch.as_tensor(beta, dtype=torch.float32).to(device).contiguous()
+        self.site = torch.as_tensor(site, dtype=torch.long).to(device).contiguous()
+        if not (len(self.tpm) == len(self.beta) == len(self.site)):
+            raise ValueError("modalities differ in length")
+
+    def __len__(self):
+        return len(self.site)
+
+    def shuffle_(self, generator=None):
+        """In-place row permutation on the device (DataLoader(shuffle=True) between epochs)."""
+        perm = torch.randperm(len(self), device=self.site.device, generator=generator)
+        self.tpm, self.beta, self.site = self.tpm[perm], self.beta[perm], self.site[perm]
+
+    @staticmethod
+    def synthetic(n, dim_a, dim_b, n_sites, device, seed=0):
+        """Synthetic rows of the reference's schema (scripts/prepare_data.py:112-125): tpm = log1p(Gamma(1, 20)),
+        beta ~ Beta(0.5, 0.5) clipped to [1e-4, 1 - 1e-4], site uniform."""
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        u = torch.rand(n, dim_a, device=device, generator=g)
+        tpm = torch.log1p(-20.0 * torch.log1p(-u))
+        v = torch.rand(n, dim_b, device=device, generator=g)
+        beta = torch.sin(0.5 * torch.pi * v).pow(2).clamp_(1e-4, 1 - 1e-4)
+        site = torch.randint(0, n_sites, (n,), device=device, generator=g)
+        return DeviceDataset(tpm, beta, site, device)
+
+
+class Trainer:
+    """Whole-step trainer.  `step()` enqueues one train step (graph replay); `loss()` reads the last losses."""
+
+    def __init__(self, module, dataset, batch_size, lr=5e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8,
+                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True):
+        self.module = module
+        self.core = module._ensure_core()
+        self.ds = dataset
+        self.batch = int(batch_size)
+        if len(dataset) < self.batch:
+            raise ValueError("dataset smaller than one batch")
+        dev = self.core.device
+        self.grads = torch.zeros_like(self.core.arena)
+        self.exp_avg = torch.zeros_like(self.core.arena)
+        self.exp_avg_sq = torch.zeros_like(self.core.arena)
+        self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.class_weights = None if class_weights is None else class_weights.to(dev, torch.float32).contiguous()
+        self.betas, self.eps, self.seed = betas, eps, seed
+        self.hyper = None
+        self.set_hyper(lr, weight_decay, beta_kl, gamma)
+        self.steps = 0
+        self.use_graph = use_graph
+        self.graph = None
+        self.injected = None
+        self._mask_arr = None
+        _lib.check(_lib.lib().vla_model_reserve(self.core.handle, self.batch), "vla_model_reserve")
+        self.reset_counters(0, 0)
+
+    # -- per-epoch scalars (beta warm-up train_rna2dna.py:80, ReduceLROnPlateau :216) ------------------
+    def set_hyper(self, lr=None, weight_decay=None, beta_kl=None, gamma=None):
+        cur = list(self.hyper) if self.hyper else [5e-4, 1e-5, 1e-3, 1.0]
+        for i, v in enumerate((lr, weight_decay, beta_kl, gamma)):
+            if v is not None:
+                cur[i] = float(v)
+        if self.hyper != tuple(cur):
+            self.hyper = tuple(cur)
+            with torch.cuda.device(self.core.device):
+                _lib.check(_lib.lib().vla_set_hyper(self.core.handle, *self.hyper, _stream()), "vla_set_hyper")
+
+    def reset_counters(self, completed_steps, batch_index):
+        with torch.cuda.device(self.core.device):
+            _lib.check(_lib.lib().vla_set_step(self.core.handle, int(completed_steps), int(batch_index), _stream()),
+                       "vla_set_step")
+
+    def _args(self):
+        core, ds = self.core, self.ds
+        eps = masks = None
+        if self.injected is not None:
+            eps = self.injected.get("eps")
+            keep = self.injected.get("keep_masks")
+            if keep is not None:
+                self._keep = [None if m is None else m.to(core.device, torch.uint8).contiguous() for m in keep]
+                self._mask_arr = (C.c_void_p * len(self._keep))(*[None if m is None else m.data_ptr() for m in self._keep])
+                masks = self._mask_arr
+        return _lib.TrainArgs(
+            params=_ptr(core.arena), grads=_ptr(self.grads), exp_avg=_ptr(self.exp_avg), exp_avg_sq=_ptr(self.exp_avg_sq),
+            buffers=_ptr(core.buffers), counters=_ptr(core.counters),
+            x_a=_ptr(ds.tpm), x_b=_ptr(ds.beta), site=_ptr(ds.site), class_weights=_ptr(self.class_weights),
+            batch=self.batch, dataset_rows=len(ds), eps=_ptr(eps), keep_masks=masks, seed=self.seed,
+            beta1=self.betas[0], beta2=self.betas[1], adam_eps=self.eps,
+            recon_a=None, recon_b=None, recon_c=None, mu=None, logvar=None, loss_out=_ptr(self.loss_out))
+
+    def _enqueue(self):
+        args = self._args()
+        _lib.check(_lib.lib().vla_train_step(self.core.handle, C.byref(args), _stream()), "vla_train_step")
+
+    def step(self):
+        """One optimizer step on the next resident batch.  No host synchronisation."""
+        core = self.core
+        with torch.cuda.device(core.device):
+            if core.shadow_version != core.param_version():
+                # parameters were changed from the host side (init, load_state_dict): re-derive the bf16 copies
+                _lib.check(_lib.lib().vla_refresh_shadows(core.handle, _ptr(core.arena), _stream()),
+                           "vla_refresh_shadows")
+                core.shadow_version = core.param_version()
+            if not self.use_graph:
+                self._enqueue()
+            elif self.graph is None:
+                self._first_step_and_capture()
+            else:
+                self.graph.replay()
+        self.steps += 1
+        core.generation += 1
+
+    def _first_step_and_capture(self):
+        # The first step runs eagerly on a side stream (it also loads the kernels and sizes the workspace);
+        # the same call sequence is then captured, without executing, for every later step.
+        dev = self.core.device
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+
+    def losses(self):
+        """(total, recon, class, kld) of the last completed step -- one 16-byte device->host read."""
+        return tuple(self.loss_out.tolist())
