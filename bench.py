@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: train samples/sec (forward + loss + backward + AdamW) at batch 4096 per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract: metric/value/unit, ms_per_step, e2e (host buffers,
+H2D + D2H inside the timed region), roofline (dominant kernel, live CUDA-event timing), cpu_baseline, clocks,
+gpu_launches.  Workload = BASELINE.json configs[1]: RNA2DNAVAE train step at batch 4096 (synthetic 782 / 572 / 24).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "vae-los-angeles_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+DIMS = dict(A=782, B=572, S=24, L=20, E=32)
+# algorithmic work per sample (fwd + bwd FLOP; compulsory HBM bytes) and parameter counts
+WORK = {
+    "rna2dna": dict(flop=3_013_120, bytes=7_872, params=538_124),
+    "dna2rna": dict(flop=2_642_944, bytes=8_712, params=542_174),
+    "multimodal": dict(flop=5_665_280, bytes=11_096, params=1_081_114),
+}
+METRIC = "train samples/sec (fwd+bwd+Adam) at batch 4096"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json, burst)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_arm(workload, batch, steps, warmup, budget_s=25.0):
+    import numpy as np
+    from oracle import vae_oracle as vo
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    state = vo.init_state(workload, DIMS, seed=0)
+    opt, step = vo.adamw_init(state)
+    tpm, beta, site = vo.synthetic_batch(batch, DIMS, seed=0)
+    data = dict(a=tpm, b=beta, site=site)
+    eps, masks = vo.synthetic_noise(batch, DIMS, workload, seed=0)
+    done, t_total = 0, 0.0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, _, step = vo.train_step(workload, DIMS, state, opt, step, data, eps, masks)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            done += 1
+            t_total += dt
+            if t_total > budget_s:
+                break
+    sps = done * batch / t_total
+    sample = f"{done} steps of batch {batch} after {warmup} warm-up steps, fp32 numpy (oracle/vae_oracle.py train_step)"
+    return sps, threads, sample, 1e3 * t_total / done
+
+
+def reference_main(args, rank):
+    if rank != 0:
+        return
+    sps, threads, sample, ms = cpu_arm(args.workload, args.batch, min(args.steps, 20), min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} train step (fwd+loss+bwd+AdamW), batch {args.batch}, 782/572/24/latent 20",
+                   "timing": "host wall clock (perf_counter)"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from src.models import DNA2RNAVAE, MultiModalVAE, RNA2DNAVAE
+    from vla_b200 import DeviceDataset, Trainer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    cls = {"rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE, "multimodal": MultiModalVAE}[args.workload]
+    torch.manual_seed(0)                       # identical replicas on every rank
+    model = cls(DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"]).to(dev).train()
+    B = args.batch
+    n_batches = args.resident_batches
+    ds = DeviceDataset.synthetic(B * n_batches, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=1000 + rank)
+    trainer = Trainer(model, ds, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        trainer.step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        trainer.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    losses = trainer.losses()
+    assert all(x == x and abs(x) < 1e30 for x in losses), f"non-finite loss {losses}"
+    value = args.steps * B * world / (ms * 1e-3)
+
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the loss, double buffered -------------------
+    e2e = None
+    host = [DeviceDataset.synthetic(B, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=77 + i + 10 * rank) for i in range(4)]
+    pinned = [(h.tpm.cpu().pin_memory(), h.beta.cpu().pin_memory(), h.site.cpu().pin_memory()) for h in host]
+    del host
+    slots = [DeviceDataset.synthetic(B, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=5 + i) for i in range(2)]
+    tr2 = Trainer(model, slots, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg)
+    loss_host = [torch.zeros(4).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    h2d_bytes = sum(x.numel() * x.element_size() for x in pinned[0])
+    k_e2e = max(8, min(args.steps, 64))
+
+    def e2e_loop(k, timed):
+        copied = [torch.cuda.Event() for _ in range(k)]
+        done = [torch.cuda.Event() for _ in range(k)]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(copy_stream):
+            s0.record()
+        for i in range(k):
+            slot = slots[i % 2]
+            src = pinned[i % len(pinned)]
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(done[i - 2])          # the slot's previous step has consumed it
+                slot.tpm.copy_(src[0], non_blocking=True)
+                slot.beta.copy_(src[1], non_blocking=True)
+                slot.site.copy_(src[2], non_blocking=True)
+                copied[i].record()
+            main_stream.wait_event(copied[i])
+            tr2.step(i % 2)
+            loss_host[i % 2].copy_(tr2.loss_out, non_blocking=True)
+            done[i].record()
+        s1.record()
+        torch.cuda.synchronize(dev)
+        return s0.elapsed_time(s1)
+
+    e2e_loop(4, False)          # warm-up: captures both graphs
+    barrier()
+    ms2 = e2e_loop(k_e2e, True)
+    t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t.item())
+    e2e = {"value": k_e2e * B * world / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
+           "d2h_bytes_per_step": 16 * world, "steps": k_e2e, "ms_per_step": ms2 / k_e2e,
+           "how": "pinned host batch -> cudaMemcpyAsync H2D (copy stream, double buffered) -> fused step graph -> 16 B loss D2H"}
+
+    # ---- per-launch timing (eager, CUDA events inside the library) -> dominant kernel roofline ----------------
+    peaks = load_peaks()
+    prof_steps = 5
+    trainer.profile(2)
+    entries = trainer.profile(prof_steps)
+    agg = {}
+    for name, pms, fl, by in entries:
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += pms; a[2] += fl; a[3] += by
+    total_ms = sum(a[1] for a in agg.values()) or 1.0
+    kernels = []
+    for name, (cnt, pms, fl, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        avg_ms, fl, by = pms / cnt, fl / cnt, by / cnt
+        t_t = fl / (peaks["bf16_tflops"] * 1e12)
+        t_h = by / (peaks["hbm_gbs"] * 1e9)
+        kernels.append(dict(name=name, launches_per_step=cnt / prof_steps, avg_us=1e3 * avg_ms, share=pms / total_ms,
+                            flops=fl, bytes=by, bound="tensor" if t_t > t_h else "hbm",
+                            frac=max(t_t, t_h) / (avg_ms * 1e-3) if avg_ms > 0 else None))
+    top = kernels[0]
+    if top["bound"] == "tensor":
+        ach, peak, unit = top["flops"] / (top["avg_us"] * 1e-6) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+    else:
+        ach, peak, unit = top["bytes"] / (top["avg_us"] * 1e-6) / 1e9, peaks["hbm_gbs"], "GB/s"
+    roofline = {"kernel": top["name"], "bound": top["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "traffic": None, "peak_source": peaks["source"], "avg_us": top["avg_us"], "share_of_step": top["share"],
+                "how": "CUDA events around each launch on the launching stream, 5 eager steps (vla_profile_*)"}
+    w = WORK[args.workload]
+    t_tensor = w["flop"] * B / (peaks["bf16_tflops"] * 1e12)
+    t_hbm = (w["bytes"] * B + 32 * w["params"]) / (peaks["hbm_gbs"] * 1e9)
+    step_s = ms * 1e-3 / args.steps
+    step_roofline = {"bound": "tensor" if t_tensor > t_hbm else "hbm", "t_tensor_us": 1e6 * t_tensor, "t_hbm_us": 1e6 * t_hbm,
+                     "t_step_us": 1e6 * step_s, "frac": max(t_tensor, t_hbm) / step_s,
+                     "flop_per_sample": w["flop"], "bytes_per_sample": w["bytes"], "param_bytes_per_step": 32 * w["params"]}
+    launches_per_step = sum(k["launches_per_step"] for k in kernels)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sps, threads, sample, _ = cpu_arm(args.workload, B, 10, 2, budget_s=20.0)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload} train step (fwd+loss+bwd+AdamW), batch {B} per GPU, 782/572/24/latent 20",
+                       "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": f"inputs larger than L2: {n_batches} resident batches ({B * n_batches} rows, "
+                             f"{B * n_batches * (DIMS['A'] + DIMS['B']) * 4 / 1e6:.0f} MB) visited in turn",
+                       "arithmetic": "bf16 tensor-core operands, fp32 accumulate, fp32 master weights / loss / AdamW",
+                       "graph": "CUDA graph replay per step, no host sync in the timed region"},
+            "e2e": e2e, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:8],
+            "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
+            "cpu_baseline": cpu, "clocks": clocks, "final_losses": losses,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rna2dna", choices=sorted(WORK))
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--resident-batches", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        reference_main(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun for --gpus > 1 (one rank per GPU)")
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,10 +158,24 @@ typedef struct {
   float beta1, beta2, adam_eps;
   float* recon_a; float* recon_b; float* recon_c; float* mu; float* logvar;   /* optional outputs */
   float* loss_out;
+  int phases;                   /* 0 or 3: whole step; 1: forward + loss + backward only (gradients left in `grads`, e.g. for a
+                                   data-parallel all-reduce); 2: AdamW only (consumes and clears `grads`) */
 } vla_train_args_t;
 int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream);
 int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, float gamma, vla_stream_t stream);
 int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, vla_stream_t stream);
+
+/* Per-launch device timing (CUDA events on `stream`, recorded around every kernel launch the library makes between
+ * vla_profile_begin and vla_profile_collect).  flops / bytes are the ALGORITHMIC work of the launch.
+ * vla_profile_collect synchronises the stream's events and returns how many entries it wrote. */
+typedef struct {
+  char name[48];
+  float ms;
+  double flops;
+  double bytes;
+} vla_prof_entry_t;
+int vla_profile_begin(vla_model_t* m);
+int vla_profile_collect(vla_model_t* m, vla_prof_entry_t* out, int max_entries);
 
 /* Test hook: C[M,N] = A[M,K] * B[N,K]^T (mode 0) or C[M,N] = A[K,M]^T * B[K,N] (mode 1) on the tcgen05 path.
  * A, B bf16 (uint16 storage) with element pitches lda / ldb (multiples of 8), C fp32 dense, zero-filled by

@@ -11,6 +11,14 @@ from oracle import vae_oracle as vo
 # gradients; argmax site predictions exact.  "relative" is measured as ||x - ref||_2 / ||ref||_2 per tensor.
 TOL_FP32 = 1e-5
 TOL_BF16 = 2e-2
+# Parameter gradients against the EXACT (fp64) arithmetic: bf16 operand rounding (relative step 2^-9) flips the
+# ReLU decision of pre-activations that lie within that distance of zero; each flip switches one (sample, unit)
+# gradient contribution on or off, so the error scales like sqrt(fraction flipped) ~ sqrt(2^-9) ~ 5-10 %, not
+# like 2^-9 (measured in numpy with no GPU involved: DESIGN.md "Precision").  The implementation itself is held
+# to TOL_BF16 against the oracle evaluated at the same operand precision; against the exact arithmetic the
+# gradients must stay within this looser, documented envelope and point the same way.
+TOL_GRAD_VS_EXACT = 0.25
+MIN_COSINE_VS_EXACT = 0.97
 
 
 def rel_l2(x, ref):
@@ -71,12 +79,14 @@ def to_t(x, device="cuda"):
     return None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(device)
 
 
-def oracle_step(kind, dims, state, batch, present, eps, masks, beta, gamma, cw, train=True, dtype=np.float64):
-    """Oracle forward + loss + backward on a private fp64 copy of `state`."""
+def oracle_step(kind, dims, state, batch, present, eps, masks, beta, gamma, cw, train=True, dtype=np.float64, q=None):
+    """Oracle forward + loss + backward on a private fp64 copy of `state`.
+    q=None: exact reference arithmetic; q=vo.round_bf16: same algorithm at the CUDA path's declared GEMM-operand
+    precision (oracle/vae_oracle.py header)."""
     st = {k: (v.astype(dtype) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
     bt = {k: (v.astype(dtype) if v.dtype.kind == "f" else v) for k, v in batch.items()}
     inputs = {k: (bt[k] if k in present else None) for k in ("a", "b", "site")}
-    out, cache = vo.forward(kind, dims, st, inputs, eps.astype(dtype), masks, train=train)
+    out, cache = vo.forward(kind, dims, st, inputs, eps.astype(dtype), masks, train=train, q=q)
     scalars, og = vo.loss_and_output_grads(kind, out, bt, beta, gamma, None if cw is None else cw.astype(dtype))
     grads = vo.backward(kind, dims, st, cache, og, train=train)
     return out, scalars, grads, st
@@ -90,3 +100,9 @@ def assert_close(name, got, ref, tol, atol=0.0):
     bound = tol * np.linalg.norm(ref) + atol
     assert np.isfinite(got).all(), name
     assert err <= bound, f"{name}: |err|={err:.4g} > {bound:.4g} (rel {err / max(np.linalg.norm(ref), 1e-30):.3g})"
+
+
+def cosine(x, ref):
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    return float(x @ ref / max(np.linalg.norm(x) * np.linalg.norm(ref), 1e-300))

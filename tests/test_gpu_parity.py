@@ -11,8 +11,8 @@ import torch
 
 from golden.make_golden import CASES, SAMPLE_STRIDE, case_inputs
 from oracle import vae_oracle as vo
-from parity_util import (TOL_BF16, TOL_FP32, assert_close, call_module, is_pre_bn_bias, loss_for, make_module,
-                         oracle_step, rel_l2, to_t)
+from parity_util import (MIN_COSINE_VS_EXACT, TOL_BF16, TOL_FP32, TOL_GRAD_VS_EXACT, assert_close, call_module, cosine,
+                         is_pre_bn_bias, loss_for, make_module, oracle_step, rel_l2, to_t)
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -41,6 +41,8 @@ def test_forward_loss_backward_vs_oracle(case):
     state, batch, eps, masks, cw = case_inputs(case)
     o_out, o_scal, o_grads, _ = oracle_step(case["kind"], case["dims"], state, batch, case["present"], eps, masks,
                                             case["beta"], case["gamma"], cw, train=case["train"])
+    q_out, q_scal, q_grads, _ = oracle_step(case["kind"], case["dims"], state, batch, case["present"], eps, masks,
+                                            case["beta"], case["gamma"], cw, train=case["train"], q=vo.round_bf16)
     m, out, total, (recon, cls, kld), grads = _run_cuda(case, state, batch, eps, masks, cw, backward=case["steps"] > 0)
     for prefix, ref in o_out["recon"].items():
         assert_close("recon." + prefix, out["recon"][prefix].detach().cpu().numpy(), ref, TOL_BF16)
@@ -57,17 +59,26 @@ def test_forward_loss_backward_vs_oracle(case):
         decided = (top2[:, 1] - top2[:, 0]) > 2 * err
         assert (got.argmax(1)[decided] == ref.argmax(1)[decided]).all()
         assert decided.mean() > 0.5
+    # same algorithm at the declared operand precision: everything within the bf16 tolerance
+    for prefix, ref in q_out["recon"].items():
+        assert_close("matched recon." + prefix, out["recon"][prefix].detach().cpu().numpy(), ref, TOL_BF16)
+    np.testing.assert_allclose(total, q_scal["total"], rtol=TOL_BF16)
     if grads is not None:
-        for name, ref in o_grads.items():
+        for name, ref in q_grads.items():
             g = grads[name]
             assert g is not None, name
             scale = np.linalg.norm(ref)
             if is_pre_bn_bias(name):
                 # exactly-zero true gradient (BatchNorm removes the mean): compare against the layer's weight-gradient scale
                 wname = name[:-4] + "weight"
-                assert np.linalg.norm(g) <= 2e-2 * np.linalg.norm(o_grads[wname]) + 1e-4, name
+                assert np.linalg.norm(g) <= 2e-2 * np.linalg.norm(q_grads[wname]) + 1e-4, name
                 continue
-            assert_close("grad." + name, g, ref, TOL_BF16, atol=1e-5 * max(scale, 1.0))
+            assert_close("matched grad." + name, g, ref, TOL_BF16, atol=1e-5 * max(scale, 1.0))
+            # exact arithmetic: documented envelope (parity_util.TOL_GRAD_VS_EXACT)
+            exact = o_grads[name]
+            if np.linalg.norm(exact) > 1e-6:
+                assert rel_l2(g, exact) <= TOL_GRAD_VS_EXACT, ("exact grad." + name, rel_l2(g, exact))
+                assert cosine(g, exact) >= MIN_COSINE_VS_EXACT, ("cosine grad." + name, cosine(g, exact))
         for name, g in grads.items():
             if name not in o_grads:
                 assert g is None, f"{name} should have no gradient"
@@ -89,8 +100,11 @@ def test_against_reference_fixture(case):
         else:
             ref = fix[prefix + "|sample"]
             got = arr.reshape(-1)[::SAMPLE_STRIDE]
-        assert rel_l2(got, ref) <= TOL_BF16 or np.linalg.norm(got - ref) <= 1e-5 * max(np.linalg.norm(ref), 1.0), \
+        tol = TOL_GRAD_VS_EXACT if prefix.startswith("grad.") else TOL_BF16
+        assert rel_l2(got, ref) <= tol or np.linalg.norm(got - ref) <= 1e-5 * max(np.linalg.norm(ref), 1.0), \
             (prefix, rel_l2(got, ref))
+        if prefix.startswith("grad.") and np.linalg.norm(ref) > 1e-6:
+            assert cosine(got, ref) >= MIN_COSINE_VS_EXACT, (prefix, cosine(got, ref))
 
     for prefix, t in out["recon"].items():
         check("out.recon." + prefix, t.detach().cpu().numpy())

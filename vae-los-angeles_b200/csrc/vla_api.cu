@@ -68,7 +68,11 @@ struct TmapKey {
 
 }  // namespace
 
+struct ProfEntry { char name[48]; cudaEvent_t e0, e1; double flops, bytes; };
+
 struct vla_model {
+  bool prof_on = false;
+  std::vector<ProfEntry> prof;
   vla_config_t cfg{};
   int L = 0, E = 0, S = 0;
   std::vector<Enc> encs;
@@ -101,6 +105,41 @@ struct vla_model {
 };
 
 namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Optional per-launch timing
+// ---------------------------------------------------------------------------------------------
+struct ProfScope {
+  vla_model* m; cudaStream_t st; int idx = -1;
+  ProfScope(vla_model* m_, cudaStream_t st_, const char* name, double flops, double bytes) : m(m_), st(st_) {
+    if (!m->prof_on) return;
+    ProfEntry e{};
+    snprintf(e.name, sizeof(e.name), "%s", name);
+    e.flops = flops; e.bytes = bytes;
+    if (cudaEventCreate(&e.e0) != cudaSuccess || cudaEventCreate(&e.e1) != cudaSuccess) return;
+    cudaEventRecord(e.e0, st);
+    m->prof.push_back(e);
+    idx = static_cast<int>(m->prof.size()) - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(m->prof[idx].e1, st); }
+};
+void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
+  *flops = 0; *bytes = 0;
+  for (int i = 0; i < g.nprob; ++i) {
+    const GemmProblem& p = g.p[i];
+    *flops += 2.0 * p.M * p.N * p.K;
+    const double out_b = (p.flags & (GF_OUT_F32 | GF_RED)) ? 4.0 : 0.0;
+    *bytes += 2.0 * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K) +
+              (out_b + ((p.flags & GF_OUT_BF16) ? 2.0 : 0.0)) * p.M * p.N;
+  }
+}
+int timed_gemm(vla_model* m, const GemmGroup& g, int mode, const char* name, cudaStream_t st) {
+  double fl, by; gemm_work(g, &fl, &by);
+  ProfScope ps(m, st, name, fl, by);
+  cudaError_t e = launch_gemm_group(g, mode, st);
+  if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("gemm launch (") + name + "): " + cudaGetErrorString(e));
+  return VLA_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Layout
@@ -433,7 +472,7 @@ int run_shadow_refresh(vla_model* m, const float* params, cudaStream_t st) {
   a.p = const_cast<float*>(params); a.shadow = m->shadow;
   a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
   a.update = 0;
-  CK(launch_adamw(a, st));
+  { ProfScope ps(m, st, "shadow_refresh", 0, 6.0 * m->n_params); CK(launch_adamw(a, st)); }
   return VLA_OK;
 }
 
@@ -466,7 +505,8 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       }
     }
     a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches;
-    CK(launch_ingest(a, st));
+    { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * (4.0 * a.width[e] + 2.0 * a.ld_dst[e]);
+      ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); }
   }
   const int mt = ceil_div(B, GEMM_BM);
   // ---- encoders, round by round ----
@@ -493,7 +533,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         p->bias = P + l.b_off; p->out_f32 = w.ml; p->ld_f32 = 2 * L;
       }
     }
-    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+    if (g.nprob && (rc = timed_gemm(m, g, 0, r == 0 ? "gemm_enc_l0" : (r == 1 ? "gemm_enc_l1" : "gemm_enc_l2"), st))) return rc;
     for (size_t i = 0; i < m->encs.size(); ++i) {
       if (!(present >> i & 1)) continue;
       const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
@@ -509,7 +549,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
-      CK(launch_bn_act(a, st));
+      { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
     }
   }
   // ---- latent ----
@@ -520,7 +560,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     a.eps_in = io.eps; a.seed = io.seed; a.offset = io.offset * 16; a.dyn = io.engine ? m->dyn : nullptr;
     a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz;
     a.kl_partials = m->kl_partials; a.rows = B; a.L = L;
-    CK(launch_latent_fwd(a, &m->kl_grid, st));
+    { ProfScope ps(m, st, "latent_fwd", 0, static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0)); CK(launch_latent_fwd(a, &m->kl_grid, st)); }
     if (io.mu) CK(cudaMemcpyAsync(io.mu, m->mu, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
     if (io.logvar) CK(cudaMemcpyAsync(io.logvar, m->logvar, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
   }
@@ -530,7 +570,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     const Lin& l = m->cat;
     if ((rc = add_nt(m, g, m->z, m->ldz, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p))) return rc;
     p->bias = P + l.b_off; p->out_bf16 = m->d0; p->ld_bf16 = l.out;
-    CK(launch_gemm_group(g, 0, st));
+    if ((rc = timed_gemm(m, g, 0, "gemm_dec_l0", st))) return rc;
   }
   size_t max_rest = 0;
   for (const Dec& d : m->decs) max_rest = std::max(max_rest, d.rest.size());
@@ -555,7 +595,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         p->bias = P + l.b_off; p->out_bf16 = w.act[r]; p->ld_bf16 = l.out;
       }
     }
-    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+    if (g.nprob && (rc = timed_gemm(m, g, 0, r == 0 ? "gemm_dec_l1" : "gemm_dec_l2", st))) return rc;
   }
   m->saved = true; m->saved_batch = B; m->saved_present = present; m->saved_train = io.train;
   m->generation++;
@@ -590,7 +630,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       og[n].dst = w.g_out; og[n].ld_dst = w.ld_gout; og[n].rows = B; n++;
       active[i] = true;
     }
-    CK(launch_out_grad(og, n, st));
+    { ProfScope ps(m, st, "out_grad", 0, 0); CK(launch_out_grad(og, n, st)); }
   } else {
     for (size_t i = 0; i < m->decs.size(); ++i) active[i] = true;
   }
@@ -620,7 +660,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       }
       p->mask_scale = 1.0f;
     }
-    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+    if (g.nprob && (rc = timed_gemm(m, g, 0, rr == 0 ? "dgrad_dec_l1" : "dgrad_dec_l2", st))) return rc;
   }
   // inactive decoders contribute zero to dL/dz: clear their slice of g_d0
   if (any_dec)
@@ -632,7 +672,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     const Lin& l = m->cat;
     if ((rc = add_nt(m, g, m->g_d0, l.out, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
     p->out_f32 = m->gz; p->ld_f32 = L;
-    CK(launch_gemm_group(g, 0, st));
+    if ((rc = timed_gemm(m, g, 0, "dgrad_dec_l0", st))) return rc;
   }
   // ---- latent ----
   int n_present = 0;
@@ -644,7 +684,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     a.mu = m->mu; a.logvar = m->logvar; a.eps = m->eps;
     a.beta = 0.f; a.dyn = io.engine ? m->dyn : nullptr;
     a.n_modalities = n_present; a.gml = m->gml; a.ld_gml = m->ldgml; a.rows = B; a.L = L;
-    CK(launch_latent_bwd(a, st));
+    { ProfScope ps(m, st, "latent_bwd", 0, static_cast<double>(B) * L * 20.0); CK(launch_latent_bwd(a, st)); }
   }
   const int mt = ceil_div(B, GEMM_BM);
   // ---- encoder data gradients ----
@@ -679,7 +719,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;
       bn_todo.emplace_back(i, tgt);
     }
-    if (g.nprob) CK(launch_gemm_group(g, 0, st));
+    if (g.nprob && (rc = timed_gemm(m, g, 0, r == 1 ? "dgrad_enc_l1" : "dgrad_enc_l2", st))) return rc;
     for (auto& it : bn_todo) {
       const Enc& e = m->encs[it.first]; EncWS& w = m->ews[it.first]; const Bn& bn = e.bn[it.second];
       BnBwdArgs a{};
@@ -688,7 +728,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       a.mean = w.mean[it.second]; a.rstd = w.rstd[it.second]; a.gamma = P + bn.g_off;
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
-      CK(launch_bn_bwd(a, st));
+      { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
     }
   }
   if (!site_done) {
@@ -698,7 +738,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const Lin& l = m->encs[i].heads; EncWS& w = m->ews[i];
       if ((rc = add_nt(m, g, m->gml, m->ldgml, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
       p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
-      CK(launch_gemm_group(g, 0, st));
+      if ((rc = timed_gemm(m, g, 0, "dgrad_site", st))) return rc;
     }
   }
   // ---- every weight (and bias) gradient in one grouped split-K launch ----
@@ -739,7 +779,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       }
     }
     finalize_tn(g, B);
-    CK(launch_gemm_group(g, 1, st));
+    if ((rc = timed_gemm(m, g, 1, "wgrad_all", st))) return rc;
   }
   return VLA_OK;
 }
@@ -873,7 +913,7 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
   a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
   a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd; a.step = step;
   a.dyn = dyn ? m->dyn : nullptr; a.update = 1; a.zero_grad = zero_grad ? 1 : 0;
-  CK(launch_adamw(a, st));
+  { ProfScope ps(m, st, "adamw", 0, 34.0 * m->n_params); CK(launch_adamw(a, st)); }
   return VLA_OK;
 }
 
@@ -914,6 +954,10 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
   io.recon[0] = a->recon_a; io.recon[1] = a->recon_b; io.recon[2] = a->recon_c;
   io.mu = a->mu; io.logvar = a->logvar; io.engine = true;
   if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
+  const bool do_fb = a->phases != 2, do_opt = a->phases != 1;
+  if (!do_fb)
+    return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
+                     true, st);
   io.n_batches = a->dataset_rows > a->batch ? static_cast<int>(a->dataset_rows / a->batch) : 1;
   int rc;
   if ((rc = run_forward(m, io, st))) return rc;
@@ -939,13 +983,43 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
     }
     l.kl_partials = m->kl_partials; l.n_kl_partials = m->kl_grid; l.mu = m->mu; l.logvar = m->logvar; l.L = m->L;
     l.partials = m->loss_partials; l.counter = m->loss_counter; l.out = a->loss_out;
-    CK(launch_loss(l, st));
+    { double by = 0;
+      if (l.recon_a) by += static_cast<double>(l.rows) * l.width_a * 10.0;
+      if (l.recon_b) by += static_cast<double>(l.rows) * l.width_b * 10.0;
+      if (l.logits) by += static_cast<double>(l.rows) * l.n_sites * 6.0;
+      ProfScope ps(m, st, "loss", 0, by); CK(launch_loss(l, st)); }
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
   if ((rc = run_backward(m, bo, st))) return rc;
+  if (!do_opt) return VLA_OK;
   return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
                    true, st);
+}
+
+int vla_profile_begin(vla_model_t* m) {
+  if (!m) return fail(VLA_ERR_INVALID, "null model");
+  for (ProfEntry& e : m->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  m->prof.clear();
+  m->prof_on = true;
+  return VLA_OK;
+}
+int vla_profile_collect(vla_model_t* m, vla_prof_entry_t* out, int max_entries) {
+  if (!m || !out) return fail(VLA_ERR_INVALID, "null argument");
+  m->prof_on = false;
+  int n = 0;
+  for (ProfEntry& e : m->prof) {
+    if (cudaEventSynchronize(e.e1) == cudaSuccess && n < max_entries) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e.e0, e.e1);
+      memcpy(out[n].name, e.name, sizeof(out[n].name));
+      out[n].ms = ms; out[n].flops = e.flops; out[n].bytes = e.bytes;
+      ++n;
+    }
+    cudaEventDestroy(e.e0); cudaEventDestroy(e.e1);
+  }
+  m->prof.clear();
+  return n;
 }
 
 int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K, int bn,

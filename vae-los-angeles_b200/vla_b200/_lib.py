@@ -62,7 +62,11 @@ class TrainArgs(C.Structure):
                 ("eps", C.c_void_p), ("keep_masks", C.POINTER(C.c_void_p)), ("seed", C.c_ulonglong),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("recon_a", C.c_void_p), ("recon_b", C.c_void_p), ("recon_c", C.c_void_p),
-                ("mu", C.c_void_p), ("logvar", C.c_void_p), ("loss_out", C.c_void_p)]
+                ("mu", C.c_void_p), ("logvar", C.c_void_p), ("loss_out", C.c_void_p), ("phases", C.c_int)]
+
+
+class ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("flops", C.c_double), ("bytes", C.c_double)]
 
 
 EXPORTS = {
@@ -85,6 +89,8 @@ EXPORTS = {
     "vla_train_step": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "vla_set_hyper": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "vla_set_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vla_profile_begin": (C.c_int, [C.c_void_p]),
+    "vla_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
     "vla_test_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

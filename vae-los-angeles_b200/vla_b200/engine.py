@@ -52,8 +52,7 @@ class FusedAdamW(torch.optim.Optimizer):
                               step=self.steps)
         with torch.cuda.device(core.device):
             _lib.check(_lib.lib().vla_adamw(core.handle, C.byref(args), _stream()), "vla_adamw")
-        for p in core.order:              # the kernel wrote through the arena: keep version counters honest
-            p._version  # noqa: B018  (views share storage; shadows were refreshed by the kernel itself)
+        # the kernel wrote through the arena and refreshed the bf16 copies itself
         core.shadow_version = core.param_version()
         return loss
 
@@ -92,28 +91,37 @@ class DeviceDataset:
 
 
 class Trainer:
-    """Whole-step trainer.  `step()` enqueues one train step (graph replay); `loss()` reads the last losses."""
+    """Whole-step trainer: `step()` enqueues one fused train step (a CUDA-graph replay) with no host sync.
+
+    Data parallel (one process per GPU, torch.distributed NCCL): pass `process_group`; the step becomes
+    [forward + loss + backward] -> one all-reduce(SUM) of the flat gradient arena with the 4 loss scalars
+    appended -> AdamW.  SUM, not mean: the reference's losses are reduction='sum' (SURVEY D10), so the result
+    equals a single-process run on the concatenated batch up to BatchNorm, which uses per-shard statistics."""
 
     def __init__(self, module, dataset, batch_size, lr=5e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8,
-                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True):
+                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True, process_group=None):
         self.module = module
         self.core = module._ensure_core()
-        self.ds = dataset
+        self.datasets = list(dataset) if isinstance(dataset, (list, tuple)) else [dataset]
         self.batch = int(batch_size)
-        if len(dataset) < self.batch:
+        if any(len(d) < self.batch for d in self.datasets):
             raise ValueError("dataset smaller than one batch")
         dev = self.core.device
-        self.grads = torch.zeros_like(self.core.arena)
+        n = self.core.n_params
+        # gradient arena with the loss scalars appended: one collective moves both
+        self.flat = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+        self.grads = self.flat[:n]
+        self.loss_out = self.flat[n:]
         self.exp_avg = torch.zeros_like(self.core.arena)
         self.exp_avg_sq = torch.zeros_like(self.core.arena)
-        self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
         self.class_weights = None if class_weights is None else class_weights.to(dev, torch.float32).contiguous()
         self.betas, self.eps, self.seed = betas, eps, seed
+        self.pg = process_group
         self.hyper = None
         self.set_hyper(lr, weight_decay, beta_kl, gamma)
         self.steps = 0
         self.use_graph = use_graph
-        self.graph = None
+        self.graphs = {}
         self.injected = None
         self._mask_arr = None
         _lib.check(_lib.lib().vla_model_reserve(self.core.handle, self.batch), "vla_model_reserve")
@@ -135,8 +143,8 @@ class Trainer:
             _lib.check(_lib.lib().vla_set_step(self.core.handle, int(completed_steps), int(batch_index), _stream()),
                        "vla_set_step")
 
-    def _args(self):
-        core, ds = self.core, self.ds
+    def _args(self, ds, phases):
+        core = self.core
         eps = masks = None
         if self.injected is not None:
             eps = self.injected.get("eps")
@@ -151,15 +159,25 @@ class Trainer:
             x_a=_ptr(ds.tpm), x_b=_ptr(ds.beta), site=_ptr(ds.site), class_weights=_ptr(self.class_weights),
             batch=self.batch, dataset_rows=len(ds), eps=_ptr(eps), keep_masks=masks, seed=self.seed,
             beta1=self.betas[0], beta2=self.betas[1], adam_eps=self.eps,
-            recon_a=None, recon_b=None, recon_c=None, mu=None, logvar=None, loss_out=_ptr(self.loss_out))
+            recon_a=None, recon_b=None, recon_c=None, mu=None, logvar=None, loss_out=_ptr(self.loss_out), phases=phases)
 
-    def _enqueue(self):
-        args = self._args()
+    def _call(self, ds, phases):
+        args = self._args(ds, phases)
         _lib.check(_lib.lib().vla_train_step(self.core.handle, C.byref(args), _stream()), "vla_train_step")
 
-    def step(self):
-        """One optimizer step on the next resident batch.  No host synchronisation."""
+    def _enqueue(self, ds):
+        if self.pg is None:
+            self._call(ds, 0)
+        else:
+            import torch.distributed as dist
+            self._call(ds, 1)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.pg)
+            self._call(ds, 2)
+
+    def step(self, which=0):
+        """One optimizer step on the next resident batch of dataset `which`.  No host synchronisation."""
         core = self.core
+        ds = self.datasets[which]
         with torch.cuda.device(core.device):
             if core.shadow_version != core.param_version():
                 # parameters were changed from the host side (init, load_state_dict): re-derive the bf16 copies
@@ -167,29 +185,48 @@ class Trainer:
                            "vla_refresh_shadows")
                 core.shadow_version = core.param_version()
             if not self.use_graph:
-                self._enqueue()
-            elif self.graph is None:
-                self._first_step_and_capture()
+                self._enqueue(ds)
+            elif which not in self.graphs:
+                self._first_step_and_capture(which, ds)
             else:
-                self.graph.replay()
+                self.graphs[which].replay()
         self.steps += 1
         core.generation += 1
 
-    def _first_step_and_capture(self):
+    def _first_step_and_capture(self, which, ds):
         # The first step runs eagerly on a side stream (it also loads the kernels and sizes the workspace);
         # the same call sequence is then captured, without executing, for every later step.
         dev = self.core.device
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            self._enqueue()
+            self._enqueue(ds)
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._enqueue()
-        self.graph = g
+            self._enqueue(ds)
+        self.graphs[which] = g
 
     def losses(self):
-        """(total, recon, class, kld) of the last completed step -- one 16-byte device->host read."""
+        """(total, recon, class, kld) of the last completed step -- one 16-byte device->host read.
+        Under data parallelism these are the sums over all ranks."""
         return tuple(self.loss_out.tolist())
+
+    def profile(self, steps=3, which=0):
+        """Per-launch device times of `steps` eager (non-graph) steps: list of (name, ms, flops, bytes)."""
+        L = _lib.lib()
+        dev = self.core.device
+        out = []
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)
+            _lib.check(L.vla_profile_begin(self.core.handle), "vla_profile_begin")
+            for _ in range(steps):
+                self._enqueue(self.datasets[which])
+                self.steps += 1
+            buf = (_lib.ProfEntry * 4096)()
+            n = L.vla_profile_collect(self.core.handle, buf, 4096)
+            torch.cuda.synchronize(dev)
+        for i in range(max(n, 0)):
+            out.append((buf[i].name.decode(), float(buf[i].ms), float(buf[i].flops), float(buf[i].bytes)))
+        return out
