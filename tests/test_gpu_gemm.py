@@ -28,8 +28,8 @@ def _padded(rows, cols, seed):
     return buf, buf[:, :cols]
 
 
-NT_CASES = [(128, 128, 64, 128), (256, 64, 782, 32), (4096, 572, 512, 144), (33, 40, 128, 16), (4096, 128, 782, 32),
-            (100, 448, 20, 64), (4096, 20, 448, 32), (515, 160, 200, 160), (4096, 782, 128, 112)]
+NT_CASES = [(128, 128, 64, 128), (256, 64, 782, 32), (4096, 572, 512, 160), (33, 40, 128, 32), (4096, 128, 782, 32),
+            (100, 448, 20, 64), (4096, 20, 448, 32), (515, 160, 200, 160), (4096, 782, 128, 96), (4096, 572, 512, 128)]
 
 
 @pytest.mark.parametrize("M,N,K,bn", NT_CASES)

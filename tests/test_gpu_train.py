@@ -71,7 +71,7 @@ def test_fused_train_steps_match_oracle(kind, dims, batch, use_graph):
                 assert np.abs(delta).max() <= 1.05 * lr * n_steps + 1e-7, name      # sign of rounding noise: bounded only
                 continue
             assert rel_l2(delta, delta_ref) <= 0.2, (name, rel_l2(delta, delta_ref))
-            assert_close(name, got, ref, 1e-3, atol=1e-6)
+            assert_close(name, got, ref, 1e-2, atol=1e-6)
 
 
 def test_adamw_kernel_fp32():

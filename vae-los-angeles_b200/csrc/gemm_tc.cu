@@ -7,10 +7,10 @@
 // One launch covers up to GEMM_MAX_PROBLEMS independent problems (e.g. both encoders' first layers,
 // or every weight gradient of the model): CTA index -> (problem, tile) through GemmGroup.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
-// Epilogue: TMEM -> registers -> padded smem chunk (32 columns) -> column-per-lane pass that applies
-// bias / activation / masks, accumulates per-column statistics (BatchNorm forward and backward) and
-// stores fully coalesced.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.
+// Epilogue (8 warps, thread = accumulator row): TMEM -> registers, bias / mask / activation applied in registers with
+// the global operands prefetched as 128-bit vectors, per-column statistics (BatchNorm forward and backward) by a
+// shuffle butterfly, 128-bit row stores; split-K partials go through a smem transpose so every red.add is coalesced.
 //
 // Replaces, per layer, the ATen addmm / mm calls issued by nn.Linear in the reference
 // (src/models/encoders.py:13-19,31-41,54-55; src/models/decoders.py:13-15,27-31,44-46) and their
@@ -30,18 +30,42 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 40 KiB
 constexpr int ONES_OFFSET = GEMM_STAGES * STAGE_BYTES;               // 2 KiB of bf16 1.0
 constexpr int ONES_BYTES = 2048;
 constexpr int STAGE_LD = 33;
-constexpr int CHUNK_OFFSET = ONES_OFFSET + ONES_BYTES;               // fp32 [128][33]
-constexpr int CHUNK_BYTES = GEMM_BM * STAGE_LD * 4;
-constexpr int PART_OFFSET = CHUNK_OFFSET + CHUNK_BYTES;              // fp32 [4][2][32]
-constexpr int PART_BYTES = 4 * 2 * 32 * 4;
+constexpr int CHUNK_OFFSET = ONES_OFFSET + ONES_BYTES;               // 8 warps x fp32 [32][33] (split-K red path)
+constexpr int CHUNK_BYTES = 8 * 32 * STAGE_LD * 4;
+constexpr int VEC_OFFSET = CHUNK_OFFSET + CHUNK_BYTES;               // bias | mean | rstd, fp32 [3][192]
+constexpr int VEC_BYTES = 3 * GEMM_BN_MAX_TN * 4;
+constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][6][4][32]
+constexpr int MAX_CHUNKS = GEMM_BN_MAX_TN / 32;
+constexpr int PART_BYTES = 2 * MAX_CHUNKS * 4 * 32 * 4;
 constexpr int BAR_OFFSET = PART_OFFSET + PART_BYTES;                 // mbarriers
 constexpr int SMEM_USED = BAR_OFFSET + 128;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                         // slack for manual 1 KiB alignment
+constexpr int EPI_THREADS = GEMM_THREADS - 64;                       // 8 warps
 
 static_assert(B_STAGE_BYTES >= GEMM_BN_MAX_NT * 128, "B stage too small for NT tiles");
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
+static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Sum over the 32 lanes of v[j] for every j; the total of column j ends up in lane j (31 shuffles).
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? v[j] : v[j + s];
+      const float keep = upper ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmGroup grp) {
@@ -86,11 +110,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
-  if (bias_mma && warp >= 2) {
-    // 2 KiB of bf16 1.0: the B operand of the bias-gradient MMA (layout-invariant)
-    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + ONES_OFFSET);
-    for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) ones[i] = 0x3F803F80u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp >= 2) {
+    const int et = threadIdx.x - 64;
+    if (bias_mma) {
+      // 2 KiB of bf16 1.0: the B operand of the bias-gradient MMA (layout-invariant)
+      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + ONES_OFFSET);
+      for (int i = et; i < ONES_BYTES / 4; i += EPI_THREADS) ones[i] = 0x3F803F80u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // per-column epilogue vectors of this tile
+    float* vec = reinterpret_cast<float*>(smem + VEC_OFFSET);
+    for (int i = et; i < BN; i += EPI_THREADS) {
+      const int col = n0 + i;
+      const bool ok = col < P.N;
+      vec[i] = (ok && (P.flags & GF_BIAS)) ? P.bias[col] : 0.f;
+      vec[GEMM_BN_MAX_TN + i] = (ok && (P.flags & GF_BNSTATS)) ? P.mean[col] : 0.f;
+      vec[2 * GEMM_BN_MAX_TN + i] = (ok && (P.flags & GF_BNSTATS)) ? P.rstd[col] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -157,89 +193,159 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       umma_commit(acc_bar);               // accumulator complete
     }
   } else {
-    // =========================== epilogue (128 threads) ===========================
+    // =========================== epilogue (8 warps) ===========================
+    // Thread = one accumulator row (TMEM lane); the two warps that share a lane quarter take alternate
+    // 32-column chunks.  Everything stays in registers; global operands are fetched as 128-bit vectors
+    // before they are needed; column statistics use a shuffle butterfly.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int ew = warp - 2;                // 0..3, row interleave in the store pass
-    const int et = threadIdx.x - 64;        // 0..127
-    float* chunk = reinterpret_cast<float*>(smem + CHUNK_OFFSET);
+    const int half = (warp - 2) >> 2;       // 0: warps 2-5, 1: warps 6-9
+    const int et = threadIdx.x - 64;        // 0..255
+    const float* vec = reinterpret_cast<const float*>(smem + VEC_OFFSET);
     float* part = reinterpret_cast<float*>(smem + PART_OFFSET);
     const int flags = P.flags;
-    const int n_end = min(P.N, n0 + BN);
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < P.M;
+    const int n_chunks = (BN + 31) >> 5;
+    const bool want_stats = (flags & (GF_COLSTATS | GF_BNSTATS)) != 0;
 
     mbar_wait(acc_bar, 0);
     tc_fence_after();
 
-    const int n_chunks = (BN + 31) >> 5;
-    for (int c = 0; c < n_chunks; ++c) {
-      // ---- pass 1: this thread's accumulator row -> smem chunk ----
-      {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32);
-        tmem_ld16(taddr, r);
-        tmem_ld16(taddr + 16, r + 16);
-        tmem_ld_wait();
-        float* dst = chunk + (q * 32 + lane) * STAGE_LD;
+    for (int c = half; c < n_chunks; c += 2) {
+      const int col0 = n0 + c * 32;
+      const int nvalid = min(32, P.N - col0);          // <= 0: nothing to store (tile padding)
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32);
+      tmem_ld16(taddr, r);
+      tmem_ld16(taddr + 16, r + 16);
+      // ---- global operands of this row, issued before the TMEM data is needed ----
+      uint4 mk[4];
+      float4 pr[8];
+      const bool full = nvalid == 32;
+      if ((flags & GF_MASK) && row_ok && full) {
+        const uint4* src = reinterpret_cast<const uint4*>(P.mask_src + static_cast<size_t>(row) * P.ld_mask + col0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r[j]);
+        for (int i = 0; i < 4; ++i) mk[i] = __ldg(src + i);
       }
-      named_bar_sync(1, 128);
-      // ---- pass 2: lane = column, warps interleave rows; everything global is coalesced ----
-      {
-        const int col = n0 + c * 32 + lane;
-        const bool col_ok = col < n_end;
-        float bias_v = 0.f, mean_v = 0.f, rstd_v = 0.f;
-        if (col_ok) {
-          if (flags & GF_BIAS) bias_v = P.bias[col];
-          if (flags & GF_BNSTATS) { mean_v = P.mean[col]; rstd_v = P.rstd[col]; }
+      if ((flags & GF_BNSTATS) && row_ok && full) {
+        const float4* src = reinterpret_cast<const float4*>(P.pre + static_cast<size_t>(row) * P.ld_pre + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pr[i] = __ldg(src + i);
+      }
+      tmem_ld_wait();
+      float v[32];
+      float w[32];                                     // second statistic (v*v or v*xhat)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) + vec[c * 32 + j];
+        if (flags & GF_COLSTATS) w[j] = x * x;
+        if (flags & GF_MASK) {
+          float m;
+          if (full) {
+            const uint32_t word = reinterpret_cast<const uint32_t*>(mk)[j >> 1];
+            m = __uint_as_float((j & 1) ? (word & 0xFFFF0000u) : (word << 16));
+          } else {
+            m = (row_ok && j < nvalid) ? __bfloat162float(P.mask_src[static_cast<size_t>(row) * P.ld_mask + col0 + j]) : 0.f;
+          }
+          x = m > 0.f ? x * P.mask_scale : 0.f;
         }
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int r = i * 4 + ew;
-          const int row = m0 + r;
-          if (row < P.M && col_ok) {
-            float v = chunk[r * STAGE_LD + lane] + bias_v;
-            if (flags & GF_COLSTATS) { s1 += v; s2 += v * v; }
-            if (flags & GF_MASK) {
-              const float mk = __bfloat162float(P.mask_src[static_cast<size_t>(row) * P.ld_mask + col]);
-              v = mk > 0.f ? v * P.mask_scale : 0.f;
-            }
-            if (flags & GF_BNSTATS) {
-              const float xh = (P.pre[static_cast<size_t>(row) * P.ld_pre + col] - mean_v) * rstd_v;
-              s1 += v; s2 += v * xh;
-            }
-            if (flags & GF_RELU) v = fmaxf(v, 0.f);
-            if (flags & GF_SIGMOID) v = sigmoidf_(v);
-            if (flags & GF_RED) {
-              atomicAdd(P.out_f32 + static_cast<size_t>(row) * P.ld_f32 + col, v);
-            } else {
-              if (flags & GF_OUT_F32) P.out_f32[static_cast<size_t>(row) * P.ld_f32 + col] = v;
-              if (flags & GF_OUT_BF16) P.out_bf16[static_cast<size_t>(row) * P.ld_bf16 + col] = __float2bfloat16(v);
-            }
+        if (flags & GF_BNSTATS) {
+          float p;
+          if (full) p = reinterpret_cast<const float*>(pr)[j];
+          else p = (row_ok && j < nvalid) ? P.pre[static_cast<size_t>(row) * P.ld_pre + col0 + j] : 0.f;
+          const float xh = (p - vec[GEMM_BN_MAX_TN + c * 32 + j]) * vec[2 * GEMM_BN_MAX_TN + c * 32 + j];
+          w[j] = x * xh;
+        }
+        v[j] = x;
+      }
+      if (want_stats) {
+        // statistics are taken before the activation (BatchNorm forward) / on the masked gradient (backward)
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1[j] = row_ok ? v[j] : 0.f; s2[j] = row_ok ? w[j] : 0.f; }
+        const float t1 = warp_column_sums(s1, lane);
+        const float t2 = warp_column_sums(s2, lane);
+        part[((0 * MAX_CHUNKS + c) * 4 + q) * 32 + lane] = t1;
+        part[((1 * MAX_CHUNKS + c) * 4 + q) * 32 + lane] = t2;
+      }
+      if (flags & (GF_RELU | GF_SIGMOID)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (flags & GF_RELU) v[j] = fmaxf(v[j], 0.f);
+          if (flags & GF_SIGMOID) v[j] = sigmoidf_(v[j]);
+        }
+      }
+      if (flags & GF_RED) {
+        // split-K partial sums: transpose through this warp's smem patch so that each red covers 32 consecutive
+        // floats of one row (one 128-byte L2 atomic request instead of 32 scattered ones)
+        float* chunk = reinterpret_cast<float*>(smem + CHUNK_OFFSET) + (warp - 2) * (32 * STAGE_LD);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) chunk[lane * STAGE_LD + j] = v[j];
+        __syncwarp();
+        if (lane < nvalid) {
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int rr = m0 + q * 32 + i;
+            if (rr < P.M) red_add_f32(P.out_f32 + static_cast<size_t>(rr) * P.ld_f32 + col0 + lane, chunk[i * STAGE_LD + lane]);
           }
         }
-        if (flags & (GF_COLSTATS | GF_BNSTATS)) {
-          part[(ew * 2 + 0) * 32 + lane] = s1;
-          part[(ew * 2 + 1) * 32 + lane] = s2;
+        __syncwarp();
+      } else if (row_ok && nvalid > 0) {
+        if (flags & GF_OUT_F32) {
+          float* dst = P.out_f32 + static_cast<size_t>(row) * P.ld_f32 + col0;
+          const bool a16 = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          const bool a8 = full && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+          if (a16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (a8) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) reinterpret_cast<float2*>(dst)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j] = v[j];
+          }
         }
-      }
-      named_bar_sync(1, 128);
-      if ((flags & (GF_COLSTATS | GF_BNSTATS)) && et < 64) {
-        const int which = et >> 5;          // 0: first statistic, 1: second
-        const int col = n0 + c * 32 + lane;
-        if (col < n_end) {
-          const float t = part[(0 * 2 + which) * 32 + lane] + part[(1 * 2 + which) * 32 + lane] +
-                          part[(2 * 2 + which) * 32 + lane] + part[(3 * 2 + which) * 32 + lane];
-          P.stats[(static_cast<size_t>(m_tile) * 2 + which) * P.N + col] = t;
+        if (flags & GF_OUT_BF16) {
+          bf16* dst = P.out_bf16 + static_cast<size_t>(row) * P.ld_bf16 + col0;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+              o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+              reinterpret_cast<uint4*>(dst)[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+          }
         }
       }
     }
-    if (bias_mma) {
+    if (bias_mma && half == 0) {
       uint32_t r1[1];
       tmem_ld1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + GEMM_BIAS_TMEM_COL, r1);
       tmem_ld_wait();
-      const int row = m0 + q * 32 + lane;
-      if (row < P.M) atomicAdd(P.bias_grad + row, __uint_as_float(r1[0]));
+      if (row_ok) red_add_f32(P.bias_grad + row, __uint_as_float(r1[0]));
+    }
+    if (want_stats) {
+      named_bar_sync(3, EPI_THREADS);
+      for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+        const int which = i / BN, cc = i - which * BN;
+        const int col = n0 + cc;
+        if (col < P.N) {
+          const float* pp = part + ((which * MAX_CHUNKS + (cc >> 5)) * 4) * 32 + (cc & 31);
+          P.stats[(static_cast<size_t>(m_tile) * 2 + which) * P.N + col] = pp[0] + pp[32] + pp[64] + pp[96];
+        }
+      }
     }
   }
 

@@ -368,8 +368,8 @@ int get_tmap(vla_model* m, CUtensorMap* out, const void* base, uint64_t inner, u
 
 int choose_bn_nt(int M, int N) {
   const int mt = ceil_div(M, GEMM_BM);
-  int best = 16; double best_cost = 1e30;
-  for (int bn = 16; bn <= GEMM_BN_MAX_NT; bn += 16) {
+  int best = 32; double best_cost = 1e30;
+  for (int bn = 32; bn <= GEMM_BN_MAX_NT; bn += 32) {   // whole 32-column epilogue chunks
     const int tiles = mt * ceil_div(N, bn);
     const double cost = static_cast<double>(ceil_div(tiles, 148)) * (bn + 24);
     if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) { best = bn; best_cost = cost; }
@@ -427,7 +427,7 @@ void finalize_tn(GemmGroup& g, int Kb, int force_splits = 0) {
   int base = 0;
   for (int i = 0; i < g.nprob; ++i) base += g.p[i].m_tiles * g.p[i].n_tiles;
   const int kb_total = ceil_div(Kb, GEMM_BK);
-  int splits = force_splits ? force_splits : std::max(1, (2 * 148 + base / 2) / std::max(base, 1));
+  int splits = force_splits ? force_splits : std::max(1, (148 + base / 2) / std::max(base, 1));
   splits = std::min(splits, kb_total);
   const int per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, per);

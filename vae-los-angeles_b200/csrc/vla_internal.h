@@ -32,7 +32,7 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_BN_MAX_NT = 160;   // multiple of 16
 constexpr int GEMM_BN_MAX_TN = 192;   // multiple of 64
 constexpr int GEMM_MAX_PROBLEMS = 16;
-constexpr int GEMM_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int GEMM_THREADS = 320;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int GEMM_TMEM_COLS = 256;
 constexpr int GEMM_BIAS_TMEM_COL = 224;
 
