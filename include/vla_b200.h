@@ -163,7 +163,8 @@ typedef struct {
 } vla_train_args_t;
 int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream);
 int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, float gamma, vla_stream_t stream);
-int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, vla_stream_t stream);
+/* Resets the device-side step counter (and beta1^t, beta2^t for the bias corrections) and the resident-batch index. */
+int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float beta1, float beta2, vla_stream_t stream);
 
 /* Per-launch device timing (CUDA events on `stream`, recorded around every kernel launch the library makes between
  * vla_profile_begin and vla_profile_collect).  flops / bytes are the ALGORITHMIC work of the launch.
@@ -182,6 +183,11 @@ int vla_profile_collect(vla_model_t* m, vla_prof_entry_t* out, int max_entries);
  * the caller in mode 1 (split-K accumulation).  bias_grad (mode 1, optional) receives sum_k A[k, m]. */
 int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K,
                   int bn, int k_splits, float* bias_grad, vla_stream_t stream);
+
+/* Test hook: device buffer [tiles][8] of %globaltimer stamps written by the following vla_test_gemm calls
+ * (kernel entry, dependency resolved, setup done, first operands landed, MMAs issued, accumulator ready, epilogue done). */
+int vla_test_set_timeline(unsigned long long* dbg);
+int vla_test_set_flags(int flags);   /* debugging switches of the GEMM test hook (profiles/cta_turnaround.py) */
 
 #ifdef __cplusplus
 }

@@ -58,3 +58,18 @@ def test_gemm_tn_with_bias_grad(M, N, Kb, bn, splits):
     bref = G.float().sum(0)
     berr = (bias - bref).norm() / bref.norm()
     assert berr < 2e-3, float(berr)
+
+
+NN_CASES = [(128, 64, 64, 64), (4096, 128, 40, 128), (4096, 512, 572, 128), (4096, 20, 448, 64), (300, 256, 512, 192),
+            (4096, 32, 40, 64)]
+
+
+@pytest.mark.parametrize("M,N,K,bn", NN_CASES)
+def test_gemm_nn_mixed_major(M, N, K, bn):
+    """C[M,N] = A[M,K] * B[K,N]: A K-major, B MN-major (data gradients read the forward weight copy)."""
+    Ab, A = _padded(M, K, 5)
+    Bb, B = _padded(K, N, 6)
+    out, _ = _run(2, Ab, Bb, M, N, K, bn, 1)
+    ref = A.float() @ B.float()
+    err = (out - ref).norm() / ref.norm()
+    assert err < 2e-3, float(err)

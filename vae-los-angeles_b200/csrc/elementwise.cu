@@ -3,8 +3,10 @@
 // (modality mean, reparameterisation, per-sample KL), the fused loss (MSE + BCE + weighted CE + KL
 // with their gradients), BatchNorm backward, the latent backward and the fused multi-tensor AdamW.
 // All arithmetic is fp32; reductions are deterministic (fixed-order partials, no float atomics).
+#include "tc_ptx.cuh"
 #include "vla_internal.h"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace vla {
@@ -55,39 +57,55 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 // ---------------------------------------------------------------------------------------------
 // ingest: fp32 inputs -> bf16 padded operands; embedding gather; one-hot; step counter
 // ---------------------------------------------------------------------------------------------
-__global__ void ingest_kernel(IngestArgs a) {
-  if (a.bump_step && blockIdx.x == 0 && threadIdx.x == 0) a.dyn->step += 1;
+__global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (a.bump_step && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.dyn->step += 1;
+    a.dyn->b1pow *= static_cast<double>(a.beta1);
+    a.dyn->b2pow *= static_cast<double>(a.beta2);
+  }
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = static_cast<int>(tid >> 5), nwarps = static_cast<int>(nthr >> 5);
   for (int e = 0; e < a.n; ++e) {
-    const int half_ld = a.ld_dst[e] >> 1;
-    const long long total = static_cast<long long>(a.rows) * half_ld;
+    const int quads = a.ld_dst[e] >> 2;                        // ld_dst is a multiple of 8
     const float* __restrict__ src = a.src[e];
-    __nv_bfloat162* __restrict__ dst = reinterpret_cast<__nv_bfloat162*>(a.dst[e]);
     const int w = a.width[e];
-    for (long long i = tid; i < total; i += nthr) {
-      const int r = static_cast<int>(i / half_ld);
-      const int c = static_cast<int>(i - static_cast<long long>(r) * half_ld) * 2;
-      const float* s = src + (row0 + r) * w + c;
-      const float x0 = (c < w) ? __ldg(s) : 0.f;
-      const float x1 = (c + 1 < w) ? __ldg(s + 1) : 0.f;
-      dst[i] = __floats2bfloat162_rn(x0, x1);
+    const bool vec_ok = (w % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+    for (int r = gwarp; r < a.rows; r += nwarps) {             // one warp per row: no index division
+      const float* sp = src + (row0 + r) * w;
+      uint2* dp = reinterpret_cast<uint2*>(a.dst[e] + static_cast<size_t>(r) * a.ld_dst[e]);
+#pragma unroll 4
+      for (int qd = lane; qd < quads; qd += 32) {
+        const int c = qd * 4;
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        if (vec_ok) {
+          if (c + 1 < w) { const float2 t = __ldg(reinterpret_cast<const float2*>(sp + c)); x0 = t.x; x1 = t.y; }
+          if (c + 3 < w) { const float2 t = __ldg(reinterpret_cast<const float2*>(sp + c + 2)); x2 = t.x; x3 = t.y; }
+        } else {
+          if (c < w) x0 = __ldg(sp + c);
+          if (c + 1 < w) x1 = __ldg(sp + c + 1);
+          if (c + 2 < w) x2 = __ldg(sp + c + 2);
+          if (c + 3 < w) x3 = __ldg(sp + c + 3);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x0, x1), hi = __floats2bfloat162_rn(x2, x3);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        dp[qd] = o;
+      }
     }
   }
   if (a.site != nullptr) {
-    const long long tot_h = static_cast<long long>(a.rows) * a.ld_hsite;
-    for (long long i = tid; i < tot_h; i += nthr) {
-      const int r = static_cast<int>(i / a.ld_hsite);
-      const int c = static_cast<int>(i - static_cast<long long>(r) * a.ld_hsite);
+    for (int r = gwarp; r < a.rows; r += nwarps) {
       const long long s = a.site[row0 + r];
-      a.h_site[i] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
-    }
-    const long long tot_o = static_cast<long long>(a.rows) * a.ld_onehot;
-    for (long long i = tid; i < tot_o; i += nthr) {
-      const int r = static_cast<int>(i / a.ld_onehot);
-      const int c = static_cast<int>(i - static_cast<long long>(r) * a.ld_onehot);
-      a.onehot[i] = __float2bfloat16(a.site[row0 + r] == c ? 1.f : 0.f);
+      for (int c = lane; c < a.ld_hsite; c += 32)
+        a.h_site[static_cast<size_t>(r) * a.ld_hsite + c] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
+      for (int c = lane; c < a.ld_onehot; c += 32)
+        a.onehot[static_cast<size_t>(r) * a.ld_onehot + c] = __float2bfloat16(s == c ? 1.f : 0.f);
     }
   }
 }
@@ -124,6 +142,8 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ stats,
 }
 
 __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_block) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ double sh[8][BN_COLS][2];
   __shared__ float s_mean[BN_COLS], s_rstd[BN_COLS];
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -171,8 +191,9 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_b
   unsigned long long offset = a.offset;
   if (a.dyn) offset += static_cast<unsigned long long>(a.dyn->step) << 20;
   const int row_end = min(a.rows, static_cast<int>(blockIdx.y + 1) * rows_per_block);
+#pragma unroll 2
   for (int row = blockIdx.y * rows_per_block + ty; row < row_end; row += 8) {
-    const float2 x = *reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col);
+    const float2 x = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
     float y0 = fmaxf((x.x - m0) * r0 + b0, 0.f);
     float y1 = fmaxf((x.y - m1) * r1 + b1, 0.f);
     if (drop) {
@@ -195,6 +216,8 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_b
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdArgs a, int rows_per_block) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ double sh[8][BN_COLS][2];
   __shared__ float s_s1[BN_COLS], s_s2[BN_COLS];
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -223,10 +246,11 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdArgs a, int rows_per_b
   const float c10 = a.train ? s_s1[lane * 2] * inv_n : 0.f, c11 = a.train ? s_s1[lane * 2 + 1] * inv_n : 0.f;
   const float c20 = a.train ? s_s2[lane * 2] * inv_n : 0.f, c21 = a.train ? s_s2[lane * 2 + 1] * inv_n : 0.f;
   const int row_end = min(a.rows, static_cast<int>(blockIdx.y + 1) * rows_per_block);
+#pragma unroll 4
   for (int row = blockIdx.y * rows_per_block + ty; row < row_end; row += 8) {
     const float2 gy = __bfloat1622float2(
         *reinterpret_cast<const __nv_bfloat162*>(a.gy + static_cast<size_t>(row) * a.ld_gy + col));
-    const float2 x = *reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col);
+    const float2 x = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
     const float xh0 = (x.x - m0) * rs0, xh1 = (x.y - m1) * rs1;
     const float o0 = g0 * (gy.x - c10 - xh0 * c20);
     const float o1 = g1 * (gy.y - c11 - xh1 * c21);
@@ -239,13 +263,15 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdArgs a, int rows_per_b
 // (vae.py:11-15, 64-73; losses.py:42)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) latent_fwd_kernel(LatentFwdArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sh[32];
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(a.rows) * a.L;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;       // rows * L < 2^31 (checked by the launcher)
+  const unsigned total = static_cast<unsigned>(a.rows) * a.L;
   float kl = 0.f;
   if (idx < total) {
-    const int r = static_cast<int>(idx / a.L);
-    const int j = static_cast<int>(idx - static_cast<long long>(r) * a.L);
+    const int r = static_cast<int>(idx / static_cast<unsigned>(a.L));
+    const int j = static_cast<int>(idx - static_cast<unsigned>(r) * a.L);
     float mu = 0.f, lv = 0.f;
     for (int e = 0; e < a.n_enc; ++e) {
       const float* p = a.ml[e] + static_cast<size_t>(r) * a.ld_ml[e];
@@ -259,8 +285,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(LatentFwdArgs a) {
     } else {
       unsigned long long offset = a.offset;
       if (a.dyn) offset += static_cast<unsigned long long>(a.dyn->step) << 20;
-      const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32),
-                                                 static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32) ^ 0x5EEDu),
+      const uint4 rnd = philox4x32_10(make_uint4(idx, 0u, static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32) ^ 0x5EEDu),
                                       make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
       eps = normal_from(rnd.x, rnd.y);
     }
@@ -277,11 +302,13 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(LatentFwdArgs a) {
 }
 
 __global__ void __launch_bounds__(256) latent_bwd_kernel(LatentBwdArgs a) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(a.rows) * a.L;
+  pdl_wait();
+  pdl_launch_dependents();
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = static_cast<unsigned>(a.rows) * a.L;
   if (idx >= total) return;
-  const int r = static_cast<int>(idx / a.L);
-  const int j = static_cast<int>(idx - static_cast<long long>(r) * a.L);
+  const int r = static_cast<int>(idx / static_cast<unsigned>(a.L));
+  const int j = static_cast<int>(idx - static_cast<unsigned>(r) * a.L);
   const float beta = a.dyn ? a.dyn->beta_kl : a.beta;
   const float gz = a.gz ? a.gz[static_cast<size_t>(r) * a.ld_gz + j] : 0.f;
   const float mu = a.mu[idx], lv = a.logvar[idx], eps = a.eps[idx];
@@ -299,22 +326,77 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(LatentBwdArgs a) {
 // (losses.py:27-46; directional_losses.py:23-30, 48-55).  Block roles by blockIdx range.
 // ---------------------------------------------------------------------------------------------
 constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_WARPS = LOSS_THREADS / 32;
 constexpr int LOSS_PER_THREAD = 16;
 constexpr int LOSS_PER_BLOCK = LOSS_THREADS * LOSS_PER_THREAD;
 
 __host__ __device__ inline int ceil_div_ll(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+// Block roles by blockIdx range: [MSE rows | BCE rows | CE rows | KL elements].  MSE / BCE: one warp per sample row,
+// lanes stride over 8-byte pairs (both 782 and 572 are even), so no per-element index arithmetic is needed for the
+// padded bf16 gradient rows.
 struct LossGrid { int nb_a, nb_b, nb_c, nb_k; };
 __host__ __device__ inline LossGrid loss_grid(const LossArgs& a) {
   LossGrid g;
-  g.nb_a = a.recon_a ? ceil_div_ll(static_cast<long long>(a.rows) * a.width_a, LOSS_PER_BLOCK) : 0;
-  g.nb_b = a.recon_b ? ceil_div_ll(static_cast<long long>(a.rows) * a.width_b, LOSS_PER_BLOCK) : 0;
+  g.nb_a = a.recon_a ? ceil_div_ll(a.rows, LOSS_WARPS) : 0;
+  g.nb_b = a.recon_b ? ceil_div_ll(a.rows, LOSS_WARPS) : 0;
   g.nb_c = a.logits ? ceil_div_ll(a.rows, LOSS_THREADS) : 0;
   g.nb_k = (a.mu && !a.kl_partials) ? ceil_div_ll(static_cast<long long>(a.rows) * a.L, LOSS_PER_BLOCK) : 0;
   return g;
 }
 
+template <bool BCE>
+__device__ __forceinline__ float loss_elem(float y, float t, float gs, float& g_out, float& g_logit) {
+  if (BCE) {
+    // lg2.approx-based logs (absolute error ~1e-7 per term, far below the 1e-5 relative budget of the summed loss)
+    const float ly = fmaxf(__logf(y), -100.0f);
+    const float l1 = fmaxf(__logf(1.0f - y), -100.0f);
+    const float yy = y * (1.0f - y);
+    g_out = __fdividef(y - t, fmaxf(yy, 1e-12f)) * gs;   // dL/dy (ATen's backward floor)
+    g_logit = g_out * yy;                           // dL/d(pre-sigmoid)
+    return -(t * ly + (1.0f - t) * l1);
+  } else {
+    const float d = y - t;
+    g_out = 2.0f * d * gs;
+    g_logit = g_out;
+    return d * d;
+  }
+}
+
+template <bool BCE>
+__device__ __forceinline__ float loss_row(const float* __restrict__ rp, const float* __restrict__ tp, int w, float gs,
+                                          float* __restrict__ gf, bf16* __restrict__ gb, int lane) {
+  float acc = 0.f;
+  const bool vec = (w % 2 == 0) && (((reinterpret_cast<uintptr_t>(rp) | reinterpret_cast<uintptr_t>(tp)) & 7) == 0) &&
+                   (gf == nullptr || (reinterpret_cast<uintptr_t>(gf) & 7) == 0);
+  if (vec) {
+    const int n2 = w >> 1;
+    const float2* r2 = reinterpret_cast<const float2*>(rp);
+    const float2* t2 = reinterpret_cast<const float2*>(tp);
+#pragma unroll 2
+    for (int i = lane; i < n2; i += 32) {
+      const float2 y = r2[i];
+      const float2 t = __ldg(t2 + i);
+      float g0, g1, l0, l1;
+      acc += loss_elem<BCE>(y.x, t.x, gs, g0, l0);
+      acc += loss_elem<BCE>(y.y, t.y, gs, g1, l1);
+      if (gf) reinterpret_cast<float2*>(gf)[i] = make_float2(g0, g1);
+      if (gb) reinterpret_cast<__nv_bfloat162*>(gb)[i] = __floats2bfloat162_rn(l0, l1);
+    }
+  } else {
+    for (int i = lane; i < w; i += 32) {
+      float g0, l0;
+      acc += loss_elem<BCE>(rp[i], __ldg(tp + i), gs, g0, l0);
+      if (gf) gf[i] = g0;
+      if (gb) gb[i] = __float2bfloat16(l0);
+    }
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(LossArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sh[32];
   __shared__ bool s_last;
   const LossGrid G = loss_grid(a);
@@ -322,50 +404,21 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(LossArgs a) {
   const float gamma = a.dyn ? a.dyn->gamma : a.gamma;
   const float gs = a.grad_scale;
   const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int b = blockIdx.x;
   float acc = 0.f;
   if (b < G.nb_a) {
-    // ---- MSE ----
-    const long long total = static_cast<long long>(a.rows) * a.width_a;
-    const long long base = static_cast<long long>(b) * LOSS_PER_BLOCK;
-#pragma unroll 4
-    for (int i = 0; i < LOSS_PER_THREAD; ++i) {
-      const long long idx = base + static_cast<long long>(i) * LOSS_THREADS + threadIdx.x;
-      if (idx < total) {
-        const float d = a.recon_a[idx] - __ldg(a.a + row0 * a.width_a + idx);
-        acc += d * d;
-        const float g = 2.0f * d * gs;
-        if (a.ga_f32) a.ga_f32[idx] = g;
-        if (a.ga_bf16) {
-          const int r = static_cast<int>(idx / a.width_a);
-          const int c = static_cast<int>(idx - static_cast<long long>(r) * a.width_a);
-          a.ga_bf16[static_cast<size_t>(r) * a.ld_ga + c] = __float2bfloat16(g);
-        }
-      }
-    }
+    const int r = b * LOSS_WARPS + warp;
+    if (r < a.rows)
+      acc = loss_row<false>(a.recon_a + static_cast<size_t>(r) * a.width_a, a.a + (row0 + r) * a.width_a, a.width_a, gs,
+                            a.ga_f32 ? a.ga_f32 + static_cast<size_t>(r) * a.width_a : nullptr,
+                            a.ga_bf16 ? a.ga_bf16 + static_cast<size_t>(r) * a.ld_ga : nullptr, lane);
   } else if ((b -= G.nb_a) < G.nb_b) {
-    // ---- BCE ----
-    const long long total = static_cast<long long>(a.rows) * a.width_b;
-    const long long base = static_cast<long long>(b) * LOSS_PER_BLOCK;
-#pragma unroll 4
-    for (int i = 0; i < LOSS_PER_THREAD; ++i) {
-      const long long idx = base + static_cast<long long>(i) * LOSS_THREADS + threadIdx.x;
-      if (idx < total) {
-        const float y = a.recon_b[idx];
-        const float t = __ldg(a.b + row0 * a.width_b + idx);
-        const float ly = fmaxf(logf(y), -100.0f);
-        const float l1 = fmaxf(log1pf(-y), -100.0f);
-        acc -= t * ly + (1.0f - t) * l1;
-        const float yy = y * (1.0f - y);
-        const float gy = (y - t) / fmaxf(yy, 1e-12f) * gs;
-        if (a.gb_f32) a.gb_f32[idx] = gy;
-        if (a.gb_bf16) {
-          const int r = static_cast<int>(idx / a.width_b);
-          const int c = static_cast<int>(idx - static_cast<long long>(r) * a.width_b);
-          a.gb_bf16[static_cast<size_t>(r) * a.ld_gb + c] = __float2bfloat16(gy * yy);   // w.r.t. the logit
-        }
-      }
-    }
+    const int r = b * LOSS_WARPS + warp;
+    if (r < a.rows)
+      acc = loss_row<true>(a.recon_b + static_cast<size_t>(r) * a.width_b, a.b + (row0 + r) * a.width_b, a.width_b, gs,
+                           a.gb_f32 ? a.gb_f32 + static_cast<size_t>(r) * a.width_b : nullptr,
+                           a.gb_bf16 ? a.gb_bf16 + static_cast<size_t>(r) * a.ld_gb : nullptr, lane);
   } else if ((b -= G.nb_b) < G.nb_c) {
     // ---- weighted cross-entropy, one thread per sample ----
     const int r = b * LOSS_THREADS + threadIdx.x;
@@ -392,6 +445,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(LossArgs a) {
     // ---- KL directly from mu / logvar (functional loss API) ----
     const long long total = static_cast<long long>(a.rows) * a.L;
     const long long base = static_cast<long long>(b) * LOSS_PER_BLOCK;
+#pragma unroll 4
     for (int i = 0; i < LOSS_PER_THREAD; ++i) {
       const long long idx = base + static_cast<long long>(i) * LOSS_THREADS + threadIdx.x;
       if (idx < total) {
@@ -447,6 +501,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_kernel(LossArgs a) {
 // ---------------------------------------------------------------------------------------------
 struct OutGradPack { OutGradArgs e[3]; int n; };
 __global__ void out_grad_kernel(OutGradPack p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
   for (int e = 0; e < p.n; ++e) {
@@ -467,41 +523,65 @@ __global__ void out_grad_kernel(OutGradPack p) {
 // (torch.optim.AdamW semantics; call sites train_rna2dna.py:94-96, 185-189)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const AdamChunk ch = a.chunks[blockIdx.x];
   const AdamSegment sg = a.segs[ch.seg];
   const long long seg_n = static_cast<long long>(sg.rows) * sg.cols;
-  float lr = a.lr, wd = a.weight_decay;
-  int step = a.step;
-  if (a.dyn) { lr = a.dyn->lr; wd = a.dyn->weight_decay; step = a.dyn->step; }
-  float bc1 = 1.f, bc2s = 1.f;
-  if (a.update) {
-    bc1 = 1.0f - powf(a.beta1, static_cast<float>(step));
-    bc2s = sqrtf(1.0f - powf(a.beta2, static_cast<float>(step)));
+  const long long e = static_cast<long long>(ch.start) + 4LL * threadIdx.x;
+  if (e >= seg_n) return;
+  float lr = a.lr, wd = a.weight_decay, bc1 = a.bc1, inv_bc2s = a.inv_bc2_sqrt;
+  if (a.dyn) {
+    lr = a.dyn->lr; wd = a.dyn->weight_decay;
+    bc1 = static_cast<float>(1.0 - a.dyn->b1pow);
+    inv_bc2s = static_cast<float>(1.0 / sqrt(1.0 - a.dyn->b2pow));
   }
   const float step_size = lr / bc1;
-#pragma unroll 4
-  for (int i = 0; i < ADAM_CHUNK / 256; ++i) {
-    const long long e = static_cast<long long>(ch.start) + i * 256 + threadIdx.x;
-    if (e >= seg_n) break;
-    const long long gi = sg.offset + e;
-    float p = a.p[gi];
+  const float decay = 1.0f - lr * wd;
+  const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
+  const long long gi = sg.offset + e;                 // multiple of 4: 16-byte aligned in every arena
+  const int nv = static_cast<int>(min(4LL, seg_n - e));
+  float p[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (nv == 4) {
+    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(a.p + gi);
     if (a.update) {
-      const float g = a.g[gi];
-      float m = a.m[gi], v = a.v[gi];
-      p *= (1.0f - lr * wd);
-      m = a.beta1 * m + (1.0f - a.beta1) * g;
-      v = a.beta2 * v + (1.0f - a.beta2) * g * g;
-      const float denom = sqrtf(v) / bc2s + a.eps;
-      p -= step_size * (m / denom);
-      a.p[gi] = p; a.m[gi] = m; a.v[gi] = v;
-      if (a.zero_grad) a.g[gi] = 0.f;
+      *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(a.g + gi);
+      *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(a.m + gi);
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.v + gi);
     }
-    if (sg.shadow_off >= 0 || sg.shadow_t_off >= 0) {
-      const int r = static_cast<int>(e / sg.cols);
-      const int c = static_cast<int>(e - static_cast<long long>(r) * sg.cols);
-      const bf16 pb = __float2bfloat16(p);
-      if (sg.shadow_off >= 0) a.shadow[sg.shadow_off + static_cast<long long>(r) * sg.ld_shadow + c] = pb;
-      if (sg.shadow_t_off >= 0) a.shadow[sg.shadow_t_off + static_cast<long long>(c) * sg.ld_shadow_t + r] = pb;
+  } else {
+    for (int k = 0; k < nv; ++k) {
+      p[k] = a.p[gi + k];
+      if (a.update) { g[k] = a.g[gi + k]; m[k] = a.m[gi + k]; v[k] = a.v[gi + k]; }
+    }
+  }
+  if (a.update) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      p[k] *= decay;
+      m[k] = b1 * m[k] + (1.0f - b1) * g[k];
+      v[k] = b2 * v[k] + (1.0f - b2) * g[k] * g[k];
+      p[k] -= step_size * __fdividef(m[k], sqrtf(v[k]) * inv_bc2s + eps);
+    }
+    if (nv == 4) {
+      *reinterpret_cast<float4*>(a.p + gi) = *reinterpret_cast<const float4*>(p);
+      *reinterpret_cast<float4*>(a.m + gi) = *reinterpret_cast<const float4*>(m);
+      *reinterpret_cast<float4*>(a.v + gi) = *reinterpret_cast<const float4*>(v);
+      if (a.zero_grad) *reinterpret_cast<float4*>(a.g + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int k = 0; k < nv; ++k) {
+        a.p[gi + k] = p[k]; a.m[gi + k] = m[k]; a.v[gi + k] = v[k];
+        if (a.zero_grad) a.g[gi + k] = 0.f;
+      }
+    }
+  }
+  if (sg.shadow_off >= 0) {
+    // bf16 copy [rows, ld_shadow] used as the tensor-core operand (K-major for forward, MN-major for data gradients)
+    int r = static_cast<int>(static_cast<unsigned>(e) / static_cast<unsigned>(sg.cols));   // one tensor < 2^31 elements
+    int c = static_cast<int>(static_cast<unsigned>(e) - static_cast<unsigned>(r) * sg.cols);
+    for (int k = 0; k < nv; ++k) {
+      a.shadow[sg.shadow_off + static_cast<long long>(r) * sg.ld_shadow + c] = __float2bfloat16(p[k]);
+      if (++c == sg.cols) { c = 0; ++r; }
     }
   }
 }
@@ -516,16 +596,13 @@ inline int grid_for(long long work_items, int threads, int max_blocks) {
 }  // namespace
 
 cudaError_t launch_ingest(const IngestArgs& a, cudaStream_t s) {
-  long long work = 0;
-  for (int e = 0; e < a.n; ++e) work = std::max(work, static_cast<long long>(a.rows) * (a.ld_dst[e] / 2));
-  if (a.site) work = std::max(work, static_cast<long long>(a.rows) * std::max(a.ld_hsite, a.ld_onehot));
-  ingest_kernel<<<grid_for(work, 256, 148 * 8), 256, 0, s>>>(a);
-  return cudaGetLastError();
+  // one warp per row, 8 warps per block
+  return launch_pdl(ingest_kernel, dim3(grid_for(static_cast<long long>(a.rows) * 32, 256, 148 * 8)), dim3(256), 0, s, a);
 }
 
 static int bn_rows_per_block(int rows, int m_tiles) {
-  int rpb = 64;
-  if (m_tiles * 2 > rpb) rpb = m_tiles * 2;
+  int rpb = 32;
+  if (m_tiles > rpb) rpb = m_tiles;      // keep the per-block re-reduction of the tile partials below the tile's own traffic
   return rpb;
 }
 
@@ -533,30 +610,26 @@ cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s) {
   if (a.n % 2) return cudaErrorInvalidValue;
   const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0);
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
-  bn_act_kernel<<<grid, 256, 0, s>>>(a, rpb);
-  return cudaGetLastError();
+  return launch_pdl(bn_act_kernel, grid, dim3(256), 0, s, a, rpb);
 }
 
 cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {
   if (a.n % 2) return cudaErrorInvalidValue;
   const int rpb = bn_rows_per_block(a.rows, a.m_tiles);
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
-  bn_bwd_kernel<<<grid, 256, 0, s>>>(a, rpb);
-  return cudaGetLastError();
+  return launch_pdl(bn_bwd_kernel, grid, dim3(256), 0, s, a, rpb);
 }
 
 cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_t s) {
   const long long total = static_cast<long long>(a.rows) * a.L;
   const int grid = static_cast<int>((total + 255) / 256);
   if (grid_out) *grid_out = grid;
-  latent_fwd_kernel<<<grid, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(latent_fwd_kernel, dim3(grid), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
   const long long total = static_cast<long long>(a.rows) * a.L;
-  latent_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(latent_bwd_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, a);
 }
 
 int loss_grid_size(int rows, int width_a, int width_b, int n_sites) {
@@ -574,8 +647,7 @@ cudaError_t launch_loss(const LossArgs& a, cudaStream_t s) {
   const LossGrid g = loss_grid(a);
   int grid = g.nb_a + g.nb_b + g.nb_c + g.nb_k;
   if (grid == 0) grid = 1;   // KL-from-partials only: one block does the final reduction
-  loss_kernel<<<grid, LOSS_THREADS, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(loss_kernel, dim3(grid), dim3(LOSS_THREADS), 0, s, a);
 }
 
 cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s) {
@@ -584,14 +656,12 @@ cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s) {
   p.n = n;
   long long work = 0;
   for (int i = 0; i < n; ++i) { p.e[i] = a[i]; work = std::max(work, static_cast<long long>(a[i].rows) * a[i].width); }
-  out_grad_kernel<<<grid_for(work, 256, 148 * 8), 256, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(out_grad_kernel, dim3(grid_for(work, 256, 148 * 8)), dim3(256), 0, s, p);
 }
 
 cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s) {
   if (a.n_chunks <= 0) return cudaSuccess;
-  adamw_kernel<<<a.n_chunks, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(adamw_kernel, dim3(a.n_chunks), dim3(256), 0, s, a);
 }
 
 }  // namespace vla

@@ -1,8 +1,9 @@
 // Grouped bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
 // staged by TMA into 128-byte-swizzled shared memory, one 128 x BN output tile per CTA.
 //
-//   mode NT: C[M,N] = A[M,K] * B[N,K]^T   both operands K-major    (Linear forward, data gradients)
-//   mode TN: C[M,N] = A[K,M]^T * B[K,N]   both operands MN-major   (weight gradients, split-K + red.add)
+//   mode 0 NT: C[M,N] = A[M,K] * B[N,K]^T   both operands K-major       (Linear forward)
+//   mode 1 TN: C[M,N] = A[K,M]^T * B[K,N]   both operands MN-major      (weight gradients, split-K + red.add)
+//   mode 2 NN: C[M,N] = A[M,K] * B[K,N]     A K-major, B MN-major       (data gradients: B = the forward weight copy)
 //
 // One launch covers up to GEMM_MAX_PROBLEMS independent problems (e.g. both encoders' first layers,
 // or every weight gradient of the model): CTA index -> (problem, tile) through GemmGroup.
@@ -29,9 +30,9 @@ constexpr int B_STAGE_BYTES = GEMM_BN_MAX_TN * GEMM_BK * 2;          // 24 KiB (
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 40 KiB
 constexpr int ONES_OFFSET = GEMM_STAGES * STAGE_BYTES;               // 2 KiB of bf16 1.0
 constexpr int ONES_BYTES = 2048;
-constexpr int STAGE_LD = 33;
-constexpr int CHUNK_OFFSET = ONES_OFFSET + ONES_BYTES;               // 8 warps x fp32 [32][33] (split-K red path)
-constexpr int CHUNK_BYTES = 8 * 32 * STAGE_LD * 4;
+constexpr int PATCH_LD = 36;                                         // floats; 144-byte rows: 16-byte aligned, conflict-free
+constexpr int CHUNK_OFFSET = ONES_OFFSET + ONES_BYTES;               // 8 warps x fp32 [32][36] transpose patches
+constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;
 constexpr int VEC_OFFSET = CHUNK_OFFSET + CHUNK_BYTES;               // bias | mean | rstd, fp32 [3][192]
 constexpr int VEC_BYTES = 3 * GEMM_BN_MAX_TN * 4;
 constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][6][4][32]
@@ -46,7 +47,7 @@ static_assert(B_STAGE_BYTES >= GEMM_BN_MAX_NT * 128, "B stage too small for NT t
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
 static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // Sum over the 32 lanes of v[j] for every j; the total of column j ends up in lane j (31 shuffles).
 __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
@@ -62,6 +63,13 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   }
   return v[0];
 }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define STAMP(slot) do { if (grp.dbg) grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + (slot)] = gtime(); } while (0)
 
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
@@ -79,6 +87,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    STAMP(0);                                                      // kernel entry
+    if (grp.dbg) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] = smid; }
+  }
 
   // ---- which problem / tile ----
   int pi = 0;
@@ -109,7 +121,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     mbar_init(acc_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  const int dbgf = grp.dbg_flags;
+  if (warp == 1 && !(dbgf & 4)) tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  pdl_wait();                    // everything above overlaps the previous kernel's tail
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) STAMP(1);                                  // past the grid dependency
   if (warp >= 2) {
     const int et = threadIdx.x - 64;
     if (bias_mma) {
@@ -132,8 +148,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) STAMP(2);                                  // setup done
 
-  if (warp == 0) {
+  if (dbgf & 2) {
+    // test hook: no main loop, no epilogue
+  } else if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0;
@@ -142,17 +161,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
-        if (MODE == 0) {
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN * 128);
-          tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * GEMM_BK, m0);   // box 64 (K) x 128 (M)
-          tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * GEMM_BK, n0);   // box 64 (K) x BN (N)
-        } else {
-          const int nb = BN >> 6;
-          mbar_expect_tx(&full_bar[stage], (2 + nb) * 8192);
+        const int nb = BN >> 6;
+        mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (MODE == 0 ? BN * 128 : nb * 8192));
+        if (MODE == 1) {
           tma_load_2d(sa, &P.tmA, &full_bar[stage], m0, kb * GEMM_BK);           // box 64 (M) x 64 (K)
           tma_load_2d(sa + 8192, &P.tmA, &full_bar[stage], m0 + 64, kb * GEMM_BK);
+        } else {
+          tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * GEMM_BK, m0);           // box 64 (K) x 128 (M)
+        }
+        if (MODE == 0) {
+          tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * GEMM_BK, n0);           // box 64 (K) x BN (N)
+        } else {
           for (int i = 0; i < nb; ++i)
-            tma_load_2d(sb + i * 8192, &P.tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);
+            tma_load_2d(sb + i * 8192, &P.tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);   // box 64 (N) x 64 (K)
         }
         if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -160,26 +181,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MODE, MODE);
+      const uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MODE == 1 ? 1 : 0, MODE == 0 ? 0 : 1);
       const uint32_t idesc_ones = make_idesc_bf16(GEMM_BM, 16, 1, 0);
       const uint32_t ones_addr = smem_u32(smem + ONES_OFFSET);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (kb == kb0) STAMP(3);                                   // first operands landed
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) {
           uint64_t adesc, bdesc;
-          if (MODE == 0) {
-            adesc = make_smem_desc(sa + k * 32, 16, 1024);     // +16 bf16 of K inside the swizzle atom
-            bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-          } else {
-            adesc = make_smem_desc(sa + k * 2048, 8192, 1024);  // +16 K-rows of 128 B
-            bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
-          }
+          if (MODE == 1) adesc = make_smem_desc(sa + k * 2048, 8192, 1024);  // MN-major: +16 K-rows of 128 B
+          else           adesc = make_smem_desc(sa + k * 32, 16, 1024);       // K-major: +16 bf16 of K inside the swizzle atom
+          if (MODE == 0) bdesc = make_smem_desc(sb + k * 32, 16, 1024);
+          else           bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
           const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
           umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
           if (bias_mma) {
@@ -191,6 +210,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(acc_bar);               // accumulator complete
+      STAMP(4);                                                    // all MMAs issued
     }
   } else {
     // =========================== epilogue (8 warps) ===========================
@@ -210,125 +230,172 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    if (et == 0) STAMP(5);                                         // accumulator ready
 
-    for (int c = half; c < n_chunks; c += 2) {
+    // Per-warp transpose patch: global traffic of the epilogue is always issued with consecutive lanes on consecutive
+    // addresses of one row (1 L1 wavefront per 128 bytes) instead of 32 rows per instruction.
+    float* patch = reinterpret_cast<float*>(smem + CHUNK_OFFSET) + (warp - 2) * (32 * PATCH_LD);
+    const int rbase = m0 + q * 32;                      // first accumulator row of this warp
+    const bool f32_vec = ((reinterpret_cast<uintptr_t>(P.out_f32) & 15) == 0) && ((P.ld_f32 & 3) == 0);
+    const bool bf16_vec = ((reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0) && ((P.ld_bf16 & 7) == 0);
+
+    for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
       const int col0 = n0 + c * 32;
       const int nvalid = min(32, P.N - col0);          // <= 0: nothing to store (tile padding)
+      const bool full = nvalid == 32;
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32);
-      tmem_ld16(taddr, r);
-      tmem_ld16(taddr + 16, r + 16);
-      // ---- global operands of this row, issued before the TMEM data is needed ----
+      if (!(dbgf & 16)) {
+        tmem_ld16(taddr, r);
+        tmem_ld16(taddr + 16, r + 16);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = lane + j;
+      }
+      // ---- per-row operands: coalesced loads -> patch -> this thread's row ----
       uint4 mk[4];
       float4 pr[8];
-      const bool full = nvalid == 32;
-      if ((flags & GF_MASK) && row_ok && full) {
-        const uint4* src = reinterpret_cast<const uint4*>(P.mask_src + static_cast<size_t>(row) * P.ld_mask + col0);
+      const bool mask_fast = (flags & GF_MASK) != 0;     // host side guarantees N % 32 == 0 and 16-byte aligned rows
+      const bool pre_fast = (flags & GF_BNSTATS) != 0;
+      if (mask_fast) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mk[i] = __ldg(src + i);
-      }
-      if ((flags & GF_BNSTATS) && row_ok && full) {
-        const float4* src = reinterpret_cast<const float4*>(P.pre + static_cast<size_t>(row) * P.ld_pre + col0);
+        for (int k = 0; k < 4; ++k) {                   // 8 rows x 64 bytes per instruction
+          const int rr = 8 * k + (lane >> 2);
+          uint4 t = make_uint4(0u, 0u, 0u, 0u);
+          if (rbase + rr < P.M)
+            t = __ldg(reinterpret_cast<const uint4*>(P.mask_src + static_cast<size_t>(rbase + rr) * P.ld_mask + col0) + (lane & 3));
+          *reinterpret_cast<uint4*>(patch + rr * PATCH_LD + (lane & 3) * 4) = t;
+        }
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pr[i] = __ldg(src + i);
+        for (int i = 0; i < 4; ++i) mk[i] = *reinterpret_cast<const uint4*>(patch + lane * PATCH_LD + i * 4);
+        __syncwarp();
       }
-      tmem_ld_wait();
+      if (pre_fast) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                   // 4 rows x 128 bytes per instruction
+          const int rr = 4 * k + (lane >> 3);
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rbase + rr < P.M)
+            t = __ldg(reinterpret_cast<const float4*>(P.pre + static_cast<size_t>(rbase + rr) * P.ld_pre + col0) + (lane & 7));
+          *reinterpret_cast<float4*>(patch + rr * PATCH_LD + (lane & 7) * 4) = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pr[i] = *reinterpret_cast<const float4*>(patch + lane * PATCH_LD + i * 4);
+        __syncwarp();
+      }
+      if (!(dbgf & 16)) tmem_ld_wait();
+      // One flag-uniform pass over the register row per feature (compact code: no per-element branching).
       float v[32];
-      float w[32];                                     // second statistic (v*v or v*xhat)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) + vec[c * 32 + j];
-        if (flags & GF_COLSTATS) w[j] = x * x;
-        if (flags & GF_MASK) {
-          float m;
-          if (full) {
-            const uint32_t word = reinterpret_cast<const uint32_t*>(mk)[j >> 1];
-            m = __uint_as_float((j & 1) ? (word & 0xFFFF0000u) : (word << 16));
-          } else {
-            m = (row_ok && j < nvalid) ? __bfloat162float(P.mask_src[static_cast<size_t>(row) * P.ld_mask + col0 + j]) : 0.f;
-          }
-          x = m > 0.f ? x * P.mask_scale : 0.f;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(vec + c * 32 + j);
+        v[j] = __uint_as_float(r[j]) + bv.x;         v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+      }
+      if (flags & GF_MASK) {                           // ReLU / dropout backward: keep where the saved activation is > 0
+        const float sc = P.mask_scale;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t word = reinterpret_cast<const uint32_t*>(mk)[j >> 1];
+          const float m = __uint_as_float((j & 1) ? (word & 0xFFFF0000u) : (word << 16));
+          v[j] = m > 0.f ? v[j] * sc : 0.f;
         }
-        if (flags & GF_BNSTATS) {
-          float p;
-          if (full) p = reinterpret_cast<const float*>(pr)[j];
-          else p = (row_ok && j < nvalid) ? P.pre[static_cast<size_t>(row) * P.ld_pre + col0 + j] : 0.f;
-          const float xh = (p - vec[GEMM_BN_MAX_TN + c * 32 + j]) * vec[2 * GEMM_BN_MAX_TN + c * 32 + j];
-          w[j] = x * xh;
-        }
-        v[j] = x;
       }
       if (want_stats) {
         // statistics are taken before the activation (BatchNorm forward) / on the masked gradient (backward)
         float s1[32], s2[32];
+        if (flags & GF_BNSTATS) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s1[j] = row_ok ? v[j] : 0.f; s2[j] = row_ok ? w[j] : 0.f; }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 mv = *reinterpret_cast<const float4*>(vec + GEMM_BN_MAX_TN + c * 32 + j);
+            const float4 rv = *reinterpret_cast<const float4*>(vec + 2 * GEMM_BN_MAX_TN + c * 32 + j);
+            const float4 pv = pr[j >> 2];
+            s2[j] = v[j] * (pv.x - mv.x) * rv.x;         s2[j + 1] = v[j + 1] * (pv.y - mv.y) * rv.y;
+            s2[j + 2] = v[j + 2] * (pv.z - mv.z) * rv.z; s2[j + 3] = v[j + 3] * (pv.w - mv.w) * rv.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s2[j] = v[j] * v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1[j] = row_ok ? v[j] : 0.f; s2[j] = row_ok ? s2[j] : 0.f; }
         const float t1 = warp_column_sums(s1, lane);
         const float t2 = warp_column_sums(s2, lane);
         part[((0 * MAX_CHUNKS + c) * 4 + q) * 32 + lane] = t1;
         part[((1 * MAX_CHUNKS + c) * 4 + q) * 32 + lane] = t2;
       }
-      if (flags & (GF_RELU | GF_SIGMOID)) {
+      if ((flags & GF_RELU) && !(dbgf & 32)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (flags & GF_RELU) v[j] = fmaxf(v[j], 0.f);
-          if (flags & GF_SIGMOID) v[j] = sigmoidf_(v[j]);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
+      if ((flags & GF_SIGMOID) && !(dbgf & 32)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+      }
+      if (nvalid <= 0) continue;
+      if (dbgf & 8) {            // test hook: keep the math alive, skip patch + global stores
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += v[j];
+        if (acc == 123.456f) P.out_f32[0] = acc;
+        continue;
+      }
+      // ---- this thread's row -> patch; then row-contiguous global accesses ----
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(patch + lane * PATCH_LD + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      __syncwarp();
       if (flags & GF_RED) {
-        // split-K partial sums: transpose through this warp's smem patch so that each red covers 32 consecutive
-        // floats of one row (one 128-byte L2 atomic request instead of 32 scattered ones)
-        float* chunk = reinterpret_cast<float*>(smem + CHUNK_OFFSET) + (warp - 2) * (32 * STAGE_LD);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) chunk[lane * STAGE_LD + j] = v[j];
-        __syncwarp();
+        // split-K partial sums: one 128-byte red per row
         if (lane < nvalid) {
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int rr = m0 + q * 32 + i;
-            if (rr < P.M) red_add_f32(P.out_f32 + static_cast<size_t>(rr) * P.ld_f32 + col0 + lane, chunk[i * STAGE_LD + lane]);
-          }
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i)
+            if (rbase + i < P.M)
+              red_add_f32(P.out_f32 + static_cast<size_t>(rbase + i) * P.ld_f32 + col0 + lane, patch[i * PATCH_LD + lane]);
         }
-        __syncwarp();
-      } else if (row_ok && nvalid > 0) {
+      } else {
         if (flags & GF_OUT_F32) {
-          float* dst = P.out_f32 + static_cast<size_t>(row) * P.ld_f32 + col0;
-          const bool a16 = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          const bool a8 = full && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
-          if (a16) {
+          if (full && f32_vec) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else if (a8) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) reinterpret_cast<float2*>(dst)[i] = make_float2(v[2 * i], v[2 * i + 1]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = v[j];
+            for (int k = 0; k < 8; ++k) {               // 4 rows x 128 bytes per instruction
+              const int rr = 4 * k + (lane >> 3);
+              if (rbase + rr < P.M)
+                reinterpret_cast<float4*>(P.out_f32 + static_cast<size_t>(rbase + rr) * P.ld_f32 + col0)[lane & 7] =
+                    *reinterpret_cast<const float4*>(patch + rr * PATCH_LD + (lane & 7) * 4);
+            }
+          } else if (lane < nvalid) {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i)
+              if (rbase + i < P.M) P.out_f32[static_cast<size_t>(rbase + i) * P.ld_f32 + col0 + lane] = patch[i * PATCH_LD + lane];
           }
         }
         if (flags & GF_OUT_BF16) {
-          bf16* dst = P.out_bf16 + static_cast<size_t>(row) * P.ld_bf16 + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (full && bf16_vec) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
-              o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
-              reinterpret_cast<uint4*>(dst)[i] = o;
+            for (int k = 0; k < 4; ++k) {               // 8 rows x 64 bytes per instruction
+              const int rr = 8 * k + (lane >> 2);
+              if (rbase + rr < P.M) {
+                const float4 lo = *reinterpret_cast<const float4*>(patch + rr * PATCH_LD + (lane & 3) * 8);
+                const float4 hi = *reinterpret_cast<const float4*>(patch + rr * PATCH_LD + (lane & 3) * 8 + 4);
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(lo.x, lo.y), b1 = __floats2bfloat162_rn(lo.z, lo.w);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(hi.x, hi.y), b3 = __floats2bfloat162_rn(hi.z, hi.w);
+                uint4 o;
+                o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+                o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+                reinterpret_cast<uint4*>(P.out_bf16 + static_cast<size_t>(rbase + rr) * P.ld_bf16 + col0)[lane & 3] = o;
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+          } else if (lane < nvalid) {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i)
+              if (rbase + i < P.M)
+                P.out_bf16[static_cast<size_t>(rbase + i) * P.ld_bf16 + col0 + lane] = __float2bfloat16(patch[i * PATCH_LD + lane]);
           }
         }
       }
+      __syncwarp();
     }
     if (bias_mma && half == 0) {
       uint32_t r1[1];
@@ -352,7 +419,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (threadIdx.x == 0) STAMP(6);                                  // epilogue done
+  if (warp == 1 && !(dbgf & 4)) {
     tc_fence_after();
     tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
   }
@@ -370,14 +438,17 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
     g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (g_attr_err == cudaSuccess)
       g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (g_attr_err == cudaSuccess)
+      g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (g_attr_err != cudaSuccess) return g_attr_err;
   if (g.total_tiles <= 0) return cudaSuccess;
-  if (mode == 0)
-    gemm_tc_kernel<0><<<g.total_tiles, GEMM_THREADS, SMEM_BYTES, stream>>>(g);
-  else
-    gemm_tc_kernel<1><<<g.total_tiles, GEMM_THREADS, SMEM_BYTES, stream>>>(g);
-  return cudaGetLastError();
+  if (g.dbg_flags & 0xFFFF00) {   // test hook: dynamic smem override (only valid together with dbg_flags & 2)
+    return launch_pdl(gemm_tc_kernel<0>, dim3(g.total_tiles), dim3(GEMM_THREADS), static_cast<size_t>(g.dbg_flags >> 8), stream, g);
+  }
+  if (mode == 0) return launch_pdl(gemm_tc_kernel<0>, dim3(g.total_tiles), dim3(GEMM_THREADS), SMEM_BYTES, stream, g);
+  if (mode == 1) return launch_pdl(gemm_tc_kernel<1>, dim3(g.total_tiles), dim3(GEMM_THREADS), SMEM_BYTES, stream, g);
+  return launch_pdl(gemm_tc_kernel<2>, dim3(g.total_tiles), dim3(GEMM_THREADS), SMEM_BYTES, stream, g);
 }
 
 // ---------------------------------------------------------------------------------------------

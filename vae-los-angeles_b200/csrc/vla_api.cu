@@ -4,6 +4,7 @@
 #include "vla_internal.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -30,8 +31,8 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 struct Lin {
   int out = 0, in = 0;
   long long w_off = -1, b_off = -1;
-  long long sh_off = -1; int sh_ld = 0;      // bf16 [out, sh_ld]   (K-major B operand of forward GEMMs)
-  long long sht_off = -1; int sht_ld = 0;    // bf16 [in, sht_ld]   (K-major B operand of data-gradient GEMMs)
+  long long sh_off = -1; int sh_ld = 0;      // bf16 copy [out, sh_ld]: K-major B operand of the forward GEMM and
+                                             // MN-major B operand of the data-gradient GEMM
 };
 struct Bn { int n = 0; long long g_off = -1, b_off = -1, rm_off = -1, rv_off = -1; int counter = -1; };
 struct Enc {
@@ -134,6 +135,13 @@ void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
   }
 }
 int timed_gemm(vla_model* m, const GemmGroup& g, int mode, const char* name, cudaStream_t st) {
+  for (int i = 0; i < g.nprob; ++i) {
+    const GemmProblem& p = g.p[i];
+    if ((p.flags & GF_MASK) && ((p.N & 31) || (p.ld_mask & 7) || (reinterpret_cast<uintptr_t>(p.mask_src) & 15)))
+      return fail(VLA_ERR_STATE, std::string(name) + ": masked epilogue needs N % 32 == 0 and 16-byte aligned rows");
+    if ((p.flags & GF_BNSTATS) && ((p.N & 31) || (p.ld_pre & 3) || (reinterpret_cast<uintptr_t>(p.pre) & 15)))
+      return fail(VLA_ERR_STATE, std::string(name) + ": BatchNorm-statistics epilogue needs N % 32 == 0 and 16-byte aligned rows");
+  }
   double fl, by; gemm_work(g, &fl, &by);
   ProfScope ps(m, st, name, fl, by);
   cudaError_t e = launch_gemm_group(g, mode, st);
@@ -158,23 +166,22 @@ struct ArenaBuilder {
     t.shape[0] = d0 < 0 ? 0 : d0; t.shape[1] = d1 < 0 ? 0 : d1;
     m->infos.push_back(t);
   }
-  void seg(long long off, int rows, int cols, long long sh_off, int sh_ld, long long sht_off, int sht_ld) {
-    AdamSegment s{off, rows, cols, sh_off, sh_ld, sht_off, sht_ld};
+  void seg(long long off, int rows, int cols, long long sh_off, int sh_ld) {
+    AdamSegment s{off, rows, cols, sh_off, sh_ld, 0};
     const int idx = static_cast<int>(m->segs_h.size());
     m->segs_h.push_back(s);
     const long long n = static_cast<long long>(rows) * cols;
     for (long long st = 0; st < n; st += ADAM_CHUNK) m->chunks_h.push_back(AdamChunk{idx, static_cast<int>(st)});
   }
   // A Linear whose weight rows may be exposed under several state_dict names (fused groups).
-  Lin linear(int out, int in, bool need_t) {
+  Lin linear(int out, int in) {
     Lin l; l.out = out; l.in = in;
     l.w_off = take_p(static_cast<long long>(out) * in);
     l.b_off = take_p(out);
     l.sh_ld = pad8(in);
     l.sh_off = take_sh(static_cast<long long>(out) * l.sh_ld);
-    if (need_t) { l.sht_ld = pad8(out); l.sht_off = take_sh(static_cast<long long>(in) * l.sht_ld); }
-    seg(l.w_off, out, in, l.sh_off, l.sh_ld, l.sht_off, l.sht_ld);
-    seg(l.b_off, out, 1, -1, 0, -1, 0);
+    seg(l.w_off, out, in, l.sh_off, l.sh_ld);
+    seg(l.b_off, out, 1, -1, 0);
     return l;
   }
 };
@@ -206,7 +213,7 @@ int build_layout(vla_model* m) {
     if (s.type == 'C') {
       e.in_dim = c.n_sites;
       e.emb_off = ab.take_p(static_cast<long long>(c.n_sites) * c.embed);
-      ab.seg(e.emb_off, c.n_sites, c.embed, -1, 0, -1, 0);
+      ab.seg(e.emb_off, c.n_sites, c.embed, -1, 0);
       ab.info(e.prefix + ".embedding.weight", VLA_TENSOR_PARAM, e.emb_off, c.n_sites, c.embed);
       last = c.embed;
     } else {
@@ -215,10 +222,10 @@ int build_layout(vla_model* m) {
       last = e.in_dim;
       for (size_t i = 0; i < hidden.size(); ++i) {
         const int h = hidden[i];
-        Lin l = ab.linear(h, last, /*need_t=*/i > 0);   // no data gradient for the input layer
+        Lin l = ab.linear(h, last);
         Bn bn; bn.n = h;
-        bn.g_off = ab.take_p(h); ab.seg(bn.g_off, h, 1, -1, 0, -1, 0);
-        bn.b_off = ab.take_p(h); ab.seg(bn.b_off, h, 1, -1, 0, -1, 0);
+        bn.g_off = ab.take_p(h); ab.seg(bn.g_off, h, 1, -1, 0);
+        bn.b_off = ab.take_p(h); ab.seg(bn.b_off, h, 1, -1, 0);
         bn.rm_off = ab.take_b(h); bn.rv_off = ab.take_b(h);
         bn.counter = m->n_bn++;
         const std::string fc = e.prefix + ".fc." + std::to_string(4 * i);
@@ -236,7 +243,7 @@ int build_layout(vla_model* m) {
       }
     }
     // fused heads: rows [0, L) = fc_mu, rows [L, 2L) = fc_logvar
-    e.heads = ab.linear(2 * L, last, /*need_t=*/true);
+    e.heads = ab.linear(2 * L, last);
     ab.info(e.prefix + ".fc_mu.weight", VLA_TENSOR_PARAM, e.heads.w_off, L, last);
     ab.info(e.prefix + ".fc_mu.bias", VLA_TENSOR_PARAM, e.heads.b_off, L);
     ab.info(e.prefix + ".fc_logvar.weight", VLA_TENSOR_PARAM, e.heads.w_off + static_cast<long long>(L) * last, L, last);
@@ -246,7 +253,7 @@ int build_layout(vla_model* m) {
   // fused first decoder layers: one [sum of first hidden widths, L] matrix
   int cat_w = 0;
   for (const auto& s : ds) cat_w += s.type == 'A' ? 128 : (s.type == 'B' ? 256 : 64);
-  m->cat = ab.linear(cat_w, L, /*need_t=*/true);
+  m->cat = ab.linear(cat_w, L);
   int off = 0;
   for (const auto& s : ds) {
     Dec d; d.type = s.type; d.prefix = s.prefix;
@@ -258,7 +265,7 @@ int build_layout(vla_model* m) {
     std::vector<int> widths = s.type == 'B' ? std::vector<int>{512, d.out_dim} : std::vector<int>{d.out_dim};
     int last = d.cat_w;
     for (size_t i = 0; i < widths.size(); ++i) {
-      Lin l = ab.linear(widths[i], last, true);
+      Lin l = ab.linear(widths[i], last);
       const std::string fc = d.prefix + ".fc." + std::to_string(2 * (i + 1));
       ab.info(fc + ".weight", VLA_TENSOR_PARAM, l.w_off, widths[i], last);
       ab.info(fc + ".bias", VLA_TENSOR_PARAM, l.b_off, widths[i]);
@@ -366,13 +373,19 @@ int get_tmap(vla_model* m, CUtensorMap* out, const void* base, uint64_t inner, u
   return VLA_OK;
 }
 
-int choose_bn_nt(int M, int N) {
-  const int mt = ceil_div(M, GEMM_BM);
+// Tile-width choice: modelled time = waves x (fixed per-CTA latency + K-loop at ~150 KB/us per SM + epilogue).
+// At batch 4096 there are only 32 row tiles, so the choice is between one wave of wide tiles and two waves of narrow ones.
+double tile_cost(int M, int N, int K, int bn, int b_bytes_per_kblock) {
+  const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, bn);
+  const int waves = ceil_div(tiles, 148);
+  const double t_kb = (16384.0 + b_bytes_per_kblock) / 150e3;
+  return waves * (5.0 + ceil_div(K, GEMM_BK) * t_kb + 0.4 * ceil_div(bn, 64));
+}
+int choose_bn_nt(int M, int N, int K) {
   int best = 32; double best_cost = 1e30;
   for (int bn = 32; bn <= GEMM_BN_MAX_NT; bn += 32) {   // whole 32-column epilogue chunks
-    const int tiles = mt * ceil_div(N, bn);
-    const double cost = static_cast<double>(ceil_div(tiles, 148)) * (bn + 24);
-    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) { best = bn; best_cost = cost; }
+    const double cost = tile_cost(M, N, K, bn, bn * 128);
+    if (cost < best_cost - 1e-9) { best = bn; best_cost = cost; }
   }
   return best;
 }
@@ -392,13 +405,43 @@ int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, in
   GemmProblem& p = g.p[g.nprob];
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
-  p.BN = force_bn ? force_bn : choose_bn_nt(M, N);
+  p.BN = force_bn ? force_bn : choose_bn_nt(M, N, K);
   p.m_tiles = ceil_div(M, GEMM_BM); p.n_tiles = ceil_div(N, p.BN);
   p.k_splits = 1; p.kb_per_split = ceil_div(K, GEMM_BK);
   p.flags = flags;
   int rc;
   if ((rc = get_tmap(m, &p.tmA, A, K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
   if ((rc = get_tmap(m, &p.tmB, W, K, N, static_cast<uint64_t>(ldw) * 2, p.BN))) return rc;
+  p.tile_begin = g.total_tiles;
+  g.total_tiles += p.m_tiles * p.n_tiles;
+  g.nprob++;
+  *out = &p;
+  return VLA_OK;
+}
+
+int choose_bn_nn(int M, int N, int K) {
+  int best = 64; double best_cost = 1e30;
+  for (int bn = 64; bn <= GEMM_BN_MAX_TN; bn += 64) {
+    const double cost = tile_cost(M, N, K, bn, bn * 128);
+    if (cost < best_cost - 1e-9) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+// dX[M,N] = dY[M,K] * W[K,N] ; dY bf16 [M, lda] (K-major A), W bf16 [K, ldw] = the forward weight copy [out, in] (MN-major B)
+int add_nn(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int flags,
+           GemmProblem** out, int force_bn = 0) {
+  if (g.nprob >= GEMM_MAX_PROBLEMS) return fail(VLA_ERR_STATE, "too many problems in one GEMM group");
+  GemmProblem& p = g.p[g.nprob];
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.BN = force_bn ? force_bn : choose_bn_nn(M, N, K);
+  p.m_tiles = ceil_div(M, GEMM_BM); p.n_tiles = ceil_div(N, p.BN);
+  p.k_splits = 1; p.kb_per_split = ceil_div(K, GEMM_BK);
+  p.flags = flags;
+  int rc;
+  if ((rc = get_tmap(m, &p.tmA, A, K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
+  if ((rc = get_tmap(m, &p.tmB, W, N, K, static_cast<uint64_t>(ldw) * 2, 64))) return rc;
   p.tile_begin = g.total_tiles;
   g.total_tiles += p.m_tiles * p.n_tiles;
   g.nprob++;
@@ -440,7 +483,7 @@ void finalize_tn(GemmGroup& g, int Kb, int force_splits = 0) {
   }
 }
 
-void init_group(GemmGroup& g) { g.nprob = 0; g.total_tiles = 0; }
+void init_group(GemmGroup& g) { g.nprob = 0; g.total_tiles = 0; g.dbg = nullptr; g.dbg_flags = 0; }
 
 // ---------------------------------------------------------------------------------------------
 // Sequencing
@@ -455,6 +498,7 @@ struct FwdIO {
   float* mu; float* logvar;
   bool engine;       // train step: dyn-driven Philox offsets / step bump
   int n_batches;     // train step over a resident dataset
+  float beta1, beta2;
 };
 
 int present_mask(const vla_model* m, const FwdIO& io) {
@@ -504,7 +548,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         a.src[a.n] = io.x[e.slot]; a.dst[a.n] = w.x; a.width[a.n] = e.in_dim; a.ld_dst[a.n] = w.ldx; a.n++;
       }
     }
-    a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches;
+    a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches; a.beta1 = io.beta1; a.beta2 = io.beta2;
     { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * (4.0 * a.width[e] + 2.0 * a.ld_dst[e]);
       ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); }
   }
@@ -649,8 +693,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const bf16* A = last ? w.g_out : w.gact[rr];
       const int lda = last ? w.ld_gout : l.out;
       GemmProblem* p;
-      // dX[B, in] = dY[B, out] * W[out, in]  ->  NT with the transposed shadow [in, out]
-      if ((rc = add_nt(m, g, A, lda, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_MASK | GF_OUT_BF16, &p))) return rc;
+      // dX[B, in] = dY[B, out] * W[out, in]  ->  A K-major, B = forward weight copy read MN-major
+      if ((rc = add_nn(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_MASK | GF_OUT_BF16, &p))) return rc;
       if (rr == 0) {
         p->mask_src = m->d0 + d.cat_off; p->ld_mask = m->cat.out;
         p->out_bf16 = m->g_d0 + d.cat_off; p->ld_bf16 = m->cat.out;
@@ -660,7 +704,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       }
       p->mask_scale = 1.0f;
     }
-    if (g.nprob && (rc = timed_gemm(m, g, 0, rr == 0 ? "dgrad_dec_l1" : "dgrad_dec_l2", st))) return rc;
+    if (g.nprob && (rc = timed_gemm(m, g, 2, rr == 0 ? "dgrad_dec_l1" : "dgrad_dec_l2", st))) return rc;
   }
   // inactive decoders contribute zero to dL/dz: clear their slice of g_d0
   if (any_dec)
@@ -670,9 +714,9 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   if (any_dec) {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
-    if ((rc = add_nt(m, g, m->g_d0, l.out, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
+    if ((rc = add_nn(m, g, m->g_d0, l.out, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
     p->out_f32 = m->gz; p->ld_f32 = L;
-    if ((rc = timed_gemm(m, g, 0, "dgrad_dec_l0", st))) return rc;
+    if ((rc = timed_gemm(m, g, 2, "dgrad_dec_l0", st))) return rc;
   }
   // ---- latent ----
   int n_present = 0;
@@ -701,7 +745,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       if (e.type == 'C') {
         if (site_done) continue;
         const Lin& l = e.heads;
-        if ((rc = add_nt(m, g, m->gml, m->ldgml, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
+        if ((rc = add_nn(m, g, m->gml, m->ldgml, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
         p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
         site_done = true;
         continue;
@@ -712,14 +756,14 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const bf16* A = r == depth ? m->gml : w.gpre[r];
       const int lda = r == depth ? m->ldgml : l.out;
       const size_t tgt = r - 1;                       // gradient w.r.t. act[tgt]
-      if ((rc = add_nt(m, g, A, lda, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_MASK | GF_BNSTATS | GF_OUT_BF16, &p))) return rc;
+      if ((rc = add_nn(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_MASK | GF_BNSTATS | GF_OUT_BF16, &p))) return rc;
       p->mask_src = w.act[tgt]; p->ld_mask = l.in; p->mask_scale = train ? 1.0f / 0.9f : 1.0f;
       p->pre = w.pre[tgt]; p->ld_pre = l.in; p->mean = w.mean[tgt]; p->rstd = w.rstd[tgt];
       p->stats = w.bstats[tgt];
       p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;
       bn_todo.emplace_back(i, tgt);
     }
-    if (g.nprob && (rc = timed_gemm(m, g, 0, r == 1 ? "dgrad_enc_l1" : "dgrad_enc_l2", st))) return rc;
+    if (g.nprob && (rc = timed_gemm(m, g, 2, r == 1 ? "dgrad_enc_l1" : "dgrad_enc_l2", st))) return rc;
     for (auto& it : bn_todo) {
       const Enc& e = m->encs[it.first]; EncWS& w = m->ews[it.first]; const Bn& bn = e.bn[it.second];
       BnBwdArgs a{};
@@ -736,9 +780,9 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       if (!(present >> i & 1) || m->encs[i].type != 'C') continue;
       GemmGroup g; init_group(g); GemmProblem* p;
       const Lin& l = m->encs[i].heads; EncWS& w = m->ews[i];
-      if ((rc = add_nt(m, g, m->gml, m->ldgml, SH + l.sht_off, l.sht_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
+      if ((rc = add_nn(m, g, m->gml, m->ldgml, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
       p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
-      if ((rc = timed_gemm(m, g, 0, "dgrad_site", st))) return rc;
+      if ((rc = timed_gemm(m, g, 2, "dgrad_site", st))) return rc;
     }
   }
   // ---- every weight (and bias) gradient in one grouped split-K launch ----
@@ -825,7 +869,7 @@ int vla_model_create(const vla_config_t* cfg, vla_model_t** out) {
   if ((e = cudaMemcpy(m->segs_d, m->segs_h.data(), sizeof(AdamSegment) * m->segs_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy segs");
   if ((e = cudaMemcpy(m->chunks_d, m->chunks_h.data(), sizeof(AdamChunk) * m->chunks_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy chunks");
   if ((e = cudaMalloc(&m->dyn, sizeof(DynParams))) != cudaSuccess) return bail(e, "cudaMalloc dyn");
-  DynParams d{5e-4f, 1e-5f, 1e-3f, 1.0f, 0, 0, {0, 0}};
+  DynParams d{5e-4f, 1e-5f, 1e-3f, 1.0f, 0, 0, {0, 0}, 1.0, 1.0};
   if ((e = cudaMemcpy(m->dyn, &d, sizeof(d), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy dyn");
   if ((e = cudaMalloc(&m->loss_counter, 64)) != cudaSuccess) return bail(e, "cudaMalloc counter");
   if ((e = cudaMemset(m->loss_counter, 0, 64)) != cudaSuccess) return bail(e, "memset counter");
@@ -911,7 +955,11 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
   AdamArgs a{};
   a.p = p; a.g = const_cast<float*>(g); a.m = ea; a.v = eas; a.shadow = m->shadow;
   a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
-  a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd; a.step = step;
+  a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd;
+  if (step > 0) {
+    a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));
+    a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), step)));
+  }
   a.dyn = dyn ? m->dyn : nullptr; a.update = 1; a.zero_grad = zero_grad ? 1 : 0;
   { ProfScope ps(m, st, "adamw", 0, 34.0 * m->n_params); CK(launch_adamw(a, st)); }
   return VLA_OK;
@@ -930,10 +978,12 @@ int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, f
   CK(cudaMemcpyAsync(m->dyn, h, sizeof(h), cudaMemcpyHostToDevice, as_stream(stream)));
   return VLA_OK;
 }
-int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, vla_stream_t stream) {
+int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float beta1, float beta2, vla_stream_t stream) {
   if (!m) return fail(VLA_ERR_INVALID, "null model");
   const int v[2] = {completed_steps, batch_index};
   CK(cudaMemcpyAsync(&m->dyn->step, v, sizeof(v), cudaMemcpyHostToDevice, as_stream(stream)));
+  const double pw[2] = {pow(static_cast<double>(beta1), completed_steps), pow(static_cast<double>(beta2), completed_steps)};
+  CK(cudaMemcpyAsync(&m->dyn->b1pow, pw, sizeof(pw), cudaMemcpyHostToDevice, as_stream(stream)));
   return VLA_OK;
 }
 
@@ -959,6 +1009,7 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
     return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
                      true, st);
   io.n_batches = a->dataset_rows > a->batch ? static_cast<int>(a->dataset_rows / a->batch) : 1;
+  io.beta1 = a->beta1; io.beta2 = a->beta2;
   int rc;
   if ((rc = run_forward(m, io, st))) return rc;
   // ---- loss: values + bf16 gradients for the backward GEMMs ----
@@ -1022,6 +1073,12 @@ int vla_profile_collect(vla_model_t* m, vla_prof_entry_t* out, int max_entries) 
   return n;
 }
 
+static unsigned long long* g_test_dbg = nullptr;
+static int g_test_flags = 0;
+int vla_test_set_flags(int flags) { g_test_flags = flags; return VLA_OK; }
+/* Test hook: device buffer [tiles][8] that the next vla_test_gemm calls fill with %globaltimer stamps (NULL = off). */
+int vla_test_set_timeline(unsigned long long* dbg) { g_test_dbg = dbg; return VLA_OK; }
+
 int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K, int bn,
                   int k_splits, float* bias_grad, vla_stream_t stream) {
   static vla_model scratch;   // only its tensor-map cache is used
@@ -1031,10 +1088,16 @@ int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, floa
     GemmProblem* p;
     if ((rc = add_nt(&scratch, g, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, M, N, K, GF_OUT_F32, &p, bn))) return rc;
     p->out_f32 = C; p->ld_f32 = N;
+  } else if (mode == 2) {
+    GemmProblem* p;
+    if ((rc = add_nn(&scratch, g, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, M, N, K, GF_OUT_F32, &p, bn))) return rc;
+    p->out_f32 = C; p->ld_f32 = N;
   } else {
     if ((rc = add_tn(&scratch, g, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb, M, N, K, C, N, bias_grad, bn))) return rc;
     finalize_tn(g, K, k_splits);
   }
+  g.dbg = g_test_dbg;
+  g.dbg_flags = g_test_flags;
   CK(launch_gemm_group(g, mode, as_stream(stream)));
   scratch.tmaps.clear();
   return VLA_OK;

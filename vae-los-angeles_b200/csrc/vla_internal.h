@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 namespace vla {
@@ -61,12 +62,30 @@ struct alignas(64) GemmProblem {
 struct GemmGroup {
   int nprob;
   int total_tiles;
-  int pad[14];
+  unsigned long long* dbg;   // optional [total_tiles][8] globaltimer stamps (test hook only)
+  int dbg_flags;             // test hook: 1 = skip epilogue stores, 2 = skip main loop, 4 = skip TMEM alloc (with 2)
+  int pad[11];
   GemmProblem p[GEMM_MAX_PROBLEMS];
 };
 
-// mode 0: NT (both operands K-major; forward and data gradients); mode 1: TN (both MN-major; weight gradients)
+// mode 0: NT  C = A[M,K] B[N,K]^T   (both K-major; forward)
+// mode 1: TN  C = A[K,M]^T B[K,N]   (both MN-major; weight gradients, split-K)
+// mode 2: NN  C = A[M,K] B[K,N]     (A K-major, B MN-major; data gradients read the forward weight copy [out,in] directly)
 cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream);
+
+// Launch with the programmatic-stream-serialization attribute (PDL); every kernel of this library calls
+// griddepcontrol.wait before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool pdl_on = [] { const char* e = getenv("VLA_NO_PDL"); return !(e && e[0] == '1'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 size_t gemm_smem_bytes();
 
 // Builds a 2-D bf16 tensor map with 128-byte swizzle.  inner/outer are extents in elements,
@@ -84,6 +103,7 @@ struct DynParams {
   int step;          // number of the optimizer step in flight (1-based); bumped by the ingest kernel
   int batch_index;   // which resident batch the step in flight trains on; bumped by the loss kernel's last block
   int pad[2];
+  double b1pow, b2pow;   // beta1^step, beta2^step, advanced together with `step` (no powf in the AdamW kernel)
 };
 
 struct IngestArgs {           // fp32 [rows, width] (dense) -> bf16 [rows, ld_dst]
@@ -98,6 +118,7 @@ struct IngestArgs {           // fp32 [rows, width] (dense) -> bf16 [rows, ld_ds
   int n_sites, embed;
   // train step bookkeeping: dyn->step += 1 (first kernel of a train step)
   struct DynParams* dyn; int bump_step;
+  float beta1, beta2;         // Adam betas, to advance dyn->b1pow / b2pow with the step
   int n_batches;              // > 1: rows are read at offset (dyn->batch_index % n_batches) * rows
 };
 cudaError_t launch_ingest(const IngestArgs& a, cudaStream_t s);
@@ -196,18 +217,17 @@ struct AdamSegment {          // one parameter tensor of the flat arena
   int rows, cols;             // matrix shape (vectors: rows = numel, cols = 1)
   long long shadow_off;       // bf16 shadow [rows, ld_shadow] offset, -1 = none
   int ld_shadow;
-  long long shadow_t_off;     // bf16 transposed shadow [cols, ld_shadow_t], -1 = none
-  int ld_shadow_t;
+  int pad;
 };
 struct AdamChunk { int seg; int start; };   // start = element offset inside the segment
-constexpr int ADAM_CHUNK = 4096;
+constexpr int ADAM_CHUNK = 1024;   // one float4 per thread
 struct AdamArgs {
   float* p; float* g; float* m; float* v;
   bf16* shadow;
   const AdamSegment* segs; const AdamChunk* chunks; int n_chunks;
   float lr, beta1, beta2, eps, weight_decay;
-  int step;                   // 1-based step count for the bias corrections
-  const struct DynParams* dyn;// if set, lr / weight_decay / step are read from it
+  float bc1, inv_bc2_sqrt;    // 1 - beta1^t and 1 / sqrt(1 - beta2^t), computed in double on the host
+  const struct DynParams* dyn;// if set, lr / weight_decay / bias corrections are read from it
   int update;                 // 0: only refresh the bf16 shadows from p
   int zero_grad;              // 1: clear g after use
 };

@@ -140,8 +140,8 @@ class Trainer:
 
     def reset_counters(self, completed_steps, batch_index):
         with torch.cuda.device(self.core.device):
-            _lib.check(_lib.lib().vla_set_step(self.core.handle, int(completed_steps), int(batch_index), _stream()),
-                       "vla_set_step")
+            _lib.check(_lib.lib().vla_set_step(self.core.handle, int(completed_steps), int(batch_index),
+                                               float(self.betas[0]), float(self.betas[1]), _stream()), "vla_set_step")
 
     def _args(self, ds, phases):
         core = self.core
