@@ -51,6 +51,9 @@ const char* vla_last_error(void);
 int vla_abi_version(void);
 
 int vla_model_create(const vla_config_t* cfg, vla_model_t** out);
+/* Same handle without any device state: only the layout queries below work (no GPU needed).  Used by host-side
+ * tooling and the CPU tests of the data-parallel gradient packing. */
+int vla_model_create_layout_only(const vla_config_t* cfg, vla_model_t** out);
 void vla_model_destroy(vla_model_t* m);
 /* Makes sure workspace for `batch` rows exists (also done lazily by the calls below). */
 int vla_model_reserve(vla_model_t* m, int batch);

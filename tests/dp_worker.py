@@ -1,0 +1,78 @@
+"""torchrun worker of tests/test_gpu_dp.py: 2+ ranks, NCCL, fused DP train steps vs the per-shard oracle with summed gradients."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "vae-los-angeles_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+from oracle import vae_oracle as vo  # noqa: E402
+from parity_util import is_pre_bn_bias, make_module, rel_l2, to_t  # noqa: E402
+from vla_b200 import DeviceDataset, Trainer  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kind, dims, per_rank, steps = "rna2dna", dict(A=782, B=572, S=24, L=20, E=32), 64, 3
+    state = vo.init_state(kind, dims, seed=31)
+    tpm, beta, site = vo.synthetic_batch(per_rank * world, dims, seed=31)
+    eps, masks = vo.synthetic_noise(per_rank * world, dims, kind, seed=31)
+    sl = slice(rank * per_rank, (rank + 1) * per_rank)
+    m = make_module(kind, dims, state, device=f"cuda:{local}").train()
+    ds = DeviceDataset(tpm[sl], beta[sl], site[sl], f"cuda:{local}")
+    tr = Trainer(m, ds, per_rank, beta_kl=1e-3, process_group=dist.group.WORLD, use_graph=os.environ.get("DP_GRAPH", "1") == "1")
+    tr.injected = dict(eps=to_t(eps[sl], f"cuda:{local}"), keep_masks=[to_t(v[sl], f"cuda:{local}") for v in masks.values()])
+    losses = []
+    for _ in range(steps):
+        tr.step()
+        losses.append(tr.losses())
+    torch.cuda.synchronize()
+    # replicas must stay bit-identical
+    flat = tr.core.arena.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(flat, ref), "replicas diverged"
+    if rank == 0:
+        # oracle: every shard forward/backward separately (per-shard BatchNorm statistics), gradients summed, one AdamW
+        st = {k: (v.astype(np.float64) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
+        opt, step = vo.adamw_init(st)
+        ref_losses = []
+        for _ in range(steps):
+            total, tot_loss = None, np.zeros(4)
+            for r in range(world):
+                s2 = slice(r * per_rank, (r + 1) * per_rank)
+                stc = {k: v.copy() for k, v in st.items()}
+                batch = dict(a=tpm[s2].astype(np.float64), b=beta[s2].astype(np.float64), site=site[s2])
+                out, cache = vo.forward(kind, dims, stc, dict(a=batch["a"], site=batch["site"]), eps[s2].astype(np.float64),
+                                        {k: v[s2] for k, v in masks.items()}, train=True, q=vo.round_bf16)
+                scal, og = vo.loss_and_output_grads(kind, out, batch, 1e-3, 1.0, None)
+                g = vo.backward(kind, dims, stc, cache, og, train=True)
+                total = g if total is None else {k: total[k] + g[k] for k in g}
+                tot_loss += [scal["total"], scal["recon"], scal["cls"], scal["kld"]]
+                if r == 0:
+                    bn_state = {k: stc[k] for k in stc if vo.is_buffer(k)}      # rank 0's running statistics
+            st.update(bn_state)
+            step = vo.adamw_step(st, total, opt, step)
+            ref_losses.append(tot_loss)
+        got = np.array(losses)
+        np.testing.assert_allclose(got[:, 0], np.array(ref_losses)[:, 0], rtol=2e-2)
+        sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        worst = 0.0
+        for name, refv in st.items():
+            if vo.is_buffer(name) or is_pre_bn_bias(name):
+                continue
+            d_ref = refv - state[name].astype(np.float64)
+            d_got = sd[name].astype(np.float64) - state[name].astype(np.float64)
+            worst = max(worst, rel_l2(d_got, d_ref))
+        assert worst <= 0.2, worst
+        print(f"DP_OK world={world} worst displacement rel err {worst:.3f} losses {got[-1].tolist()}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,7 @@ struct TmapKey {
 struct ProfEntry { char name[48]; cudaEvent_t e0, e1; double flops, bytes; };
 
 struct vla_model {
+  bool layout_only = false;
   bool prof_on = false;
   std::vector<ProfEntry> prof;
   vla_config_t cfg{};
@@ -341,6 +342,7 @@ void carve(vla_model* m, Bump& b, int cap) {
 }
 
 int reserve(vla_model* m, int batch) {
+  if (m->layout_only) return fail(VLA_ERR_STATE, "layout-only handle: no device state");
   if (batch <= m->cap) return VLA_OK;
   int cap = std::max(batch, 32);
   if (m->ws) { CK(cudaDeviceSynchronize()); CK(cudaFree(m->ws)); m->ws = nullptr; m->cap = 0; }
@@ -878,8 +880,22 @@ int vla_model_create(const vla_config_t* cfg, vla_model_t** out) {
   return VLA_OK;
 }
 
+int vla_model_create_layout_only(const vla_config_t* cfg, vla_model_t** out) {
+  if (!cfg || !out) return fail(VLA_ERR_INVALID, "null argument");
+  if (cfg->dim_a < 1 || cfg->dim_b < 1 || cfg->n_sites < 1 || cfg->latent < 1 || cfg->embed < 1)
+    return fail(VLA_ERR_INVALID, "dimensions must be positive");
+  vla_model* m = new vla_model();
+  m->cfg = *cfg;
+  int rc = build_layout(m);
+  if (rc) { delete m; return rc; }
+  m->layout_only = true;
+  *out = m;
+  return VLA_OK;
+}
+
 void vla_model_destroy(vla_model_t* m) {
   if (!m) return;
+  if (m->layout_only) { delete m; return; }
   cudaFree(m->shadow); cudaFree(m->segs_d); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
   cudaFree(m->ws);
   delete m;

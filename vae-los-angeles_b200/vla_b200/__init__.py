@@ -4,7 +4,9 @@ Everything numeric runs in libvla_b200.so (hand-written CUDA, C ABI in include/v
 device memory, streams, autograd plumbing and torch.distributed.  There is no CPU fallback.
 """
 from .core import VaeModule, Stack, KINDS
+from .dp import Layout, allreduce_gradients
 from .engine import DeviceDataset, FusedAdamW, Trainer
 from .losses import fused_vae_loss
 
-__all__ = ["VaeModule", "Stack", "KINDS", "DeviceDataset", "FusedAdamW", "Trainer", "fused_vae_loss"]
+__all__ = ["VaeModule", "Stack", "KINDS", "DeviceDataset", "FusedAdamW", "Trainer", "fused_vae_loss", "Layout",
+           "allreduce_gradients"]

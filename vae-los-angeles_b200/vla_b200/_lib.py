@@ -73,6 +73,7 @@ EXPORTS = {
     "vla_last_error": (C.c_char_p, []),
     "vla_abi_version": (C.c_int, []),
     "vla_model_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "vla_model_create_layout_only": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "vla_model_destroy": (None, [C.c_void_p]),
     "vla_model_reserve": (C.c_int, [C.c_void_p, C.c_int]),
     "vla_param_count": (C.c_longlong, [C.c_void_p]),

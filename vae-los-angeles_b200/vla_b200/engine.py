@@ -169,9 +169,9 @@ class Trainer:
         if self.pg is None:
             self._call(ds, 0)
         else:
-            import torch.distributed as dist
+            from .dp import allreduce_gradients
             self._call(ds, 1)
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.pg)
+            allreduce_gradients(self.flat, self.pg)
             self._call(ds, 2)
 
     def step(self, which=0):
