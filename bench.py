@@ -133,6 +133,20 @@ def reference_main(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def shutdown_distributed(trainers, dev):
+    """Release graphs that contain NCCL kernels, then tear the process group down; never hang at exit."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    threading.Timer(20.0, lambda: os._exit(0)).start()       # watchdog: the result line is already printed
+    for t in trainers:
+        t.close()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    dist.destroy_process_group()
+    os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
@@ -286,7 +300,7 @@ def run_gpu(args, rank, local_rank, world):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed([trainer, tr2], dev)
 
 
 def main():

@@ -17,6 +17,6 @@ def test_two_rank_dp_matches_summed_shard_oracle(graph):
     env = dict(os.environ, DP_GRAPH=graph)
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29617", os.path.join(HERE, "dp_worker.py")], capture_output=True, text=True, env=env,
-                         timeout=600)
+                         timeout=180)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DP_OK world=2" in res.stdout

@@ -208,6 +208,11 @@ class Trainer:
             self._enqueue(ds)
         self.graphs[which] = g
 
+    def close(self):
+        """Release the captured graphs (do this before destroying a process group whose collectives they contain)."""
+        torch.cuda.synchronize(self.core.device)
+        self.graphs.clear()
+
     def losses(self):
         """(total, recon, class, kld) of the last completed step -- one 16-byte device->host read.
         Under data parallelism these are the sums over all ranks."""
