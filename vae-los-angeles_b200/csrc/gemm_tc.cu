@@ -75,7 +75,9 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-template <int MODE>
+// FEATS: compile-time superset of the epilogue flags that may occur in this launch; everything else is compiled out
+// (smaller code: the epilogue is instruction-fetch sensitive).
+template <int MODE, int FEATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmGroup grp) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KiB-aligned base (SWIZZLE_128B atoms)
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int kb_total = (P.K + GEMM_BK - 1) / GEMM_BK;
   const int kb0 = k_split * P.kb_per_split;
   const int kb1 = min(kb0 + P.kb_per_split, kb_total);
-  const bool bias_mma = (MODE == 1) && (P.flags & GF_BIASGRAD) && n_tile == 0;
+  const bool bias_mma = (MODE == 1) && (FEATS & GF_BIASGRAD) && (P.flags & GF_BIASGRAD) && n_tile == 0;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int et = threadIdx.x - 64;        // 0..255
     const float* vec = reinterpret_cast<const float*>(smem + VEC_OFFSET);
     float* part = reinterpret_cast<float*>(smem + PART_OFFSET);
-    const int flags = P.flags;
+    const int flags = P.flags & FEATS;
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < P.M;
     const int n_chunks = (BN + 31) >> 5;
@@ -426,29 +428,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
 }
 
-std::once_flag g_attr_once;
-cudaError_t g_attr_err = cudaSuccess;
-
 }  // namespace
 
 size_t gemm_smem_bytes() { return SMEM_BYTES; }
 
+constexpr int FEATS_FWD_PLAIN = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;                      // hidden decoder layers, heads
+constexpr int FEATS_FWD_FULL = FEATS_FWD_PLAIN | GF_SIGMOID | GF_COLSTATS;                         // + BatchNorm statistics / sigmoid
+constexpr int FEATS_DGRAD_PLAIN = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;                              // decoder data gradients
+constexpr int FEATS_DGRAD_FULL = FEATS_DGRAD_PLAIN | GF_BNSTATS;                                   // + BatchNorm backward statistics
+constexpr int FEATS_WGRAD = GF_RED | GF_BIASGRAD;
+
+template <int MODE, int FEATS>
+cudaError_t launch_one(const GemmGroup& g, cudaStream_t stream, size_t smem) {
+  static cudaError_t attr = cudaFuncSetAttribute(gemm_tc_kernel<MODE, FEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (attr != cudaSuccess) return attr;
+  return launch_pdl(gemm_tc_kernel<MODE, FEATS>, dim3(g.total_tiles), dim3(GEMM_THREADS), smem, stream, g);
+}
+
 cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream) {
-  std::call_once(g_attr_once, [] {
-    g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (g_attr_err == cudaSuccess)
-      g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (g_attr_err == cudaSuccess)
-      g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  });
-  if (g_attr_err != cudaSuccess) return g_attr_err;
   if (g.total_tiles <= 0) return cudaSuccess;
-  if (g.dbg_flags & 0xFFFF00) {   // test hook: dynamic smem override (only valid together with dbg_flags & 2)
-    return launch_pdl(gemm_tc_kernel<0>, dim3(g.total_tiles), dim3(GEMM_THREADS), static_cast<size_t>(g.dbg_flags >> 8), stream, g);
+  int used = 0;
+  for (int i = 0; i < g.nprob; ++i) used |= g.p[i].flags;
+  size_t smem = SMEM_BYTES;
+  if (g.dbg_flags & 0xFFFF00) smem = static_cast<size_t>(g.dbg_flags >> 8);   // test hook (only valid with dbg_flags & 2)
+  if (mode == 0) {
+    if (!(used & ~FEATS_FWD_PLAIN)) return launch_one<0, FEATS_FWD_PLAIN>(g, stream, smem);
+    return launch_one<0, FEATS_FWD_FULL>(g, stream, smem);
   }
-  if (mode == 0) return launch_pdl(gemm_tc_kernel<0>, dim3(g.total_tiles), dim3(GEMM_THREADS), SMEM_BYTES, stream, g);
-  if (mode == 1) return launch_pdl(gemm_tc_kernel<1>, dim3(g.total_tiles), dim3(GEMM_THREADS), SMEM_BYTES, stream, g);
-  return launch_pdl(gemm_tc_kernel<2>, dim3(g.total_tiles), dim3(GEMM_THREADS), SMEM_BYTES, stream, g);
+  if (mode == 2) {
+    if (!(used & ~FEATS_DGRAD_PLAIN)) return launch_one<2, FEATS_DGRAD_PLAIN>(g, stream, smem);
+    return launch_one<2, FEATS_DGRAD_FULL>(g, stream, smem);
+  }
+  return launch_one<1, FEATS_WGRAD>(g, stream, smem);
 }
 
 // ---------------------------------------------------------------------------------------------
