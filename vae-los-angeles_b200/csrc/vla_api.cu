@@ -60,6 +60,8 @@ struct DecWS {
   float* recon = nullptr;                                 // fp32 output when the caller passes none
 };
 
+struct PendingB { const void* base; uint64_t inner, outer, pitch; int mode; int K; bool fixed; };
+
 struct TmapKey {
   uintptr_t base; uint64_t inner, outer, pitch; uint32_t box_outer;
   bool operator<(const TmapKey& o) const {
@@ -125,6 +127,7 @@ struct ProfScope {
   }
   ~ProfScope() { if (idx >= 0) cudaEventRecord(m->prof[idx].e1, st); }
 };
+int finalize_group(vla_model* m, GemmGroup& g, int mode);
 void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
   *flops = 0; *bytes = 0;
   for (int i = 0; i < g.nprob; ++i) {
@@ -135,7 +138,8 @@ void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
               (out_b + ((p.flags & GF_OUT_BF16) ? 2.0 : 0.0)) * p.M * p.N;
   }
 }
-int timed_gemm(vla_model* m, const GemmGroup& g, int mode, const char* name, cudaStream_t st) {
+int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStream_t st) {
+  if (mode != 1) { int rc0 = finalize_group(m, g, mode); if (rc0) return rc0; }
   for (int i = 0; i < g.nprob; ++i) {
     const GemmProblem& p = g.p[i];
     if ((p.flags & GF_MASK) && ((p.N & 31) || (p.ld_mask & 7) || (reinterpret_cast<uintptr_t>(p.mask_src) & 15)))
@@ -375,22 +379,6 @@ int get_tmap(vla_model* m, CUtensorMap* out, const void* base, uint64_t inner, u
   return VLA_OK;
 }
 
-// Tile-width choice: modelled time = waves x (fixed per-CTA latency + K-loop at ~150 KB/us per SM + epilogue).
-// At batch 4096 there are only 32 row tiles, so the choice is between one wave of wide tiles and two waves of narrow ones.
-double tile_cost(int M, int N, int K, int bn, int b_bytes_per_kblock) {
-  const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, bn);
-  const int waves = ceil_div(tiles, 148);
-  const double t_kb = (16384.0 + b_bytes_per_kblock) / 150e3;
-  return waves * (5.0 + ceil_div(K, GEMM_BK) * t_kb + 0.4 * ceil_div(bn, 64));
-}
-int choose_bn_nt(int M, int N, int K) {
-  int best = 32; double best_cost = 1e30;
-  for (int bn = 32; bn <= GEMM_BN_MAX_NT; bn += 32) {   // whole 32-column epilogue chunks
-    const double cost = tile_cost(M, N, K, bn, bn * 128);
-    if (cost < best_cost - 1e-9) { best = bn; best_cost = cost; }
-  }
-  return best;
-}
 int choose_bn_tn(int N) {
   int best = 64; int best_cost = 1 << 30;
   for (int bn = 64; bn <= GEMM_BN_MAX_TN; bn += 64) {
@@ -400,6 +388,9 @@ int choose_bn_tn(int N) {
   return best;
 }
 
+// Per-group list of the B operands whose tensor maps wait for the joint tile-width choice (finalize_group)
+thread_local PendingB g_pending[GEMM_MAX_PROBLEMS];
+
 // C[M,N] = A[M,K] * W[N,K]^T ; A bf16 [M, lda], W bf16 [N, ldw]
 int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int flags,
            GemmProblem** out, int force_bn = 0) {
@@ -407,27 +398,16 @@ int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, in
   GemmProblem& p = g.p[g.nprob];
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
-  p.BN = force_bn ? force_bn : choose_bn_nt(M, N, K);
-  p.m_tiles = ceil_div(M, GEMM_BM); p.n_tiles = ceil_div(N, p.BN);
+  p.BN = force_bn;
+  p.m_tiles = ceil_div(M, GEMM_BM);
   p.k_splits = 1; p.kb_per_split = ceil_div(K, GEMM_BK);
   p.flags = flags;
   int rc;
   if ((rc = get_tmap(m, &p.tmA, A, K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
-  if ((rc = get_tmap(m, &p.tmB, W, K, N, static_cast<uint64_t>(ldw) * 2, p.BN))) return rc;
-  p.tile_begin = g.total_tiles;
-  g.total_tiles += p.m_tiles * p.n_tiles;
+  g_pending[g.nprob] = PendingB{W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, 0, K, force_bn != 0};
   g.nprob++;
   *out = &p;
   return VLA_OK;
-}
-
-int choose_bn_nn(int M, int N, int K) {
-  int best = 64; double best_cost = 1e30;
-  for (int bn = 64; bn <= GEMM_BN_MAX_TN; bn += 64) {
-    const double cost = tile_cost(M, N, K, bn, bn * 128);
-    if (cost < best_cost - 1e-9) { best = bn; best_cost = cost; }
-  }
-  return best;
 }
 
 // dX[M,N] = dY[M,K] * W[K,N] ; dY bf16 [M, lda] (K-major A), W bf16 [K, ldw] = the forward weight copy [out, in] (MN-major B)
@@ -437,17 +417,70 @@ int add_nn(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, in
   GemmProblem& p = g.p[g.nprob];
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
-  p.BN = force_bn ? force_bn : choose_bn_nn(M, N, K);
-  p.m_tiles = ceil_div(M, GEMM_BM); p.n_tiles = ceil_div(N, p.BN);
+  p.BN = force_bn;
+  p.m_tiles = ceil_div(M, GEMM_BM);
   p.k_splits = 1; p.kb_per_split = ceil_div(K, GEMM_BK);
   p.flags = flags;
   int rc;
   if ((rc = get_tmap(m, &p.tmA, A, K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
-  if ((rc = get_tmap(m, &p.tmB, W, N, K, static_cast<uint64_t>(ldw) * 2, 64))) return rc;
-  p.tile_begin = g.total_tiles;
-  g.total_tiles += p.m_tiles * p.n_tiles;
+  g_pending[g.nprob] = PendingB{W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw) * 2, 2, K, force_bn != 0};
   g.nprob++;
   *out = &p;
+  return VLA_OK;
+}
+
+// Joint tile-width choice for an NT / NN group: minimise waves x slowest tile (exhaustive over <= 5 widths per problem,
+// greedy coordinate descent when the group is large), then build the B tensor maps and the tile index ranges.
+int finalize_group(vla_model* m, GemmGroup& g, int mode) {
+  const int n = g.nprob;
+  int cand[GEMM_MAX_PROBLEMS][8], nc[GEMM_MAX_PROBLEMS], pick[GEMM_MAX_PROBLEMS];
+  for (int i = 0; i < n; ++i) {
+    nc[i] = 0;
+    if (g_pending[i].fixed) { cand[i][nc[i]++] = g.p[i].BN; }
+    else if (mode == 0) { for (int bn = 32; bn <= GEMM_BN_MAX_NT; bn += 32) cand[i][nc[i]++] = bn; }
+    else { for (int bn = 64; bn <= GEMM_BN_MAX_TN; bn += 64) cand[i][nc[i]++] = bn; }
+    // a width beyond the padded N only wastes MMA columns
+    int keep = 0;
+    for (int c = 0; c < nc[i]; ++c) { cand[i][keep++] = cand[i][c]; if (cand[i][c] >= g.p[i].N) break; }
+    nc[i] = keep;
+    pick[i] = 0;
+  }
+  auto cost = [&](const int* pk) {
+    int tiles = 0; double slow = 0;
+    for (int i = 0; i < n; ++i) {
+      const int bn = cand[i][pk[i]];
+      tiles += g.p[i].m_tiles * ceil_div(g.p[i].N, bn);
+      const double t = 5.0 + ceil_div(g.p[i].K, GEMM_BK) * (16384.0 + bn * 128.0) / 150e3 + 0.4 * ceil_div(bn, 64);
+      slow = std::max(slow, t);
+    }
+    return ceil_div(tiles, 148) * slow + 1e-3 * tiles;
+  };
+  // coordinate descent from the narrowest tiles (a handful of sweeps converges for these tiny search spaces)
+  double best = cost(pick);
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    bool moved = false;
+    for (int i = 0; i < n; ++i) {
+      int keep = pick[i];
+      for (int c = 0; c < nc[i]; ++c) {
+        pick[i] = c;
+        const double v = cost(pick);
+        if (v < best - 1e-9) { best = v; keep = c; moved = true; }
+      }
+      pick[i] = keep;
+    }
+    if (!moved) break;
+  }
+  g.total_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    GemmProblem& p = g.p[i];
+    p.BN = cand[i][pick[i]];
+    p.n_tiles = ceil_div(p.N, p.BN);
+    const PendingB& b = g_pending[i];
+    int rc;
+    if ((rc = get_tmap(m, &p.tmB, b.base, b.inner, b.outer, b.pitch, mode == 0 ? static_cast<uint32_t>(p.BN) : 64u))) return rc;
+    p.tile_begin = g.total_tiles;
+    g.total_tiles += p.m_tiles * p.n_tiles;
+  }
   return VLA_OK;
 }
 
@@ -1114,6 +1147,7 @@ int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, floa
   }
   g.dbg = g_test_dbg;
   g.dbg_flags = g_test_flags;
+  if (mode != 1 && (rc = finalize_group(&scratch, g, mode))) return rc;
   CK(launch_gemm_group(g, mode, as_stream(stream)));
   scratch.tmaps.clear();
   return VLA_OK;
