@@ -150,6 +150,88 @@ def shutdown_distributed(trainers, dev):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def train_throughput(workload, B, dev, steps, warmup):
+    """Fused train step of another model kind at the same per-GPU batch (device-timed, CUDA graph replay)."""
+    import torch
+    from src.models import DNA2RNAVAE, MultiModalVAE, RNA2DNAVAE
+    from vla_b200 import DeviceDataset, Trainer
+    cls = {"rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE, "multimodal": MultiModalVAE}[workload]
+    torch.manual_seed(0)
+    model = cls(DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"]).to(dev).train()
+    ds = DeviceDataset.synthetic(B * 32, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=3)
+    tr = Trainer(model, ds, B)
+    for _ in range(max(warmup, 3)):
+        tr.step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    w = WORK[workload]
+    peaks = load_peaks()
+    t_roof = max(w["flop"] * B / (peaks["bf16_tflops"] * 1e12), (w["bytes"] * B + 32 * w["params"]) / (peaks["hbm_gbs"] * 1e9))
+    out = {"workload": f"{workload} train step, batch {B}", "value": steps * B / (ms * 1e-3), "unit": "samples/s",
+           "ms_per_step": ms / steps, "step_roofline_frac": t_roof / (ms * 1e-3 / steps), "losses": tr.losses()}
+    tr.close()
+    del tr, model, ds
+    torch.cuda.empty_cache()
+    return out
+
+
+def inference_throughput(dev, batch, steps, warmup):
+    """BASELINE configs[3]: tri-modal cross-modal inference `model(a=x)` in eval mode (BatchNorm running statistics, no
+    dropout, epsilon still sampled), all three decoders, fp32 outputs written; vla_forward replayed from a CUDA graph."""
+    import ctypes as C
+    import torch
+    from src.models import MultiModalVAE
+    from vla_b200 import _lib
+    from vla_b200.core import _ptr, _stream
+    torch.manual_seed(0)
+    model = MultiModalVAE(DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"]).to(dev).eval()
+    core = model._ensure_core()
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    x = torch.log1p(-20.0 * torch.log1p(-torch.rand(batch, DIMS["A"], device=dev, generator=g)))
+    outs = [torch.empty(batch, n, device=dev) for n in (DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"], DIMS["L"])]
+    L = _lib.lib()
+
+    def call(refresh):
+        args = _lib.ForwardArgs(params=_ptr(core.arena), buffers=_ptr(core.buffers), counters=_ptr(core.counters), x_a=_ptr(x),
+                                x_b=None, site=None, batch=batch, train=0, refresh_shadows=refresh, eps=None, keep_masks=None,
+                                seed=1, offset=0, recon_a=_ptr(outs[0]), recon_b=_ptr(outs[1]), recon_c=_ptr(outs[2]),
+                                mu=_ptr(outs[3]), logvar=_ptr(outs[4]))
+        _lib.check(L.vla_forward(core.handle, C.byref(args), _stream()), "vla_forward")
+
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        call(1)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call(0)
+    for _ in range(warmup):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    peaks = load_peaks()
+    # SURVEY section 8d: a-only eval forward = 639 744 MACs, 3 128 B in + 5 672 B out per sample
+    t_roof = max(2 * 639_744 * batch / (peaks["bf16_tflops"] * 1e12), 8_800 * batch / (peaks["hbm_gbs"] * 1e9))
+    ok = bool(torch.isfinite(outs[1]).all().item()) and float(outs[1].min()) >= 0.0 and float(outs[1].max()) <= 1.0
+    out = {"workload": f"multimodal eval inference model(a=x), batch {batch}", "value": steps * batch / (ms * 1e-3), "unit": "samples/s",
+           "ms_per_step": ms / steps, "step_roofline_frac": t_roof / (ms * 1e-3 / steps), "bound": "hbm", "outputs_valid": ok}
+    del graph, outs, x, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -246,13 +328,17 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- per-launch timing (eager, CUDA events inside the library) -> dominant kernel roofline ----------------
     peaks = load_peaks()
-    prof_steps = 5
-    trainer.profile(2)
+    prof_steps = 10
     entries = trainer.profile(prof_steps)
     agg = {}
     for name, pms, fl, by in entries:
         a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += pms; a[2] += fl; a[3] += by
+    # an event pair with nothing between it measures the timing overhead itself: subtract it from every launch
+    empty = agg.pop("_empty_pair", None)
+    overhead_ms = (empty[1] / empty[0]) if empty else 0.0
+    for a in agg.values():
+        a[1] = max(a[1] - overhead_ms * a[0], 0.05e-3 * a[0])
     total_ms = sum(a[1] for a in agg.values()) or 1.0
     kernels = []
     for name, (cnt, pms, fl, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -267,9 +353,16 @@ def run_gpu(args, rank, local_rank, world):
         ach, peak, unit = top["flops"] / (top["avg_us"] * 1e-6) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
     else:
         ach, peak, unit = top["bytes"] / (top["avg_us"] * 1e-6) / 1e9, peaks["hbm_gbs"], "GB/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.workload == "rna2dna" and B == 4096:
+        with open(tpath) as f:
+            traffic = json.load(f).get(top["name"])          # DRAM bytes per launch from the committed ncu --set full capture
     roofline = {"kernel": top["name"], "bound": top["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                "traffic": None, "peak_source": peaks["source"], "avg_us": top["avg_us"], "share_of_step": top["share"],
-                "how": "CUDA events around each launch on the launching stream, 5 eager steps (vla_profile_*)"}
+                "traffic": traffic, "peak_source": peaks["source"], "avg_us": top["avg_us"], "share_of_step": top["share"],
+                "event_pair_overhead_us": 1e3 * overhead_ms,
+                "how": "CUDA event pair around each launch, recorded as nodes of the captured step graph, 10 replays; the duration of "
+                       "an empty event pair is subtracted (vla_profile_*)"}
     w = WORK[args.workload]
     t_tensor = w["flop"] * B / (peaks["bf16_tflops"] * 1e12)
     t_hbm = (w["bytes"] * B + 32 * w["params"]) / (peaks["hbm_gbs"] * 1e9)
@@ -278,6 +371,15 @@ def run_gpu(args, rank, local_rank, world):
                      "t_step_us": 1e6 * step_s, "frac": max(t_tensor, t_hbm) / step_s,
                      "flop_per_sample": w["flop"], "bytes_per_sample": w["bytes"], "param_bytes_per_step": 32 * w["params"]}
     launches_per_step = sum(k["launches_per_step"] for k in kernels)
+
+    # ---- the other BASELINE.json configurations, short runs (reported under "also"; not the headline) ----------------
+    also = []
+    if world == 1 and not args.no_also:
+        for wl in ("multimodal", "dna2rna", "rna2dna"):
+            if wl == args.workload:
+                continue
+            also.append(train_throughput(wl, B, dev, steps=60, warmup=5))
+        also.append(inference_throughput(dev, batch=args.infer_batch, steps=10, warmup=3))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -296,7 +398,7 @@ def run_gpu(args, rank, local_rank, world):
                        "graph": "CUDA graph replay per step, no host sync in the timed region"},
             "e2e": e2e, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:8],
             "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
-            "cpu_baseline": cpu, "clocks": clocks, "final_losses": losses,
+            "cpu_baseline": cpu, "clocks": clocks, "final_losses": losses, "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -313,6 +415,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--resident-batches", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (tri-modal, dna2rna, inference)")
+    ap.add_argument("--infer-batch", type=int, default=262144)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

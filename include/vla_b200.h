@@ -180,6 +180,10 @@ typedef struct {
 } vla_prof_entry_t;
 int vla_profile_begin(vla_model_t* m);
 int vla_profile_collect(vla_model_t* m, vla_prof_entry_t* out, int max_entries);
+/* Like vla_profile_collect but keeps the events (they may be nodes of a captured graph that is replayed again). */
+int vla_profile_read(vla_model_t* m, vla_prof_entry_t* out, int max_entries);
+/* Stops recording without touching the events already recorded (call after capturing a profiled graph). */
+int vla_profile_pause(vla_model_t* m);
 
 /* Test hook: C[M,N] = A[M,K] * B[N,K]^T (mode 0) or C[M,N] = A[K,M]^T * B[K,N] (mode 1) on the tcgen05 path.
  * A, B bf16 (uint16 storage) with element pitches lda / ldb (multiples of 8), C fp32 dense, zero-filled by

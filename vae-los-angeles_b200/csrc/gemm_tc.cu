@@ -31,9 +31,9 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 40 KiB
 constexpr int ONES_OFFSET = GEMM_STAGES * STAGE_BYTES;               // 2 KiB of bf16 1.0
 constexpr int ONES_BYTES = 2048;
 constexpr int PATCH_LD = 36;                                         // floats; 144-byte rows: 16-byte aligned, conflict-free
-constexpr int CHUNK_OFFSET = ONES_OFFSET + ONES_BYTES;               // 8 warps x fp32 [32][36] transpose patches
-constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;
-constexpr int VEC_OFFSET = CHUNK_OFFSET + CHUNK_BYTES;               // bias | mean | rstd, fp32 [3][192]
+constexpr int CHUNK_OFFSET = 0;                                      // 8 warps x fp32 [32][36] transpose patches: they alias
+constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;                   // pipeline stage 0, which is idle once the accumulator is ready
+constexpr int VEC_OFFSET = ONES_OFFSET + ONES_BYTES;                 // bias | mean | rstd, fp32 [3][192]
 constexpr int VEC_BYTES = 3 * GEMM_BN_MAX_TN * 4;
 constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][6][4][32]
 constexpr int MAX_CHUNKS = GEMM_BN_MAX_TN / 32;
@@ -44,6 +44,8 @@ constexpr int SMEM_BYTES = SMEM_USED + 1024;                         // slack fo
 constexpr int EPI_THREADS = GEMM_THREADS - 64;                       // 8 warps
 
 static_assert(B_STAGE_BYTES >= GEMM_BN_MAX_NT * 128, "B stage too small for NT tiles");
+static_assert(CHUNK_BYTES <= STAGE_BYTES, "epilogue patches must fit in one pipeline stage");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
 static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
 

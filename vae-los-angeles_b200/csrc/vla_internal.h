@@ -29,7 +29,7 @@ enum GemmFlags : int {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_STAGES = 5;
 constexpr int GEMM_BN_MAX_NT = 160;   // multiple of 16
 constexpr int GEMM_BN_MAX_TN = 192;   // multiple of 64
 constexpr int GEMM_MAX_PROBLEMS = 16;

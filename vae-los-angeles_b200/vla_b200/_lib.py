@@ -92,6 +92,8 @@ EXPORTS = {
     "vla_set_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "vla_profile_begin": (C.c_int, [C.c_void_p]),
     "vla_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
+    "vla_profile_read": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
+    "vla_profile_pause": (C.c_int, [C.c_void_p]),
     "vla_test_set_timeline": (C.c_int, [C.c_void_p]),
     "vla_test_set_flags": (C.c_int, [C.c_int]),
     "vla_test_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,

@@ -219,19 +219,31 @@ class Trainer:
         return tuple(self.loss_out.tolist())
 
     def profile(self, steps=3, which=0):
-        """Per-launch device times of `steps` eager (non-graph) steps: list of (name, ms, flops, bytes)."""
+        """Per-launch device times inside a replayed CUDA graph: the step is captured once with an event pair around every
+        launch (event-record nodes), the graph is replayed `steps` times and the pairs are read after each replay.
+        Returns a list of (name, ms, flops, bytes), `steps` entries per launch."""
         L = _lib.lib()
         dev = self.core.device
+        ds = self.datasets[which]
         out = []
+        buf = (_lib.ProfEntry * 512)()
         with torch.cuda.device(dev):
             torch.cuda.synchronize(dev)
             _lib.check(L.vla_profile_begin(self.core.handle), "vla_profile_begin")
-            for _ in range(steps):
-                self._enqueue(self.datasets[which])
-                self.steps += 1
-            buf = (_lib.ProfEntry * 4096)()
-            n = L.vla_profile_collect(self.core.handle, buf, 4096)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(ds)
+            _lib.check(L.vla_profile_pause(self.core.handle), "vla_profile_pause")
+            g.replay()                                   # warm
             torch.cuda.synchronize(dev)
-        for i in range(max(n, 0)):
-            out.append((buf[i].name.decode(), float(buf[i].ms), float(buf[i].flops), float(buf[i].bytes)))
+            self.steps += 1
+            for _ in range(steps):
+                g.replay()
+                torch.cuda.synchronize(dev)
+                self.steps += 1
+                n = L.vla_profile_read(self.core.handle, buf, 512)
+                for i in range(max(n, 0)):
+                    out.append((buf[i].name.decode(), float(buf[i].ms), float(buf[i].flops), float(buf[i].bytes)))
+            L.vla_profile_collect(self.core.handle, buf, 512)   # releases the events
+            del g
         return out
