@@ -149,6 +149,17 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_b
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * BN_COLS + lane * 2;
   const bool col_ok = col < a.n;     // n is even
+  // this thread's rows are independent of the statistics: fetch them first so the two latencies overlap
+  constexpr int PF = 4;
+  float2 xpf[PF];
+  const int row_first = blockIdx.y * rows_per_block + ty;
+  const int row_end = min(a.rows, static_cast<int>(blockIdx.y + 1) * rows_per_block);
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    const int row = row_first + 8 * i;
+    xpf[i] = (col_ok && row < row_end) ? __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col))
+                                       : make_float2(0.f, 0.f);
+  }
   if (a.train) {
     double r[4];
     reduce_partials(a.stats, a.m_tiles, a.n, col, col_ok, sh, r);
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_b
         const double mean = r[j] / a.rows;
         double var = r[2 + j] / a.rows - mean * mean;
         var = var < 0 ? 0 : var;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+        const float rstd = rsqrtf(static_cast<float>(var) + 1e-5f);
         s_mean[lane * 2 + j] = static_cast<float>(mean);
         s_rstd[lane * 2 + j] = rstd;
         if (blockIdx.y == 0) {
@@ -190,10 +201,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_b
   const float keep_scale = drop ? 1.0f / (1.0f - a.p_drop) : 1.0f;
   unsigned long long offset = a.offset;
   if (a.dyn) offset += static_cast<unsigned long long>(a.dyn->step) << 20;
-  const int row_end = min(a.rows, static_cast<int>(blockIdx.y + 1) * rows_per_block);
-#pragma unroll 2
-  for (int row = blockIdx.y * rows_per_block + ty; row < row_end; row += 8) {
-    const float2 x = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
+  auto do_row = [&](int row, float2 x) {
     float y0 = fmaxf((x.x - m0) * r0 + b0, 0.f);
     float y1 = fmaxf((x.y - m1) * r1 + b1, 0.f);
     if (drop) {
@@ -212,7 +220,14 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActArgs a, int rows_per_b
       y1 = k1 ? y1 * keep_scale : 0.f;
     }
     *reinterpret_cast<__nv_bfloat162*>(a.out + static_cast<size_t>(row) * a.ld_out + col) = __floats2bfloat162_rn(y0, y1);
+  };
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    const int row = row_first + 8 * i;
+    if (row < row_end) do_row(row, xpf[i]);
   }
+  for (int row = row_first + 8 * PF; row < row_end; row += 8)
+    do_row(row, __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col)));
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdArgs a, int rows_per_block) {
@@ -373,15 +388,25 @@ __device__ __forceinline__ float loss_row(const float* __restrict__ rp, const fl
     const int n2 = w >> 1;
     const float2* r2 = reinterpret_cast<const float2*>(rp);
     const float2* t2 = reinterpret_cast<const float2*>(tp);
-#pragma unroll 2
-    for (int i = lane; i < n2; i += 32) {
-      const float2 y = r2[i];
-      const float2 t = __ldg(t2 + i);
-      float g0, g1, l0, l1;
-      acc += loss_elem<BCE>(y.x, t.x, gs, g0, l0);
-      acc += loss_elem<BCE>(y.y, t.y, gs, g1, l1);
-      if (gf) reinterpret_cast<float2*>(gf)[i] = make_float2(g0, g1);
-      if (gb) reinterpret_cast<__nv_bfloat162*>(gb)[i] = __floats2bfloat162_rn(l0, l1);
+    // batches of 4 independent load pairs per lane before any arithmetic (memory-level parallelism)
+    for (int base = lane; base < n2; base += 128) {
+      float2 y[4], t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = base + 32 * k;
+        if (i < n2) { y[k] = r2[i]; t[k] = __ldg(t2 + i); }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = base + 32 * k;
+        if (i < n2) {
+          float g0, g1, l0, l1;
+          acc += loss_elem<BCE>(y[k].x, t[k].x, gs, g0, l0);
+          acc += loss_elem<BCE>(y[k].y, t[k].y, gs, g1, l1);
+          if (gf) reinterpret_cast<float2*>(gf)[i] = make_float2(g0, g1);
+          if (gb) reinterpret_cast<__nv_bfloat162*>(gb)[i] = __floats2bfloat162_rn(l0, l1);
+        }
+      }
     }
   } else {
     for (int i = lane; i < w; i += 32) {
@@ -526,12 +551,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   pdl_wait();
   pdl_launch_dependents();
   const AdamChunk ch = a.chunks[blockIdx.x];
-  const AdamSegment sg = a.segs[ch.seg];
-  const long long seg_n = static_cast<long long>(sg.rows) * sg.cols;
-  const long long e = static_cast<long long>(ch.start) + 4LL * threadIdx.x;
-  if (e >= seg_n) return;
+  const int e = 4 * threadIdx.x;                       // element index inside the chunk
+  if (e >= ch.n) return;
   float lr = a.lr, wd = a.weight_decay, bc1 = a.bc1, inv_bc2s = a.inv_bc2_sqrt;
-  if (a.dyn) {
+  if (a.dyn) {   // independent of the chunk-table read above: the loads overlap
     lr = a.dyn->lr; wd = a.dyn->weight_decay;
     bc1 = static_cast<float>(1.0 - a.dyn->b1pow);
     inv_bc2s = static_cast<float>(1.0 / sqrt(1.0 - a.dyn->b2pow));
@@ -539,8 +562,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   const float step_size = lr / bc1;
   const float decay = 1.0f - lr * wd;
   const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
-  const long long gi = sg.offset + e;                 // multiple of 4: 16-byte aligned in every arena
-  const int nv = static_cast<int>(min(4LL, seg_n - e));
+  const long long gi = ch.offset + e;                  // multiple of 4: 16-byte aligned in every arena
+  const int nv = min(4, ch.n - e);
   float p[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
   if (nv == 4) {
     *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(a.p + gi);
@@ -575,13 +598,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
       }
     }
   }
-  if (sg.shadow_off >= 0) {
+  if (ch.shadow_off >= 0) {
     // bf16 copy [rows, ld_shadow] used as the tensor-core operand (K-major for forward, MN-major for data gradients)
-    int r = static_cast<int>(static_cast<unsigned>(e) / static_cast<unsigned>(sg.cols));   // one tensor < 2^31 elements
-    int c = static_cast<int>(static_cast<unsigned>(e) - static_cast<unsigned>(r) * sg.cols);
+    const unsigned idx = static_cast<unsigned>(ch.first + e);                                // one tensor < 2^31 elements
+    int r = static_cast<int>(idx / static_cast<unsigned>(ch.cols));
+    int c = static_cast<int>(idx - static_cast<unsigned>(r) * ch.cols);
     for (int k = 0; k < nv; ++k) {
-      a.shadow[sg.shadow_off + static_cast<long long>(r) * sg.ld_shadow + c] = __float2bfloat16(p[k]);
-      if (++c == sg.cols) { c = 0; ++r; }
+      a.shadow[ch.shadow_off + static_cast<long long>(r) * ch.ld_shadow + c] = __float2bfloat16(p[k]);
+      if (++c == ch.cols) { c = 0; ++r; }
     }
   }
 }

@@ -86,11 +86,9 @@ struct vla_model {
   long long n_params = 0, n_buffers = 0, n_shadow = 0;
   int n_bn = 0;
   std::vector<vla_tensor_info_t> infos;
-  std::vector<AdamSegment> segs_h;
   std::vector<AdamChunk> chunks_h;
   // device-resident, batch independent
   bf16* shadow = nullptr;
-  AdamSegment* segs_d = nullptr;
   AdamChunk* chunks_d = nullptr;
   DynParams* dyn = nullptr;
   float* loss_partials = nullptr; unsigned int* loss_counter = nullptr; float* loss_out = nullptr;
@@ -177,11 +175,13 @@ struct ArenaBuilder {
     m->infos.push_back(t);
   }
   void seg(long long off, int rows, int cols, long long sh_off, int sh_ld) {
-    AdamSegment s{off, rows, cols, sh_off, sh_ld, 0};
-    const int idx = static_cast<int>(m->segs_h.size());
-    m->segs_h.push_back(s);
     const long long n = static_cast<long long>(rows) * cols;
-    for (long long st = 0; st < n; st += ADAM_CHUNK) m->chunks_h.push_back(AdamChunk{idx, static_cast<int>(st)});
+    for (long long st = 0; st < n; st += ADAM_CHUNK) {
+      AdamChunk c{};
+      c.offset = off + st; c.shadow_off = sh_off; c.n = static_cast<int>(std::min<long long>(ADAM_CHUNK, n - st));
+      c.first = static_cast<int>(st); c.cols = cols; c.ld_shadow = sh_ld;
+      m->chunks_h.push_back(c);
+    }
   }
   // A Linear whose weight rows may be exposed under several state_dict names (fused groups).
   Lin linear(int out, int in) {
@@ -554,7 +554,7 @@ int present_mask(const vla_model* m, const FwdIO& io) {
 int run_shadow_refresh(vla_model* m, const float* params, cudaStream_t st) {
   AdamArgs a{};
   a.p = const_cast<float*>(params); a.shadow = m->shadow;
-  a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
+  a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
   a.update = 0;
   { ProfScope ps(m, st, "shadow_refresh", 0, 6.0 * m->n_params); CK(launch_adamw(a, st)); }
   return VLA_OK;
@@ -905,9 +905,7 @@ int vla_model_create(const vla_config_t* cfg, vla_model_t** out) {
   cudaError_t e;
   if ((e = cudaMalloc(&m->shadow, sizeof(bf16) * m->n_shadow)) != cudaSuccess) return bail(e, "cudaMalloc shadow");
   if ((e = cudaMemset(m->shadow, 0, sizeof(bf16) * m->n_shadow)) != cudaSuccess) return bail(e, "cudaMemset shadow");
-  if ((e = cudaMalloc(&m->segs_d, sizeof(AdamSegment) * m->segs_h.size())) != cudaSuccess) return bail(e, "cudaMalloc segs");
   if ((e = cudaMalloc(&m->chunks_d, sizeof(AdamChunk) * m->chunks_h.size())) != cudaSuccess) return bail(e, "cudaMalloc chunks");
-  if ((e = cudaMemcpy(m->segs_d, m->segs_h.data(), sizeof(AdamSegment) * m->segs_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy segs");
   if ((e = cudaMemcpy(m->chunks_d, m->chunks_h.data(), sizeof(AdamChunk) * m->chunks_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy chunks");
   if ((e = cudaMalloc(&m->dyn, sizeof(DynParams))) != cudaSuccess) return bail(e, "cudaMalloc dyn");
   DynParams d{5e-4f, 1e-5f, 1e-3f, 1.0f, 0, 0, {0, 0}, 1.0, 1.0};
@@ -935,7 +933,7 @@ int vla_model_create_layout_only(const vla_config_t* cfg, vla_model_t** out) {
 void vla_model_destroy(vla_model_t* m) {
   if (!m) return;
   if (m->layout_only) { delete m; return; }
-  cudaFree(m->shadow); cudaFree(m->segs_d); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
+  cudaFree(m->shadow); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
   cudaFree(m->ws);
   delete m;
 }
@@ -1009,7 +1007,7 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
                      float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st) {
   AdamArgs a{};
   a.p = p; a.g = const_cast<float*>(g); a.m = ea; a.v = eas; a.shadow = m->shadow;
-  a.segs = m->segs_d; a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
+  a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
   a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd;
   if (step > 0) {
     a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));

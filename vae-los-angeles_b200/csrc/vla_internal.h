@@ -212,19 +212,20 @@ struct OutGradArgs {  // autograd path: fp32 upstream dL/d(recon) -> bf16 GEMM o
 };
 cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s);
 
-struct AdamSegment {          // one parameter tensor of the flat arena
-  long long offset;           // element offset in the arena
-  int rows, cols;             // matrix shape (vectors: rows = numel, cols = 1)
-  long long shadow_off;       // bf16 shadow [rows, ld_shadow] offset, -1 = none
+// One 1024-element piece of a parameter tensor, self-contained so the kernel needs a single table read.
+struct alignas(16) AdamChunk {
+  long long offset;       // arena element offset of the chunk's first element (multiple of 4)
+  long long shadow_off;   // bf16 copy [rows, ld_shadow] offset of the tensor, -1 = none
+  int n;                  // valid elements in this chunk (<= ADAM_CHUNK)
+  int first;              // element index of the chunk's first element inside its tensor
+  int cols;               // tensor columns (vectors: 1)
   int ld_shadow;
-  int pad;
 };
-struct AdamChunk { int seg; int start; };   // start = element offset inside the segment
 constexpr int ADAM_CHUNK = 1024;   // one float4 per thread
 struct AdamArgs {
   float* p; float* g; float* m; float* v;
   bf16* shadow;
-  const AdamSegment* segs; const AdamChunk* chunks; int n_chunks;
+  const AdamChunk* chunks; int n_chunks;
   float lr, beta1, beta2, eps, weight_decay;
   float bc1, inv_bc2_sqrt;    // 1 - beta1^t and 1 / sqrt(1 - beta2^t), computed in double on the host
   const struct DynParams* dyn;// if set, lr / weight_decay / bias corrections are read from it
