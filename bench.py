@@ -349,6 +349,13 @@ def run_gpu(args, rank, local_rank, world):
                             flops=fl, bytes=by, bound="tensor" if t_t > t_h else "hbm",
                             frac=max(t_t, t_h) / (avg_ms * 1e-3) if avg_ms > 0 else None))
     top = kernels[0]
+    w = WORK[args.workload]
+    if top["name"] == "train_step_fused":
+        # the whole step is one kernel: its algorithmic work is SURVEY section 8d's per-sample figure x batch (+ 32 B per parameter)
+        top["flops"], top["bytes"] = float(w["flop"] * B), float(w["bytes"] * B + 32 * w["params"])
+        t_t, t_h = top["flops"] / (peaks["bf16_tflops"] * 1e12), top["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        top["bound"] = "tensor" if t_t > t_h else "hbm"
+        top["frac"] = max(t_t, t_h) / (top["avg_us"] * 1e-6)
     if top["bound"] == "tensor":
         ach, peak, unit = top["flops"] / (top["avg_us"] * 1e-6) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
     else:
@@ -362,8 +369,12 @@ def run_gpu(args, rank, local_rank, world):
                 "traffic": traffic, "peak_source": peaks["source"], "avg_us": top["avg_us"], "share_of_step": top["share"],
                 "event_pair_overhead_us": 1e3 * overhead_ms,
                 "how": "CUDA event pair around each launch, recorded as nodes of the captured step graph, 10 replays; the duration of "
-                       "an empty event pair is subtracted (vla_profile_*)"}
-    w = WORK[args.workload]
+                       "an empty event pair is subtracted (vla_profile_*); achieved = algorithmic flops or bytes of the launch / that time"}
+    phases = None
+    if world == 1 and top["name"] == "train_step_fused":
+        # inside the whole-step kernel: per-phase spans from the %globaltimer stamps every unit writes (one replayed step)
+        tl_us, tl = trainer.timeline()
+        phases = {"step_us": tl_us, "phases": [{k: (round(v, 2) if isinstance(v, float) else v) for k, v in ph.items()} for ph in tl]}
     t_tensor = w["flop"] * B / (peaks["bf16_tflops"] * 1e12)
     t_hbm = (w["bytes"] * B + 32 * w["params"]) / (peaks["hbm_gbs"] * 1e9)
     step_s = ms * 1e-3 / args.steps
@@ -396,7 +407,7 @@ def run_gpu(args, rank, local_rank, world):
                              f"{B * n_batches * (DIMS['A'] + DIMS['B']) * 4 / 1e6:.0f} MB) visited in turn",
                        "arithmetic": "bf16 tensor-core operands, fp32 accumulate, fp32 master weights / loss / AdamW",
                        "graph": "CUDA graph replay per step, no host sync in the timed region"},
-            "e2e": e2e, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:8],
+            "e2e": e2e, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:8], "timeline": phases,
             "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
             "cpu_baseline": cpu, "clocks": clocks, "final_losses": losses, "also": also,
         }

@@ -169,6 +169,20 @@ int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, f
 /* Resets the device-side step counter (and beta1^t, beta2^t for the bias corrections) and the resident-batch index. */
 int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float beta1, float beta2, vla_stream_t stream);
 
+
+/* Whole-step kernel.  vla_train_step (phases 0 / 1 / 3) runs as ONE persistent cooperative kernel: the launches of the
+ * step become phases whose units (GEMM tiles, element-wise blocks) wait on per-row-block completion counters instead of
+ * kernel boundaries (csrc/step_kernel.cu).  The first call for a new argument set builds the plan (device allocation +
+ * upload, not capturable); later calls and CUDA-graph replays only launch.  VLA_FUSED_STEP=0 in the environment selects
+ * the separate launches instead (same device code per phase).
+ * Timeline: when enabled, every unit writes %globaltimer stamps [8]: 0 unit start, 1 dependencies resolved, 3 first
+ * operands landed, 4 MMAs issued, 5 accumulator ready, 6 unit published, 7 (phase << 32 | SM id). */
+int vla_step_timeline(vla_model_t* m, int enable);
+int vla_step_timeline_phases(vla_model_t* m);
+int vla_step_timeline_units(vla_model_t* m);
+int vla_step_phase_info(vla_model_t* m, int phase, char* name48, int* n_units, int* unit_base, double* flops, double* bytes);
+int vla_step_timeline_read(vla_model_t* m, unsigned long long* out, int max_units);   /* out[max_units][8]; returns units */
+
 /* Per-launch device timing (CUDA events on `stream`, recorded around every kernel launch the library makes between
  * vla_profile_begin and vla_profile_collect).  flops / bytes are the ALGORITHMIC work of the launch.
  * vla_profile_collect synchronises the stream's events and returns how many entries it wrote. */

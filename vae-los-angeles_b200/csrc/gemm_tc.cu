@@ -16,8 +16,7 @@
 // Replaces, per layer, the ATen addmm / mm calls issued by nn.Linear in the reference
 // (src/models/encoders.py:13-19,31-41,54-55; src/models/decoders.py:13-15,27-31,44-46) and their
 // autograd backward.
-#include "tc_ptx.cuh"
-#include "vla_internal.h"
+#include "gemm_tile.cuh"
 
 #include <mutex>
 
@@ -25,420 +24,39 @@ namespace vla {
 
 namespace {
 
-constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;                 // 16 KiB
-constexpr int B_STAGE_BYTES = GEMM_BN_MAX_TN * GEMM_BK * 2;          // 24 KiB (>= 160 * 128 B)
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 40 KiB
-constexpr int ONES_OFFSET = GEMM_STAGES * STAGE_BYTES;               // 2 KiB of bf16 1.0
-constexpr int ONES_BYTES = 2048;
-constexpr int PATCH_LD = 36;                                         // floats; 144-byte rows: 16-byte aligned, conflict-free
-constexpr int CHUNK_OFFSET = 0;                                      // 8 warps x fp32 [32][36] transpose patches: they alias
-constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;                   // pipeline stage 0, which is idle once the accumulator is ready
-constexpr int VEC_OFFSET = ONES_OFFSET + ONES_BYTES;                 // bias | mean | rstd, fp32 [3][192]
-constexpr int VEC_BYTES = 3 * GEMM_BN_MAX_TN * 4;
-constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][6][4][32]
-constexpr int MAX_CHUNKS = GEMM_BN_MAX_TN / 32;
-constexpr int PART_BYTES = 2 * MAX_CHUNKS * 4 * 32 * 4;
-constexpr int BAR_OFFSET = PART_OFFSET + PART_BYTES;                 // mbarriers
-constexpr int SMEM_USED = BAR_OFFSET + 128;
-constexpr int SMEM_BYTES = SMEM_USED + 1024;                         // slack for manual 1 KiB alignment
-constexpr int EPI_THREADS = GEMM_THREADS - 64;                       // 8 warps
-
-static_assert(B_STAGE_BYTES >= GEMM_BN_MAX_NT * 128, "B stage too small for NT tiles");
-static_assert(CHUNK_BYTES <= STAGE_BYTES, "epilogue patches must fit in one pipeline stage");
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
-static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
-
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-
-// Sum over the 32 lanes of v[j] for every j; the total of column j ends up in lane j (31 shuffles).
-__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; ++j) {
-      const float send = upper ? v[j] : v[j + s];
-      const float keep = upper ? v[j + s] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define STAMP(slot) do { if (grp.dbg) grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + (slot)] = gtime(); } while (0)
-
-__device__ __forceinline__ void red_add_f32(float* p, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-
-// FEATS: compile-time superset of the epilogue flags that may occur in this launch; everything else is compiled out
-// (smaller code: the epilogue is instruction-fetch sensitive).
 template <int MODE, int FEATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmGroup grp) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1 KiB-aligned base (SWIZZLE_128B atoms)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* acc_bar = empty_bar + GEMM_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    STAMP(0);                                                      // kernel entry
-    if (grp.dbg) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] = smid; }
+  if (threadIdx.x == 0 && grp.dbg) {
+    grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 0] = gtime();                                  // kernel entry
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] = smid;
   }
-
   // ---- which problem / tile ----
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
     if (i < grp.nprob && static_cast<int>(blockIdx.x) >= grp.p[i].tile_begin) pi = i;
   const GemmProblem& P = grp.p[pi];
-  const int local = blockIdx.x - P.tile_begin;
-  const int n_tile = local % P.n_tiles;
-  const int m_tile = (local / P.n_tiles) % P.m_tiles;
-  const int k_split = local / (P.n_tiles * P.m_tiles);
-  const int m0 = m_tile * GEMM_BM;
-  const int n0 = n_tile * P.BN;
-  const int BN = P.BN;
-  const int kb_total = (P.K + GEMM_BK - 1) / GEMM_BK;
-  const int kb0 = k_split * P.kb_per_split;
-  const int kb1 = min(kb0 + P.kb_per_split, kb_total);
-  const bool bias_mma = (MODE == 1) && (FEATS & GF_BIASGRAD) && (P.flags & GF_BIASGRAD) && n_tile == 0;
-
-  // ---- one-time setup ----
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&P.tmA);
-    tma_prefetch_desc(&P.tmB);
-    for (int s = 0; s < GEMM_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(acc_bar, 1);
-    fence_mbar_init();
-  }
-  const int dbgf = grp.dbg_flags;
-  if (warp == 1 && !(dbgf & 4)) tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
-  pdl_wait();                    // everything above overlaps the previous kernel's tail
+  if (threadIdx.x == 0) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
+  // ---- one-time setup (overlaps the previous kernel's tail) ----
+  TileCtx ctx = tile_setup(!(grp.dbg_flags & 4), !(grp.dbg_flags & 2));
+  ctx.dbg = grp.dbg; ctx.dbg_row = blockIdx.x; ctx.dbg_flags = grp.dbg_flags;
+  pdl_wait();
   pdl_launch_dependents();
-  if (threadIdx.x == 0) STAMP(1);                                  // past the grid dependency
-  if (warp >= 2) {
-    const int et = threadIdx.x - 64;
-    if (bias_mma) {
-      // 2 KiB of bf16 1.0: the B operand of the bias-gradient MMA (layout-invariant)
-      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + ONES_OFFSET);
-      for (int i = et; i < ONES_BYTES / 4; i += EPI_THREADS) ones[i] = 0x3F803F80u;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    // per-column epilogue vectors of this tile
-    float* vec = reinterpret_cast<float*>(smem + VEC_OFFSET);
-    for (int i = et; i < BN; i += EPI_THREADS) {
-      const int col = n0 + i;
-      const bool ok = col < P.N;
-      vec[i] = (ok && (P.flags & GF_BIAS)) ? P.bias[col] : 0.f;
-      vec[GEMM_BN_MAX_TN + i] = (ok && (P.flags & GF_BNSTATS)) ? P.mean[col] : 0.f;
-      vec[2 * GEMM_BN_MAX_TN + i] = (ok && (P.flags & GF_BNSTATS)) ? P.rstd[col] : 0.f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) STAMP(2);                                  // setup done
-
-  if (dbgf & 2) {
-    // test hook: no main loop, no epilogue
-  } else if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        const int nb = BN >> 6;
-        mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (MODE == 0 ? BN * 128 : nb * 8192));
-        if (MODE == 1) {
-          tma_load_2d(sa, &P.tmA, &full_bar[stage], m0, kb * GEMM_BK);           // box 64 (M) x 64 (K)
-          tma_load_2d(sa + 8192, &P.tmA, &full_bar[stage], m0 + 64, kb * GEMM_BK);
-        } else {
-          tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * GEMM_BK, m0);           // box 64 (K) x 128 (M)
-        }
-        if (MODE == 0) {
-          tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * GEMM_BK, n0);           // box 64 (K) x BN (N)
-        } else {
-          for (int i = 0; i < nb; ++i)
-            tma_load_2d(sb + i * 8192, &P.tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);   // box 64 (N) x 64 (K)
-        }
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MODE == 1 ? 1 : 0, MODE == 0 ? 0 : 1);
-      const uint32_t idesc_ones = make_idesc_bf16(GEMM_BM, 16, 1, 0);
-      const uint32_t ones_addr = smem_u32(smem + ONES_OFFSET);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        if (kb == kb0) STAMP(3);                                   // first operands landed
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          uint64_t adesc, bdesc;
-          if (MODE == 1) adesc = make_smem_desc(sa + k * 2048, 8192, 1024);  // MN-major: +16 K-rows of 128 B
-          else           adesc = make_smem_desc(sa + k * 32, 16, 1024);       // K-major: +16 bf16 of K inside the swizzle atom
-          if (MODE == 0) bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-          else           bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
-          const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
-          if (bias_mma) {
-            const uint64_t odesc = make_smem_desc(ones_addr, 16, 1024);
-            umma_bf16(tmem_base + GEMM_BIAS_TMEM_COL, adesc, odesc, idesc_ones, acc);
-          }
-        }
-        umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(acc_bar);               // accumulator complete
-      STAMP(4);                                                    // all MMAs issued
-    }
-  } else {
-    // =========================== epilogue (8 warps) ===========================
-    // Thread = one accumulator row (TMEM lane); the two warps that share a lane quarter take alternate
-    // 32-column chunks.  Everything stays in registers; global operands are fetched as 128-bit vectors
-    // before they are needed; column statistics use a shuffle butterfly.
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // 0: warps 2-5, 1: warps 6-9
-    const int et = threadIdx.x - 64;        // 0..255
-    const float* vec = reinterpret_cast<const float*>(smem + VEC_OFFSET);
-    float* part = reinterpret_cast<float*>(smem + PART_OFFSET);
-    const int flags = P.flags & FEATS;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < P.M;
-    const int n_chunks = (BN + 31) >> 5;
-    const bool want_stats = (flags & (GF_COLSTATS | GF_BNSTATS)) != 0;
-
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    if (et == 0) STAMP(5);                                         // accumulator ready
-
-    // Per-warp transpose patch: global traffic of the epilogue is always issued with consecutive lanes on consecutive
-    // addresses of one row (1 L1 wavefront per 128 bytes) instead of 32 rows per instruction.
-    float* patch = reinterpret_cast<float*>(smem + CHUNK_OFFSET) + (warp - 2) * (32 * PATCH_LD);
-    const int rbase = m0 + q * 32;                      // first accumulator row of this warp
-    const bool f32_vec = ((reinterpret_cast<uintptr_t>(P.out_f32) & 15) == 0) && ((P.ld_f32 & 3) == 0);
-    const bool bf16_vec = ((reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0) && ((P.ld_bf16 & 7) == 0);
-
-    for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
-      const int col0 = n0 + c * 32;
-      const int nvalid = min(32, P.N - col0);          // <= 0: nothing to store (tile padding)
-      const bool full = nvalid == 32;
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32);
-      if (!(dbgf & 16)) {
-        tmem_ld16(taddr, r);
-        tmem_ld16(taddr + 16, r + 16);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = lane + j;
-      }
-      // ---- per-row operands: coalesced loads -> patch -> this thread's row ----
-      uint4 mk[4];
-      float4 pr[8];
-      const bool mask_fast = (flags & GF_MASK) != 0;     // host side guarantees N % 32 == 0 and 16-byte aligned rows
-      const bool pre_fast = (flags & GF_BNSTATS) != 0;
-      if (mask_fast) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {                   // 8 rows x 64 bytes per instruction
-          const int rr = 8 * k + (lane >> 2);
-          uint4 t = make_uint4(0u, 0u, 0u, 0u);
-          if (rbase + rr < P.M)
-            t = __ldg(reinterpret_cast<const uint4*>(P.mask_src + static_cast<size_t>(rbase + rr) * P.ld_mask + col0) + (lane & 3));
-          *reinterpret_cast<uint4*>(patch + rr * PATCH_LD + (lane & 3) * 4) = t;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mk[i] = *reinterpret_cast<const uint4*>(patch + lane * PATCH_LD + i * 4);
-        __syncwarp();
-      }
-      if (pre_fast) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {                   // 4 rows x 128 bytes per instruction
-          const int rr = 4 * k + (lane >> 3);
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rbase + rr < P.M)
-            t = __ldg(reinterpret_cast<const float4*>(P.pre + static_cast<size_t>(rbase + rr) * P.ld_pre + col0) + (lane & 7));
-          *reinterpret_cast<float4*>(patch + rr * PATCH_LD + (lane & 7) * 4) = t;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pr[i] = *reinterpret_cast<const float4*>(patch + lane * PATCH_LD + i * 4);
-        __syncwarp();
-      }
-      if (!(dbgf & 16)) tmem_ld_wait();
-      // One flag-uniform pass over the register row per feature (compact code: no per-element branching).
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 bv = *reinterpret_cast<const float4*>(vec + c * 32 + j);
-        v[j] = __uint_as_float(r[j]) + bv.x;         v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-        v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
-      }
-      if (flags & GF_MASK) {                           // ReLU / dropout backward: keep where the saved activation is > 0
-        const float sc = P.mask_scale;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint32_t word = reinterpret_cast<const uint32_t*>(mk)[j >> 1];
-          const float m = __uint_as_float((j & 1) ? (word & 0xFFFF0000u) : (word << 16));
-          v[j] = m > 0.f ? v[j] * sc : 0.f;
-        }
-      }
-      if (want_stats) {
-        // statistics are taken before the activation (BatchNorm forward) / on the masked gradient (backward)
-        float s1[32], s2[32];
-        if (flags & GF_BNSTATS) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 mv = *reinterpret_cast<const float4*>(vec + GEMM_BN_MAX_TN + c * 32 + j);
-            const float4 rv = *reinterpret_cast<const float4*>(vec + 2 * GEMM_BN_MAX_TN + c * 32 + j);
-            const float4 pv = pr[j >> 2];
-            s2[j] = v[j] * (pv.x - mv.x) * rv.x;         s2[j + 1] = v[j + 1] * (pv.y - mv.y) * rv.y;
-            s2[j + 2] = v[j + 2] * (pv.z - mv.z) * rv.z; s2[j + 3] = v[j + 3] * (pv.w - mv.w) * rv.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s2[j] = v[j] * v[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { s1[j] = row_ok ? v[j] : 0.f; s2[j] = row_ok ? s2[j] : 0.f; }
-        const float t1 = warp_column_sums(s1, lane);
-        const float t2 = warp_column_sums(s2, lane);
-        part[((0 * MAX_CHUNKS + c) * 4 + q) * 32 + lane] = t1;
-        part[((1 * MAX_CHUNKS + c) * 4 + q) * 32 + lane] = t2;
-      }
-      if ((flags & GF_RELU) && !(dbgf & 32)) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if ((flags & GF_SIGMOID) && !(dbgf & 32)) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
-      }
-      if (nvalid <= 0) continue;
-      if (dbgf & 8) {            // test hook: keep the math alive, skip patch + global stores
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc += v[j];
-        if (acc == 123.456f) P.out_f32[0] = acc;
-        continue;
-      }
-      // ---- this thread's row -> patch; then row-contiguous global accesses ----
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(patch + lane * PATCH_LD + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      __syncwarp();
-      if (flags & GF_RED) {
-        // split-K partial sums: one 128-byte red per row
-        if (lane < nvalid) {
-#pragma unroll 4
-          for (int i = 0; i < 32; ++i)
-            if (rbase + i < P.M)
-              red_add_f32(P.out_f32 + static_cast<size_t>(rbase + i) * P.ld_f32 + col0 + lane, patch[i * PATCH_LD + lane]);
-        }
-      } else {
-        if (flags & GF_OUT_F32) {
-          if (full && f32_vec) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {               // 4 rows x 128 bytes per instruction
-              const int rr = 4 * k + (lane >> 3);
-              if (rbase + rr < P.M)
-                reinterpret_cast<float4*>(P.out_f32 + static_cast<size_t>(rbase + rr) * P.ld_f32 + col0)[lane & 7] =
-                    *reinterpret_cast<const float4*>(patch + rr * PATCH_LD + (lane & 7) * 4);
-            }
-          } else if (lane < nvalid) {
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i)
-              if (rbase + i < P.M) P.out_f32[static_cast<size_t>(rbase + i) * P.ld_f32 + col0 + lane] = patch[i * PATCH_LD + lane];
-          }
-        }
-        if (flags & GF_OUT_BF16) {
-          if (full && bf16_vec) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {               // 8 rows x 64 bytes per instruction
-              const int rr = 8 * k + (lane >> 2);
-              if (rbase + rr < P.M) {
-                const float4 lo = *reinterpret_cast<const float4*>(patch + rr * PATCH_LD + (lane & 3) * 8);
-                const float4 hi = *reinterpret_cast<const float4*>(patch + rr * PATCH_LD + (lane & 3) * 8 + 4);
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(lo.x, lo.y), b1 = __floats2bfloat162_rn(lo.z, lo.w);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(hi.x, hi.y), b3 = __floats2bfloat162_rn(hi.z, hi.w);
-                uint4 o;
-                o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
-                o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
-                reinterpret_cast<uint4*>(P.out_bf16 + static_cast<size_t>(rbase + rr) * P.ld_bf16 + col0)[lane & 3] = o;
-              }
-            }
-          } else if (lane < nvalid) {
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i)
-              if (rbase + i < P.M)
-                P.out_bf16[static_cast<size_t>(rbase + i) * P.ld_bf16 + col0 + lane] = __float2bfloat16(patch[i * PATCH_LD + lane]);
-          }
-        }
-      }
-      __syncwarp();
-    }
-    if (bias_mma && half == 0) {
-      uint32_t r1[1];
-      tmem_ld1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + GEMM_BIAS_TMEM_COL, r1);
-      tmem_ld_wait();
-      if (row_ok) red_add_f32(P.bias_grad + row, __uint_as_float(r1[0]));
-    }
-    if (want_stats) {
-      named_bar_sync(3, EPI_THREADS);
-      for (int i = et; i < 2 * BN; i += EPI_THREADS) {
-        const int which = i / BN, cc = i - which * BN;
-        const int col = n0 + cc;
-        if (col < P.N) {
-          const float* pp = part + ((which * MAX_CHUNKS + (cc >> 5)) * 4) * 32 + (cc & 31);
-          P.stats[(static_cast<size_t>(m_tile) * 2 + which) * P.N + col] = pp[0] + pp[32] + pp[64] + pp[96];
-        }
-      }
-    }
-  }
-
+  if (threadIdx.x == 0 && grp.dbg) grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 2] = gtime();  // setup done, dependency resolved
+  gemm_tile<MODE, FEATS, false>(ctx, P, static_cast<int>(blockIdx.x) - P.tile_begin, NoDeps{});
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) STAMP(6);                                  // epilogue done
-  if (warp == 1 && !(dbgf & 4)) {
+  if (threadIdx.x == 0 && grp.dbg) grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 6] = gtime();  // epilogue done
+  if ((threadIdx.x >> 5) == 1 && !(grp.dbg_flags & 4)) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+    tmem_dealloc(ctx.tmem_base, GEMM_TMEM_COLS);
   }
 }
 
 }  // namespace
 
 size_t gemm_smem_bytes() { return SMEM_BYTES; }
-
-constexpr int FEATS_FWD_PLAIN = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;                      // hidden decoder layers, heads
-constexpr int FEATS_FWD_FULL = FEATS_FWD_PLAIN | GF_SIGMOID | GF_COLSTATS;                         // + BatchNorm statistics / sigmoid
-constexpr int FEATS_DGRAD_PLAIN = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;                              // decoder data gradients
-constexpr int FEATS_DGRAD_FULL = FEATS_DGRAD_PLAIN | GF_BNSTATS;                                   // + BatchNorm backward statistics
-constexpr int FEATS_WGRAD = GF_RED | GF_BIASGRAD;
 
 template <int MODE, int FEATS>
 cudaError_t launch_one(const GemmGroup& g, cudaStream_t stream, size_t smem) {

@@ -25,6 +25,8 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
       return fail(VLA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
   } while (0)
 
+constexpr int FEATS_FWD_PLAIN_HOST = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;     // must match gemm_tile.cuh
+constexpr int FEATS_DGRAD_PLAIN_HOST = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;
 inline int pad8(int x) { return (x + 7) & ~7; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -73,6 +75,31 @@ struct TmapKey {
 
 struct ProfEntry { char name[48]; cudaEvent_t e0, e1; double flops, bytes; };
 
+// Records the launches of one train step as phases of the whole-step kernel (step_kernel.cu) instead of issuing them.
+struct StepRecorder {
+  StepPlan plan{};
+  std::vector<char> args;                 // argument structs, 64-byte aligned, offsets relative to the start of this vector
+  std::vector<std::string> names;
+  std::vector<double> flops, bytes;
+  std::vector<int> frontier, siblings;    // phases a new phase must wait for (ROW); BatchNorm siblings pending promotion
+  int last_gemm = -1, ph_ingest = -1;
+  int rows = 0;
+  std::string why;                        // non-empty: this step cannot be fused (caller falls back to separate launches)
+};
+enum { DEP_CHAIN = 0, DEP_BN_SIBLING = 1, DEP_ALL = 2 };
+
+struct CachedStep {
+  std::vector<char> key;
+  char* dev = nullptr;                    // [StepPlan | args | counters | targets | finish | timeline]
+  StepPlan plan{};                        // host copy of the header (device pointers)
+  std::vector<std::string> names;
+  std::vector<double> ph_flops, ph_bytes;
+  int units_total = 0;
+  double flops = 0, bytes = 0;
+  int saved_batch = 0, saved_present = 0, kl_grid = 0;
+  size_t timeline_off = 0;
+};
+
 struct vla_model {
   bool layout_only = false;
   bool prof_on = false;
@@ -104,6 +131,12 @@ struct vla_model {
   // what the last forward left in the workspace
   bool saved = false; int saved_batch = 0, saved_present = 0, saved_train = 0, kl_grid = 0;
   unsigned long long generation = 0;
+  // whole-step kernel
+  StepRecorder* rec = nullptr;
+  std::vector<CachedStep*> steps;
+  CachedStep* last_step = nullptr;
+  bool timeline_on = false;
+  int step_grid = 0;
 };
 
 namespace {
@@ -114,7 +147,7 @@ namespace {
 struct ProfScope {
   vla_model* m; cudaStream_t st; int idx = -1;
   ProfScope(vla_model* m_, cudaStream_t st_, const char* name, double flops, double bytes) : m(m_), st(st_) {
-    if (!m->prof_on) return;
+    if (!m->prof_on || m->rec) return;
     ProfEntry e{};
     snprintf(e.name, sizeof(e.name), "%s", name);
     e.flops = flops; e.bytes = bytes;
@@ -130,6 +163,52 @@ struct ProfScope {
   ~ProfScope() { if (idx >= 0) cudaEventRecordWithFlags(m->prof[idx].e1, st, flags); }
   unsigned flags = cudaEventRecordDefault;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Whole-step recording
+// ---------------------------------------------------------------------------------------------
+void free_steps(vla_model* m) {
+  for (CachedStep* c : m->steps) { cudaFree(c->dev); delete c; }
+  m->steps.clear();
+  m->last_step = nullptr;
+}
+
+// Adds one phase.  dep_mode: DEP_CHAIN = wait (ROW) for the frontier and become the frontier; DEP_BN_SIBLING = wait for ALL
+// units of the latest GEMM phase, join the siblings that replace the frontier once the next ordinary phase arrives;
+// DEP_ALL = wait for ALL units of every frontier phase.  extra_all >= 0 adds an ALL dependency on that phase.
+StepPhase* rec_phase(vla_model* m, int kind, const char* name, const void* args, size_t args_size, int n_units,
+                     int dep_mode, double flops, double bytes, int extra_all = -1) {
+  StepRecorder* r = m->rec;
+  if (!r->why.empty()) return nullptr;
+  if (r->plan.n_phases >= STEP_MAX_PHASES) { r->why = "too many phases"; return nullptr; }
+  if (dep_mode != DEP_BN_SIBLING && !r->siblings.empty()) { r->frontier = r->siblings; r->siblings.clear(); }
+  const int id = r->plan.n_phases++;
+  StepPhase& ph = r->plan.ph[id];
+  memset(&ph, 0, sizeof(ph));
+  ph.kind = kind; ph.n_units = n_units; ph.rows = r->rows; ph.sub = 1; ph.n_blocks = n_units; ph.gx = 1; ph.rpb = 1; ph.L = 1;
+  if (dep_mode == DEP_BN_SIBLING) {
+    if (r->last_gemm < 0) { r->why = "BatchNorm phase without a preceding GEMM"; return nullptr; }
+    ph.dep_phase[ph.n_deps] = r->last_gemm; ph.dep_all[ph.n_deps] = 1; ph.n_deps++;
+    r->siblings.push_back(id);
+  } else {
+    for (int f : r->frontier) {
+      if (ph.n_deps >= STEP_MAX_DEPS) { r->why = "too many dependencies"; return nullptr; }
+      ph.dep_phase[ph.n_deps] = f; ph.dep_all[ph.n_deps] = dep_mode == DEP_ALL ? 1 : 0; ph.n_deps++;
+    }
+    r->frontier.assign(1, id);
+  }
+  if (extra_all >= 0) {
+    if (ph.n_deps >= STEP_MAX_DEPS) { r->why = "too many dependencies"; return nullptr; }
+    ph.dep_phase[ph.n_deps] = extra_all; ph.dep_all[ph.n_deps] = 1; ph.n_deps++;
+  }
+  if (kind <= SK_GEMM_TN) r->last_gemm = id;
+  size_t off = (r->args.size() + 63) & ~size_t(63);
+  r->args.resize(off + args_size);
+  memcpy(r->args.data() + off, args, args_size);
+  ph.args_off = static_cast<long long>(off);
+  r->names.push_back(name); r->flops.push_back(flops); r->bytes.push_back(bytes);
+  return &ph;
+}
 int finalize_group(vla_model* m, GemmGroup& g, int mode);
 void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
   *flops = 0; *bytes = 0;
@@ -151,6 +230,15 @@ int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStrea
       return fail(VLA_ERR_STATE, std::string(name) + ": BatchNorm-statistics epilogue needs N % 32 == 0 and 16-byte aligned rows");
   }
   double fl, by; gemm_work(g, &fl, &by);
+  if (m->rec) {
+    int used = 0;
+    for (int i = 0; i < g.nprob; ++i) used |= g.p[i].flags;
+    int kind = SK_GEMM_TN;
+    if (mode == 0) kind = (used & ~FEATS_FWD_PLAIN_HOST) ? SK_GEMM_NT_FULL : SK_GEMM_NT_PLAIN;
+    if (mode == 2) kind = (used & ~FEATS_DGRAD_PLAIN_HOST) ? SK_GEMM_NN_FULL : SK_GEMM_NN_PLAIN;
+    rec_phase(m, kind, name, &g, sizeof(g), g.total_tiles, DEP_CHAIN, fl, by);
+    return VLA_OK;
+  }
   ProfScope ps(m, st, name, fl, by);
   cudaError_t e = launch_gemm_group(g, mode, st);
   if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("gemm launch (") + name + "): " + cudaGetErrorString(e));
@@ -354,8 +442,10 @@ int reserve(vla_model* m, int batch) {
   if (m->layout_only) return fail(VLA_ERR_STATE, "layout-only handle: no device state");
   if (batch <= m->cap) return VLA_OK;
   int cap = std::max(batch, 32);
+  if (m->rec) return fail(VLA_ERR_STATE, "workspace growth while recording a fused step");
   if (m->ws) { CK(cudaDeviceSynchronize()); CK(cudaFree(m->ws)); m->ws = nullptr; m->cap = 0; }
   m->tmaps.clear();
+  free_steps(m);
   m->saved = false;
   Bump dry; carve(m, dry, cap);
   const size_t bytes = dry.off + 256;
@@ -591,7 +681,10 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     }
     a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches; a.beta1 = io.beta1; a.beta2 = io.beta2;
     { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * (4.0 * a.width[e] + 2.0 * a.ld_dst[e]);
-      ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); }
+      if (m->rec) {
+        StepPhase* ph = rec_phase(m, SK_INGEST, "ingest", &a, sizeof(a), ceil_div(B, 32), DEP_CHAIN, 0, by);
+        if (ph) { ph->rpb = 32; m->rec->ph_ingest = m->rec->plan.n_phases - 1; }
+      } else { ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); } }
   }
   const int mt = ceil_div(B, GEMM_BM);
   // ---- encoders, round by round ----
@@ -634,7 +727,11 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
-      { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
+      if (m->rec) {
+        const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0), gx = ceil_div(a.n, 64), gy = ceil_div(a.rows, rpb);
+        StepPhase* ph = rec_phase(m, SK_BN_ACT, "bn_act", &a, sizeof(a), gx * gy, DEP_BN_SIBLING, 0, 6.0 * B * bn.n);
+        if (ph) { ph->rpb = rpb; ph->gx = gx; }
+      } else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
     }
   }
   // ---- latent ----
@@ -645,9 +742,18 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     a.eps_in = io.eps; a.seed = io.seed; a.offset = io.offset * 16; a.dyn = io.engine ? m->dyn : nullptr;
     a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz;
     a.kl_partials = m->kl_partials; a.rows = B; a.L = L;
-    { ProfScope ps(m, st, "latent_fwd", 0, static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0)); CK(launch_latent_fwd(a, &m->kl_grid, st)); }
-    if (io.mu) CK(cudaMemcpyAsync(io.mu, m->mu, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
-    if (io.logvar) CK(cudaMemcpyAsync(io.logvar, m->logvar, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+    if (m->rec) {
+      const int nb = ceil_div(B * L, 256), sub = 4;
+      m->kl_grid = nb;
+      StepPhase* ph = rec_phase(m, SK_LATENT_FWD, "latent_fwd", &a, sizeof(a), ceil_div(nb, sub), DEP_CHAIN,
+                                0, static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0), m->rec->ph_ingest);
+      if (ph) { ph->sub = sub; ph->n_blocks = nb; ph->L = L; }
+      if (io.mu || io.logvar) m->rec->why = "optional mu / logvar outputs";
+    } else {
+      { ProfScope ps(m, st, "latent_fwd", 0, static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0)); CK(launch_latent_fwd(a, &m->kl_grid, st)); }
+      if (io.mu) CK(cudaMemcpyAsync(io.mu, m->mu, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+      if (io.logvar) CK(cudaMemcpyAsync(io.logvar, m->logvar, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+    }
   }
   // ---- decoders ----
   {
@@ -701,7 +807,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   const int B = m->saved_batch, L = m->L, present = m->saved_present, train = m->saved_train;
   const float* P = io.params; const bf16* SH = m->shadow; float* G = io.grads;
   int rc;
-  if (io.zero_grads) CK(cudaMemsetAsync(G, 0, sizeof(float) * m->n_params, st));
+  if (io.zero_grads) { if (m->rec) m->rec->why = "gradient clear"; else CK(cudaMemsetAsync(G, 0, sizeof(float) * m->n_params, st)); }
   // which decoders carry a gradient
   std::vector<bool> active(m->decs.size(), false);
   if (!io.engine) {
@@ -750,7 +856,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   // inactive decoders contribute zero to dL/dz: clear their slice of g_d0
   if (any_dec)
     for (size_t i = 0; i < m->decs.size(); ++i)
-      if (!active[i])
+      if (!active[i] && m->rec) m->rec->why = "inactive decoder";
+      else if (!active[i])
         CK(cudaMemset2DAsync(m->g_d0 + m->decs[i].cat_off, sizeof(bf16) * m->cat.out, 0, sizeof(bf16) * m->decs[i].cat_w, B, st));
   if (any_dec) {
     GemmGroup g; init_group(g); GemmProblem* p;
@@ -769,7 +876,11 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     a.mu = m->mu; a.logvar = m->logvar; a.eps = m->eps;
     a.beta = 0.f; a.dyn = io.engine ? m->dyn : nullptr;
     a.n_modalities = n_present; a.gml = m->gml; a.ld_gml = m->ldgml; a.rows = B; a.L = L;
-    { ProfScope ps(m, st, "latent_bwd", 0, static_cast<double>(B) * L * 20.0); CK(launch_latent_bwd(a, st)); }
+    if (m->rec) {
+      const int nb = ceil_div(B * L, 256), sub = 4;
+      StepPhase* ph = rec_phase(m, SK_LATENT_BWD, "latent_bwd", &a, sizeof(a), ceil_div(nb, sub), DEP_CHAIN, 0, static_cast<double>(B) * L * 20.0);
+      if (ph) { ph->sub = sub; ph->n_blocks = nb; ph->L = L; }
+    } else { ProfScope ps(m, st, "latent_bwd", 0, static_cast<double>(B) * L * 20.0); CK(launch_latent_bwd(a, st)); }
   }
   const int mt = ceil_div(B, GEMM_BM);
   // ---- encoder data gradients ----
@@ -813,7 +924,11 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       a.mean = w.mean[it.second]; a.rstd = w.rstd[it.second]; a.gamma = P + bn.g_off;
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
-      { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
+      if (m->rec) {
+        const int rpb = bn_rows_per_block(a.rows, a.m_tiles), gx = ceil_div(a.n, 64), gy = ceil_div(a.rows, rpb);
+        StepPhase* ph = rec_phase(m, SK_BN_BWD, "bn_bwd", &a, sizeof(a), gx * gy, DEP_BN_SIBLING, 0, 8.0 * B * bn.n);
+        if (ph) { ph->rpb = rpb; ph->gx = gx; }
+      } else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
     }
   }
   if (!site_done) {
@@ -933,6 +1048,7 @@ int vla_model_create_layout_only(const vla_config_t* cfg, vla_model_t** out) {
 void vla_model_destroy(vla_model_t* m) {
   if (!m) return;
   if (m->layout_only) { delete m; return; }
+  free_steps(m);
   cudaFree(m->shadow); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
   cudaFree(m->ws);
   delete m;
@@ -1014,6 +1130,12 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
     a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), step)));
   }
   a.dyn = dyn ? m->dyn : nullptr; a.update = 1; a.zero_grad = zero_grad ? 1 : 0;
+  if (m->rec) {
+    const int sub = std::max(1, ceil_div(a.n_chunks, 148));
+    StepPhase* ph = rec_phase(m, SK_ADAMW, "adamw", &a, sizeof(a), ceil_div(a.n_chunks, sub), DEP_ALL, 0, 34.0 * m->n_params);
+    if (ph) { ph->sub = sub; ph->n_blocks = a.n_chunks; }
+    return VLA_OK;
+  }
   { ProfScope ps(m, st, "adamw", 0, 34.0 * m->n_params); CK(launch_adamw(a, st)); }
   return VLA_OK;
 }
@@ -1040,10 +1162,8 @@ int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float bet
   return VLA_OK;
 }
 
-int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream) {
-  if (!m || !a || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->buffers || !a->loss_out)
-    return fail(VLA_ERR_INVALID, "null argument");
-  cudaStream_t st = as_stream(stream);
+// The launches of one train step, in order (issued on `st`, or recorded when m->rec is set).
+static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaStream_t st) {
   FwdIO io{};
   io.params = a->params; io.buffers = a->buffers; io.counters = a->counters;
   // encoder inputs per kind (train_rna2dna.py:86, train_dna2rna.py:86, optimize_hyperparameters.py:106)
@@ -1091,7 +1211,12 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
       if (l.recon_a) by += static_cast<double>(l.rows) * l.width_a * 10.0;
       if (l.recon_b) by += static_cast<double>(l.rows) * l.width_b * 10.0;
       if (l.logits) by += static_cast<double>(l.rows) * l.n_sites * 6.0;
-      ProfScope ps(m, st, "loss", 0, by); CK(launch_loss(l, st)); }
+      if (m->rec) {
+        const LossGridInfo lg = loss_grid_info(l);
+        const int nb = std::max(1, lg.nb_a + lg.nb_b + lg.nb_c + lg.nb_k), sub = 4;
+        StepPhase* ph = rec_phase(m, SK_LOSS, "loss", &l, sizeof(l), ceil_div(nb, sub), DEP_CHAIN, 0, by);
+        if (ph) { ph->sub = sub; ph->n_blocks = nb; }
+      } else { ProfScope ps(m, st, "loss", 0, by); CK(launch_loss(l, st)); } }
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
@@ -1099,6 +1224,150 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
   if (!do_opt) return VLA_OK;
   return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
                    true, st);
+}
+
+
+// Builds (first call for these arguments) and launches the whole-step kernel.  Returns 1 when this step cannot be fused
+// (the caller then issues the separate launches), 0 on success, < 0 on error.
+static int train_step_fused(vla_model_t* m, const vla_train_args_t* a, cudaStream_t st) {
+  std::vector<char> key(sizeof(*a) + sizeof(void*) * (1 + m->n_drop));
+  memcpy(key.data(), a, sizeof(*a));
+  for (int i = 0; i < m->n_drop; ++i) {
+    const void* p = a->keep_masks ? a->keep_masks[i] : nullptr;
+    memcpy(key.data() + sizeof(*a) + sizeof(void*) * i, &p, sizeof(void*));
+  }
+  CachedStep* cs = nullptr;
+  for (CachedStep* c : m->steps) if (c->key == key) { cs = c; break; }
+  if (!cs) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(VLA_ERR_STATE, "vla_train_step: the first call for a new argument set builds the fused step plan "
+                                 "(device allocation + upload) and cannot run inside a stream capture; call it once outside");
+    if (m->step_grid == 0) {
+      cudaError_t e = cudaSuccess;
+      m->step_grid = step_max_grid(&e);
+      if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("whole-step kernel setup: ") + cudaGetErrorString(e));
+      if (m->step_grid <= 0) return fail(VLA_ERR_CUDA, "whole-step kernel does not fit on this device");
+    }
+    int rc;
+    if ((rc = reserve(m, a->batch))) return rc;       // before recording: the plan holds workspace pointers
+    StepRecorder rec;
+    rec.rows = a->batch;
+    m->rec = &rec;
+    rc = train_step_sequence(m, a, st);
+    m->rec = nullptr;
+    if (rc) return rc;
+    if (!rec.why.empty()) return 1;
+    // ---- finalize: CTA assignment, counters, targets ----
+    StepPlan& pl = rec.plan;
+    const int G = m->step_grid;
+    pl.grid = G;
+    pl.mt = ceil_div(a->batch, STEP_ROW_BLOCK);
+    pl.n_counters = pl.n_phases * (pl.mt + 1);
+    std::vector<unsigned int> targets(pl.n_counters, 0u);
+    int units = 0;
+    for (int p = 0; p < pl.n_phases; ++p) {
+      StepPhase& ph = pl.ph[p];
+      ph.unit_base = units; ph.unit_rot = units % G; ph.cbase = p * (pl.mt + 1);
+      const void* args = rec.args.data() + ph.args_off;
+      for (int u = 0; u < ph.n_units; ++u) {
+        int r0, r1;
+        step_unit_rows_host(ph, args, u, &r0, &r1);
+        if (r1 > r0) {
+          if (r1 > a->batch) return fail(VLA_ERR_STATE, "fused step: unit rows out of range");
+          for (int b = r0 / STEP_ROW_BLOCK; b <= (r1 - 1) / STEP_ROW_BLOCK; ++b) targets[ph.cbase + b]++;
+        }
+      }
+      targets[ph.cbase + pl.mt] = static_cast<unsigned int>(ph.n_units);
+      units += ph.n_units;
+    }
+    // ---- device image: [StepPlan | args | counters | targets | finish | timeline] ----
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t off_args = up(sizeof(StepPlan));
+    const size_t off_cnt = up(off_args + rec.args.size());
+    const size_t off_tgt = up(off_cnt + sizeof(unsigned int) * pl.n_counters);
+    const size_t off_fin = up(off_tgt + sizeof(unsigned int) * pl.n_counters);
+    const size_t off_tl = up(off_fin + 64);
+    const size_t total = off_tl + sizeof(unsigned long long) * 8 * units;
+    cs = new CachedStep();
+    cudaError_t e = cudaMalloc(&cs->dev, total);
+    if (e != cudaSuccess) { delete cs; return fail(VLA_ERR_CUDA, std::string("cudaMalloc fused step: ") + cudaGetErrorString(e)); }
+    for (int p = 0; p < pl.n_phases; ++p) pl.ph[p].args_off += static_cast<long long>(off_args);
+    pl.counters = reinterpret_cast<unsigned int*>(cs->dev + off_cnt);
+    pl.targets = reinterpret_cast<const unsigned int*>(cs->dev + off_tgt);
+    pl.finish = reinterpret_cast<unsigned int*>(cs->dev + off_fin);
+    pl.dbg = m->timeline_on ? reinterpret_cast<unsigned long long*>(cs->dev + off_tl) : nullptr;
+    std::vector<char> img(total, 0);
+    memcpy(img.data(), &pl, sizeof(pl));
+    memcpy(img.data() + off_args, rec.args.data(), rec.args.size());
+    memcpy(img.data() + off_tgt, targets.data(), sizeof(unsigned int) * pl.n_counters);
+    e = cudaMemcpy(cs->dev, img.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(cs->dev); delete cs; return fail(VLA_ERR_CUDA, std::string("upload fused step: ") + cudaGetErrorString(e)); }
+    cs->key = key; cs->plan = pl; cs->names = rec.names; cs->ph_flops = rec.flops; cs->ph_bytes = rec.bytes;
+    cs->units_total = units; cs->timeline_off = off_tl;
+    for (double f : rec.flops) cs->flops += f;
+    for (double b : rec.bytes) cs->bytes += b;
+    cs->saved_batch = m->saved_batch; cs->saved_present = m->saved_present; cs->kl_grid = m->kl_grid;
+    m->steps.push_back(cs);
+  }
+  m->saved = true; m->saved_batch = cs->saved_batch; m->saved_present = cs->saved_present; m->saved_train = 1;
+  m->kl_grid = cs->kl_grid; m->generation++;
+  m->last_step = cs;
+  if (m->prof_on) { ProfScope calib(m, st, "_empty_pair", 0, 0); }   // event-pair overhead, subtracted by the reader
+  {
+    ProfScope ps(m, st, "train_step_fused", cs->flops, cs->bytes);
+    cudaError_t e = launch_step(reinterpret_cast<const StepPlan*>(cs->dev), cs->plan.grid, st);
+    if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("whole-step kernel launch: ") + cudaGetErrorString(e));
+  }
+  return VLA_OK;
+}
+
+int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream) {
+  if (!m || !a || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->buffers || !a->loss_out)
+    return fail(VLA_ERR_INVALID, "null argument");
+  if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
+  cudaStream_t st = as_stream(stream);
+  const char* env = getenv("VLA_FUSED_STEP");        // read per call: a host-side switch, not on the replay path
+  const bool fused_on = !(env && env[0] == '0');
+  if (fused_on && a->phases != 2) {
+    const int rc = train_step_fused(m, a, st);
+    if (rc <= 0) return rc;
+  }
+  return train_step_sequence(m, a, st);
+}
+
+/* Whole-step kernel timeline: %globaltimer stamps per unit (unit start, dependencies resolved, first operands, MMAs
+ * issued, accumulator ready, unit published) written by the next fused steps. */
+int vla_step_timeline(vla_model_t* m, int enable) {
+  if (!m) return fail(VLA_ERR_INVALID, "null model");
+  CK(cudaDeviceSynchronize());
+  m->timeline_on = enable != 0;
+  for (CachedStep* c : m->steps) {
+    c->plan.dbg = enable ? reinterpret_cast<unsigned long long*>(c->dev + c->timeline_off) : nullptr;
+    CK(cudaMemcpy(c->dev + offsetof(StepPlan, dbg), &c->plan.dbg, sizeof(c->plan.dbg), cudaMemcpyHostToDevice));
+  }
+  return VLA_OK;
+}
+int vla_step_timeline_phases(vla_model_t* m) { return (m && m->last_step) ? m->last_step->plan.n_phases : 0; }
+int vla_step_timeline_units(vla_model_t* m) { return (m && m->last_step) ? m->last_step->units_total : 0; }
+int vla_step_phase_info(vla_model_t* m, int phase, char* name48, int* n_units, int* unit_base, double* flops, double* bytes) {
+  if (!m || !m->last_step || phase < 0 || phase >= m->last_step->plan.n_phases) return fail(VLA_ERR_INVALID, "bad phase index");
+  const CachedStep* c = m->last_step;
+  if (name48) snprintf(name48, 48, "%s", c->names[phase].c_str());
+  if (n_units) *n_units = c->plan.ph[phase].n_units;
+  if (unit_base) *unit_base = c->plan.ph[phase].unit_base;
+  if (flops) *flops = c->ph_flops[phase];
+  if (bytes) *bytes = c->ph_bytes[phase];
+  return VLA_OK;
+}
+int vla_step_timeline_read(vla_model_t* m, unsigned long long* out, int max_units) {
+  if (!m || !out || !m->last_step) return fail(VLA_ERR_INVALID, "no fused step has run");
+  const CachedStep* c = m->last_step;
+  const int n = std::min(max_units, c->units_total);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, c->dev + c->timeline_off, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost));
+  return n;
 }
 
 int vla_profile_begin(vla_model_t* m) {

@@ -234,4 +234,58 @@ struct AdamArgs {
 };
 cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+// Whole-step kernel (step_kernel.cu): one persistent cooperative launch executes the train step as a list of PHASES
+// (the launches of the per-call path), each split into UNITS (one GEMM tile, or a few element-wise blocks).  Units of
+// phase p go to CTA (u + rot_p) mod grid; a unit waits on per-row-block completion counters of the phases it depends
+// on (ROW: the 128-row blocks it reads; ALL: every unit of that phase) instead of a kernel boundary.
+// ---------------------------------------------------------------------------------------------
+enum StepKind : int {
+  SK_GEMM_NT_PLAIN = 0, SK_GEMM_NT_FULL, SK_GEMM_NN_PLAIN, SK_GEMM_NN_FULL, SK_GEMM_TN,
+  SK_INGEST, SK_BN_ACT, SK_LATENT_FWD, SK_LOSS, SK_LATENT_BWD, SK_BN_BWD, SK_ADAMW,
+};
+constexpr int STEP_MAX_PHASES = 40;
+constexpr int STEP_MAX_DEPS = 3;
+constexpr int STEP_ROW_BLOCK = GEMM_BM;     // dependency granularity: 128 rows
+
+struct StepPhase {
+  int kind;
+  int n_units;
+  int unit_rot;            // unit u runs on CTA (u + unit_rot) % grid
+  int unit_base;           // index of unit 0 in the timeline buffer
+  int sub;                 // element-wise: stand-alone blocks per unit
+  int n_blocks;            // element-wise: number of stand-alone blocks (BatchNorm: gx * gy, block = bx + gx * by)
+  int gx;                  // BatchNorm: column blocks
+  int rpb;                 // ingest: rows per unit; BatchNorm: rows per block
+  int L;                   // latent width
+  int rows;                // batch rows
+  int cbase;               // counters [cbase, cbase + mt): per row block; [cbase + mt]: all units
+  int n_deps;
+  int dep_phase[STEP_MAX_DEPS];
+  int dep_all[STEP_MAX_DEPS];
+  long long args_off;      // byte offset of the argument struct (GemmGroup, IngestArgs, ...) from the plan base
+};
+
+struct StepPlan {
+  int n_phases;
+  int mt;                  // number of 128-row blocks
+  int n_counters;
+  int grid;
+  unsigned int* counters;  // [n_counters], zero between launches (the last CTA to finish re-arms them)
+  const unsigned int* targets;   // [n_counters]
+  unsigned int* finish;    // CTA exit ticket
+  unsigned long long* dbg; // optional [total units][8] globaltimer stamps
+  StepPhase ph[STEP_MAX_PHASES];
+};
+
+struct LossGridInfo { int nb_a, nb_b, nb_c, nb_k; };
+LossGridInfo loss_grid_info(const LossArgs& a);
+int bn_rows_per_block(int rows, int m_tiles);
+size_t step_smem_bytes();
+// Rows [r0, r1) a unit reads / writes (empty for AdamW); shared by the host (targets) and the kernel (signals, waits).
+// `args` points at the phase's argument struct.
+void step_unit_rows_host(const StepPhase& ph, const void* args, int u, int* r0, int* r1);
+cudaError_t launch_step(const StepPlan* plan_dev, int grid, cudaStream_t s);
+int step_max_grid(cudaError_t* err);
+
 }  // namespace vla

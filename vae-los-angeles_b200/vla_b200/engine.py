@@ -218,6 +218,46 @@ class Trainer:
         Under data parallelism these are the sums over all ranks."""
         return tuple(self.loss_out.tolist())
 
+    def timeline(self, which=0):
+        """Per-phase timing of the whole-step kernel for ONE replayed step, from the %globaltimer stamps every unit writes
+        (vla_step_timeline).  Returns (step_us, phases): phases is a list of dicts with the phase's name, number of units,
+        first unit start / last unit published relative to the first stamp of the step (us), the mean unit duration and the
+        mean time a unit spent waiting for its dependencies, plus the phase's algorithmic flops / bytes."""
+        import numpy as np
+        L = _lib.lib()
+        dev = self.core.device
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)
+            self.step(which)                               # make sure the plan exists
+            torch.cuda.synchronize(dev)
+            _lib.check(L.vla_step_timeline(self.core.handle, 1), "vla_step_timeline")
+            self.step(which)
+            torch.cuda.synchronize(dev)
+            n_units = L.vla_step_timeline_units(self.core.handle)
+            n_ph = L.vla_step_timeline_phases(self.core.handle)
+            buf = (C.c_ulonglong * (8 * max(n_units, 1)))()
+            got = L.vla_step_timeline_read(self.core.handle, buf, n_units)
+            _lib.check(L.vla_step_timeline(self.core.handle, 0), "vla_step_timeline")
+        if got <= 0:
+            return 0.0, []
+        t = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 8)[:got].astype(np.int64)
+        t0 = int(t[:, 0].min())
+        out = []
+        for p in range(n_ph):
+            name = C.create_string_buffer(48)
+            nu, ub, fl, by = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+            _lib.check(L.vla_step_phase_info(self.core.handle, p, name, C.byref(nu), C.byref(ub), C.byref(fl), C.byref(by)),
+                       "vla_step_phase_info")
+            rows = t[ub.value:ub.value + nu.value]
+            out.append(dict(name=name.value.decode(), units=nu.value,
+                            start_us=(int(rows[:, 0].min()) - t0) / 1e3, ready_us=(int(rows[:, 1].min()) - t0) / 1e3,
+                            end_us=(int(rows[:, 6].max()) - t0) / 1e3,
+                            unit_us=float((rows[:, 6] - rows[:, 0]).mean()) / 1e3,
+                            wait_us=float((rows[:, 1] - rows[:, 0]).mean()) / 1e3,
+                            work_us=float((rows[:, 6] - rows[:, 1]).mean()) / 1e3,
+                            flops=fl.value, bytes=by.value))
+        return (int(t[:, 6].max()) - t0) / 1e3, out
+
     def profile(self, steps=3, which=0):
         """Per-launch device times inside a replayed CUDA graph: the step is captured once with an event pair around every
         launch (event-record nodes), the graph is replayed `steps` times and the pairs are read after each replay.
