@@ -170,11 +170,11 @@ int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, f
 int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float beta1, float beta2, vla_stream_t stream);
 
 
-/* Whole-step kernel.  vla_train_step (phases 0 / 1 / 3) runs as ONE persistent cooperative kernel: the launches of the
+/* Whole-step kernel.  vla_train_step (phases 0 / 1 / 3) can run as ONE persistent cooperative kernel: the launches of the
  * step become phases whose units (GEMM tiles, element-wise blocks) wait on per-row-block completion counters instead of
  * kernel boundaries (csrc/step_kernel.cu).  The first call for a new argument set builds the plan (device allocation +
- * upload, not capturable); later calls and CUDA-graph replays only launch.  VLA_FUSED_STEP=0 in the environment selects
- * the separate launches instead (same device code per phase).
+ * upload, not capturable); later calls and CUDA-graph replays only launch.  Selected with VLA_FUSED_STEP=1 in the
+ * environment; the default issues the same phases as separate launches (same device code per phase).
  * Timeline: when enabled, every unit writes %globaltimer stamps [8]: 0 unit start, 1 dependencies resolved, 3 first
  * operands landed, 4 MMAs issued, 5 accumulator ready, 6 unit published, 7 (phase << 32 | SM id). */
 int vla_step_timeline(vla_model_t* m, int enable);

@@ -8,6 +8,8 @@ import sys
 import numpy as np
 import torch
 
+os.environ["VLA_FUSED_STEP"] = "1"
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "vae-los-angeles_b200")]
 from src.models import DNA2RNAVAE, MultiModalVAE, RNA2DNAVAE  # noqa: E402
@@ -46,6 +48,26 @@ for p in range(n_ph):
     f = lambda a, b: float((r[:, a] - r[:, b]).mean()) / 1e3
     if gemm:
         cols = f"{f(1, 0):6.2f} {f(3, 1):6.2f} {f(4, 3):6.2f} {f(5, 4):6.2f} {f(2, 5):6.2f} {f(6, 2):6.2f}"
+    elif name.value.decode() in ("ingest", "adamw"):
+        cols = f"{f(1, 0):6.2f} {f(2, 1):6.2f} {f(3, 2):6.2f} {f(4, 3):6.2f} {f(5 if name.value.decode() == 'ingest' else 4, 4):6.2f} {f(6, 5 if name.value.decode() == 'ingest' else 4):6.2f}"
     else:
         cols = f"{f(1, 0):6.2f} {'':6s} {'':6s} {'':6s} {f(6, 1):6.2f} {'':6s}"
     print(f"{name.value.decode():14s} {nu.value:5d} {(r[:, 0].min() - t0) / 1e3:7.2f} {(r[:, 6].max() - t0) / 1e3:7.2f} | {cols} | {f(6, 0):6.2f}")
+
+if os.environ.get("VLA_TL_UNITS"):
+    # per-unit rows of one phase: which = phase name; shows first vs later units on the same CTA
+    which = os.environ["VLA_TL_UNITS"]
+    for p in range(n_ph):
+        name = C.create_string_buffer(48)
+        nu, ub = C.c_int(), C.c_int()
+        L.vla_step_phase_info(tr.core.handle, p, name, C.byref(nu), C.byref(ub), None, None)
+        if name.value.decode() != which:
+            continue
+        r = t[ub.value:ub.value + nu.value]
+        G = 148
+        first = r[:min(G, nu.value)]
+        later = r[G:]
+        for lab, rr in (("first unit on its CTA", first), ("later units", later)):
+            if len(rr):
+                d = lambda a, b: float((rr[:, a] - rr[:, b]).mean()) / 1e3
+                print(f"{which} {lab:22s} n={len(rr):4d}: 1-0 {d(1,0):6.2f}  2-1 {d(2,1):6.2f}  3-2 {d(3,2):6.2f}  4-3 {d(4,3):6.2f}  5-4 {d(5,4):6.2f}  6-5 {d(6,5):6.2f}  total {d(6,0):6.2f}")

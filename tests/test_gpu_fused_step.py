@@ -61,7 +61,7 @@ def test_fused_steps_equal_separate_launches(kind, batch):
         if k.endswith("num_batches_tracked"):
             assert int(sd_fus[k]) == int(v) == 5
         elif k.endswith(("running_mean", "running_var")):
-            np.testing.assert_allclose(sd_fus[k], v, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sd_fus[k], v, rtol=1e-3, atol=1e-4)
         else:
             # Adam turns rounding-level gradient differences of near-zero gradients into +-lr steps
             assert np.abs(sd_fus[k] - v).max() <= 2 * 5e-4 * 5 + 1e-6, k
@@ -76,15 +76,19 @@ def test_fused_step_graph_replay_and_timeline():
     state = vo.init_state(kind, FULL, seed=4)
     m = make_module(kind, FULL, state).train()
     ds = DeviceDataset.synthetic(batch * 4, FULL["A"], FULL["B"], FULL["S"], "cuda", seed=1)
-    tr = Trainer(m, ds, batch, use_graph=True)
-    first = None
-    for i in range(12):
-        tr.step()
-        if i == 0:
-            first = tr.losses()[0]
-    last = tr.losses()
-    assert np.isfinite(last).all() and last[0] < first          # it trains
-    step_us, phases = tr.timeline()
+    os.environ["VLA_FUSED_STEP"] = "1"
+    try:
+        tr = Trainer(m, ds, batch, use_graph=True)
+        first = None
+        for i in range(12):
+            tr.step()
+            if i == 0:
+                first = tr.losses()[0]
+        last = tr.losses()
+        assert np.isfinite(last).all() and last[0] < first          # it trains
+        step_us, phases = tr.timeline()
+    finally:
+        os.environ.pop("VLA_FUSED_STEP", None)
     assert step_us > 0 and len(phases) >= 15
     names = [p["name"] for p in phases]
     assert names[0] == "ingest" and names[-1] == "adamw" and "wgrad_all" in names

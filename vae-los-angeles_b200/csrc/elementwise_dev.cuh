@@ -6,6 +6,7 @@
 // the eight epilogue warps of the CTA form the block and synchronise on a named barrier).
 // All arithmetic is fp32; reductions are deterministic (fixed-order partials, no float atomics).
 #pragma once
+#include "loss_math.cuh"
 #include "tc_ptx.cuh"
 #include "vla_internal.h"
 
@@ -15,6 +16,15 @@ namespace vla {
 
 constexpr int EW_THREADS = 256;
 constexpr int EW_SCRATCH_BYTES = 8 * 64 * 2 * 8 + 2 * 64 * 4;   // BatchNorm: double [8][64][2] + 2 x float [64] (largest user)
+
+// Optional progress stamps of thread 0 inside an element-wise unit of the whole-step kernel (slots 2..5 of its row).
+__device__ __forceinline__ void ew_stamp(unsigned long long* row, int slot, int tid) {
+  if (row != nullptr && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    row[slot] = t;
+  }
+}
 
 template <bool MEGA>
 __device__ __forceinline__ void ew_sync() {
@@ -66,6 +76,26 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int tid) {
 // ---------------------------------------------------------------------------------------------
 // ingest: fp32 inputs -> bf16 padded operands; embedding gather; one-hot; step counter
 // ---------------------------------------------------------------------------------------------
+// Site encoder input for rows [r_begin, r_end): gathered embedding rows and the one-hot operand of the embedding
+// gradient.  One element per thread and iteration (site and table loads of different rows are independent).
+__device__ __forceinline__ void ingest_site(const IngestArgs& a, int r_begin, int r_end, int t, int nthreads, long long row0) {
+  if (a.site == nullptr) return;
+  const int nrows = r_end - r_begin;
+  const int n_h = nrows * a.ld_hsite, n_o = nrows * a.ld_onehot;
+#pragma unroll 4
+  for (int i = t; i < n_h; i += nthreads) {
+    const int r = i / a.ld_hsite, c = i - r * a.ld_hsite;
+    const long long s = __ldg(a.site + row0 + r_begin + r);
+    a.h_site[static_cast<size_t>(r_begin + r) * a.ld_hsite + c] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
+  }
+#pragma unroll 4
+  for (int i = t; i < n_o; i += nthreads) {
+    const int r = i / a.ld_onehot, c = i - r * a.ld_onehot;
+    const long long s = __ldg(a.site + row0 + r_begin + r);
+    a.onehot[static_cast<size_t>(r_begin + r) * a.ld_onehot + c] = __float2bfloat16(s == c ? 1.f : 0.f);
+  }
+}
+
 // Rows [r_begin, r_end) are converted by `nwarps` warps of which this is number `gwarp` (one warp per row).
 __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, int r_end, int gwarp, int nwarps, int lane,
                                             bool first_thread) {
@@ -83,36 +113,105 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
     for (int r = r_begin + gwarp; r < r_end; r += nwarps) {    // one warp per row: no index division
       const float* sp = src + (row0 + r) * w;
       uint2* dp = reinterpret_cast<uint2*>(a.dst[e] + static_cast<size_t>(r) * a.ld_dst[e]);
-#pragma unroll 4
-      for (int qd = lane; qd < quads; qd += 32) {
-        const int c = qd * 4;
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-        if (vec_ok) {
-          if (c + 1 < w) { const float2 t = __ldg(reinterpret_cast<const float2*>(sp + c)); x0 = t.x; x1 = t.y; }
-          if (c + 3 < w) { const float2 t = __ldg(reinterpret_cast<const float2*>(sp + c + 2)); x2 = t.x; x3 = t.y; }
-        } else {
-          if (c < w) x0 = __ldg(sp + c);
-          if (c + 1 < w) x1 = __ldg(sp + c + 1);
-          if (c + 2 < w) x2 = __ldg(sp + c + 2);
-          if (c + 3 < w) x3 = __ldg(sp + c + 3);
+      for (int base = lane; base < quads; base += 128) {       // batches of four quads: all loads before the stores
+        float x[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = (base + 32 * k) * 4;
+          x[k][0] = x[k][1] = x[k][2] = x[k][3] = 0.f;
+          if (vec_ok) {
+            if (c + 1 < w) { const float2 t = __ldg(reinterpret_cast<const float2*>(sp + c)); x[k][0] = t.x; x[k][1] = t.y; }
+            if (c + 3 < w) { const float2 t = __ldg(reinterpret_cast<const float2*>(sp + c + 2)); x[k][2] = t.x; x[k][3] = t.y; }
+          } else {
+            if (c < w) x[k][0] = __ldg(sp + c);
+            if (c + 1 < w) x[k][1] = __ldg(sp + c + 1);
+            if (c + 2 < w) x[k][2] = __ldg(sp + c + 2);
+            if (c + 3 < w) x[k][3] = __ldg(sp + c + 3);
+          }
         }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(x0, x1), hi = __floats2bfloat162_rn(x2, x3);
-        uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&lo);
-        o.y = *reinterpret_cast<uint32_t*>(&hi);
-        dp[qd] = o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int qd = base + 32 * k;
+          if (qd < quads) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(x[k][0], x[k][1]), hi = __floats2bfloat162_rn(x[k][2], x[k][3]);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            dp[qd] = o;
+          }
+        }
       }
     }
   }
-  if (a.site != nullptr) {
-    for (int r = r_begin + gwarp; r < r_end; r += nwarps) {
-      const long long s = a.site[row0 + r];
-      for (int c = lane; c < a.ld_hsite; c += 32)
-        a.h_site[static_cast<size_t>(r) * a.ld_hsite + c] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
-      for (int c = lane; c < a.ld_onehot; c += 32)
-        a.onehot[static_cast<size_t>(r) * a.ld_onehot + c] = __float2bfloat16(s == c ? 1.f : 0.f);
+  ingest_site(a, r_begin, r_end, gwarp * 32 + lane, nwarps * 32, row0);
+}
+
+// Whole-step kernel: rows [r_begin, r_end) of every dense modality arrive in shared memory as ONE bulk copy each (the
+// rows of a unit are contiguous in the source), then are converted from there -- the unit keeps ~100 KB in flight with
+// a single issuing thread instead of a few hundred bytes per warp.  Falls back to ingest_body when the source block is
+// not 16-byte aligned or does not fit `stage_bytes`.  `bar` / `parity`: a CTA-local mbarrier used only here.
+template <bool MEGA>
+__device__ __forceinline__ void ingest_body_bulk(const IngestArgs& a, int r_begin, int r_end, int tid, bool first_unit,
+                                                 uint8_t* stage, uint32_t stage_bytes, uint64_t* bar, uint32_t parity,
+                                                 unsigned long long* dbg_row = nullptr) {
+  const int nrows = r_end - r_begin;
+  const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
+  uint32_t off[2] = {0u, 0u}, total = 0u;
+  bool ok = nrows > 0;
+  for (int e = 0; e < a.n; ++e) {
+    const uint32_t bytes = static_cast<uint32_t>(nrows) * a.width[e] * 4u;
+    const uintptr_t src = reinterpret_cast<uintptr_t>(a.src[e] + (row0 + r_begin) * a.width[e]);
+    off[e] = total;
+    total += (bytes + 127u) & ~127u;
+    ok = ok && (bytes % 16u == 0u) && (src % 16u == 0u);
+  }
+  ok = ok && total <= stage_bytes && a.n > 0;
+  if (!ok) {
+    if (tid == 0) mbar_arrive(bar);        // keep the barrier's phase in step with the caller's parity
+    ingest_body(a, r_begin, r_end, tid >> 5, EW_THREADS / 32, tid & 31, first_unit && tid == 0);
+    return;
+  }
+  if (tid == 0) {
+    uint32_t tx = 0;
+    for (int e = 0; e < a.n; ++e) tx += static_cast<uint32_t>(nrows) * a.width[e] * 4u;
+    mbar_expect_tx(bar, tx);
+    for (int e = 0; e < a.n; ++e)
+      bulk_load_1d(stage + off[e], a.src[e] + (row0 + r_begin) * a.width[e], static_cast<uint32_t>(nrows) * a.width[e] * 4u, bar);
+    if (a.bump_step && first_unit) {
+      a.dyn->step += 1;
+      a.dyn->b1pow *= static_cast<double>(a.beta1);
+      a.dyn->b2pow *= static_cast<double>(a.beta2);
     }
   }
+  ew_stamp(dbg_row, 2, tid);
+  ingest_site(a, r_begin, r_end, tid, EW_THREADS, row0);      // independent of the bulk copies: overlaps their latency
+  ew_stamp(dbg_row, 3, tid);
+  mbar_wait(bar, parity);
+  ew_stamp(dbg_row, 4, tid);
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int e = 0; e < a.n; ++e) {
+    const int w = a.width[e];
+    const int octs = a.ld_dst[e] >> 3;                         // ld_dst is a multiple of 8: 16-byte bf16 stores
+    const float* sbase = reinterpret_cast<const float*>(stage + off[e]);
+    for (int r = warp; r < nrows; r += EW_THREADS / 32) {
+      const float* sp = sbase + static_cast<size_t>(r) * w;
+      uint4* dp = reinterpret_cast<uint4*>(a.dst[e] + static_cast<size_t>(r_begin + r) * a.ld_dst[e]);
+#pragma unroll 4
+      for (int o = lane; o < octs; o += 32) {
+        const int c = o * 8;
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (c + k < w) ? sp[c + k] : 0.f;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]), b1 = __floats2bfloat162_rn(x[2], x[3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(x[4], x[5]), b3 = __floats2bfloat162_rn(x[6], x[7]);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+        v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+        dp[o] = v;
+      }
+    }
+  }
+  ew_stamp(dbg_row, 5, tid);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -128,10 +227,19 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ stats,
   const int lane = tid & 31, ty = tid >> 5;
   double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
   if (col_ok) {
-    for (int t = ty; t < m_tiles; t += 8) {
-      const float2 s0 = __ldcg(reinterpret_cast<const float2*>(stats + (static_cast<size_t>(t) * 2 + 0) * n + col));
-      const float2 s1 = __ldcg(reinterpret_cast<const float2*>(stats + (static_cast<size_t>(t) * 2 + 1) * n + col));
-      a0 += s0.x; a1 += s0.y; b0 += s1.x; b1 += s1.y;
+    for (int tb = ty; tb < m_tiles; tb += 32) {       // batches of 4 tiles: 8 independent loads in flight per thread
+      float2 s0[4], s1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = tb + 8 * k;
+        s0[k] = s1[k] = make_float2(0.f, 0.f);
+        if (t < m_tiles) {
+          s0[k] = __ldcg(reinterpret_cast<const float2*>(stats + (static_cast<size_t>(t) * 2 + 0) * n + col));
+          s1[k] = __ldcg(reinterpret_cast<const float2*>(stats + (static_cast<size_t>(t) * 2 + 1) * n + col));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a0 += s0[k].x; a1 += s0[k].y; b0 += s1[k].x; b1 += s1[k].y; }
     }
   }
   sh[ty][lane * 2][0] = a0; sh[ty][lane * 2 + 1][0] = a1;
@@ -237,8 +345,19 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
     const int row = row_first + 8 * i;
     if (row < row_end) do_row(row, xpf[i]);
   }
-  for (int row = row_first + 8 * PF; row < row_end; row += 8)
-    do_row(row, __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col)));
+  for (int rb = row_first + 8 * PF; rb < row_end; rb += 8 * PF) {      // further batches of PF rows: loads before the stores
+    float2 xb[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int row = rb + 8 * i;
+      xb[i] = row < row_end ? __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int row = rb + 8 * i;
+      if (row < row_end) do_row(row, xb[i]);
+    }
+  }
 }
 
 template <bool MEGA>
@@ -272,15 +391,27 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdArgs& a, int rows_per_blo
   const float c10 = a.train ? s_s1[lane * 2] * inv_n : 0.f, c11 = a.train ? s_s1[lane * 2 + 1] * inv_n : 0.f;
   const float c20 = a.train ? s_s2[lane * 2] * inv_n : 0.f, c21 = a.train ? s_s2[lane * 2 + 1] * inv_n : 0.f;
   const int row_end = min(a.rows, (by + 1) * rows_per_block);
-#pragma unroll 4
-  for (int row = by * rows_per_block + ty; row < row_end; row += 8) {
-    const float2 gy = __bfloat1622float2(
-        *reinterpret_cast<const __nv_bfloat162*>(a.gy + static_cast<size_t>(row) * a.ld_gy + col));
-    const float2 x = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
-    const float xh0 = (x.x - m0) * rs0, xh1 = (x.y - m1) * rs1;
-    const float o0 = g0 * (gy.x - c10 - xh0 * c20);
-    const float o1 = g1 * (gy.y - c11 - xh1 * c21);
-    *reinterpret_cast<__nv_bfloat162*>(a.gpre + static_cast<size_t>(row) * a.ld_gpre + col) = __floats2bfloat162_rn(o0, o1);
+  for (int rb = by * rows_per_block + ty; rb < row_end; rb += 32) {   // batches of four rows: all loads before the stores
+    float2 gy[4], x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = rb + 8 * k;
+      gy[k] = x[k] = make_float2(0.f, 0.f);
+      if (row < row_end) {
+        gy[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.gy + static_cast<size_t>(row) * a.ld_gy + col));
+        x[k] = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = rb + 8 * k;
+      if (row < row_end) {
+        const float xh0 = (x[k].x - m0) * rs0, xh1 = (x[k].y - m1) * rs1;
+        const float o0 = g0 * (gy[k].x - c10 - xh0 * c20);
+        const float o1 = g1 * (gy[k].y - c11 - xh1 * c21);
+        *reinterpret_cast<__nv_bfloat162*>(a.gpre + static_cast<size_t>(row) * a.ld_gpre + col) = __floats2bfloat162_rn(o0, o1);
+      }
+    }
   }
 }
 
@@ -367,24 +498,6 @@ __host__ __device__ inline LossGrid loss_grid(const LossArgs& a) {
   g.nb_c = a.logits ? ceil_div_ll(a.rows, LOSS_THREADS) : 0;
   g.nb_k = (a.mu && !a.kl_partials) ? ceil_div_ll(static_cast<long long>(a.rows) * a.L, LOSS_PER_BLOCK) : 0;
   return g;
-}
-
-template <bool BCE>
-__device__ __forceinline__ float loss_elem(float y, float t, float gs, float& g_out, float& g_logit) {
-  if (BCE) {
-    // lg2.approx-based logs (absolute error ~1e-7 per term, far below the 1e-5 relative budget of the summed loss)
-    const float ly = fmaxf(__logf(y), -100.0f);
-    const float l1 = fmaxf(__logf(1.0f - y), -100.0f);
-    const float yy = y * (1.0f - y);
-    g_out = __fdividef(y - t, fmaxf(yy, 1e-12f)) * gs;   // dL/dy (ATen's backward floor)
-    g_logit = g_out * yy;                           // dL/d(pre-sigmoid)
-    return -(t * ly + (1.0f - t) * l1);
-  } else {
-    const float d = y - t;
-    g_out = 2.0f * d * gs;
-    g_logit = g_out;
-    return d * d;
-  }
 }
 
 template <bool BCE>
@@ -597,5 +710,74 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
   }
 }
 
+// Whole-step kernel: chunks [c0, c1) of the table in batches of four, so that a thread has 16 independent 128-bit loads
+// in flight (the unit runs alone on its SM: memory-level parallelism has to come from the thread itself).
+__device__ __forceinline__ void adamw_unit(const AdamArgs& a, int c0, int c1, int tid, unsigned long long* dbg_row = nullptr) {
+  float lr = a.lr, wd = a.weight_decay, bc1 = a.bc1, inv_bc2s = a.inv_bc2_sqrt;
+  if (a.dyn) {
+    lr = a.dyn->lr; wd = a.dyn->weight_decay;
+    bc1 = static_cast<float>(1.0 - __ldcg(&a.dyn->b1pow));
+    inv_bc2s = static_cast<float>(1.0 / sqrt(1.0 - __ldcg(&a.dyn->b2pow)));
+  }
+  const float step_size = lr / bc1;
+  const float decay = 1.0f - lr * wd;
+  const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
+  const int e = 4 * tid;
+  for (int base = c0; base < c1; base += 4) {
+    AdamChunk ch[4];
+    bool fast[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool valid = base + k < c1;
+      ch[k] = a.chunks[valid ? base + k : c0];
+      fast[k] = valid && a.update && (ch[k].n - e >= 4);
+    }
+    float4 P[4], Gr[4], M[4], V[4];
+    ew_stamp(dbg_row, 2, tid);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (fast[k]) {
+        const long long gi = ch[k].offset + e;
+        P[k] = *reinterpret_cast<const float4*>(a.p + gi);
+        Gr[k] = *reinterpret_cast<const float4*>(a.g + gi);
+        M[k] = *reinterpret_cast<const float4*>(a.m + gi);
+        V[k] = *reinterpret_cast<const float4*>(a.v + gi);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (fast[k]) {
+        const long long gi = ch[k].offset + e;
+        float p[4] = {P[k].x, P[k].y, P[k].z, P[k].w}, g[4] = {Gr[k].x, Gr[k].y, Gr[k].z, Gr[k].w};
+        float m[4] = {M[k].x, M[k].y, M[k].z, M[k].w}, v[4] = {V[k].x, V[k].y, V[k].z, V[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          p[j] *= decay;
+          m[j] = b1 * m[j] + (1.0f - b1) * g[j];
+          v[j] = b2 * v[j] + (1.0f - b2) * g[j] * g[j];
+          p[j] -= step_size * __fdividef(m[j], sqrtf(v[j]) * inv_bc2s + eps);
+        }
+        *reinterpret_cast<float4*>(a.p + gi) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(a.m + gi) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(a.v + gi) = make_float4(v[0], v[1], v[2], v[3]);
+        if (a.zero_grad) *reinterpret_cast<float4*>(a.g + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch[k].shadow_off >= 0) {
+          const unsigned idx = static_cast<unsigned>(ch[k].first + e);
+          int r = static_cast<int>(idx / static_cast<unsigned>(ch[k].cols));
+          int c = static_cast<int>(idx - static_cast<unsigned>(r) * ch[k].cols);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a.shadow[ch[k].shadow_off + static_cast<long long>(r) * ch[k].ld_shadow + c] = __float2bfloat16(p[j]);
+            if (++c == ch[k].cols) { c = 0; ++r; }
+          }
+        }
+      } else if (base + k < c1) {
+        adamw_body(a, base + k, tid);                 // chunk tails and the refresh-only mode
+      }
+      if (k == 0) ew_stamp(dbg_row, 3, tid);
+    }
+    ew_stamp(dbg_row, 4, tid);
+  }
+}
 
 }  // namespace vla

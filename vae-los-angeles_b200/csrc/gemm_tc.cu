@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   pdl_wait();
   pdl_launch_dependents();
   if (threadIdx.x == 0 && grp.dbg) grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 2] = gtime();  // setup done, dependency resolved
-  gemm_tile<MODE, FEATS, false>(ctx, P, static_cast<int>(blockIdx.x) - P.tile_begin, NoDeps{});
+  gemm_tile<MODE, FEATS, false>(ctx, P, static_cast<int>(blockIdx.x) - P.tile_begin, NoDeps{}, &grp.tail);
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
@@ -73,6 +73,10 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
   if (g.dbg_flags & 0xFFFF00) smem = static_cast<size_t>(g.dbg_flags >> 8);   // test hook (only valid with dbg_flags & 2)
   if (mode == 0) {
     if (!(used & ~FEATS_FWD_PLAIN)) return launch_one<0, FEATS_FWD_PLAIN>(g, stream, smem);
+    if (used & GF_LOSS) {
+      if (used & ~FEATS_FWD_LOSS) return cudaErrorInvalidValue;
+      return launch_one<0, FEATS_FWD_LOSS>(g, stream, smem);
+    }
     return launch_one<0, FEATS_FWD_FULL>(g, stream, smem);
   }
   if (mode == 2) {

@@ -12,8 +12,11 @@
 // the global operands prefetched as 128-bit vectors, per-column statistics (BatchNorm forward and backward) by a
 // shuffle butterfly, 128-bit row stores; split-K partials go through a smem transpose so every red.add is coalesced.
 #pragma once
+#include "loss_math.cuh"
 #include "tc_ptx.cuh"
 #include "vla_internal.h"
+
+#include <cfloat>
 
 namespace vla {
 
@@ -31,7 +34,7 @@ constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-s
 constexpr int MAX_CHUNKS = GEMM_BN_MAX_TN / 32;
 constexpr int PART_BYTES = 2 * MAX_CHUNKS * 4 * 32 * 4;
 constexpr int BAR_OFFSET = PART_OFFSET + PART_BYTES;                 // mbarriers: full[S] | empty[S] | acc | dep | tmem slot
-constexpr int SMEM_USED = BAR_OFFSET + 128;
+constexpr int SMEM_USED = BAR_OFFSET + 128;            // barrier block: 13 mbarriers (the last one: element-wise bulk loads) + slot
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                         // slack for manual 1 KiB alignment
 constexpr int EPI_THREADS = GEMM_THREADS - 64;                       // 8 warps
 
@@ -40,10 +43,11 @@ static_assert(CHUNK_BYTES <= STAGE_BYTES, "epilogue patches must fit in one pipe
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
 static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
-static_assert((2 * GEMM_STAGES + 2) * 8 + 4 <= 128, "barrier block");
+static_assert((2 * GEMM_STAGES + 3) * 8 + 4 <= 128, "barrier block");
 
 constexpr int FEATS_FWD_PLAIN = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;                      // hidden decoder layers, heads
 constexpr int FEATS_FWD_FULL = FEATS_FWD_PLAIN | GF_SIGMOID | GF_COLSTATS;                         // + BatchNorm statistics / sigmoid
+constexpr int FEATS_FWD_LOSS = FEATS_FWD_PLAIN | GF_SIGMOID | GF_LOSS;                             // last decoder layers of a train step
 constexpr int FEATS_DGRAD_PLAIN = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;                              // decoder data gradients
 constexpr int FEATS_DGRAD_FULL = FEATS_DGRAD_PLAIN | GF_BNSTATS;                                   // + BatchNorm backward statistics
 constexpr int FEATS_WGRAD = GF_RED | GF_BIASGRAD;
@@ -90,12 +94,14 @@ struct TileCtx {
   uint32_t tmem_base;
   int stage; uint32_t phase;  // position in the shared-memory ring (producer and MMA roles advance identically)
   uint32_t tile_parity;       // parity of acc_bar / dep_bar for the tile in flight
+  uint32_t ew_parity;         // parity of the element-wise bulk-load barrier
   unsigned long long* dbg;    // optional [.][8] globaltimer stamps
   int dbg_row;
   int dbg_flags;              // test hook: 1 = skip epilogue stores, 2 = skip main loop, ...
 };
 
 __device__ __forceinline__ uint64_t* tile_bars(uint8_t* smem) { return reinterpret_cast<uint64_t*>(smem + BAR_OFFSET); }
+__device__ __forceinline__ uint64_t* tile_ew_bar(uint8_t* smem) { return tile_bars(smem) + 2 * GEMM_STAGES + 2; }
 
 // One-time CTA setup shared by both kernels: barriers, bf16 ones for the bias-gradient MMA, TMEM.
 // Ends with a CTA-wide barrier; returns the context with the ring at its origin.
@@ -106,7 +112,8 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
   uint64_t* acc_bar = empty_bar + GEMM_STAGES;
   uint64_t* dep_bar = acc_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dep_bar + 1);
+  uint64_t* ew_bar = dep_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ew_bar + 1);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) {
@@ -115,6 +122,7 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
     }
     mbar_init(acc_bar, 1);
     mbar_init(dep_bar, 1);
+    mbar_init(ew_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1 && alloc_tmem) tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
@@ -128,7 +136,7 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
   __syncthreads();
   tc_fence_after();
   c.tmem_base = alloc_tmem ? *tmem_slot : 0u;
-  c.stage = 0; c.phase = 0; c.tile_parity = 0;
+  c.stage = 0; c.phase = 0; c.tile_parity = 0; c.ew_parity = 0;
   c.dbg = nullptr; c.dbg_row = 0; c.dbg_flags = 0;
   return c;
 }
@@ -145,7 +153,8 @@ struct NoDeps {
 // warps' reads of BatchNorm statistics through dep_bar.  All threads of the CTA call this; on return the tile's global
 // writes have been issued by the epilogue threads (the caller orders them: barrier + fence) and ctx has advanced.
 template <int MODE, int FEATS, bool MEGA, class Deps>
-__device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc, int local, const Deps& deps) {
+__device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc, int local, const Deps& deps,
+                                          const LossTail* tail_desc = nullptr) {
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
@@ -162,11 +171,17 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     float mask_scale;
     const float* bias; float* out_f32; bf16* out_bf16; const bf16* mask_src; const float* pre; const float* mean;
     const float* rstd; float* stats; float* bias_grad;
+    const float* aux0; const float* aux1; const long long* aux_site; float* aux_partials; const DynParams* dyn;
+    int aux_n, loss_kind; float aux_scale;
   } P;
   P.M = Pd.M; P.N = Pd.N; P.K = Pd.K; P.BN = Pd.BN; P.m_tiles = Pd.m_tiles; P.n_tiles = Pd.n_tiles;
   P.kb_per_split = Pd.kb_per_split; P.flags = Pd.flags; P.ld_f32 = Pd.ld_f32; P.ld_bf16 = Pd.ld_bf16; P.ld_mask = Pd.ld_mask;
   P.ld_pre = Pd.ld_pre; P.mask_scale = Pd.mask_scale; P.bias = Pd.bias; P.out_f32 = Pd.out_f32; P.out_bf16 = Pd.out_bf16;
   P.mask_src = Pd.mask_src; P.pre = Pd.pre; P.mean = Pd.mean; P.rstd = Pd.rstd; P.stats = Pd.stats; P.bias_grad = Pd.bias_grad;
+  if (FEATS & GF_LOSS) {
+    P.aux0 = Pd.aux0; P.aux1 = Pd.aux1; P.aux_site = Pd.aux_site; P.aux_partials = Pd.aux_partials; P.dyn = Pd.dyn;
+    P.aux_n = Pd.aux_n; P.loss_kind = Pd.loss_kind; P.aux_scale = Pd.aux_scale;
+  }
   const CUtensorMap* tmA = &Pd.tmA;
   const CUtensorMap* tmB = &Pd.tmB;
   const int n_tile = local % P.n_tiles;
@@ -293,6 +308,10 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     const bool f32_vec = ((reinterpret_cast<uintptr_t>(P.out_f32) & 15) == 0) && ((P.ld_f32 & 3) == 0);
     const bool bf16_vec = ((reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0) && ((P.ld_bf16 & 7) == 0);
 
+    float loss_acc = 0.f;                                // GF_LOSS: this thread's share of the loss value
+    long long tgt_row0 = 0;
+    if ((FEATS & GF_LOSS) && (flags & GF_LOSS) && P.aux_n > 1) tgt_row0 = static_cast<long long>(P.dyn->batch_index % P.aux_n) * P.M;
+
     for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
       const int col0 = n0 + c * 32;
       const int nvalid = min(32, P.N - col0);          // <= 0: nothing to store (tile padding)
@@ -384,9 +403,10 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if ((flags & GF_SIGMOID) && !(dbgf & 32)) {
+      const bool bce_fused = (FEATS & GF_LOSS) && (flags & GF_LOSS) && P.loss_kind == LOSS_BCE;
+      if ((flags & GF_SIGMOID) && !(dbgf & 32) && !(bce_fused && !(flags & GF_OUT_F32))) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);      // (a fused BCE loss works on the pre-sigmoid value)
       }
       if (nvalid <= 0) continue;
       if (dbgf & 8) {            // test hook: keep the math alive, skip patch + global stores
@@ -425,6 +445,83 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
               if (rbase + i < P.M) P.out_f32[static_cast<size_t>(rbase + i) * P.ld_f32 + col0 + lane] = patch[i * PATCH_LD + lane];
           }
         }
+        if ((FEATS & GF_LOSS) && (flags & GF_LOSS)) {
+          // v holds the model output of this row chunk.  Loss value into loss_acc, dL/d(pre-activation) into v (then
+          // stored as the bf16 operand of the backward GEMMs).  losses.py:27-42; directional_losses.py:23-24, 48-49.
+          __syncwarp();
+          if (P.loss_kind == LOSS_CE) {
+            // weighted cross-entropy: the whole logit row (N <= 32) is in this thread
+            float mx = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) mx = fmaxf(mx, v[j]);
+            float se = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) se += expf(v[j] - mx);
+            const float lse = logf(se) + mx;
+            const int t = row_ok ? static_cast<int>(P.aux_site[tgt_row0 + row]) : 0;
+            const float w = P.aux1 ? P.aux1[t] : 1.0f;
+            const float gamma = P.dyn ? P.dyn->gamma : P.aux_scale;
+            float xt = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j == t) xt = v[j];
+              v[j] = (expf(v[j] - lse) - (j == t ? 1.0f : 0.0f)) * (w * gamma);
+            }
+            if (row_ok) loss_acc += -w * (xt - lse);
+          } else {
+            // targets: coalesced row reads (all 32 in flight) -> patch -> this thread's row
+            {
+              float tv[32];
+              const float* tp = P.aux0 + (tgt_row0 + rbase) * P.N + col0 + lane;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                tv[i] = 0.f;
+                if (rbase + i < P.M && lane < nvalid) tv[i] = __ldg(tp + static_cast<size_t>(i) * P.N);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) patch[i * PATCH_LD + lane] = tv[i];
+            }
+            __syncwarp();
+            float tg[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q4 = *reinterpret_cast<const float4*>(patch + lane * PATCH_LD + i * 4);
+              tg[4 * i] = q4.x; tg[4 * i + 1] = q4.y; tg[4 * i + 2] = q4.z; tg[4 * i + 3] = q4.w;
+            }
+            __syncwarp();
+            float part = 0.f;
+            if (P.loss_kind == LOSS_BCE && !(flags & GF_OUT_F32)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {                      // v = pre-sigmoid value
+                float y, g1;
+                const float l = bce_from_logit(v[j], tg[j], y, g1);
+                part += (j < nvalid) ? l : 0.f;
+                v[j] = g1;
+              }
+            } else if (P.loss_kind == LOSS_BCE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {                      // v = sigmoid output (also stored as fp32 above)
+                float g0, g1;
+                const float l = loss_elem<true>(v[j], tg[j], 1.0f, g0, g1);
+                part += (j < nvalid) ? l : 0.f;
+                v[j] = g1;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float g0, g1;
+                const float l = loss_elem<false>(v[j], tg[j], 1.0f, g0, g1);
+                part += (j < nvalid) ? l : 0.f;
+                v[j] = g1;
+              }
+            }
+            if (row_ok) loss_acc += part;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(patch + lane * PATCH_LD + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+        }
         if (flags & GF_OUT_BF16) {
           if (full && bf16_vec) {
 #pragma unroll
@@ -452,6 +549,50 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
       __syncwarp();
     }
     if (MEGA && et == 0) VLA_STAMP(2);                             // first epilogue warp: chunks stored
+    if ((FEATS & GF_LOSS) && (flags & GF_LOSS)) {
+      // ---- loss partials of this tile, ticket, and (last tile of the step) the fixed-order final reduction ----
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+      if (lane == 0) P.aux_partials[static_cast<size_t>(local) * 8 + (warp - 2)] = loss_acc;
+      int* s_flag = reinterpret_cast<int*>(part);                  // column-stat scratch is unused by loss tiles
+      double* dsh = reinterpret_cast<double*>(part + 8);
+      named_bar_sync(3, EPI_THREADS);
+      const LossTail T = *tail_desc;
+      if (et == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(T.counter, 1u);
+        *s_flag = (ticket == static_cast<unsigned int>(T.total_tickets) - 1u) ? 1 : 0;
+      }
+      named_bar_sync(3, EPI_THREADS);
+      if (*s_flag) {
+        __threadfence();
+        const int starts[4] = {0, T.n_mse, T.n_mse + T.n_bce, T.n_mse + T.n_bce + T.n_ce};
+        double sums[4] = {0, 0, 0, 0};                             // mse, bce, ce, kl
+        for (int role = 0; role < 4; ++role) {
+          double sacc = 0;
+          if (role < 3) { for (int i = starts[role] + et; i < starts[role + 1]; i += EPI_THREADS) sacc += __ldcg(T.partials + i); }
+          else          { for (int i = et; i < T.n_kl; i += EPI_THREADS) sacc += __ldcg(T.kl_partials + i); }
+          dsh[et] = sacc;
+          named_bar_sync(3, EPI_THREADS);
+          for (int o = EPI_THREADS / 2; o > 0; o >>= 1) {
+            if (et < o) dsh[et] += dsh[et + o];
+            named_bar_sync(3, EPI_THREADS);
+          }
+          sums[role] = dsh[0];
+          named_bar_sync(3, EPI_THREADS);
+        }
+        if (et == 0) {
+          const double beta = T.dyn->beta_kl, gamma = T.dyn->gamma;
+          const double recon = sums[0] + sums[1];
+          T.out[0] = static_cast<float>(recon + gamma * sums[2] + beta * sums[3]);
+          T.out[1] = static_cast<float>(recon);
+          T.out[2] = static_cast<float>(sums[2]);
+          T.out[3] = static_cast<float>(sums[3]);
+          *T.counter = 0u;                                         // re-arm for the next step (graph replays)
+          if (T.dyn_bump) T.dyn_bump->batch_index += 1;
+        }
+      }
+    }
     if (bias_mma && half == 0) {
       uint32_t r1[1];
       tmem_ld1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + GEMM_BIAS_TMEM_COL, r1);

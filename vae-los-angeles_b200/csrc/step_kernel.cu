@@ -43,7 +43,7 @@ __host__ __device__ inline void loss_block_rows(const LossGrid& G, int rows, int
 
 __host__ __device__ inline void unit_rows(const StepPhase& ph, const void* args, int u, int* r0, int* r1) {
   switch (ph.kind) {
-    case SK_GEMM_NT_PLAIN: case SK_GEMM_NT_FULL: case SK_GEMM_NN_PLAIN: case SK_GEMM_NN_FULL: {
+    case SK_GEMM_NT_PLAIN: case SK_GEMM_NT_FULL: case SK_GEMM_NT_LOSS: case SK_GEMM_NN_PLAIN: case SK_GEMM_NN_FULL: {
       const GemmProblem* P = find_problem(static_cast<const GemmGroup*>(args), u);
       const int local = u - P->tile_begin;
       const int m_tile = (local / P->n_tiles) % P->m_tiles;
@@ -140,37 +140,54 @@ __device__ __forceinline__ UnitDeps make_deps(const StepPlan& pl, const StepPhas
 // Separate functions (not inlined): each GEMM variant keeps its own register allocation for the epilogue hot loop; the
 // walker's state is saved around the call once per unit.
 template <int MODE, int FEATS>
-__device__ __noinline__ void gemm_unit(TileCtx& ctx, const GemmProblem& P, int local, const UnitDeps& deps) {
-  gemm_tile<MODE, FEATS, true>(ctx, P, local, deps);
+__device__ __noinline__ void gemm_unit(TileCtx& ctx, const GemmProblem& P, int local, const UnitDeps& deps, const LossTail* tail) {
+  gemm_tile<MODE, FEATS, true>(ctx, P, local, deps, tail);
 }
 
-__device__ __noinline__ void ew_unit(const StepPhase& ph, const void* args, int u, int r0, int r1, int tid, int lane) {
-  void* scratch = aligned_smem() + SCRATCH_OFFSET;
-  switch (ph.kind) {
-    case SK_INGEST:
-      ingest_body(*static_cast<const IngestArgs*>(args), r0, r1, tid >> 5, EW_THREADS / 32, lane, u == 0 && tid == 0);
+// The argument structs live in global memory (the plan image).  Every unit works on a by-value copy: field reads then
+// come from registers instead of being re-fetched after each global store (the stores could alias the struct).
+__device__ __noinline__ void ew_unit(const StepPhase& ph_s, const void* args, int u, int r0, int r1, int tid, uint32_t ew_parity,
+                                   unsigned long long* dbg_row) {
+  uint8_t* smem = aligned_smem();
+  void* scratch = smem + SCRATCH_OFFSET;
+  const int kind = ph_s.kind, sub = ph_s.sub, n_blocks = ph_s.n_blocks, gx = ph_s.gx, rpb = ph_s.rpb;
+  const int b0 = u * sub, b1 = min((u + 1) * sub, n_blocks);
+  switch (kind) {
+    case SK_INGEST: {
+      const IngestArgs a = *static_cast<const IngestArgs*>(args);
+      // staging area: the GEMM operand ring (idle during element-wise units)
+      ingest_body_bulk<true>(a, r0, r1, tid, u == 0, smem, GEMM_STAGES * STAGE_BYTES, tile_ew_bar(smem), ew_parity, dbg_row);
       break;
-    case SK_BN_ACT:
-      bn_act_body<true>(*static_cast<const BnActArgs*>(args), ph.rpb, u % ph.gx, u / ph.gx, tid, scratch);
+    }
+    case SK_BN_ACT: {
+      const BnActArgs a = *static_cast<const BnActArgs*>(args);
+      bn_act_body<true>(a, rpb, u % gx, u / gx, tid, scratch);
       break;
-    case SK_BN_BWD:
-      bn_bwd_body<true>(*static_cast<const BnBwdArgs*>(args), ph.rpb, u % ph.gx, u / ph.gx, tid, scratch);
+    }
+    case SK_BN_BWD: {
+      const BnBwdArgs a = *static_cast<const BnBwdArgs*>(args);
+      bn_bwd_body<true>(a, rpb, u % gx, u / gx, tid, scratch);
       break;
-    case SK_LATENT_FWD:
-      for (int b = u * ph.sub; b < min((u + 1) * ph.sub, ph.n_blocks); ++b)
-        latent_fwd_body<true>(*static_cast<const LatentFwdArgs*>(args), b, tid, scratch);
+    }
+    case SK_LATENT_FWD: {
+      const LatentFwdArgs a = *static_cast<const LatentFwdArgs*>(args);
+      for (int b = b0; b < b1; ++b) latent_fwd_body<true>(a, b, tid, scratch);
       break;
-    case SK_LATENT_BWD:
-      for (int b = u * ph.sub; b < min((u + 1) * ph.sub, ph.n_blocks); ++b)
-        latent_bwd_body(*static_cast<const LatentBwdArgs*>(args), b, tid);
+    }
+    case SK_LATENT_BWD: {
+      const LatentBwdArgs a = *static_cast<const LatentBwdArgs*>(args);
+      for (int b = b0; b < b1; ++b) latent_bwd_body(a, b, tid);
       break;
-    case SK_LOSS:
-      for (int b = u * ph.sub; b < min((u + 1) * ph.sub, ph.n_blocks); ++b)
-        loss_body<true>(*static_cast<const LossArgs*>(args), b, ph.n_blocks, tid, scratch);
+    }
+    case SK_LOSS: {
+      const LossArgs a = *static_cast<const LossArgs*>(args);
+      for (int b = b0; b < b1; ++b) loss_body<true>(a, b, n_blocks, tid, scratch);
       break;
-    default:   // SK_ADAMW
-      for (int b = u * ph.sub; b < min((u + 1) * ph.sub, ph.n_blocks); ++b)
-        adamw_body(*static_cast<const AdamArgs*>(args), b, tid);
+    }
+    default: {   // SK_ADAMW
+      const AdamArgs a = *static_cast<const AdamArgs*>(args);
+      adamw_unit(a, b0, b1, tid, dbg_row);
+    }
   }
 }
 
@@ -204,14 +221,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const StepPlan* _
       unit_rows(ph, args, u, &r0, &r1);
       const UnitDeps deps = make_deps(pl, ph, r0, r1);
       if (ph.kind <= SK_GEMM_TN) {
-        const GemmProblem& P = *find_problem(static_cast<const GemmGroup*>(args), u);
+        const GemmGroup* grp = static_cast<const GemmGroup*>(args);
+        const GemmProblem& P = *find_problem(grp, u);
         const int local = u - P.tile_begin;
+        const LossTail* tail = &grp->tail;
         switch (ph.kind) {
-          case SK_GEMM_NT_PLAIN: gemm_unit<0, FEATS_FWD_PLAIN>(ctx, P, local, deps); break;
-          case SK_GEMM_NT_FULL:  gemm_unit<0, FEATS_FWD_FULL>(ctx, P, local, deps); break;
-          case SK_GEMM_NN_PLAIN: gemm_unit<2, FEATS_DGRAD_PLAIN>(ctx, P, local, deps); break;
-          case SK_GEMM_NN_FULL:  gemm_unit<2, FEATS_DGRAD_FULL>(ctx, P, local, deps); break;
-          default:               gemm_unit<1, FEATS_WGRAD>(ctx, P, local, deps); break;
+          case SK_GEMM_NT_PLAIN:  gemm_unit<0, FEATS_FWD_PLAIN>(ctx, P, local, deps, tail); break;
+          case SK_GEMM_NT_FULL:   gemm_unit<0, FEATS_FWD_FULL>(ctx, P, local, deps, tail); break;
+          case SK_GEMM_NT_LOSS:   gemm_unit<0, FEATS_FWD_LOSS>(ctx, P, local, deps, tail); break;
+          case SK_GEMM_NN_PLAIN:  gemm_unit<2, FEATS_DGRAD_PLAIN>(ctx, P, local, deps, tail); break;
+          case SK_GEMM_NN_FULL:   gemm_unit<2, FEATS_DGRAD_FULL>(ctx, P, local, deps, tail); break;
+          default:                gemm_unit<1, FEATS_WGRAD>(ctx, P, local, deps, tail); break;
         }
       } else if (warp >= 2) {
         // element-wise unit: the eight epilogue warps are the 256-thread block
@@ -219,8 +239,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const StepPlan* _
         if (warp == 2) deps.wait(lane);
         ew_sync<true>();
         if (tid == 0 && ctx.dbg) ctx.dbg[static_cast<size_t>(ctx.dbg_row) * 8 + 1] = gtime();
-        ew_unit(ph, args, u, r0, r1, tid, lane);
+        ew_unit(ph, args, u, r0, r1, tid, ctx.ew_parity, ctx.dbg ? ctx.dbg + static_cast<size_t>(ctx.dbg_row) * 8 : nullptr);
       }
+      if (ph.kind == SK_INGEST) ctx.ew_parity ^= 1u;     // every thread tracks the bulk-load barrier's phase
       // ---- unit boundary: order this unit's shared-memory / TMEM use before the next unit, then publish ----
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes (patches) before later TMA writes
       tc_fence_before();

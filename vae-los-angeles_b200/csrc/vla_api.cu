@@ -119,6 +119,7 @@ struct vla_model {
   AdamChunk* chunks_d = nullptr;
   DynParams* dyn = nullptr;
   float* loss_partials = nullptr; unsigned int* loss_counter = nullptr; float* loss_out = nullptr;
+  float* eloss_partials = nullptr;   // partial sums of the loss-fused decoder epilogues
   // workspace sized for `cap` rows
   int cap = 0;
   char* ws = nullptr;
@@ -173,6 +174,13 @@ void free_steps(vla_model* m) {
   m->last_step = nullptr;
 }
 
+// BatchNorm units of the whole-step kernel: one round over the grid (<= 148 units), at least the stand-alone block height.
+int fused_bn_rpb(int rows, int gx, int base_rpb) {
+  const int gy_max = std::max(1, 148 / std::max(gx, 1));
+  const int rpb = std::max(base_rpb, ceil_div(rows, gy_max));
+  return (rpb + 7) & ~7;
+}
+
 // Adds one phase.  dep_mode: DEP_CHAIN = wait (ROW) for the frontier and become the frontier; DEP_BN_SIBLING = wait for ALL
 // units of the latest GEMM phase, join the siblings that replace the frontier once the next ordinary phase arrives;
 // DEP_ALL = wait for ALL units of every frontier phase.  extra_all >= 0 adds an ALL dependency on that phase.
@@ -220,8 +228,8 @@ void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
               (out_b + ((p.flags & GF_OUT_BF16) ? 2.0 : 0.0)) * p.M * p.N;
   }
 }
-int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStream_t st) {
-  if (mode != 1) { int rc0 = finalize_group(m, g, mode); if (rc0) return rc0; }
+int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStream_t st, bool finalized = false) {
+  if (mode != 1 && !finalized) { int rc0 = finalize_group(m, g, mode); if (rc0) return rc0; }
   for (int i = 0; i < g.nprob; ++i) {
     const GemmProblem& p = g.p[i];
     if ((p.flags & GF_MASK) && ((p.N & 31) || (p.ld_mask & 7) || (reinterpret_cast<uintptr_t>(p.mask_src) & 15)))
@@ -234,7 +242,7 @@ int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStrea
     int used = 0;
     for (int i = 0; i < g.nprob; ++i) used |= g.p[i].flags;
     int kind = SK_GEMM_TN;
-    if (mode == 0) kind = (used & ~FEATS_FWD_PLAIN_HOST) ? SK_GEMM_NT_FULL : SK_GEMM_NT_PLAIN;
+    if (mode == 0) kind = (used & GF_LOSS) ? SK_GEMM_NT_LOSS : ((used & ~FEATS_FWD_PLAIN_HOST) ? SK_GEMM_NT_FULL : SK_GEMM_NT_PLAIN);
     if (mode == 2) kind = (used & ~FEATS_DGRAD_PLAIN_HOST) ? SK_GEMM_NN_FULL : SK_GEMM_NN_PLAIN;
     rec_phase(m, kind, name, &g, sizeof(g), g.total_tiles, DEP_CHAIN, fl, by);
     return VLA_OK;
@@ -436,6 +444,9 @@ void carve(vla_model* m, Bump& b, int cap) {
   }
   const int lg = loss_grid_size(cap, m->cfg.dim_a, m->cfg.dim_b, m->S);
   m->loss_partials = b.take<float>(lg);
+  size_t ep = 0;
+  for (const Dec& d : m->decs) ep += static_cast<size_t>(mt) * ceil_div(d.out_dim, 32) * 8;
+  m->eloss_partials = b.take<float>(ep + 8);
 }
 
 int reserve(vla_model* m, int batch) {
@@ -629,6 +640,10 @@ struct FwdIO {
   bool engine;       // train step: dyn-driven Philox offsets / step bump
   int n_batches;     // train step over a resident dataset
   float beta1, beta2;
+  // train step: the last decoder layers also produce the loss partials and dL/d(pre-activation) (no separate loss pass)
+  bool fuse_loss = false;
+  const float* tgt_a = nullptr; const float* tgt_b = nullptr; const long long* tgt_site = nullptr;
+  const float* class_w = nullptr; float* loss_out = nullptr;
 };
 
 int present_mask(const vla_model* m, const FwdIO& io) {
@@ -682,8 +697,10 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches; a.beta1 = io.beta1; a.beta2 = io.beta2;
     { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * (4.0 * a.width[e] + 2.0 * a.ld_dst[e]);
       if (m->rec) {
-        StepPhase* ph = rec_phase(m, SK_INGEST, "ingest", &a, sizeof(a), ceil_div(B, 32), DEP_CHAIN, 0, by);
-        if (ph) { ph->rpb = 32; m->rec->ph_ingest = m->rec->plan.n_phases - 1; }
+        const char* env_rpb = getenv("VLA_INGEST_RPB");           // experiment hook: rows per ingest unit
+        const int rpu = env_rpb ? std::max(1, atoi(env_rpb)) : 32;
+        StepPhase* ph = rec_phase(m, SK_INGEST, "ingest", &a, sizeof(a), ceil_div(B, rpu), DEP_CHAIN, 0, by);
+        if (ph) { ph->rpb = rpu; m->rec->ph_ingest = m->rec->plan.n_phases - 1; }
       } else { ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); } }
   }
   const int mt = ceil_div(B, GEMM_BM);
@@ -728,7 +745,8 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
       if (m->rec) {
-        const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0), gx = ceil_div(a.n, 64), gy = ceil_div(a.rows, rpb);
+        const int gx = ceil_div(a.n, 64), rpb = fused_bn_rpb(a.rows, gx, bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0));
+        const int gy = ceil_div(a.rows, rpb);
         StepPhase* ph = rec_phase(m, SK_BN_ACT, "bn_act", &a, sizeof(a), gx * gy, DEP_BN_SIBLING, 0, 6.0 * B * bn.n);
         if (ph) { ph->rpb = rpb; ph->gx = gx; }
       } else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
@@ -765,6 +783,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
   }
   size_t max_rest = 0;
   for (const Dec& d : m->decs) max_rest = std::max(max_rest, d.rest.size());
+  std::vector<GemmGroup> dec_groups;
   for (size_t r = 0; r < max_rest; ++r) {
     GemmGroup g; init_group(g);
     for (size_t i = 0; i < m->decs.size(); ++i) {
@@ -777,17 +796,53 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       const bool last = r + 1 == d.rest.size();
       if (last) {
         const int slot = d.type == 'A' ? 0 : (d.type == 'B' ? 1 : 2);
-        float* dst = io.recon[slot] ? io.recon[slot] : w.recon;
-        const int flags = GF_BIAS | GF_OUT_F32 | (d.type == 'B' ? GF_SIGMOID : 0);
-        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
-        p->bias = P + l.b_off; p->out_f32 = dst; p->ld_f32 = l.out;
+        if (io.fuse_loss) {
+          // output -> loss partials + bf16 dL/d(pre-activation); the fp32 output is written only if the caller wants it
+          const int flags = GF_BIAS | GF_LOSS | GF_OUT_BF16 | (io.recon[slot] ? GF_OUT_F32 : 0) | (d.type == 'B' ? GF_SIGMOID : 0);
+          if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+          p->bias = P + l.b_off; p->out_f32 = io.recon[slot]; p->ld_f32 = l.out;
+          p->out_bf16 = w.g_out; p->ld_bf16 = w.ld_gout;
+          p->loss_kind = d.type == 'A' ? LOSS_MSE : (d.type == 'B' ? LOSS_BCE : LOSS_CE);
+          p->aux0 = d.type == 'A' ? io.tgt_a : (d.type == 'B' ? io.tgt_b : nullptr);
+          p->aux1 = d.type == 'C' ? io.class_w : nullptr;
+          p->aux_site = d.type == 'C' ? io.tgt_site : nullptr;
+          p->aux_n = io.n_batches; p->dyn = m->dyn;
+        } else {
+          float* dst = io.recon[slot] ? io.recon[slot] : w.recon;
+          const int flags = GF_BIAS | GF_OUT_F32 | (d.type == 'B' ? GF_SIGMOID : 0);
+          if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+          p->bias = P + l.b_off; p->out_f32 = dst; p->ld_f32 = l.out;
+        }
       } else {
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p))) return rc;
         p->bias = P + l.b_off; p->out_bf16 = w.act[r]; p->ld_bf16 = l.out;
       }
     }
-    if (g.nprob && (rc = timed_gemm(m, g, 0, r == 0 ? "gemm_dec_l1" : "gemm_dec_l2", st))) return rc;
+    if (g.nprob) {
+      if ((rc = finalize_group(m, g, 0))) return rc;
+      dec_groups.push_back(g);
+    }
   }
+  if (io.fuse_loss) {
+    // partial-sum layout [mse | bce | ce] and the ticket count of the final reduction, shared by every loss launch
+    LossTail T{};
+    int tiles[4] = {0, 0, 0, 0};
+    for (const GemmGroup& g : dec_groups)
+      for (int i = 0; i < g.nprob; ++i)
+        if (g.p[i].flags & GF_LOSS) tiles[g.p[i].loss_kind] += g.p[i].m_tiles * g.p[i].n_tiles;
+    T.counter = m->loss_counter; T.total_tickets = tiles[LOSS_MSE] + tiles[LOSS_BCE] + tiles[LOSS_CE];
+    T.n_mse = 8 * tiles[LOSS_MSE]; T.n_bce = 8 * tiles[LOSS_BCE]; T.n_ce = 8 * tiles[LOSS_CE];
+    T.partials = m->eloss_partials; T.kl_partials = m->kl_partials; T.n_kl = m->kl_grid;
+    T.out = io.loss_out; T.dyn = m->dyn; T.dyn_bump = m->dyn;
+    const int base[4] = {0, 0, T.n_mse, T.n_mse + T.n_bce};
+    for (GemmGroup& g : dec_groups) {
+      g.tail = T;
+      for (int i = 0; i < g.nprob; ++i)
+        if (g.p[i].flags & GF_LOSS) g.p[i].aux_partials = m->eloss_partials + base[g.p[i].loss_kind];
+    }
+  }
+  for (size_t r = 0; r < dec_groups.size(); ++r)
+    if ((rc = timed_gemm(m, dec_groups[r], 0, r == 0 ? "gemm_dec_l1" : "gemm_dec_l2", st, true))) return rc;
   m->saved = true; m->saved_batch = B; m->saved_present = present; m->saved_train = io.train;
   m->generation++;
   return VLA_OK;
@@ -859,6 +914,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       if (!active[i] && m->rec) m->rec->why = "inactive decoder";
       else if (!active[i])
         CK(cudaMemset2DAsync(m->g_d0 + m->decs[i].cat_off, sizeof(bf16) * m->cat.out, 0, sizeof(bf16) * m->decs[i].cat_w, B, st));
+  int n_present = 0;
+  for (size_t i = 0; i < m->encs.size(); ++i) n_present += present >> i & 1;
   if (any_dec) {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
@@ -867,8 +924,6 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     if ((rc = timed_gemm(m, g, 2, "dgrad_dec_l0", st))) return rc;
   }
   // ---- latent ----
-  int n_present = 0;
-  for (size_t i = 0; i < m->encs.size(); ++i) n_present += present >> i & 1;
   {
     LatentBwdArgs a{};
     a.gz = any_dec ? m->gz : nullptr; a.ld_gz = L;
@@ -925,7 +980,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
       if (m->rec) {
-        const int rpb = bn_rows_per_block(a.rows, a.m_tiles), gx = ceil_div(a.n, 64), gy = ceil_div(a.rows, rpb);
+        const int gx = ceil_div(a.n, 64), rpb = fused_bn_rpb(a.rows, gx, bn_rows_per_block(a.rows, a.m_tiles));
+        const int gy = ceil_div(a.rows, rpb);
         StepPhase* ph = rec_phase(m, SK_BN_BWD, "bn_bwd", &a, sizeof(a), gx * gy, DEP_BN_SIBLING, 0, 8.0 * B * bn.n);
         if (ph) { ph->rpb = rpb; ph->gx = gx; }
       } else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
@@ -1183,10 +1239,18 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
                      true, st);
   io.n_batches = a->dataset_rows > a->batch ? static_cast<int>(a->dataset_rows / a->batch) : 1;
   io.beta1 = a->beta1; io.beta2 = a->beta2;
+  // loss fused into the last decoder layers' epilogues (the CE term needs the whole logit row in one 32-column chunk)
+  io.fuse_loss = m->S <= 32;
+  for (const Dec& d : m->decs) {
+    if (d.type == 'A' && !a->x_a) return fail(VLA_ERR_INVALID, "x_a (target) missing");
+    if (d.type == 'B' && !a->x_b) return fail(VLA_ERR_INVALID, "x_b (target) missing");
+    if (d.type == 'C' && !a->site) return fail(VLA_ERR_INVALID, "site (target) missing");
+  }
+  io.tgt_a = a->x_a; io.tgt_b = a->x_b; io.tgt_site = a->site; io.class_w = a->class_weights; io.loss_out = a->loss_out;
   int rc;
   if ((rc = run_forward(m, io, st))) return rc;
-  // ---- loss: values + bf16 gradients for the backward GEMMs ----
-  {
+  // ---- loss: values + bf16 gradients for the backward GEMMs (only when it could not be fused) ----
+  if (!io.fuse_loss) {
     LossArgs l{};
     l.rows = a->batch; l.dyn = m->dyn; l.grad_scale = 1.0f; l.dyn_bump = m->dyn; l.n_batches = io.n_batches;
     for (size_t i = 0; i < m->decs.size(); ++i) {
@@ -1328,8 +1392,10 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
     return fail(VLA_ERR_INVALID, "null argument");
   if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
   cudaStream_t st = as_stream(stream);
-  const char* env = getenv("VLA_FUSED_STEP");        // read per call: a host-side switch, not on the replay path
-  const bool fused_on = !(env && env[0] == '0');
+  // Read per call (a host-side switch, not on the replay path).  Default: separate launches -- at one CTA per SM the
+  // element-wise phases of the whole-step kernel are latency-bound (DESIGN.md section 5 has the measured timeline).
+  const char* env = getenv("VLA_FUSED_STEP");
+  const bool fused_on = env && env[0] == '1';
   if (fused_on && a->phases != 2) {
     const int rc = train_step_fused(m, a, st);
     if (rc <= 0) return rc;

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstddef>
 #include <cstdlib>
 #include <string>
 
@@ -25,7 +26,9 @@ enum GemmFlags : int {
   GF_OUT_BF16 = 1 << 7,   // store bf16
   GF_RED = 1 << 8,        // accumulate into out_f32 with red.global.add (split-K weight gradients)
   GF_BIASGRAD = 1 << 9,   // TN mode: also produce sum_k A[m, k] into bias_grad[m] (ones-MMA)
+  GF_LOSS = 1 << 11,      // NT mode, last decoder layer: loss value partials + dL/d(pre-activation) as bf16 (loss_kind)
 };
+enum LossKind : int { LOSS_NONE = 0, LOSS_MSE = 1, LOSS_BCE = 2, LOSS_CE = 3 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -57,6 +60,31 @@ struct alignas(64) GemmProblem {
   const float* rstd;
   float* stats;
   float* bias_grad;
+  // ---- fused tails ----
+  // GF_LOSS:       aux0 = target fp32 [rows, N] dense (MSE / BCE), aux1 = class weights or nullptr (CE), aux_site = labels
+  //                (CE); the gradient goes to out_bf16; aux_partials[local_tile * 8 + warp] receives the loss partial sums;
+  //                aux_n = resident batches (targets start at row (dyn->batch_index % aux_n) * M when aux_n > 1).
+  const float* aux0; const float* aux1;
+  const long long* aux_site;
+  float* aux_partials;
+  const struct DynParams* dyn;
+  int aux_n, loss_kind;
+  float aux_scale;                   // CE: gamma when dyn == nullptr
+  int pad1;
+};
+
+// Final reduction of the fused loss: the epilogue of the tile that takes the last ticket sums every partial in a fixed
+// order (deterministic) and writes out[4] = {total, recon, class, kld} (losses.py:27-46).
+struct LossTail {
+  unsigned int* counter;       // zero between steps (re-armed by the last tile)
+  int total_tickets;           // loss tiles of the whole step (possibly spread over several launches)
+  int n_mse, n_bce, n_ce;      // partial floats per term, contiguous in `partials` in this order
+  const float* partials;
+  const float* kl_partials; int n_kl;
+  float* out;
+  const struct DynParams* dyn; // beta / gamma
+  struct DynParams* dyn_bump;  // batch_index += 1 after the reduction
+  int pad[2];
 };
 
 struct GemmGroup {
@@ -64,9 +92,13 @@ struct GemmGroup {
   int total_tiles;
   unsigned long long* dbg;   // optional [total_tiles][8] globaltimer stamps (test hook only)
   int dbg_flags;             // test hook: 1 = skip epilogue stores, 2 = skip main loop, 4 = skip TMEM alloc (with 2)
-  int pad[11];
+  int pad0;
+  LossTail tail;             // used by problems with GF_LOSS
+  int pad[8];
   GemmProblem p[GEMM_MAX_PROBLEMS];
 };
+static_assert(sizeof(LossTail) == 80, "LossTail layout");
+static_assert(offsetof(GemmGroup, p) % 64 == 0, "tensor maps need 64-byte alignment");
 
 // mode 0: NT  C = A[M,K] B[N,K]^T   (both K-major; forward)
 // mode 1: TN  C = A[K,M]^T B[K,N]   (both MN-major; weight gradients, split-K)
@@ -241,7 +273,7 @@ cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s);
 // on (ROW: the 128-row blocks it reads; ALL: every unit of that phase) instead of a kernel boundary.
 // ---------------------------------------------------------------------------------------------
 enum StepKind : int {
-  SK_GEMM_NT_PLAIN = 0, SK_GEMM_NT_FULL, SK_GEMM_NN_PLAIN, SK_GEMM_NN_FULL, SK_GEMM_TN,
+  SK_GEMM_NT_PLAIN = 0, SK_GEMM_NT_FULL, SK_GEMM_NT_LOSS, SK_GEMM_NN_PLAIN, SK_GEMM_NN_FULL, SK_GEMM_TN,
   SK_INGEST, SK_BN_ACT, SK_LATENT_FWD, SK_LOSS, SK_LATENT_BWD, SK_BN_BWD, SK_ADAMW,
 };
 constexpr int STEP_MAX_PHASES = 40;
