@@ -297,6 +297,23 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     }
     named_bar_sync(1, EPI_THREADS);
 
+    // GF_LOSS (MSE / BCE): the targets stream from HBM.  While the main loop runs, pull this warp's target lines into
+    // L2 (no registers held): the epilogue's loads then see L2 latency instead of DRAM latency.
+    long long tgt_row0 = 0;
+    if ((FEATS & GF_LOSS) && (P.flags & GF_LOSS)) {
+      if (P.aux_n > 1) tgt_row0 = static_cast<long long>(P.dyn->batch_index % P.aux_n) * P.M;
+      if (P.loss_kind != LOSS_CE && row_ok) {
+        const float* trow = P.aux0 + (tgt_row0 + row) * P.N;
+        for (int c = half; c < n_chunks; c += 2) {
+          const int c_lo = n0 + c * 32, c_hi = min(c_lo + 31, P.N - 1);
+          if (c_lo < P.N) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(trow + c_lo));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(trow + c_hi));
+          }
+        }
+      }
+    }
+
     mbar_wait(acc_bar, ctx.tile_parity);
     tc_fence_after();
     if (et == 0) VLA_STAMP(5);                                     // accumulator ready
@@ -309,8 +326,6 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     const bool bf16_vec = ((reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0) && ((P.ld_bf16 & 7) == 0);
 
     float loss_acc = 0.f;                                // GF_LOSS: this thread's share of the loss value
-    long long tgt_row0 = 0;
-    if ((FEATS & GF_LOSS) && (flags & GF_LOSS) && P.aux_n > 1) tgt_row0 = static_cast<long long>(P.dyn->batch_index % P.aux_n) * P.M;
 
     for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
       const int col0 = n0 + c * 32;
