@@ -41,28 +41,76 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The timed region is short (tens of ms), so the sampler
+    polls NVML directly every ~2 ms from a thread (nvidia_ml_py); `nvidia-smi -lms` is the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.lines, self.proc = [], None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = False
+        self.proc, self.lines = None, []
+        self.mode = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    idx = gpu_index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.mode = "smi"
+                self.thread = threading.Thread(target=self._read, daemon=True)
+                self.thread.start()
+            except Exception:
+                self.mode = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        if self.mode is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampling unavailable"], samples=0)
+        if self.mode == "nvml":
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.samples)
+            return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                        samples=len(sm), source="nvml, 2 ms period")
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -83,7 +131,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                    source="nvidia-smi -lms 20")
 
 
 # ------------------------------------------------------------------------------------------------------
