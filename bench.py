@@ -299,7 +299,8 @@ def run_gpu(args, rank, local_rank, world):
     B = args.batch
     n_batches = args.resident_batches
     ds = DeviceDataset.synthetic(B * n_batches, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=1000 + rank)
-    trainer = Trainer(model, ds, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg)
+    trainer = Trainer(model, ds, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg,
+                      exchange=args.exchange)
 
     def barrier():
         if world > 1:
@@ -324,6 +325,7 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     losses = trainer.losses()
+    dp_trace = trainer.exchange_trace()
     assert all(x == x and abs(x) < 1e30 for x in losses), f"non-finite loss {losses}"
     value = args.steps * B * world / (ms * 1e-3)
 
@@ -333,7 +335,8 @@ def run_gpu(args, rank, local_rank, world):
     pinned = [(h.tpm.cpu().pin_memory(), h.beta.cpu().pin_memory(), h.site.cpu().pin_memory()) for h in host]
     del host
     slots = [DeviceDataset.synthetic(B, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=5 + i) for i in range(2)]
-    tr2 = Trainer(model, slots, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg)
+    tr2 = Trainer(model, slots, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg,
+                  exchange=args.exchange)
     loss_host = [torch.zeros(4).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
@@ -451,14 +454,16 @@ def run_gpu(args, rank, local_rank, world):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload} train step (fwd+loss+bwd+AdamW), batch {B} per GPU, 782/572/24/latent 20",
-                       "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "global_batch": B * world, "parallelism": (f"dp{world}, batch-sharded replicas, one all-reduce(SUM) of the gradient arena per step: " +
+                                       ("own kernel over NVLink peer memory (csrc/dp_exchange.cu)" if args.exchange == "p2p"
+                                        else "NCCL all_reduce")) if world > 1 else "single",
                        "l2": f"inputs larger than L2: {n_batches} resident batches ({B * n_batches} rows, "
                              f"{B * n_batches * (DIMS['A'] + DIMS['B']) * 4 / 1e6:.0f} MB) visited in turn",
                        "arithmetic": "bf16 tensor-core operands, fp32 accumulate, fp32 master weights / loss / AdamW",
                        "graph": "CUDA graph replay per step, no host sync in the timed region"},
             "e2e": e2e, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:8], "timeline": phases,
             "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
-            "cpu_baseline": cpu, "clocks": clocks, "final_losses": losses, "also": also,
+            "cpu_baseline": cpu, "dp_exchange_trace": dp_trace, "clocks": clocks, "final_losses": losses, "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -474,6 +479,7 @@ def main():
     ap.add_argument("--workload", default="rna2dna", choices=sorted(WORK))
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--resident-batches", type=int, default=64)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="data-parallel gradient exchange (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (tri-modal, dna2rna, inference)")
     ap.add_argument("--infer-batch", type=int, default=262144)

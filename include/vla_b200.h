@@ -163,12 +163,35 @@ typedef struct {
   float* loss_out;
   int phases;                   /* 0 or 3: whole step; 1: forward + loss + backward only (gradients left in `grads`, e.g. for a
                                    data-parallel all-reduce); 2: AdamW only (consumes and clears `grads`) */
+  void* dp;                     /* NULL, or a connected vla_dp_t*: data-parallel step -- between backward and AdamW the
+                                   gradients (and the 4 loss scalars behind them) are summed over the ranks through NVLink
+                                   peer memory.  grads must be vla_dp_grads(dp), loss_out its last 4 floats; the summed
+                                   losses land in vla_dp_losses(dp).  Every rank must call in lockstep. */
 } vla_train_args_t;
 int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream);
 int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, float gamma, vla_stream_t stream);
 /* Resets the device-side step counter (and beta1^t, beta2^t for the bias corrections) and the resident-batch index. */
 int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float beta1, float beta2, vla_stream_t stream);
 
+
+/* Data-parallel gradient exchange over NVLink / NVSwitch peer memory (one process per GPU, one node).  The reference has
+ * no distributed code; this replaces what DistributedDataParallel's all-reduce would do around
+ * loss.backward() / optimizer.step() (train_rna2dna.py:94-96), with SUM semantics (src/utils/losses.py:31-42 are
+ * reduction='sum').  Each rank creates its buffers ([param_count + 4] floats: gradient arena | 4 loss scalars), the ranks
+ * exchange the 64-byte IPC handles out of band (HOST memory, e.g. torch.distributed.all_gather_object) and connect; after
+ * that vla_train_step(dp = handle) runs the collective as one kernel of the step (csrc/dp_exchange.cu).
+ * Destroy only after every rank has finished its last step (barrier first). */
+typedef struct vla_dp vla_dp_t;
+int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out);
+int vla_dp_ipc_handle(vla_dp_t* d, void* out64);             /* HOST pointer, 64 bytes */
+int vla_dp_connect(vla_dp_t* d, const void* handles);        /* HOST pointer, world x 64 bytes in rank order */
+void* vla_dp_grads(vla_dp_t* d);                             /* device: local gradients [n_floats] */
+void* vla_dp_losses(vla_dp_t* d);                            /* device: float[4], the loss scalars summed over the ranks */
+/* %globaltimer stamps (ns) of block 0 in the last exchange launch on this rank, HOST out8[8]: 0 kernel entry, 1 contributions
+ * pushed to the other ranks, 2 own shard slice reduced and pushed.
+ * Synchronises the device. */
+int vla_dp_trace(vla_dp_t* d, unsigned long long* out8);
+void vla_dp_destroy(vla_dp_t* d);
 
 /* Whole-step kernel.  vla_train_step (phases 0 / 1 / 3) can run as ONE persistent cooperative kernel: the launches of the
  * step become phases whose units (GEMM tiles, element-wise blocks) wait on per-row-block completion counters instead of

@@ -1,4 +1,8 @@
-"""torchrun worker of tests/test_gpu_dp.py: 2+ ranks, NCCL, fused DP train steps vs the per-shard oracle with summed gradients."""
+"""torchrun worker of tests/test_gpu_dp.py: 2+ ranks, fused DP train steps vs the per-shard oracle with summed gradients.
+
+DP_EXCHANGE = p2p (the library's peer-memory kernel, default) | nccl (torch.distributed.all_reduce).
+DP_SAME_GPU = 1: every rank uses cuda:0 and the process group is gloo (it only carries the IPC handles and barriers), so
+the peer-memory protocol is exercised between two PROCESSES on a one-GPU box (their kernels time-slice)."""
 import os
 import sys
 
@@ -16,8 +20,15 @@ from vla_b200 import DeviceDataset, Trainer  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    same_gpu = os.environ.get("DP_SAME_GPU", "0") == "1"
+    exchange = os.environ.get("DP_EXCHANGE", "p2p")
+    if same_gpu:
+        local = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, dims, per_rank, steps = "rna2dna", dict(A=782, B=572, S=24, L=20, E=32), 64, 3
     state = vo.init_state(kind, dims, seed=31)
     tpm, beta, site = vo.synthetic_batch(per_rank * world, dims, seed=31)
@@ -25,7 +36,8 @@ def main():
     sl = slice(rank * per_rank, (rank + 1) * per_rank)
     m = make_module(kind, dims, state, device=f"cuda:{local}").train()
     ds = DeviceDataset(tpm[sl], beta[sl], site[sl], f"cuda:{local}")
-    tr = Trainer(m, ds, per_rank, beta_kl=1e-3, process_group=dist.group.WORLD, use_graph=os.environ.get("DP_GRAPH", "1") == "1")
+    tr = Trainer(m, ds, per_rank, beta_kl=1e-3, process_group=dist.group.WORLD, use_graph=os.environ.get("DP_GRAPH", "1") == "1",
+                 exchange=exchange)
     tr.injected = dict(eps=to_t(eps[sl], f"cuda:{local}"), keep_masks=[to_t(v[sl], f"cuda:{local}") for v in masks.values()])
     losses = []
     for _ in range(steps):
@@ -34,6 +46,8 @@ def main():
     torch.cuda.synchronize()
     # replicas must stay bit-identical
     flat = tr.core.arena.clone()
+    if same_gpu:
+        flat = flat.cpu()
     ref = flat.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(flat, ref), "replicas diverged"
@@ -70,7 +84,7 @@ def main():
             d_got = sd[name].astype(np.float64) - state[name].astype(np.float64)
             worst = max(worst, rel_l2(d_got, d_ref))
         assert worst <= 0.2, worst
-        print(f"DP_OK world={world} worst displacement rel err {worst:.3f} losses {got[-1].tolist()}", flush=True)
+        print(f"DP_OK world={world} exchange={exchange} worst displacement rel err {worst:.3f} losses {got[-1].tolist()}", flush=True)
     import threading
     threading.Timer(20.0, lambda: os._exit(0)).start()       # never hang at exit: the verdict is already printed
     tr.close()

@@ -78,6 +78,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   pdl_wait();
   pdl_launch_dependents();
   adamw_body(a, blockIdx.x, threadIdx.x);
+  if (a.gframed && a.sums_out && blockIdx.x == 0 && threadIdx.x < 2) {
+    // data parallel: the summed loss scalars travel behind the gradients (vla_b200.h, vla_dp_losses)
+    const unsigned int epoch = static_cast<unsigned int>(__ldcg(&a.dyn->dp_epoch));
+    const uint4* w = a.gframed + a.tail2 + threadIdx.x;
+    const float2 v = finish_framed(w, ld_framed(w), epoch);
+    a.sums_out[2 * threadIdx.x] = v.x; a.sums_out[2 * threadIdx.x + 1] = v.y;
+  }
 }
 
 inline int grid_for(long long work_items, int threads, int max_blocks) {

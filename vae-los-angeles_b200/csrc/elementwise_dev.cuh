@@ -6,6 +6,7 @@
 // the eight epilogue warps of the CTA form the block and synchronise on a named barrier).
 // All arithmetic is fp32; reductions are deterministic (fixed-order partials, no float atomics).
 #pragma once
+#include "dp_frame.cuh"
 #include "loss_math.cuh"
 #include "tc_ptx.cuh"
 #include "vla_internal.h"
@@ -101,6 +102,7 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
                                             bool first_thread) {
   if (a.bump_step && first_thread) {
     a.dyn->step += 1;
+    a.dyn->dp_epoch += 1;
     a.dyn->b1pow *= static_cast<double>(a.beta1);
     a.dyn->b2pow *= static_cast<double>(a.beta2);
   }
@@ -665,18 +667,31 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
   const long long gi = ch.offset + e;                  // multiple of 4: 16-byte aligned in every arena
   const int nv = min(4, ch.n - e);
   float p[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool framed = a.update && a.gframed != nullptr;
+  uint4 f0 = make_uint4(0u, 0u, 0u, 0u), f1 = f0;
+  unsigned int epoch = 0u;
+  if (framed) {               // first attempt at the two framed words of this float4, in flight with the loads below
+    epoch = static_cast<unsigned int>(__ldcg(&a.dyn->dp_epoch));
+    f0 = ld_framed(a.gframed + (gi >> 1));
+    f1 = ld_framed(a.gframed + (gi >> 1) + 1);
+  }
   if (nv == 4) {
     *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(a.p + gi);
     if (a.update) {
-      *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(a.g + gi);
+      if (!framed) *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(a.g + gi);
       *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(a.m + gi);
       *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.v + gi);
     }
   } else {
     for (int k = 0; k < nv; ++k) {
       p[k] = a.p[gi + k];
-      if (a.update) { g[k] = a.g[gi + k]; m[k] = a.m[gi + k]; v[k] = a.v[gi + k]; }
+      if (a.update) { if (!framed) g[k] = a.g[gi + k]; m[k] = a.m[gi + k]; v[k] = a.v[gi + k]; }
     }
+  }
+  if (framed) {               // (the arena is padded to multiples of 4: both words exist for every chunk tail)
+    const float2 lo = finish_framed(a.gframed + (gi >> 1), f0, epoch);
+    const float2 hi = finish_framed(a.gframed + (gi >> 1) + 1, f1, epoch);
+    g[0] = lo.x; g[1] = lo.y; g[2] = hi.x; g[3] = hi.y;
   }
   if (a.update) {
 #pragma unroll
@@ -690,11 +705,11 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
       *reinterpret_cast<float4*>(a.p + gi) = *reinterpret_cast<const float4*>(p);
       *reinterpret_cast<float4*>(a.m + gi) = *reinterpret_cast<const float4*>(m);
       *reinterpret_cast<float4*>(a.v + gi) = *reinterpret_cast<const float4*>(v);
-      if (a.zero_grad) *reinterpret_cast<float4*>(a.g + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.zero_grad) *reinterpret_cast<float4*>(a.gclear + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       for (int k = 0; k < nv; ++k) {
         a.p[gi + k] = p[k]; a.m[gi + k] = m[k]; a.v[gi + k] = v[k];
-        if (a.zero_grad) a.g[gi + k] = 0.f;
+        if (a.zero_grad) a.gclear[gi + k] = 0.f;
       }
     }
   }
@@ -730,7 +745,7 @@ __device__ __forceinline__ void adamw_unit(const AdamArgs& a, int c0, int c1, in
     for (int k = 0; k < 4; ++k) {
       const bool valid = base + k < c1;
       ch[k] = a.chunks[valid ? base + k : c0];
-      fast[k] = valid && a.update && (ch[k].n - e >= 4);
+      fast[k] = valid && a.update && !a.gframed && (ch[k].n - e >= 4);
     }
     float4 P[4], Gr[4], M[4], V[4];
     ew_stamp(dbg_row, 2, tid);
@@ -760,7 +775,7 @@ __device__ __forceinline__ void adamw_unit(const AdamArgs& a, int c0, int c1, in
         *reinterpret_cast<float4*>(a.p + gi) = make_float4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<float4*>(a.m + gi) = make_float4(m[0], m[1], m[2], m[3]);
         *reinterpret_cast<float4*>(a.v + gi) = make_float4(v[0], v[1], v[2], v[3]);
-        if (a.zero_grad) *reinterpret_cast<float4*>(a.g + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.zero_grad) *reinterpret_cast<float4*>(a.gclear + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ch[k].shadow_off >= 0) {
           const unsigned idx = static_cast<unsigned>(ch[k].first + e);
           int r = static_cast<int>(idx / static_cast<unsigned>(ch[k].cols));

@@ -140,6 +140,18 @@ struct vla_model {
   int step_grid = 0;
 };
 
+// Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  One allocation per rank:
+// [G n floats | RECV world x per2 framed words | RSUM n / 2 framed words | summed losses | trace], exported / mapped with CUDA IPC.
+struct vla_dp {
+  int world = 1, rank = 0;
+  long long n = 0;                 // floats per buffer (multiple of 4)
+  long long per2 = 0;              // float2s per shard
+  char* base = nullptr;            // local allocation
+  size_t off_recv = 0, off_rsum = 0, off_sums = 0, off_trace = 0, bytes = 0;
+  char* peer[DP_MAX_WORLD] = {};   // every rank's allocation as mapped here (own: base)
+  bool connected = false;
+};
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -1079,7 +1091,7 @@ int vla_model_create(const vla_config_t* cfg, vla_model_t** out) {
   if ((e = cudaMalloc(&m->chunks_d, sizeof(AdamChunk) * m->chunks_h.size())) != cudaSuccess) return bail(e, "cudaMalloc chunks");
   if ((e = cudaMemcpy(m->chunks_d, m->chunks_h.data(), sizeof(AdamChunk) * m->chunks_h.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy chunks");
   if ((e = cudaMalloc(&m->dyn, sizeof(DynParams))) != cudaSuccess) return bail(e, "cudaMalloc dyn");
-  DynParams d{5e-4f, 1e-5f, 1e-3f, 1.0f, 0, 0, {0, 0}, 1.0, 1.0};
+  DynParams d{5e-4f, 1e-5f, 1e-3f, 1.0f, 0, 0, 0, 0, 1.0, 1.0};
   if ((e = cudaMemcpy(m->dyn, &d, sizeof(d), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "copy dyn");
   if ((e = cudaMalloc(&m->loss_counter, 64)) != cudaSuccess) return bail(e, "cudaMalloc counter");
   if ((e = cudaMemset(m->loss_counter, 0, 64)) != cudaSuccess) return bail(e, "memset counter");
@@ -1176,9 +1188,15 @@ int vla_loss(const vla_loss_args_t* a, vla_stream_t stream) {
 }
 
 static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float* eas, float lr, float b1, float b2,
-                     float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st) {
+                     float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st, vla_dp* dp = nullptr) {
   AdamArgs a{};
   a.p = p; a.g = const_cast<float*>(g); a.m = ea; a.v = eas; a.shadow = m->shadow;
+  a.gclear = a.g;
+  if (dp) {
+    a.gframed = reinterpret_cast<const uint4*>(dp->base + dp->off_rsum);
+    a.tail2 = m->n_params / 2;
+    a.sums_out = reinterpret_cast<float*>(dp->base + dp->off_sums);
+  }
   a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
   a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd;
   if (step > 0) {
@@ -1234,6 +1252,15 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   io.mu = a->mu; io.logvar = a->logvar; io.engine = true;
   if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
   const bool do_fb = a->phases != 2, do_opt = a->phases != 1;
+  vla_dp* dp = reinterpret_cast<vla_dp*>(a->dp);
+  if (dp) {
+    if (!do_fb || !do_opt) return fail(VLA_ERR_INVALID, "vla_train_step: the peer-memory exchange needs the whole step (phases 0 or 3)");
+    if (!dp->connected) return fail(VLA_ERR_STATE, "vla_train_step: vla_dp_connect has not been called");
+    if (dp->n != m->n_params + 4) return fail(VLA_ERR_INVALID, "vla_train_step: exchange buffer size != param_count + 4");
+    if (a->grads != reinterpret_cast<float*>(dp->base) || a->loss_out != a->grads + m->n_params)
+      return fail(VLA_ERR_INVALID, "vla_train_step: grads / loss_out must be vla_dp_grads() and its last 4 floats");
+    if (m->rec) m->rec->why = "data-parallel exchange";
+  }
   if (!do_fb)
     return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
                      true, st);
@@ -1286,6 +1313,22 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
   if ((rc = run_backward(m, bo, st))) return rc;
   if (!do_opt) return VLA_OK;
+  if (dp && !m->rec) {
+    // ---- the step's one collective: two-shot all-reduce(SUM) over peer memory (clears G); AdamW then reads R ----
+    DpArgs x{};
+    x.world = dp->world; x.rank = dp->rank; x.n2 = dp->n / 2; x.per2 = dp->per2; x.dyn = m->dyn;
+    x.g = reinterpret_cast<float*>(dp->base);
+    for (int r = 0; r < dp->world; ++r) {
+      x.recv[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_recv);
+      x.rsum[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_rsum);
+    }
+    x.trace = reinterpret_cast<unsigned long long*>(dp->base + dp->off_trace);
+    // algorithmic bytes: payload out + in over NVLink
+    { ProfScope ps(m, st, "dp_exchange", 0, 8.0 * dp->n * (dp->world - 1) / dp->world); CK(launch_dp_exchange(x, st)); }
+    // AdamW polls the framed sums as it walks the parameters (the exchange already cleared G)
+    return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
+                     false, st, dp);
+  }
   return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
                    true, st);
 }
@@ -1401,6 +1444,73 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
     if (rc <= 0) return rc;
   }
   return train_step_sequence(m, a, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory gradient exchange: allocation, IPC export / import
+// ---------------------------------------------------------------------------------------------
+int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out) {
+  if (!out || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world || n_floats < 4 || (n_floats & 3))
+    return fail(VLA_ERR_INVALID, "vla_dp_create: world in [1, 16], rank in [0, world), n_floats a positive multiple of 4");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "vla_dp_ipc_handle writes 64 bytes");
+  vla_dp* d = new vla_dp();
+  d->world = world; d->rank = rank; d->n = n_floats;
+  auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const long long n2 = n_floats / 2;
+  d->per2 = (n2 + world - 1) / world;
+  d->off_recv = up(sizeof(float) * n_floats);
+  d->off_rsum = d->off_recv + up(sizeof(uint4) * static_cast<size_t>(world) * d->per2);
+  d->off_sums = d->off_rsum + up(sizeof(uint4) * static_cast<size_t>(n2));
+  d->off_trace = d->off_sums + 256;
+  d->bytes = d->off_trace + 256;
+  cudaError_t e = cudaMalloc(&d->base, d->bytes);
+  if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(d->base); delete d; return fail(VLA_ERR_CUDA, std::string("vla_dp_create: ") + cudaGetErrorString(e)); }
+  d->peer[rank] = d->base;
+  d->connected = world == 1;
+  *out = d;
+  return VLA_OK;
+}
+int vla_dp_ipc_handle(vla_dp_t* d, void* out64) {
+  if (!d || !out64) return fail(VLA_ERR_INVALID, "null argument");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, d->base));
+  memcpy(out64, &h, sizeof(h));
+  return VLA_OK;
+}
+int vla_dp_connect(vla_dp_t* d, const void* handles) {
+  if (!d || !handles) return fail(VLA_ERR_INVALID, "null argument");
+  if (d->connected) return VLA_OK;
+  for (int r = 0; r < d->world; ++r) {
+    if (r == d->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + 64 * r, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(VLA_ERR_CUDA, "vla_dp_connect: cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e) +
+                                    " (the ranks must be processes on one node whose GPUs have peer access)");
+    }
+    d->peer[r] = static_cast<char*>(p);
+  }
+  d->connected = true;
+  return VLA_OK;
+}
+int vla_dp_trace(vla_dp_t* d, unsigned long long* out8) {
+  if (!d || !out8) return fail(VLA_ERR_INVALID, "null argument");
+  CK(cudaMemcpy(out8, d->base + d->off_trace, 64, cudaMemcpyDeviceToHost));
+  return VLA_OK;
+}
+void* vla_dp_grads(vla_dp_t* d) { return d ? d->base : nullptr; }
+void* vla_dp_losses(vla_dp_t* d) { return d ? d->base + d->off_sums : nullptr; }
+void vla_dp_destroy(vla_dp_t* d) {
+  if (!d) return;
+  for (int r = 0; r < d->world; ++r)
+    if (r != d->rank && d->peer[r]) cudaIpcCloseMemHandle(d->peer[r]);
+  cudaFree(d->base);
+  delete d;
 }
 
 /* Whole-step kernel timeline: %globaltimer stamps per unit (unit start, dependencies resolved, first operands, MMAs

@@ -110,6 +110,18 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   static const bool pdl_on = [] { const char* e = getenv("VLA_NO_PDL"); return !(e && e[0] == '1'); }();
+  // Experiment hook (VLA_CARVEOUT=1): ask for the maximum shared-memory carve-out on every kernel, so that consecutive
+  // launches never differ in their L1 / shared split (a differing split drains the SM before the next CTA can start).
+  static const bool carve_on = [] { const char* e = getenv("VLA_CARVEOUT"); return e && e[0] == '1'; }();
+  if (carve_on) {
+    static thread_local const void* seen[32]; static thread_local int n_seen = 0;
+    bool found = false;
+    for (int i = 0; i < n_seen; ++i) found = found || seen[i] == reinterpret_cast<const void*>(kernel);
+    if (!found) {
+      (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (n_seen < 32) seen[n_seen++] = reinterpret_cast<const void*>(kernel);
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -134,7 +146,9 @@ struct DynParams {
   float lr, weight_decay, beta_kl, gamma;
   int step;          // number of the optimizer step in flight (1-based); bumped by the ingest kernel
   int batch_index;   // which resident batch the step in flight trains on; bumped by the loss kernel's last block
-  int pad[2];
+  int dp_epoch;      // train steps started on this handle since creation (never reset): the epoch of the peer-memory
+                     // gradient exchange (dp_exchange.cu); bumped together with `step`
+  int pad;
   double b1pow, b2pow;   // beta1^step, beta2^step, advanced together with `step` (no powf in the AdamW kernel)
 };
 
@@ -262,7 +276,14 @@ struct AdamArgs {
   float bc1, inv_bc2_sqrt;    // 1 - beta1^t and 1 / sqrt(1 - beta2^t), computed in double on the host
   const struct DynParams* dyn;// if set, lr / weight_decay / bias corrections are read from it
   int update;                 // 0: only refresh the bf16 shadows from p
-  int zero_grad;              // 1: clear g after use
+  int zero_grad;              // 1: clear gclear after use
+  float* gclear;              // what zero_grad clears (normally g itself)
+  // data parallel (dp_exchange.cu): the gradients are the framed sums arriving from the shard owners -- word i holds
+  // elements 2i, 2i + 1 -- polled as the kernel walks the parameters; epoch = dyn->dp_epoch.  Block 0 also copies the
+  // summed loss scalars (framed words [tail2, tail2 + 2)) to sums_out[4].
+  const uint4* gframed;
+  long long tail2;
+  float* sums_out;
 };
 cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s);
 
@@ -309,6 +330,22 @@ struct StepPlan {
   unsigned long long* dbg; // optional [total units][8] globaltimer stamps
   StepPhase ph[STEP_MAX_PHASES];
 };
+
+// ---------------------------------------------------------------------------------------------
+// Data-parallel gradient exchange over NVLink peer memory (dp_exchange.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int DP_MAX_WORLD = 16;
+struct DpArgs {
+  int world, rank;
+  long long n2;                         // float2 elements of the flat buffer [gradient arena | 4 loss scalars]
+  long long per2;                       // float2 elements per shard = ceil(n2 / world)
+  float* g;                             // local gradients [2 n2] (cleared as they are read)
+  uint4* recv[DP_MAX_WORLD];            // every rank's RECV [world][per2] framed words (peer pointers, own included)
+  uint4* rsum[DP_MAX_WORLD];            // every rank's RSUM [n2] framed words
+  const DynParams* dyn;                 // epoch = dyn->dp_epoch
+  unsigned long long* trace;            // optional [8] %globaltimer stamps of the last launch (block 0)
+};
+cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s);
 
 struct LossGridInfo { int nb_a, nb_b, nb_c, nb_k; };
 LossGridInfo loss_grid_info(const LossArgs& a);

@@ -62,7 +62,8 @@ class TrainArgs(C.Structure):
                 ("eps", C.c_void_p), ("keep_masks", C.POINTER(C.c_void_p)), ("seed", C.c_ulonglong),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("recon_a", C.c_void_p), ("recon_b", C.c_void_p), ("recon_c", C.c_void_p),
-                ("mu", C.c_void_p), ("logvar", C.c_void_p), ("loss_out", C.c_void_p), ("phases", C.c_int)]
+                ("mu", C.c_void_p), ("logvar", C.c_void_p), ("loss_out", C.c_void_p), ("phases", C.c_int),
+                ("dp", C.c_void_p)]
 
 
 class ProfEntry(C.Structure):
@@ -90,6 +91,13 @@ EXPORTS = {
     "vla_train_step": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "vla_set_hyper": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "vla_set_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "vla_dp_create": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)]),
+    "vla_dp_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vla_dp_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vla_dp_grads": (C.c_void_p, [C.c_void_p]),
+    "vla_dp_losses": (C.c_void_p, [C.c_void_p]),
+    "vla_dp_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "vla_dp_destroy": (None, [C.c_void_p]),
     "vla_profile_begin": (C.c_int, [C.c_void_p]),
     "vla_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
     "vla_profile_read": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),

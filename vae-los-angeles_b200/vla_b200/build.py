@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
-SOURCES = ["gemm_tc.cu", "elementwise.cu", "step_kernel.cu", "vla_api.cu"]
+SOURCES = ["gemm_tc.cu", "elementwise.cu", "step_kernel.cu", "dp_exchange.cu", "vla_api.cu"]
 OUT = os.path.join(HERE, "libvla_b200.so")
 
 
@@ -18,7 +18,7 @@ def nvcc_path():
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("tc_ptx.cuh", "vla_internal.h", "gemm_tile.cuh", "elementwise_dev.cuh")] + \
+    deps = srcs + [os.path.join(CSRC, h) for h in ("tc_ptx.cuh", "vla_internal.h", "gemm_tile.cuh", "elementwise_dev.cuh", "dp_frame.cuh", "loss_math.cuh")] + \
         [os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "vla_b200.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT

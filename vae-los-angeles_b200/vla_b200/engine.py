@@ -14,6 +14,19 @@ from . import _lib
 from .core import _ptr, _stream
 
 
+class _DeviceFloats:
+    """Library-owned device memory seen through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+def _wrap_device_floats(ptr, n, device):
+    if not ptr:
+        raise RuntimeError("null device pointer from libvla_b200")
+    return torch.as_tensor(_DeviceFloats(ptr, n), device=device)
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (decoupled decay, bias correction) in one launch over the flat arena.
 
@@ -93,13 +106,15 @@ class DeviceDataset:
 class Trainer:
     """Whole-step trainer: `step()` enqueues one fused train step (a CUDA-graph replay) with no host sync.
 
-    Data parallel (one process per GPU, torch.distributed NCCL): pass `process_group`; the step becomes
+    Data parallel (one process per GPU, one node): pass `process_group`; the step becomes
     [forward + loss + backward] -> one all-reduce(SUM) of the flat gradient arena with the 4 loss scalars
     appended -> AdamW.  SUM, not mean: the reference's losses are reduction='sum' (SURVEY D10), so the result
-    equals a single-process run on the concatenated batch up to BatchNorm, which uses per-shard statistics."""
+    equals a single-process run on the concatenated batch up to BatchNorm, which uses per-shard statistics.
+    exchange="p2p" (default): the collective is this library's own kernel over NVLink peer memory (csrc/dp_exchange.cu;
+    torch.distributed only carries the 64-byte IPC handles once); exchange="nccl": torch.distributed.all_reduce."""
 
     def __init__(self, module, dataset, batch_size, lr=5e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8,
-                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True, process_group=None):
+                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True, process_group=None, exchange="p2p"):
         self.module = module
         self.core = module._ensure_core()
         self.datasets = list(dataset) if isinstance(dataset, (list, tuple)) else [dataset]
@@ -108,15 +123,24 @@ class Trainer:
             raise ValueError("dataset smaller than one batch")
         dev = self.core.device
         n = self.core.n_params
+        self.pg = process_group
+        self.dp = None
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
         # gradient arena with the loss scalars appended: one collective moves both
-        self.flat = torch.zeros(n + 4, dtype=torch.float32, device=dev)
-        self.grads = self.flat[:n]
-        self.loss_out = self.flat[n:]
+        if process_group is not None and exchange == "p2p":
+            self._connect_peers(n + 4)
+            self.grads = self.flat[:n]
+            self._loss_local = self.flat[n:]          # this rank's losses (summed into the reduced buffer with the gradients)
+            self.loss_out = self.reduced           # float[4] summed over the ranks (written by the AdamW kernel)
+        else:
+            self.flat = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+            self.grads = self.flat[:n]
+            self.loss_out = self._loss_local = self.flat[n:]
         self.exp_avg = torch.zeros_like(self.core.arena)
         self.exp_avg_sq = torch.zeros_like(self.core.arena)
         self.class_weights = None if class_weights is None else class_weights.to(dev, torch.float32).contiguous()
         self.betas, self.eps, self.seed = betas, eps, seed
-        self.pg = process_group
         self.hyper = None
         self.set_hyper(lr, weight_decay, beta_kl, gamma)
         self.steps = 0
@@ -126,6 +150,27 @@ class Trainer:
         self._mask_arr = None
         _lib.check(_lib.lib().vla_model_reserve(self.core.handle, self.batch), "vla_model_reserve")
         self.reset_counters(0, 0)
+
+    def _connect_peers(self, n_floats):
+        """Allocates this rank's exchange buffers in the library, swaps the CUDA IPC handles through the process group
+        (host bytes, once) and maps every peer's buffers."""
+        import torch.distributed as dist
+        L = _lib.lib()
+        dev = self.core.device
+        world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+        with torch.cuda.device(dev):
+            handle = C.c_void_p()
+            _lib.check(L.vla_dp_create(world, rank, n_floats, C.byref(handle)), "vla_dp_create")
+            self.dp = handle
+            mine = C.create_string_buffer(64)
+            _lib.check(L.vla_dp_ipc_handle(self.dp, mine), "vla_dp_ipc_handle")
+            gathered = [None] * world
+            dist.all_gather_object(gathered, bytes(mine.raw), group=self.pg)
+            blob = b"".join(gathered)
+            _lib.check(L.vla_dp_connect(self.dp, blob), "vla_dp_connect")
+            self.flat = _wrap_device_floats(L.vla_dp_grads(self.dp), n_floats, dev)
+            self.reduced = _wrap_device_floats(L.vla_dp_losses(self.dp), 4, dev)
+            dist.barrier(group=self.pg)               # every rank has mapped every buffer before anyone steps
 
     # -- per-epoch scalars (beta warm-up train_rna2dna.py:80, ReduceLROnPlateau :216) ------------------
     def set_hyper(self, lr=None, weight_decay=None, beta_kl=None, gamma=None):
@@ -159,15 +204,16 @@ class Trainer:
             x_a=_ptr(ds.tpm), x_b=_ptr(ds.beta), site=_ptr(ds.site), class_weights=_ptr(self.class_weights),
             batch=self.batch, dataset_rows=len(ds), eps=_ptr(eps), keep_masks=masks, seed=self.seed,
             beta1=self.betas[0], beta2=self.betas[1], adam_eps=self.eps,
-            recon_a=None, recon_b=None, recon_c=None, mu=None, logvar=None, loss_out=_ptr(self.loss_out), phases=phases)
+            recon_a=None, recon_b=None, recon_c=None, mu=None, logvar=None, loss_out=_ptr(self._loss_local), phases=phases,
+            dp=self.dp)
 
     def _call(self, ds, phases):
         args = self._args(ds, phases)
         _lib.check(_lib.lib().vla_train_step(self.core.handle, C.byref(args), _stream()), "vla_train_step")
 
     def _enqueue(self, ds):
-        if self.pg is None:
-            self._call(ds, 0)
+        if self.pg is None or self.dp is not None:
+            self._call(ds, 0)                 # (data parallel: the peer-memory exchange is a kernel of the step)
         else:
             from .dp import allreduce_gradients
             self._call(ds, 1)
@@ -212,11 +258,29 @@ class Trainer:
         """Release the captured graphs (do this before destroying a process group whose collectives they contain)."""
         torch.cuda.synchronize(self.core.device)
         self.graphs.clear()
+        if self.dp is not None:
+            import torch.distributed as dist
+            dist.barrier(group=self.pg)       # no peer may still be reading or writing this rank's buffers
+            torch.cuda.synchronize(self.core.device)
+            self.flat = self.reduced = self.grads = self.loss_out = self._loss_local = None
+            _lib.lib().vla_dp_destroy(self.dp)
+            self.dp = None
 
     def losses(self):
         """(total, recon, class, kld) of the last completed step -- one 16-byte device->host read.
         Under data parallelism these are the sums over all ranks."""
         return tuple(self.loss_out.tolist())
+
+    def exchange_trace(self):
+        """Data parallel, peer-memory exchange: spans (us) of block 0 in the last exchange kernel on this rank, from its
+        %globaltimer stamps -- push to the peers, reduce of the own shard (waits for the peers' pushes) and push of the sums."""
+        if self.dp is None:
+            return None
+        buf = (C.c_ulonglong * 8)()
+        with torch.cuda.device(self.core.device):
+            _lib.check(_lib.lib().vla_dp_trace(self.dp, buf), "vla_dp_trace")
+        t = [int(x) for x in buf]
+        return dict(push_us=(t[1] - t[0]) / 1e3, reduce_us=(t[2] - t[1]) / 1e3, total_us=(t[2] - t[0]) / 1e3)
 
     def timeline(self, which=0):
         """Per-phase timing of the whole-step kernel for ONE replayed step, from the %globaltimer stamps every unit writes
