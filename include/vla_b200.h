@@ -187,9 +187,9 @@ int vla_dp_ipc_handle(vla_dp_t* d, void* out64);             /* HOST pointer, 64
 int vla_dp_connect(vla_dp_t* d, const void* handles);        /* HOST pointer, world x 64 bytes in rank order */
 void* vla_dp_grads(vla_dp_t* d);                             /* device: local gradients [n_floats] */
 void* vla_dp_losses(vla_dp_t* d);                            /* device: float[4], the loss scalars summed over the ranks */
-/* %globaltimer stamps (ns) of block 0 in the last exchange launch on this rank, HOST out8[8]: 0 kernel entry, 1 contributions
- * pushed to the other ranks, 2 own shard slice reduced and pushed.
- * Synchronises the device. */
+/* %globaltimer stamps (ns) of block 0 in the last step's two exchange launches on this rank, HOST out8[8]: [0..2] the
+ * encoder part (main stream), [4..6] the decoder part (side stream, overlapping the encoder backward): kernel entry,
+ * contributions pushed to the other ranks, own shard slice reduced and pushed.  Synchronises the device. */
 int vla_dp_trace(vla_dp_t* d, unsigned long long* out8);
 void vla_dp_destroy(vla_dp_t* d);
 

@@ -150,6 +150,8 @@ struct vla_dp {
   size_t off_recv = 0, off_rsum = 0, off_sums = 0, off_trace = 0, bytes = 0;
   char* peer[DP_MAX_WORLD] = {};   // every rank's allocation as mapped here (own: base)
   bool connected = false;
+  cudaStream_t side = nullptr;     // the early (decoder) part of the exchange runs here, beside the encoder backward
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -623,7 +625,7 @@ void finalize_tn(GemmGroup& g, int Kb, int force_splits = 0) {
   int base = 0;
   for (int i = 0; i < g.nprob; ++i) base += g.p[i].m_tiles * g.p[i].n_tiles;
   const int kb_total = ceil_div(Kb, GEMM_BK);
-  int splits = force_splits ? force_splits : std::max(1, (148 + base / 2) / std::max(base, 1));
+  int splits = force_splits ? force_splits : std::max(1, 148 / std::max(base, 1));     // one wave
   splits = std::min(splits, kb_total);
   const int per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, per);
@@ -860,6 +862,39 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
   return VLA_OK;
 }
 
+// Arguments of the peer-memory exchange over float2s [first2, end2) of the flat gradient buffer (dp_exchange.cu).
+// part selects the RECV region and the trace slots (0: main stream, 1: side stream).
+DpArgs make_dp_args(vla_model* m, vla_dp* dp, long long first2, long long end2, int part) {
+  DpArgs x{};
+  x.world = dp->world; x.rank = dp->rank; x.dyn = m->dyn;
+  x.first2 = first2; x.n2 = std::max(0LL, end2 - first2); x.per2 = (x.n2 + dp->world - 1) / dp->world;
+  x.g = reinterpret_cast<float*>(dp->base);
+  for (int r = 0; r < dp->world; ++r) {
+    x.recv[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_recv) + static_cast<size_t>(part) * dp->world * dp->per2;
+    x.rsum[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_rsum);
+  }
+  x.trace = reinterpret_cast<unsigned long long*>(dp->base + dp->off_trace) + 4 * part;
+  return x;
+}
+// Send the decoder gradients early, on the side stream, while the encoder backward runs?  Measured (rna2dna, batch 4096 per
+// GPU, profiles/r1_dp_exchange.md): neutral at 2 GPUs (129.0 vs 128.7 us / step), -4 us at 8 GPUs (130.1 vs 134.2) where
+// the pushes are 7/8 of the buffer; the split costs one more weight-gradient launch.  Default: on from 4 ranks.
+// VLA_DP_OVERLAP=0/1 overrides (every rank must use the same setting).
+bool dp_overlap(const vla_dp* dp) {
+  const char* e = getenv("VLA_DP_OVERLAP");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  return dp->world >= 4;
+}
+// algorithmic bytes of an exchange: payload out + in over NVLink
+double dp_bytes(const DpArgs& x) { return 16.0 * x.n2 * (x.world - 1) / x.world; }
+int run_exchange(vla_model* m, vla_dp* dp, long long first2, long long end2, int part, cudaStream_t st, bool pdl) {
+  const DpArgs x = make_dp_args(m, dp, first2, end2, part);
+  if (x.n2 <= 0) return VLA_OK;
+  ProfScope ps(m, st, part ? "dp_exchange_dec" : "dp_exchange_enc", 0, dp_bytes(x));
+  CK(launch_dp_exchange(x, st, pdl));
+  return VLA_OK;
+}
+
 struct BwdIO {
   const float* params;
   const float* g_recon[3]; const float* recon_b;   // fp32 upstream gradients (autograd path), may be null
@@ -867,6 +902,7 @@ struct BwdIO {
   float* grads;
   bool engine;                                     // bf16 output gradients already written by the loss kernel
   bool zero_grads;
+  vla_dp* dp = nullptr;                            // data parallel: the decoder weight gradients are computed and sent early
 };
 
 int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
@@ -926,6 +962,61 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       if (!active[i] && m->rec) m->rec->why = "inactive decoder";
       else if (!active[i])
         CK(cudaMemset2DAsync(m->g_d0 + m->decs[i].cat_off, sizeof(bf16) * m->cat.out, 0, sizeof(bf16) * m->decs[i].cat_w, B, st));
+  // Weight-gradient group over the encoder and / or decoder layers (dW = dY^T X, bias gradients by the ones-MMA).
+  auto emit_wgrad = [&](bool enc, bool dec, const char* name, cudaStream_t wst) -> int {
+    GemmGroup g; init_group(g);
+    int rc2;
+    if (enc) {
+      for (size_t i = 0; i < m->encs.size(); ++i) {
+        if (!(present >> i & 1)) continue;
+        const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+        for (size_t r = 0; r < e.fc.size(); ++r) {
+          const Lin& l = e.fc[r];
+          const bf16* X = r == 0 ? w.x : w.act[r - 1];
+          const int ldx = r == 0 ? w.ldx : e.fc[r - 1].out;
+          if ((rc2 = add_tn(m, g, w.gpre[r], l.out, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc2;
+        }
+        const Lin& h = e.heads;
+        const bf16* X = e.fc.empty() ? w.x : w.act.back();
+        const int ldx = e.fc.empty() ? w.ldx : e.fc.back().out;
+        if ((rc2 = add_tn(m, g, m->gml, m->ldgml, X, ldx, h.out, h.in, B, G + h.w_off, h.in, G + h.b_off))) return rc2;
+        if (e.type == 'C')
+          if ((rc2 = add_tn(m, g, w.onehot, w.ld_onehot, w.g_x, w.ldx, m->S, m->E, B, G + e.emb_off, m->E, nullptr))) return rc2;
+      }
+    }
+    if (dec && any_dec) {
+      // fused first decoder layer: rows of inactive decoders receive zeros (their g_d0 slice was cleared)
+      const Lin& c = m->cat;
+      if ((rc2 = add_tn(m, g, m->g_d0, c.out, m->z, m->ldz, c.out, c.in, B, G + c.w_off, c.in, G + c.b_off))) return rc2;
+      for (size_t i = 0; i < m->decs.size(); ++i) {
+        if (!active[i]) continue;
+        const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
+        for (size_t r = 0; r < d.rest.size(); ++r) {
+          const Lin& l = d.rest[r];
+          const bool last = r + 1 == d.rest.size();
+          const bf16* Gr = last ? w.g_out : w.gact[r];
+          const int ldg = last ? w.ld_gout : l.out;
+          const bf16* X = r == 0 ? m->d0 + d.cat_off : w.act[r - 1];
+          const int ldx = r == 0 ? m->cat.out : d.rest[r - 1].out;
+          if ((rc2 = add_tn(m, g, Gr, ldg, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc2;
+        }
+      }
+    }
+    if (!g.nprob) return VLA_OK;
+    finalize_tn(g, B);
+    return timed_gemm(m, g, 1, name, wst);
+  };
+  // Data parallel: the decoder weight gradients need nothing from the encoder backward.  Compute them now and send them
+  // (with the loss scalars, which sit behind them in the flat buffer) on the side stream while the encoder backward runs.
+  const bool early_dec = io.dp != nullptr && any_dec && !m->rec && dp_overlap(io.dp);
+  if (early_dec) {
+    vla_dp* dp = io.dp;
+    CK(cudaEventRecord(dp->ev_fork, st));
+    CK(cudaStreamWaitEvent(dp->side, dp->ev_fork, 0));
+    if ((rc = emit_wgrad(false, true, "wgrad_dec", dp->side))) return rc;
+    if ((rc = run_exchange(m, dp, m->cat.w_off / 2, dp->n / 2, 1, dp->side, false))) return rc;
+    CK(cudaEventRecord(dp->ev_join, dp->side));
+  }
   int n_present = 0;
   for (size_t i = 0; i < m->encs.size(); ++i) n_present += present >> i & 1;
   if (any_dec) {
@@ -1009,47 +1100,9 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       if ((rc = timed_gemm(m, g, 2, "dgrad_site", st))) return rc;
     }
   }
-  // ---- every weight (and bias) gradient in one grouped split-K launch ----
-  {
-    GemmGroup g; init_group(g);
-    for (size_t i = 0; i < m->encs.size(); ++i) {
-      if (!(present >> i & 1)) continue;
-      const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
-      for (size_t r = 0; r < e.fc.size(); ++r) {
-        const Lin& l = e.fc[r];
-        const bf16* X = r == 0 ? w.x : w.act[r - 1];
-        const int ldx = r == 0 ? w.ldx : e.fc[r - 1].out;
-        if ((rc = add_tn(m, g, w.gpre[r], l.out, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc;
-      }
-      const Lin& h = e.heads;
-      const bf16* X = e.fc.empty() ? w.x : w.act.back();
-      const int ldx = e.fc.empty() ? w.ldx : e.fc.back().out;
-      if ((rc = add_tn(m, g, m->gml, m->ldgml, X, ldx, h.out, h.in, B, G + h.w_off, h.in, G + h.b_off))) return rc;
-      if (e.type == 'C')
-        if ((rc = add_tn(m, g, w.onehot, w.ld_onehot, w.g_x, w.ldx, m->S, m->E, B, G + e.emb_off, m->E, nullptr))) return rc;
-    }
-    if (any_dec) {
-      // fused first decoder layer: rows of inactive decoders receive zeros (their g_d0 slice was cleared)
-      const Lin& c = m->cat;
-      if ((rc = add_tn(m, g, m->g_d0, c.out, m->z, m->ldz, c.out, c.in, B, G + c.w_off, c.in, G + c.b_off))) return rc;
-      for (size_t i = 0; i < m->decs.size(); ++i) {
-        if (!active[i]) continue;
-        const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
-        for (size_t r = 0; r < d.rest.size(); ++r) {
-          const Lin& l = d.rest[r];
-          const bool last = r + 1 == d.rest.size();
-          const bf16* Gr = last ? w.g_out : w.gact[r];
-          const int ldg = last ? w.ld_gout : l.out;
-          const bf16* X = r == 0 ? m->d0 + d.cat_off : w.act[r - 1];
-          const int ldx = r == 0 ? m->cat.out : d.rest[r - 1].out;
-          if ((rc = add_tn(m, g, Gr, ldg, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc;
-        }
-      }
-    }
-    finalize_tn(g, B);
-    if ((rc = timed_gemm(m, g, 1, "wgrad_all", st))) return rc;
-  }
-  return VLA_OK;
+  // ---- weight (and bias) gradients: one grouped split-K launch (data parallel: the encoder part; the decoder part went early) ----
+  if (early_dec) return emit_wgrad(true, false, "wgrad_enc", st);
+  return emit_wgrad(true, true, "wgrad_all", st);
 }
 
 cudaStream_t as_stream(vla_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -1188,7 +1241,8 @@ int vla_loss(const vla_loss_args_t* a, vla_stream_t stream) {
 }
 
 static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float* eas, float lr, float b1, float b2,
-                     float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st, vla_dp* dp = nullptr) {
+                     float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st, vla_dp* dp = nullptr,
+                     const DpArgs* fused = nullptr) {
   AdamArgs a{};
   a.p = p; a.g = const_cast<float*>(g); a.m = ea; a.v = eas; a.shadow = m->shadow;
   a.gclear = a.g;
@@ -1208,6 +1262,10 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
     const int sub = std::max(1, ceil_div(a.n_chunks, 148));
     StepPhase* ph = rec_phase(m, SK_ADAMW, "adamw", &a, sizeof(a), ceil_div(a.n_chunks, sub), DEP_ALL, 0, 34.0 * m->n_params);
     if (ph) { ph->sub = sub; ph->n_blocks = a.n_chunks; }
+    return VLA_OK;
+  }
+  if (fused) {      // exchange of `fused`'s range + AdamW as one launch (dp_exchange.cu)
+    ProfScope ps(m, st, "dp_exchange_adamw", 0, 34.0 * m->n_params + dp_bytes(*fused)); CK(launch_dp_adamw(*fused, a, st));
     return VLA_OK;
   }
   { ProfScope ps(m, st, "adamw", 0, 34.0 * m->n_params); CK(launch_adamw(a, st)); }
@@ -1311,21 +1369,23 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
+  bo.dp = dp;
   if ((rc = run_backward(m, bo, st))) return rc;
   if (!do_opt) return VLA_OK;
   if (dp && !m->rec) {
-    // ---- the step's one collective: two-shot all-reduce(SUM) over peer memory (clears G); AdamW then reads R ----
-    DpArgs x{};
-    x.world = dp->world; x.rank = dp->rank; x.n2 = dp->n / 2; x.per2 = dp->per2; x.dyn = m->dyn;
-    x.g = reinterpret_cast<float*>(dp->base);
-    for (int r = 0; r < dp->world; ++r) {
-      x.recv[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_recv);
-      x.rsum[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_rsum);
+    // ---- the step's one collective, second part: the encoder gradients (the decoder part left from run_backward on the
+    // side stream, or goes now if there was no decoder gradient); then AdamW, which polls the framed sums of both parts ----
+    // (an engine step carries every decoder gradient, so run_backward took the early path when VLA_DP_OVERLAP=1)
+    const char* fu = getenv("VLA_DP_FUSE");
+    const bool overlap = dp_overlap(dp), fuse = !(fu && fu[0] == '0');
+    const long long end2 = overlap ? m->cat.w_off / 2 : dp->n / 2;
+    if (overlap) CK(cudaStreamWaitEvent(st, dp->ev_join, 0));
+    if (fuse) {
+      const DpArgs x = make_dp_args(m, dp, 0, end2, 0);
+      return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
+                       false, st, dp, &x);
     }
-    x.trace = reinterpret_cast<unsigned long long*>(dp->base + dp->off_trace);
-    // algorithmic bytes: payload out + in over NVLink
-    { ProfScope ps(m, st, "dp_exchange", 0, 8.0 * dp->n * (dp->world - 1) / dp->world); CK(launch_dp_exchange(x, st)); }
-    // AdamW polls the framed sums as it walks the parameters (the exchange already cleared G)
+    if ((rc = run_exchange(m, dp, 0, end2, 0, st, true))) return rc;
     return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
                      false, st, dp);
   }
@@ -1459,13 +1519,16 @@ int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out) {
   const long long n2 = n_floats / 2;
   d->per2 = (n2 + world - 1) / world;
   d->off_recv = up(sizeof(float) * n_floats);
-  d->off_rsum = d->off_recv + up(sizeof(uint4) * static_cast<size_t>(world) * d->per2);
+  d->off_rsum = d->off_recv + up(sizeof(uint4) * 2 * static_cast<size_t>(world) * d->per2);   // one RECV region per part
   d->off_sums = d->off_rsum + up(sizeof(uint4) * static_cast<size_t>(n2));
   d->off_trace = d->off_sums + 256;
   d->bytes = d->off_trace + 256;
   cudaError_t e = cudaMalloc(&d->base, d->bytes);
   if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaFree(d->base); delete d; return fail(VLA_ERR_CUDA, std::string("vla_dp_create: ") + cudaGetErrorString(e)); }
   d->peer[rank] = d->base;
   d->connected = world == 1;
@@ -1509,6 +1572,9 @@ void vla_dp_destroy(vla_dp_t* d) {
   if (!d) return;
   for (int r = 0; r < d->world; ++r)
     if (r != d->rank && d->peer[r]) cudaIpcCloseMemHandle(d->peer[r]);
+  if (d->side) cudaStreamDestroy(d->side);
+  if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+  if (d->ev_join) cudaEventDestroy(d->ev_join);
   cudaFree(d->base);
   delete d;
 }

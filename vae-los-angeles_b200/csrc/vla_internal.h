@@ -337,15 +337,17 @@ struct StepPlan {
 constexpr int DP_MAX_WORLD = 16;
 struct DpArgs {
   int world, rank;
-  long long n2;                         // float2 elements of the flat buffer [gradient arena | 4 loss scalars]
-  long long per2;                       // float2 elements per shard = ceil(n2 / world)
-  float* g;                             // local gradients [2 n2] (cleared as they are read)
-  uint4* recv[DP_MAX_WORLD];            // every rank's RECV [world][per2] framed words (peer pointers, own included)
-  uint4* rsum[DP_MAX_WORLD];            // every rank's RSUM [n2] framed words
+  long long first2;                     // this launch exchanges float2s [first2, first2 + n2) of the flat buffer
+  long long n2;
+  long long per2;                       // float2 elements per shard of this range = ceil(n2 / world)
+  float* g;                             // local gradients (whole flat buffer; cleared as they are read)
+  uint4* recv[DP_MAX_WORLD];            // every rank's RECV region of this range, [world][per2] framed words (peer pointers)
+  uint4* rsum[DP_MAX_WORLD];            // every rank's RSUM (whole flat buffer, framed words, indexed by float2 index)
   const DynParams* dyn;                 // epoch = dyn->dp_epoch
-  unsigned long long* trace;            // optional [8] %globaltimer stamps of the last launch (block 0)
+  unsigned long long* trace;            // optional [4] %globaltimer stamps of the last launch (block 0)
 };
-cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s);
+cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s, bool pdl);
+cudaError_t launch_dp_adamw(const DpArgs& x, const AdamArgs& a, cudaStream_t s);
 
 struct LossGridInfo { int nb_a, nb_b, nb_c, nb_k; };
 LossGridInfo loss_grid_info(const LossArgs& a);

@@ -280,7 +280,13 @@ class Trainer:
         with torch.cuda.device(self.core.device):
             _lib.check(_lib.lib().vla_dp_trace(self.dp, buf), "vla_dp_trace")
         t = [int(x) for x in buf]
-        return dict(push_us=(t[1] - t[0]) / 1e3, reduce_us=(t[2] - t[1]) / 1e3, total_us=(t[2] - t[0]) / 1e3)
+        out = {}
+        for part, name in ((1, "decoder_part_side_stream"), (0, "encoder_part_main_stream")):
+            o = 4 * part
+            out[name] = dict(push_us=(t[o + 1] - t[o]) / 1e3, reduce_us=(t[o + 2] - t[o + 1]) / 1e3,
+                             total_us=(t[o + 2] - t[o]) / 1e3)
+        out["decoder_part_done_before_encoder_part_starts_us"] = (t[0] - t[6]) / 1e3
+        return out
 
     def timeline(self, which=0):
         """Per-phase timing of the whole-step kernel for ONE replayed step, from the %globaltimer stamps every unit writes
