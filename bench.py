@@ -135,6 +135,41 @@ class ClockSampler:
                     source="nvidia-smi -lms 20")
 
 
+class NumaLocal:
+    """Context manager: run the enclosed host allocations on the CPUs next to GPU `gpu_index` (NVML CPU affinity), so that the
+    pinned staging buffers are first-touched on the GPU's own NUMA node; the previous affinity is restored on exit."""
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.prev, self.note = gpu_index, None, "not bound"
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[self.gpu_index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus:
+                self.prev = allowed
+                os.sched_setaffinity(0, cpus)
+                self.note = f"pinned buffers allocated on the GPU-local CPUs ({len(cpus)} of {len(allowed)})"
+        except Exception as e:                      # no NVML / no affinity support: keep the default placement
+            self.note = f"not bound ({type(e).__name__})"
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+        return False
+
+
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------------
@@ -333,12 +368,14 @@ def run_gpu(args, rank, local_rank, world):
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the loss, double buffered -------------------
     e2e = None
     host = [DeviceDataset.synthetic(B, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=77 + i + 10 * rank) for i in range(4)]
-    pinned = [(h.tpm.cpu().pin_memory(), h.beta.cpu().pin_memory(), h.site.cpu().pin_memory()) for h in host]
+    with NumaLocal(local_rank) as numa:
+        pinned = [(h.tpm.cpu().pin_memory(), h.beta.cpu().pin_memory(), h.site.cpu().pin_memory()) for h in host]
     del host
     slots = [DeviceDataset.synthetic(B, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=5 + i) for i in range(2)]
     tr2 = Trainer(model, slots, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg,
                   exchange=args.exchange)
-    loss_host = [torch.zeros(4).pin_memory() for _ in range(2)]
+    with NumaLocal(local_rank):
+        loss_host = [torch.zeros(4).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     h2d_bytes = sum(x.numel() * x.element_size() for x in pinned[0])
@@ -377,7 +414,9 @@ def run_gpu(args, rank, local_rank, world):
     ms2 = float(t.item())
     e2e = {"value": k_e2e * B * world / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
            "d2h_bytes_per_step": 16 * world, "steps": k_e2e, "ms_per_step": ms2 / k_e2e,
-           "how": "pinned host batch -> cudaMemcpyAsync H2D (copy stream, double buffered) -> fused step graph -> 16 B loss D2H"}
+           "h2d_gb_per_s": h2d_bytes / (ms2 / k_e2e * 1e-3) / 1e9, "host_numa": numa.note,
+           "how": "pinned host batch -> cudaMemcpyAsync H2D (copy stream, double buffered) -> fused step graph -> 16 B loss D2H; "
+                  "bound by the host->device link (h2d_gb_per_s), the step itself takes ms_per_step of the device-resident line"}
 
     # ---- per-launch timing (eager, CUDA events inside the library) -> dominant kernel roofline ----------------
     peaks = load_peaks()
@@ -474,8 +513,8 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rna2dna", choices=sorted(WORK))
     ap.add_argument("--batch", type=int, default=4096)
