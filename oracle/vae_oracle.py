@@ -67,11 +67,52 @@ MODEL_KINDS = {
         encoders=[("encoder_dna", "B"), ("encoder_site", "C")],
         decoders=[("decoder_rna", "A")],
     ),
+    # Directional autoencoders (src/models/directional_ae.py:10-134): the same stacks with ONE head of width L per
+    # encoder (the last Linear of the nn.Sequential / `site_projection`), latent = mean over the present encoders,
+    # no reparameterisation, no KL term.
+    "rna2dna_ae": dict(
+        encoders=[("encoder_rna", "A"), ("site", "C")],
+        decoders=[("decoder_dna", "B")],
+        ae=True,
+    ),
+    "dna2rna_ae": dict(
+        encoders=[("encoder_dna", "B"), ("site", "C")],
+        decoders=[("decoder_rna", "A")],
+        ae=True,
+    ),
 }
 
 ENC_HIDDEN = {"A": [128], "B": [512, 256]}          # encoders.py:12-17, 30-39
 DEC_HIDDEN = {"A": [128], "B": [256, 512], "C": [64]}  # decoders.py:12-16, 26-33, 43-47
 INPUT_OF = {"A": "a", "B": "b", "C": "site"}        # which input feeds which stack type
+
+
+def is_ae(kind):
+    return bool(MODEL_KINDS[kind].get("ae"))
+
+
+def enc_names(kind, prefix, t):
+    """state_dict key stems of one encoder stack: emb (embedding weight key), fc / bn / drop (one per hidden layer; drop
+    is the key of the Dropout's keep-mask in `masks`), heads ([mu, logvar] for the VAEs, [latent] for the AEs).
+    VAE names: src/models/encoders.py:12-19, 30-41, 53-55; AE names: src/models/directional_ae.py:21-32, 80-95."""
+    depth = 0 if t == "C" else len(ENC_HIDDEN[t])
+    if not is_ae(kind):
+        return dict(emb=f"{prefix}.embedding.weight", fc=[f"{prefix}.fc.{4 * i}" for i in range(depth)],
+                    bn=[f"{prefix}.fc.{4 * i + 1}" for i in range(depth)], drop=[f"{prefix}.fc.{4 * i + 3}" for i in range(depth)],
+                    heads=[f"{prefix}.fc_mu", f"{prefix}.fc_logvar"])
+    if t == "C":
+        return dict(emb="site_embedding.weight", fc=[], bn=[], drop=[], heads=["site_projection"])
+    return dict(emb=None, fc=[f"{prefix}.{4 * i}" for i in range(depth)], bn=[f"{prefix}.{4 * i + 1}" for i in range(depth)],
+                drop=[f"{prefix}.{4 * i + 3}" for i in range(depth)], heads=[f"{prefix}.{4 * depth}"])
+
+
+def bn_affine_keys(kind):
+    out = set()
+    for prefix, t in MODEL_KINDS[kind]["encoders"]:
+        for stem in enc_names(kind, prefix, t)["bn"]:
+            out.add(stem + ".weight")
+            out.add(stem + ".bias")
+    return out
 
 
 def feature_dim(stack_type, dims):
@@ -86,24 +127,24 @@ def param_shapes(kind, dims):
     out = {}
     spec = MODEL_KINDS[kind]
     for prefix, t in spec["encoders"]:
+        nm = enc_names(kind, prefix, t)
         if t == "C":
-            out[f"{prefix}.embedding.weight"] = (dims["S"], E)
+            out[nm["emb"]] = (dims["S"], E)
             last = E
         else:
             last = feature_dim(t, dims)
             for i, h in enumerate(ENC_HIDDEN[t]):
-                out[f"{prefix}.fc.{4 * i}.weight"] = (h, last)
-                out[f"{prefix}.fc.{4 * i}.bias"] = (h,)
-                out[f"{prefix}.fc.{4 * i + 1}.weight"] = (h,)
-                out[f"{prefix}.fc.{4 * i + 1}.bias"] = (h,)
-                out[f"{prefix}.fc.{4 * i + 1}.running_mean"] = (h,)
-                out[f"{prefix}.fc.{4 * i + 1}.running_var"] = (h,)
-                out[f"{prefix}.fc.{4 * i + 1}.num_batches_tracked"] = ()
+                out[nm["fc"][i] + ".weight"] = (h, last)
+                out[nm["fc"][i] + ".bias"] = (h,)
+                out[nm["bn"][i] + ".weight"] = (h,)
+                out[nm["bn"][i] + ".bias"] = (h,)
+                out[nm["bn"][i] + ".running_mean"] = (h,)
+                out[nm["bn"][i] + ".running_var"] = (h,)
+                out[nm["bn"][i] + ".num_batches_tracked"] = ()
                 last = h
-        out[f"{prefix}.fc_mu.weight"] = (L, last)
-        out[f"{prefix}.fc_mu.bias"] = (L,)
-        out[f"{prefix}.fc_logvar.weight"] = (L, last)
-        out[f"{prefix}.fc_logvar.bias"] = (L,)
+        for head in nm["heads"]:
+            out[head + ".weight"] = (L, last)
+            out[head + ".bias"] = (L,)
     for prefix, t in spec["decoders"]:
         last = L
         widths = DEC_HIDDEN[t] + [feature_dim(t, dims)]
@@ -159,8 +200,7 @@ def init_state(kind, dims, seed=0, dtype=np.float32):
             state[key] = np.ones(shape, dtype=dtype)
         elif "embedding" in key:
             state[key] = hash_normal(n, seed, i).reshape(shape).astype(dtype)
-        elif len(shape) == 1 and ".fc." in key and int(key.split(".fc.")[1].split(".")[0]) % 4 == 1 \
-                and key.split(".")[0].startswith("encoder"):
+        elif key in bn_affine_keys(kind):
             # BatchNorm affine: weight ~ 1 + 0.1 u, bias ~ 0.1 u
             u = hash_uniform(n, seed, i) * 2.0 - 1.0
             base = 1.0 if key.endswith("weight") else 0.0
@@ -197,9 +237,10 @@ def synthetic_noise(n, dims, kind, seed=0, dtype=np.float32):
     for prefix, t in MODEL_KINDS[kind]["encoders"]:
         if t == "C":
             continue
+        nm = enc_names(kind, prefix, t)
         for i, h in enumerate(ENC_HIDDEN[t]):
             keep = hash_uniform(n * h, seed, 31 + j) >= DROPOUT_P
-            masks[f"{prefix}.fc.{4 * i + 3}"] = keep.reshape(n, h).astype(np.uint8)
+            masks[nm["drop"][i]] = keep.reshape(n, h).astype(np.uint8)
             j += 1
     return eps, masks
 
@@ -237,7 +278,8 @@ def _linear(x, w, b, q=_ident):
 def forward(kind, dims, state, inputs, eps, masks=None, train=True, update_running=True, q=None):
     """Forward pass of `kind` on `inputs` = {'a':..., 'b':..., 'site':...} (missing/None = absent).
 
-    Returns (outputs, cache).  outputs = {'recon': {decoder prefix: array}, 'mu', 'logvar', 'z'}.
+    Returns (outputs, cache).  outputs = {'recon': {decoder prefix: array}, 'mu', 'logvar', 'z'}; for the autoencoder
+    kinds 'mu' is the latent (directional_ae.py:46-56) and 'logvar' is None.
     In train mode BN running statistics in `state` are updated in place (as nn.BatchNorm1d does)
     unless update_running=False.  `eps` is the injected N(0,1) draw; reparameterize always samples,
     also in eval mode (vae.py:11-15)."""
@@ -251,16 +293,17 @@ def forward(kind, dims, state, inputs, eps, masks=None, train=True, update_runni
         if x is None:
             continue
         c = {}
+        nm = enc_names(kind, prefix, t)
         if t == "C":
-            h = q(state[f"{prefix}.embedding.weight"][x])         # encoders.py:58
+            h = q(state[nm["emb"]][x])                            # encoders.py:58
             c["site"] = x
         else:
             h = q(x.reshape(x.shape[0], -1).astype(dt))           # encoders.py:44
             c["layers"] = []
             for i, width in enumerate(ENC_HIDDEN[t]):
                 lc = {"x": h}
-                pre = _linear(h, state[f"{prefix}.fc.{4 * i}.weight"], state[f"{prefix}.fc.{4 * i}.bias"], q)
-                bn = f"{prefix}.fc.{4 * i + 1}"
+                pre = _linear(h, state[nm["fc"][i] + ".weight"], state[nm["fc"][i] + ".bias"], q)
+                bn = nm["bn"][i]
                 if train:
                     n = pre.shape[0]
                     if n < 2:
@@ -280,7 +323,7 @@ def forward(kind, dims, state, inputs, eps, masks=None, train=True, update_runni
                 y = xhat * state[bn + ".weight"] + state[bn + ".bias"]
                 r = np.maximum(y, 0)
                 if train:
-                    keep = masks[f"{prefix}.fc.{4 * i + 3}"].astype(dt)
+                    keep = masks[nm["drop"][i]].astype(dt)
                     h = q(r * keep / (1 - DROPOUT_P))
                 else:
                     keep = None
@@ -288,21 +331,21 @@ def forward(kind, dims, state, inputs, eps, masks=None, train=True, update_runni
                 lc.update(xhat=xhat, rstd=rstd, y=y, keep=keep)
                 c["layers"].append(lc)
         c["h"] = h
-        mu = _linear(h, state[f"{prefix}.fc_mu.weight"], state[f"{prefix}.fc_mu.bias"], q)
-        lv = _linear(h, state[f"{prefix}.fc_logvar.weight"], state[f"{prefix}.fc_logvar.bias"], q)
+        mu = _linear(h, state[nm["heads"][0] + ".weight"], state[nm["heads"][0] + ".bias"], q)
         mus.append(mu)
-        lvs.append(lv)
+        if len(nm["heads"]) == 2:
+            lvs.append(_linear(h, state[nm["heads"][1] + ".weight"], state[nm["heads"][1] + ".bias"], q))
         cache["enc"][prefix] = c
         cache["present"].append((prefix, t))
     if not mus:
         return None, None
-    if len(mus) == 1:
-        mu, logvar = mus[0], lvs[0]
+    mu = mus[0] if len(mus) == 1 else np.stack(mus).mean(0)       # vae.py:70-71; directional_ae.py:53-56
+    if is_ae(kind):
+        logvar, std, z = None, None, mu                           # the latent itself feeds the decoder
     else:
-        mu = np.stack(mus).mean(0)                                # vae.py:70-71
-        logvar = np.stack(lvs).mean(0)
-    std = np.exp(0.5 * logvar)
-    z = mu + eps * std                                            # vae.py:13-15
+        logvar = lvs[0] if len(lvs) == 1 else np.stack(lvs).mean(0)
+        std = np.exp(0.5 * logvar)
+        z = mu + eps * std                                        # vae.py:13-15
     cache.update(mu=mu, logvar=logvar, std=std, eps=eps, z=z)
     recon = {}
     for prefix, t in spec["decoders"]:
@@ -378,6 +421,9 @@ def loss_and_output_grads(kind, outputs, targets, beta=1e-3, gamma=1.0, class_we
             cls_val += v
             g = gamma * g
         g_recon[prefix] = g
+    if outputs["logvar"] is None:                                 # autoencoders: reconstruction only (ae_losses.py:8-39)
+        return (dict(total=recon_val, recon=recon_val, cls=0.0, kld=0.0),
+                dict(recon=g_recon, mu=np.zeros_like(outputs["mu"]), logvar=None))
     kld, gmu, glv = kld_sum(outputs["mu"], outputs["logvar"])
     total = recon_val + gamma * cls_val + beta * kld
     return (dict(total=total, recon=recon_val, cls=cls_val, kld=kld),
@@ -412,26 +458,32 @@ def backward(kind, dims, state, cache, out_grads, train=True):
             if i > 0:
                 g = q(g * (acts[i] > 0))
         gz = gz + g
+    ae = is_ae(kind)
     gmu = gz + out_grads["mu"]
-    glv = gz * cache["eps"] * 0.5 * cache["std"] + out_grads["logvar"]
     m = len(cache["present"])
-    gmu_e, glv_e = q(gmu / m), q(glv / m)                         # mean fusion (identity when m == 1)
+    gmu_e = q(gmu / m)                                            # mean fusion (identity when m == 1)
+    if not ae:
+        glv = gz * cache["eps"] * 0.5 * cache["std"] + out_grads["logvar"]
+        glv_e = q(glv / m)
     for prefix, t in cache["present"]:
         c = cache["enc"][prefix]
         h = c["h"]
-        grads[f"{prefix}.fc_mu.weight"] = gmu_e.T @ h
-        grads[f"{prefix}.fc_mu.bias"] = gmu_e.sum(0)
-        grads[f"{prefix}.fc_logvar.weight"] = glv_e.T @ h
-        grads[f"{prefix}.fc_logvar.bias"] = glv_e.sum(0)
-        g = gmu_e @ q(state[f"{prefix}.fc_mu.weight"]) + glv_e @ q(state[f"{prefix}.fc_logvar.weight"])
+        nm = enc_names(kind, prefix, t)
+        grads[nm["heads"][0] + ".weight"] = gmu_e.T @ h
+        grads[nm["heads"][0] + ".bias"] = gmu_e.sum(0)
+        g = gmu_e @ q(state[nm["heads"][0] + ".weight"])
+        if not ae:
+            grads[nm["heads"][1] + ".weight"] = glv_e.T @ h
+            grads[nm["heads"][1] + ".bias"] = glv_e.sum(0)
+            g = g + glv_e @ q(state[nm["heads"][1] + ".weight"])
         if t == "C":
-            ge = np.zeros_like(state[f"{prefix}.embedding.weight"])
+            ge = np.zeros_like(state[nm["emb"]])
             np.add.at(ge, c["site"], q(g))                        # embedding_dense_backward
-            grads[f"{prefix}.embedding.weight"] = ge
+            grads[nm["emb"]] = ge
             continue
         for i in range(len(ENC_HIDDEN[t]) - 1, -1, -1):
             lc = c["layers"][i]
-            bn = f"{prefix}.fc.{4 * i + 1}"
+            bn = nm["bn"][i]
             if train:
                 g = g * lc["keep"] / (1 - DROPOUT_P)
             g = g * (lc["y"] > 0)
@@ -446,10 +498,10 @@ def backward(kind, dims, state, cache, out_grads, train=True):
             else:
                 g = g * gam * lc["rstd"]
             g = q(g)
-            grads[f"{prefix}.fc.{4 * i}.weight"] = g.T @ lc["x"]
-            grads[f"{prefix}.fc.{4 * i}.bias"] = g.sum(0)
+            grads[nm["fc"][i] + ".weight"] = g.T @ lc["x"]
+            grads[nm["fc"][i] + ".bias"] = g.sum(0)
             if i > 0:
-                g = g @ q(state[f"{prefix}.fc.{4 * i}.weight"])
+                g = g @ q(state[nm["fc"][i] + ".weight"])
     # parameters of absent stacks get no gradient (autograd leaves .grad = None)
     return grads
 

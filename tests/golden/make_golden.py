@@ -36,6 +36,10 @@ def load_reference():
     import ref_src.models as rm
     import ref_src.utils.losses as rl
     import ref_src.utils.directional_losses as rdl
+    import ref_src.models.directional_ae as rae          # not re-exported by the reference's models/__init__.py
+    import ref_src.utils.ae_losses as rael
+    rm.RNA2DNAAE, rm.DNA2RNAAE = rae.RNA2DNAAE, rae.DNA2RNAAE
+    rdl.rna2dna_ae_loss, rdl.dna2rna_ae_loss = rael.rna2dna_ae_loss, rael.dna2rna_ae_loss
     return rm, rl, rdl
 
 
@@ -82,6 +86,15 @@ CASES = [
          beta=1e-3, gamma=1.0, weights=False, present=("a",), train=True, steps=1),
     dict(name="dna2rna_eval_dna_only", kind="dna2rna", dims=dict(A=50, B=36, S=5, L=12, E=64), n=6, seed=8,
          beta=1e-3, gamma=1.0, weights=False, present=("b",), train=False, steps=0),
+    # directional autoencoders (src/models/directional_ae.py, src/utils/ae_losses.py)
+    dict(name="rna2dna_ae_full", kind="rna2dna_ae", dims=dict(A=782, B=572, S=24, L=20, E=32), n=32, seed=9,
+         beta=0.0, gamma=1.0, weights=False, present=("a", "site"), train=True, steps=2),
+    dict(name="dna2rna_ae_full", kind="dna2rna_ae", dims=dict(A=782, B=572, S=24, L=20, E=32), n=32, seed=10,
+         beta=0.0, gamma=1.0, weights=False, present=("b", "site"), train=True, steps=2),
+    dict(name="rna2dna_ae_eval_rna_only", kind="rna2dna_ae", dims=dict(A=50, B=36, S=5, L=12, E=16), n=6, seed=11,
+         beta=0.0, gamma=1.0, weights=False, present=("a",), train=False, steps=0),
+    dict(name="dna2rna_ae_train_site_only", kind="dna2rna_ae", dims=dict(A=50, B=36, S=5, L=12, E=16), n=7, seed=12,
+         beta=0.0, gamma=1.0, weights=False, present=("site",), train=True, steps=1),
 ]
 
 
@@ -91,8 +104,12 @@ def build_reference_model(rm, case):
         m = rm.MultiModalVAE(d["A"], d["B"], d["S"], d["L"], embed_dim=d["E"])
     elif case["kind"] == "rna2dna":
         m = rm.RNA2DNAVAE(d["A"], d["B"], d["S"], d["L"], embed_dim=d["E"])
-    else:
+    elif case["kind"] == "dna2rna":
         m = rm.DNA2RNAVAE(d["A"], d["B"], d["S"], d["L"], embed_dim=d["E"])
+    elif case["kind"] == "rna2dna_ae":
+        m = rm.RNA2DNAAE(d["A"], d["B"], d["S"], d["L"], embed_dim=d["E"])
+    else:
+        m = rm.DNA2RNAAE(d["A"], d["B"], d["S"], d["L"], embed_dim=d["E"])
     return m
 
 
@@ -119,8 +136,12 @@ def run_case(rm, rl, rdl, case):
     sd = {k: torch.from_numpy(np.array(v)) for k, v in state.items()}
     model.load_state_dict(sd, strict=True)
     for key, keep in masks.items():
-        prefix, _, idx = key.rpartition(".fc.")
-        seq = getattr(model, prefix).fc
+        if vo.is_ae(case["kind"]):
+            prefix, _, idx = key.rpartition(".")             # the AE encoders are bare nn.Sequentials
+            seq = getattr(model, prefix)
+        else:
+            prefix, _, idx = key.rpartition(".fc.")
+            seq = getattr(model, prefix).fc
         assert isinstance(seq[int(idx)], torch.nn.Dropout) and seq[int(idx)].p == vo.DROPOUT_P
         seq[int(idx)] = ReplayDropout(torch.from_numpy(keep.astype(np.float32)), vo.DROPOUT_P)
     model.train(case["train"])
@@ -149,16 +170,27 @@ def run_case(rm, rl, rdl, case):
                     loss, recon, kld = rdl.rna2dna_loss(rb, tb, mu, lv, beta=case["beta"])
                     cls = 0.0
                     recons = {"decoder_dna": rb}
-                else:
+                elif case["kind"] == "dna2rna":
                     ra, mu, lv = model(dna=b, site=s)
                     loss, recon, kld = rdl.dna2rna_loss(ra, ta, mu, lv, beta=case["beta"])
                     cls = 0.0
+                    recons = {"decoder_rna": ra}
+                elif case["kind"] == "rna2dna_ae":
+                    rb, mu = model(rna=a, site=s)                 # (recon, latent)
+                    loss, recon = rdl.rna2dna_ae_loss(rb, tb)
+                    cls, kld, lv = 0.0, 0.0, None
+                    recons = {"decoder_dna": rb}
+                else:
+                    ra, mu = model(dna=b, site=s)
+                    loss, recon = rdl.dna2rna_ae_loss(ra, ta)
+                    cls, kld, lv = 0.0, 0.0, None
                     recons = {"decoder_rna": ra}
             if step == 0:
                 for k, v in recons.items():
                     pack(f"out.recon.{k}", v.detach().numpy(), out)
                 pack("out.mu", mu.detach().numpy(), out)
-                pack("out.logvar", lv.detach().numpy(), out)
+                if lv is not None:
+                    pack("out.logvar", lv.detach().numpy(), out)
                 out["loss"] = np.array([loss.item(), recon, cls, kld], dtype=np.float64)
             if case["steps"] > 0:
                 opt.zero_grad()
@@ -182,7 +214,10 @@ def run_case(rm, rl, rdl, case):
 def main():
     torch.set_num_threads(1)
     rm, rl, rdl = load_reference()
+    only = sys.argv[1:]                                   # optional: fixture names to (re)generate
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         out = run_case(rm, rl, rdl, case)
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **out)
