@@ -27,6 +27,10 @@ WORK = {
     "rna2dna": dict(flop=3_013_120, bytes=7_872, params=538_124),
     "dna2rna": dict(flop=2_642_944, bytes=8_712, params=542_174),
     "multimodal": dict(flop=5_665_280, bytes=11_096, params=1_081_114),
+    # directional autoencoders: the VAE figures minus one head per encoder (fwd + dgrad + wgrad = 6 FLOP per
+    # head weight: 20 x (128 + 32) resp. 20 x (256 + 32) weights) and 80 B less output (latent only, no logvar)
+    "rna2dna_ae": dict(flop=3_013_120 - 6 * 20 * (128 + 32), bytes=7_872 - 80, params=538_124 - 20 * (128 + 32) - 40),
+    "dna2rna_ae": dict(flop=2_642_944 - 6 * 20 * (256 + 32), bytes=8_712 - 80, params=542_174 - 20 * (256 + 32) - 40),
 }
 METRIC = "train samples/sec (fwd+bwd+Adam) at batch 4096"
 
@@ -238,8 +242,10 @@ def train_throughput(workload, B, dev, steps, warmup):
     """Fused train step of another model kind at the same per-GPU batch (device-timed, CUDA graph replay)."""
     import torch
     from src.models import DNA2RNAVAE, MultiModalVAE, RNA2DNAVAE
+    from src.models.directional_ae import DNA2RNAAE, RNA2DNAAE
     from vla_b200 import DeviceDataset, Trainer
-    cls = {"rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE, "multimodal": MultiModalVAE}[workload]
+    cls = {"rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE, "multimodal": MultiModalVAE, "rna2dna_ae": RNA2DNAAE,
+           "dna2rna_ae": DNA2RNAAE}[workload]
     torch.manual_seed(0)
     model = cls(DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"]).to(dev).train()
     ds = DeviceDataset.synthetic(B * 32, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=3)
@@ -329,7 +335,9 @@ def run_gpu(args, rank, local_rank, world):
         os.environ.setdefault("MASTER_PORT", "29533"); os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
-    cls = {"rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE, "multimodal": MultiModalVAE}[args.workload]
+    from src.models.directional_ae import DNA2RNAAE, RNA2DNAAE
+    cls = {"rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE, "multimodal": MultiModalVAE, "rna2dna_ae": RNA2DNAAE,
+           "dna2rna_ae": DNA2RNAAE}[args.workload]
     torch.manual_seed(0)                       # identical replicas on every rank
     model = cls(DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"]).to(dev).train()
     B = args.batch
@@ -478,7 +486,7 @@ def run_gpu(args, rank, local_rank, world):
     # ---- the other BASELINE.json configurations, short runs (reported under "also"; not the headline) ----------------
     also = []
     if world == 1 and not args.no_also:
-        for wl in ("multimodal", "dna2rna", "rna2dna"):
+        for wl in ("multimodal", "dna2rna", "rna2dna", "rna2dna_ae", "dna2rna_ae"):
             if wl == args.workload:
                 continue
             also.append(train_throughput(wl, B, dev, steps=60, warmup=5))

@@ -21,13 +21,16 @@ extern "C" {
 typedef void* vla_stream_t;
 typedef struct vla_model vla_model_t;
 
-enum { VLA_KIND_MULTIMODAL = 0, VLA_KIND_RNA2DNA = 1, VLA_KIND_DNA2RNA = 2 };
+enum { VLA_KIND_MULTIMODAL = 0, VLA_KIND_RNA2DNA = 1, VLA_KIND_DNA2RNA = 2, VLA_KIND_RNA2DNA_AE = 3, VLA_KIND_DNA2RNA_AE = 4 };
 enum { VLA_OK = 0, VLA_ERR_INVALID = -1, VLA_ERR_CUDA = -2, VLA_ERR_STATE = -3 };
 enum { VLA_TENSOR_PARAM = 0, VLA_TENSOR_BUFFER = 1, VLA_TENSOR_COUNTER = 2 };
 
 /* Model geometry.  kind selects the encoder / decoder stacks:
  *   MULTIMODAL: MultiModalVAE.__init__ (src/models/vae.py:27-35)
- *   RNA2DNA / DNA2RNA: RNA2DNAVAE / DNA2RNAVAE.__init__ (src/models/directional_vae.py:19-23, 70-74) */
+ *   RNA2DNA / DNA2RNA: RNA2DNAVAE / DNA2RNAVAE.__init__ (src/models/directional_vae.py:19-23, 70-74)
+ *   RNA2DNA_AE / DNA2RNA_AE: RNA2DNAAE / DNA2RNAAE.__init__ (src/models/directional_ae.py:17-35, 76-98): the same stacks with
+ *     one head of width `latent` per encoder; forward (directional_ae.py:37-59, 100-123) returns the latent in `mu`
+ *     (`logvar` is written as zeros), nothing is sampled and every KL term is zero (src/utils/ae_losses.py:8-39). */
 typedef struct {
   int kind;
   int dim_a;     /* RNA features   (input_dim_a / rna_dim) */

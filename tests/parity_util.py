@@ -29,12 +29,19 @@ def rel_l2(x, ref):
 
 def is_pre_bn_bias(name):
     m = re.fullmatch(r"encoder_\w+\.fc\.(\d+)\.bias", name)
-    return bool(m) and int(m.group(1)) % 4 == 0
+    if m:
+        return int(m.group(1)) % 4 == 0
+    m = re.fullmatch(r"encoder_(rna|dna)\.(\d+)\.bias", name)      # autoencoders: the last Linear is the head (no BatchNorm behind it)
+    if m:
+        return int(m.group(2)) % 4 == 0 and int(m.group(2)) < 4 * (1 if m.group(1) == "rna" else 2)
+    return False
 
 
 def module_class(kind):
     from src.models import DNA2RNAVAE, MultiModalVAE, RNA2DNAVAE
-    return {"multimodal": MultiModalVAE, "rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE}[kind]
+    from src.models.directional_ae import DNA2RNAAE, RNA2DNAAE
+    return {"multimodal": MultiModalVAE, "rna2dna": RNA2DNAVAE, "dna2rna": DNA2RNAVAE,
+            "rna2dna_ae": RNA2DNAAE, "dna2rna_ae": DNA2RNAAE}[kind]
 
 
 def make_module(kind, dims, state, device="cuda"):
@@ -53,9 +60,15 @@ def call_module(m, kind, a=None, b=None, site=None):
     elif kind == "rna2dna":
         rb, mu, lv = m(rna=a, site=site)
         recon = {"decoder_dna": rb}
-    else:
+    elif kind == "dna2rna":
         ra, mu, lv = m(dna=b, site=site)
         recon = {"decoder_rna": ra}
+    elif kind == "rna2dna_ae":
+        rb, mu = m(rna=a, site=site)                 # (reconstruction, latent)
+        recon, lv = {"decoder_dna": rb}, None
+    else:
+        ra, mu = m(dna=b, site=site)
+        recon, lv = {"decoder_rna": ra}, None
     return dict(recon=recon, mu=mu, logvar=lv)
 
 
@@ -69,9 +82,17 @@ def loss_for(kind, out, batch_t, beta, gamma, cw):
     elif kind == "rna2dna":
         total, recon, kld = rna2dna_loss(out["recon"]["decoder_dna"], batch_t["b"], out["mu"], out["logvar"], beta=beta)
         cls = 0.0
-    else:
+    elif kind == "dna2rna":
         total, recon, kld = dna2rna_loss(out["recon"]["decoder_rna"], batch_t["a"], out["mu"], out["logvar"], beta=beta)
         cls = 0.0
+    elif kind == "rna2dna_ae":
+        from src.utils.ae_losses import rna2dna_ae_loss
+        total, recon = rna2dna_ae_loss(out["recon"]["decoder_dna"], batch_t["b"])
+        cls, kld = 0.0, 0.0
+    else:
+        from src.utils.ae_losses import dna2rna_ae_loss
+        total, recon = dna2rna_ae_loss(out["recon"]["decoder_rna"], batch_t["a"])
+        cls, kld = 0.0, 0.0
     return total, (recon, cls, kld)
 
 

@@ -29,7 +29,8 @@ def _oracle_train(kind, dims, state, data, n_steps, batch, eps, masks, beta, gam
 
 
 @pytest.mark.parametrize("kind,dims,batch,use_graph", [("rna2dna", FULL, 64, True), ("multimodal", SMALL, 48, True),
-                                                         ("dna2rna", FULL, 40, False), ("multimodal", FULL, 64, True)])
+                                                         ("dna2rna", FULL, 40, False), ("multimodal", FULL, 64, True),
+                                                         ("rna2dna_ae", FULL, 64, True), ("dna2rna_ae", SMALL, 40, False)])
 def test_fused_train_steps_match_oracle(kind, dims, batch, use_graph):
     from vla_b200 import DeviceDataset, Trainer
     n_steps, n_batches = 4, 3

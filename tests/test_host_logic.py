@@ -43,7 +43,7 @@ def test_arena_layout_matches_state_dict_contract(kind, dims):
         assert a1 <= b0
     assert spans[-1][1] <= lay.n_params
     # fused groups: fc_mu / fc_logvar rows are adjacent (one [2L, in] GEMM); decoder first layers are adjacent
-    for prefix, _ in vo.MODEL_KINDS[kind]["encoders"]:
+    for prefix, _ in ([] if vo.is_ae(kind) else vo.MODEL_KINDS[kind]["encoders"]):     # (autoencoders: one head per encoder)
         mu_off, mu_shape = lay.params[prefix + ".fc_mu.weight"]
         lv_off, _ = lay.params[prefix + ".fc_logvar.weight"]
         assert lv_off == mu_off + mu_shape[0] * mu_shape[1]
@@ -90,6 +90,31 @@ def test_dropin_surface_signatures_and_init():
     m2.load_state_dict(sd)
     for k, v in m2.state_dict().items():
         assert torch.equal(v, sd[k]), k
+
+
+def test_autoencoder_dropin_surface():
+    """RNA2DNAAE / DNA2RNAAE and their losses keep the reference's names, signatures, return arity and state_dict keys
+    (src/models/directional_ae.py:17-59, 76-123; src/utils/ae_losses.py:8-39)."""
+    from src.models.directional_ae import DNA2RNAAE, RNA2DNAAE
+    from src.utils.ae_losses import dna2rna_ae_loss, rna2dna_ae_loss
+    assert list(inspect.signature(RNA2DNAAE.__init__).parameters)[1:] == ["rna_dim", "dna_dim", "n_sites", "latent_dim", "embed_dim"]
+    assert list(inspect.signature(RNA2DNAAE.forward).parameters)[1:] == ["rna", "site"]
+    assert list(inspect.signature(DNA2RNAAE.forward).parameters)[1:] == ["dna", "site"]
+    assert list(inspect.signature(rna2dna_ae_loss).parameters) == ["recon_dna", "dna"]
+    assert list(inspect.signature(dna2rna_ae_loss).parameters) == ["recon_rna", "rna"]
+    dims = dict(A=782, B=572, S=24, L=20, E=32)
+    for cls, kind in ((RNA2DNAAE, "rna2dna_ae"), (DNA2RNAAE, "dna2rna_ae")):
+        m = cls(782, 572, 24, 20)
+        shapes = vo.param_shapes(kind, dims)
+        sd = m.state_dict()
+        assert list(sd) == list(shapes)                                       # same keys in the same order
+        for k, v in sd.items():
+            assert tuple(v.shape) == tuple(shapes[k]), k
+        assert m() == (None, None)
+        with pytest.raises(RuntimeError, match="CPU"):
+            m(site=torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CPU"):
+        rna2dna_ae_loss(torch.rand(4, 36), torch.rand(4, 36))
 
 
 def test_no_cpu_fallback_anywhere():

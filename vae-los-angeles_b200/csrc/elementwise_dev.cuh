@@ -435,10 +435,18 @@ __device__ __forceinline__ void latent_fwd_body(const LatentFwdArgs& a, int b, i
     for (int e = 0; e < a.n_enc; ++e) {
       const float* p = a.ml[e] + static_cast<size_t>(r) * a.ld_ml[e];
       mu += p[j];
-      lv += p[a.L + j];
+      if (!a.ae) lv += p[a.L + j];
     }
     if (a.n_enc > 1) { mu /= a.n_enc; lv /= a.n_enc; }
     float eps;
+    if (a.ae) {
+      // directional autoencoders (directional_ae.py:46-59): the mean of the encoder outputs IS the decoder input
+      a.mu[idx] = mu;
+      a.logvar[idx] = 0.f;
+      a.eps_save[idx] = 0.f;
+      a.z[static_cast<size_t>(r) * a.ld_z + j] = __float2bfloat16(mu);
+      eps = 0.f;
+    } else {
     if (a.eps_in) {
       eps = a.eps_in[idx];
     } else {
@@ -455,6 +463,7 @@ __device__ __forceinline__ void latent_fwd_body(const LatentFwdArgs& a, int b, i
     a.eps_save[idx] = eps;
     a.z[static_cast<size_t>(r) * a.ld_z + j] = __float2bfloat16(z);
     kl = 1.0f + lv - mu * mu - expf(lv);
+    }
   }
   const float t = block_sum<MEGA>(kl, sh, tid);
   if (tid == 0) a.kl_partials[b] = -0.5f * t;
@@ -468,6 +477,12 @@ __device__ __forceinline__ void latent_bwd_body(const LatentBwdArgs& a, int b, i
   const int j = static_cast<int>(idx - static_cast<unsigned>(r) * a.L);
   const float beta = a.dyn ? a.dyn->beta_kl : a.beta;
   const float gz = a.gz ? a.gz[static_cast<size_t>(r) * a.ld_gz + j] : 0.f;
+  if (a.ae) {
+    float g = gz + (a.gmu_in ? a.gmu_in[idx] : 0.f);
+    if (a.n_modalities > 1) g /= a.n_modalities;
+    a.gml[static_cast<size_t>(r) * a.ld_gml + j] = __float2bfloat16(g);
+    return;
+  }
   const float mu = a.mu[idx], lv = a.logvar[idx], eps = a.eps[idx];
   float gmu = gz + beta * mu;
   float glv = gz * eps * 0.5f * expf(0.5f * lv) + beta * 0.5f * (expf(lv) - 1.0f);

@@ -106,6 +106,7 @@ struct vla_model {
   std::vector<ProfEntry> prof;
   vla_config_t cfg{};
   int L = 0, E = 0, S = 0;
+  bool ae = false; int HW = 0;       // autoencoder kinds: one head of width L per encoder (HW = L), else fused mu | logvar (HW = 2L)
   std::vector<Enc> encs;
   std::vector<Dec> decs;
   Lin cat;
@@ -320,11 +321,21 @@ int build_layout(vla_model* m) {
   } else if (c.kind == VLA_KIND_DNA2RNA) {
     es = {{"encoder_dna", 'B'}, {"encoder_site", 'C'}};
     ds = {{"decoder_rna", 'A'}};
+  } else if (c.kind == VLA_KIND_RNA2DNA_AE) {     // RNA2DNAAE.__init__, src/models/directional_ae.py:17-35
+    es = {{"encoder_rna", 'A'}, {"site", 'C'}};
+    ds = {{"decoder_dna", 'B'}};
+    m->ae = true;
+  } else if (c.kind == VLA_KIND_DNA2RNA_AE) {     // DNA2RNAAE.__init__, src/models/directional_ae.py:76-98
+    es = {{"encoder_dna", 'B'}, {"site", 'C'}};
+    ds = {{"decoder_rna", 'A'}};
+    m->ae = true;
   } else {
     return fail(VLA_ERR_INVALID, "unknown model kind");
   }
   ArenaBuilder ab{m};
   const int L = m->L;
+  const bool ae = m->ae;
+  m->HW = ae ? L : 2 * L;
   for (const auto& s : es) {
     Enc e; e.type = s.type; e.prefix = s.prefix;
     e.slot = s.type == 'A' ? 0 : (s.type == 'B' ? 1 : 2);
@@ -334,7 +345,7 @@ int build_layout(vla_model* m) {
       e.in_dim = c.n_sites;
       e.emb_off = ab.take_p(static_cast<long long>(c.n_sites) * c.embed);
       ab.seg(e.emb_off, c.n_sites, c.embed, -1, 0);
-      ab.info(e.prefix + ".embedding.weight", VLA_TENSOR_PARAM, e.emb_off, c.n_sites, c.embed);
+      ab.info(ae ? std::string("site_embedding.weight") : e.prefix + ".embedding.weight", VLA_TENSOR_PARAM, e.emb_off, c.n_sites, c.embed);
       last = c.embed;
     } else {
       e.in_dim = s.type == 'A' ? c.dim_a : c.dim_b;
@@ -348,8 +359,10 @@ int build_layout(vla_model* m) {
         bn.b_off = ab.take_p(h); ab.seg(bn.b_off, h, 1, -1, 0);
         bn.rm_off = ab.take_b(h); bn.rv_off = ab.take_b(h);
         bn.counter = m->n_bn++;
-        const std::string fc = e.prefix + ".fc." + std::to_string(4 * i);
-        const std::string nb = e.prefix + ".fc." + std::to_string(4 * i + 1);
+        // the autoencoders' encoders are bare nn.Sequentials (directional_ae.py:21-27, 80-90): no ".fc" level
+        const std::string stem = ae ? e.prefix + "." : e.prefix + ".fc.";
+        const std::string fc = stem + std::to_string(4 * i);
+        const std::string nb = stem + std::to_string(4 * i + 1);
         ab.info(fc + ".weight", VLA_TENSOR_PARAM, l.w_off, h, last);
         ab.info(fc + ".bias", VLA_TENSOR_PARAM, l.b_off, h);
         ab.info(nb + ".weight", VLA_TENSOR_PARAM, bn.g_off, h);
@@ -363,11 +376,18 @@ int build_layout(vla_model* m) {
       }
     }
     // fused heads: rows [0, L) = fc_mu, rows [L, 2L) = fc_logvar
-    e.heads = ab.linear(2 * L, last);
-    ab.info(e.prefix + ".fc_mu.weight", VLA_TENSOR_PARAM, e.heads.w_off, L, last);
-    ab.info(e.prefix + ".fc_mu.bias", VLA_TENSOR_PARAM, e.heads.b_off, L);
-    ab.info(e.prefix + ".fc_logvar.weight", VLA_TENSOR_PARAM, e.heads.w_off + static_cast<long long>(L) * last, L, last);
-    ab.info(e.prefix + ".fc_logvar.bias", VLA_TENSOR_PARAM, e.heads.b_off + L, L);
+    e.heads = ab.linear(m->HW, last);
+    if (ae) {
+      // one head: the last Linear of the encoder Sequential, or site_projection (directional_ae.py:26, 30, 89, 93)
+      const std::string head = s.type == 'C' ? std::string("site_projection") : e.prefix + "." + std::to_string(4 * e.fc.size());
+      ab.info(head + ".weight", VLA_TENSOR_PARAM, e.heads.w_off, L, last);
+      ab.info(head + ".bias", VLA_TENSOR_PARAM, e.heads.b_off, L);
+    } else {
+      ab.info(e.prefix + ".fc_mu.weight", VLA_TENSOR_PARAM, e.heads.w_off, L, last);
+      ab.info(e.prefix + ".fc_mu.bias", VLA_TENSOR_PARAM, e.heads.b_off, L);
+      ab.info(e.prefix + ".fc_logvar.weight", VLA_TENSOR_PARAM, e.heads.w_off + static_cast<long long>(L) * last, L, last);
+      ab.info(e.prefix + ".fc_logvar.bias", VLA_TENSOR_PARAM, e.heads.b_off + L, L);
+    }
     m->encs.push_back(e);
   }
   // fused first decoder layers: one [sum of first hidden widths, L] matrix
@@ -434,7 +454,7 @@ void carve(vla_model* m, Bump& b, int cap) {
         w.gpre.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
       }
     }
-    w.ml = b.take<float>(static_cast<size_t>(cap) * 2 * L);
+    w.ml = b.take<float>(static_cast<size_t>(cap) * m->HW);
   }
   m->mu = b.take<float>(static_cast<size_t>(cap) * L);
   m->logvar = b.take<float>(static_cast<size_t>(cap) * L);
@@ -442,7 +462,7 @@ void carve(vla_model* m, Bump& b, int cap) {
   m->gz = b.take<float>(static_cast<size_t>(cap) * L);
   m->kl_partials = b.take<float>(ceil_div(cap * L, 256) + 1);
   m->ldz = pad8(L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
-  m->ldgml = pad8(2 * L); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
+  m->ldgml = pad8(m->HW); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
   m->d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
   m->g_d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
   m->dws.assign(m->decs.size(), DecWS{});
@@ -739,7 +759,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         const bf16* A = r == 0 ? w.x : w.act[r - 1];
         const int lda = r == 0 ? w.ldx : e.fc[r - 1].out;
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_OUT_F32, &p))) return rc;
-        p->bias = P + l.b_off; p->out_f32 = w.ml; p->ld_f32 = 2 * L;
+        p->bias = P + l.b_off; p->out_f32 = w.ml; p->ld_f32 = m->HW;
       }
     }
     if (g.nprob && (rc = timed_gemm(m, g, 0, r == 0 ? "gemm_enc_l0" : (r == 1 ? "gemm_enc_l1" : "gemm_enc_l2"), st))) return rc;
@@ -770,10 +790,10 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
   {
     LatentFwdArgs a{};
     for (size_t i = 0; i < m->encs.size(); ++i)
-      if (present >> i & 1) { a.ml[a.n_enc] = m->ews[i].ml; a.ld_ml[a.n_enc] = 2 * L; a.n_enc++; }
+      if (present >> i & 1) { a.ml[a.n_enc] = m->ews[i].ml; a.ld_ml[a.n_enc] = m->HW; a.n_enc++; }
     a.eps_in = io.eps; a.seed = io.seed; a.offset = io.offset * 16; a.dyn = io.engine ? m->dyn : nullptr;
     a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz;
-    a.kl_partials = m->kl_partials; a.rows = B; a.L = L;
+    a.kl_partials = m->kl_partials; a.rows = B; a.L = L; a.ae = m->ae ? 1 : 0;
     if (m->rec) {
       const int nb = ceil_div(B * L, 256), sub = 4;
       m->kl_grid = nb;
@@ -1033,7 +1053,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     a.gmu_in = io.g_mu; a.glv_in = io.g_logvar;
     a.mu = m->mu; a.logvar = m->logvar; a.eps = m->eps;
     a.beta = 0.f; a.dyn = io.engine ? m->dyn : nullptr;
-    a.n_modalities = n_present; a.gml = m->gml; a.ld_gml = m->ldgml; a.rows = B; a.L = L;
+    a.n_modalities = n_present; a.gml = m->gml; a.ld_gml = m->ldgml; a.rows = B; a.L = L; a.ae = m->ae ? 1 : 0;
     if (m->rec) {
       const int nb = ceil_div(B * L, 256), sub = 4;
       StepPhase* ph = rec_phase(m, SK_LATENT_BWD, "latent_bwd", &a, sizeof(a), ceil_div(nb, sub), DEP_CHAIN, 0, static_cast<double>(B) * L * 20.0);

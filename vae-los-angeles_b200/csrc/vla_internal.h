@@ -206,6 +206,7 @@ struct LatentFwdArgs {
   bf16* z; int ld_z;                              // [rows, ld_z]
   float* kl_partials;                             // [grid]
   int rows, L;
+  int ae;                                         // autoencoder: heads are [rows, L]; z = mu = mean, no sampling, KL = 0
 };
 cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_t s);
 
@@ -218,6 +219,7 @@ struct LatentBwdArgs {
   bf16* gml; int ld_gml;                          // [rows, >= 2L]
   const struct DynParams* dyn;                    // if set, beta is read from dyn->beta_kl
   int rows, L;
+  int ae;                                         // autoencoder: only d(latent) = (gz + gmu_in) / n_modalities, width L
 };
 cudaError_t launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
 

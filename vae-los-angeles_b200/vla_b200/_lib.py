@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvla_b200.so")
 
-KIND = {"multimodal": 0, "rna2dna": 1, "dna2rna": 2}
+KIND = {"multimodal": 0, "rna2dna": 1, "dna2rna": 2, "rna2dna_ae": 3, "dna2rna_ae": 4}
 TENSOR_PARAM, TENSOR_BUFFER, TENSOR_COUNTER = 0, 1, 2
 
 c_float_p = C.c_void_p  # device pointers travel as integers

@@ -21,7 +21,12 @@ KINDS = {
                        decoders=[("decoder_a", "A"), ("decoder_b", "B"), ("decoder_c", "C")]),
     "rna2dna": dict(encoders=[("encoder_rna", "A"), ("encoder_site", "C")], decoders=[("decoder_dna", "B")]),
     "dna2rna": dict(encoders=[("encoder_dna", "B"), ("encoder_site", "C")], decoders=[("decoder_rna", "A")]),
+    # directional autoencoders (src/models/directional_ae.py:17-35, 76-98): the site encoder is two top-level modules
+    "rna2dna_ae": dict(encoders=[("encoder_rna", "A"), ("site", "C")], decoders=[("decoder_dna", "B")]),
+    "dna2rna_ae": dict(encoders=[("encoder_dna", "B"), ("site", "C")], decoders=[("decoder_rna", "A")]),
 }
+# state_dict prefixes owned by an encoder when they differ from its name
+STACK_PREFIXES = {"site": ("site_embedding", "site_projection")}
 ENC_HIDDEN = {"A": (128,), "B": (512, 256)}
 DEC_HIDDEN = {"A": (128,), "B": (256, 512), "C": (64,)}
 
@@ -260,7 +265,8 @@ class Core:
                 raise RuntimeError("vla_b200: injected eps has the wrong shape")
         version = self.param_version()
         by_type = {"A": a, "B": b, "C": site}
-        self.present = tuple(name for name, t in KINDS[self.kind]["encoders"] if by_type[t] is not None)
+        self.present = tuple(p for name, t in KINDS[self.kind]["encoders"] if by_type[t] is not None
+                             for p in STACK_PREFIXES.get(name, (name,)))
         args = _lib.ForwardArgs(
             params=_ptr(self.arena), buffers=_ptr(self.buffers), counters=_ptr(self.counters),
             x_a=_ptr(a), x_b=_ptr(b), site=_ptr(site), batch=batch, train=1 if training else 0,
@@ -406,3 +412,33 @@ class VaeModule(nn.Module):
     def flat_parameters(self):
         """The flat fp32 parameter arena (all nn.Parameters are views of it)."""
         return self._ensure_core().arena
+
+
+class AeModule(VaeModule):
+    """Base of the drop-in directional autoencoders (reference src/models/directional_ae.py:10-134): the encoder is a bare
+    nn.Sequential whose last Linear is the single head, the site branch is `site_embedding` + `site_projection`, the
+    decoder is the VAEs' DecoderA / DecoderB.  forward returns (reconstruction, latent)."""
+
+    def __init__(self, dim_a, dim_b, n_sites, latent_dim, embed_dim=32):
+        nn.Module.__init__(self)
+        self.dim_a, self.dim_b, self.n_sites = int(dim_a), int(dim_b), int(n_sites)
+        self.latent_dim, self.embed_dim = int(latent_dim), int(embed_dim)
+        feat = {"A": self.dim_a, "B": self.dim_b, "C": self.n_sites}
+        (enc_name, enc_t), _ = KINDS[self.kind]["encoders"]
+        kids, last = [], feat[enc_t]
+        for i, h in enumerate(ENC_HIDDEN[enc_t]):
+            kids.append((4 * i, LinearParams(last, h)))
+            kids.append((4 * i + 1, BatchNormParams(h)))
+            last = h
+        kids.append((4 * len(ENC_HIDDEN[enc_t]), LinearParams(last, self.latent_dim)))
+        self.add_module(enc_name, Slots(kids))
+        self.site_embedding = EmbeddingParams(self.n_sites, self.embed_dim)
+        self.site_projection = LinearParams(self.embed_dim, self.latent_dim)
+        for name, t in KINDS[self.kind]["decoders"]:
+            self.add_module(name, self._make_stack("dec", t, feat[t]))
+        self.__dict__["_core"] = None
+        self.__dict__["_injected"] = None
+
+    def _run_ae(self, a, b, site):
+        recon, latent, _ = self._run(a, b, site)
+        return recon, latent

@@ -88,9 +88,12 @@ class _LossFunction(torch.autograd.Function):
 
 
 def fused_vae_loss(recon_a=None, a=None, recon_b=None, b=None, recon_c=None, site=None, mu=None, logvar=None,
-                   beta=1e-3, gamma=1.0, class_weights=None):
-    """Returns (total 0-d tensor with grad, stats tensor [total, recon, class, kld] on the device)."""
-    if mu is None or logvar is None:
+                   beta=1e-3, gamma=1.0, class_weights=None, kl=True):
+    """Returns (total 0-d tensor with grad, stats tensor [total, recon, class, kld] on the device).
+    kl=False: reconstruction terms only (the autoencoder losses, reference src/utils/ae_losses.py)."""
+    if not kl:
+        mu = logvar = None
+    elif mu is None or logvar is None:
         raise RuntimeError("vla_b200: mu and logvar are required")
     if recon_a is None or a is None:
         recon_a = a = None
