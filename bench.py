@@ -271,6 +271,66 @@ def train_throughput(workload, B, dev, steps, warmup):
     return out
 
 
+def population_throughput(dev, B, n_models, steps, warmup):
+    """BASELINE configs[4] on one GPU: `n_models` independent tri-modal VAEs with hyper-parameters drawn from the ranges of
+    optimize_hyperparameters.py:71-76 (latent 10..100, embed 16/32/64, lr, weight decay, beta, gamma), each with its own
+    fused step graph on its own stream (vla_b200.Population), against the same models stepped one after the other."""
+    import numpy as np
+    import torch
+    from src.models import MultiModalVAE
+    from vla_b200 import DeviceDataset, Population
+    rng = np.random.default_rng(0)
+    ds = DeviceDataset.synthetic(B * 8, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=9)
+
+    def specs():
+        out = []
+        torch.manual_seed(0)
+        r = np.random.default_rng(1)
+        for i in range(n_models):
+            L, E = int(r.integers(10, 101)), int(r.choice([16, 32, 64]))
+            out.append(dict(model=MultiModalVAE(DIMS["A"], DIMS["B"], DIMS["S"], L, embed_dim=E), seed=i,
+                            lr=float(10 ** r.uniform(-5, -2)), weight_decay=float(10 ** r.uniform(-6, -3)),
+                            beta_start=float(10 ** r.uniform(-4, -2)), gamma=float(r.uniform(0.5, 5.0))))
+        return out
+
+    def timed(pop, fn):
+        for _ in range(warmup):
+            fn()
+        pop.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        for mem in pop.members:
+            torch.cuda.current_stream(dev).wait_stream(mem.stream)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1)
+
+    pop = Population(specs(), ds, B, device=dev)
+    ms_conc = timed(pop, lambda: pop.step(1))
+
+    def one_by_one():
+        for mem in pop.members:                       # same graphs, serialised: every member's step waits for the previous member's
+            with torch.cuda.stream(mem.stream):
+                mem.trainer.step()
+            torch.cuda.current_stream(dev).wait_stream(mem.stream)
+            for other in pop.members:
+                other.stream.wait_stream(torch.cuda.current_stream(dev))
+
+    ms_seq = timed(pop, one_by_one)
+    losses = pop.losses()
+    pop.close()
+    del rng
+    ok = all(all(x == x and abs(x) < 1e30 for x in l) for l in losses)
+    out = {"workload": f"population: {n_models} independent tri-modal VAEs (latent 10..100, embed 16/32/64), batch {B} each, one GPU",
+           "value": steps * B * n_models / (ms_conc * 1e-3), "unit": "samples/s (all members)",
+           "ms_per_round": ms_conc / steps, "one_after_the_other_samples_per_s": steps * B * n_models / (ms_seq * 1e-3),
+           "concurrency_gain": ms_seq / ms_conc, "losses_finite": ok}
+    torch.cuda.empty_cache()
+    return out
+
+
 def inference_throughput(dev, batch, steps, warmup):
     """BASELINE configs[3]: tri-modal cross-modal inference `model(a=x)` in eval mode (BatchNorm running statistics, no
     dropout, epsilon still sampled), all three decoders, fp32 outputs written; vla_forward replayed from a CUDA graph."""
@@ -491,6 +551,8 @@ def run_gpu(args, rank, local_rank, world):
                 continue
             also.append(train_throughput(wl, B, dev, steps=60, warmup=5))
         also.append(inference_throughput(dev, batch=args.infer_batch, steps=10, warmup=3))
+        also.append(population_throughput(dev, B, n_models=8, steps=30, warmup=3))
+        also.append(population_throughput(dev, 32, n_models=8, steps=100, warmup=5))       # the reference's default batch size
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

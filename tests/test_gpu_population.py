@@ -1,0 +1,90 @@
+"""Population of independent models on one GPU (vla_b200.Population; BASELINE configs[4]): concurrent members equal the same
+models trained alone, and the per-epoch control flow (beta warm-up, ReduceLROnPlateau, early stopping, best-state restore)
+follows the reference loops (optimize_hyperparameters.py:68-133, vae_cross_modality_cv.py:113-196)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vae_oracle as vo
+from parity_util import make_module, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SPECS = [("multimodal", dict(A=50, B=36, S=5, L=10, E=16), dict(lr=1e-3, weight_decay=1e-4, beta_start=2e-3, gamma=2.0)),
+         ("multimodal", dict(A=50, B=36, S=5, L=37, E=64), dict(lr=3e-4, weight_decay=1e-6, beta_start=5e-4, gamma=0.7)),
+         ("multimodal", dict(A=50, B=36, S=5, L=24, E=32), dict(lr=5e-3, weight_decay=1e-5, beta_start=1e-3, gamma=1.0))]
+
+
+def _members():
+    out = []
+    for i, (kind, dims, hyper) in enumerate(SPECS):
+        state = vo.init_state(kind, dims, seed=40 + i)
+        out.append((kind, dims, hyper, state))
+    return out
+
+
+def test_concurrent_members_equal_solo_training():
+    from vla_b200 import DeviceDataset, Population, Trainer
+    batch, n_steps = 48, 5
+    tpm, beta_v, site = vo.synthetic_batch(batch * 3, SPECS[0][1], seed=3)
+    ds = DeviceDataset(tpm, beta_v, site, "cuda")
+    members = _members()
+    specs = [dict(model=make_module(k, d, st, device="cpu"), seed=7 + i, **h) for i, (k, d, h, st) in enumerate(members)]
+    pop = Population(specs, ds, batch)
+    pop.begin_epoch(50)
+    pop.step(n_steps)
+    pop_losses = pop.losses()
+    for i, (k, d, h, st) in enumerate(members):
+        m = make_module(k, d, st).train()
+        tr = Trainer(m, ds, batch, lr=h["lr"], weight_decay=h["weight_decay"], beta_kl=h["beta_start"], gamma=h["gamma"], seed=7 + i)
+        for _ in range(n_steps):
+            tr.step()
+        solo = tr.losses()
+        np.testing.assert_allclose(pop_losses[i], solo, rtol=1e-4)
+        got = pop.members[i].trainer.core.arena.cpu().numpy()
+        ref = tr.core.arena.cpu().numpy()
+        assert rel_l2(got, ref) < 1e-4, (i, rel_l2(got, ref))     # (split-K red.add order is the only non-determinism)
+        tr.close()
+    pop.close()
+
+
+def test_epoch_control_flow():
+    from vla_b200 import DeviceDataset, Population, fused_vae_loss
+    batch = 32
+    dims = SPECS[0][1]
+    tpm, beta_v, site = vo.synthetic_batch(batch * 2, dims, seed=5)
+    ds = DeviceDataset(tpm, beta_v, site, "cuda")
+    members = _members()[:2]
+    specs = [dict(model=make_module(k, d, st, device="cpu"), **h) for k, d, h, st in members]
+    pop = Population(specs, ds, batch, beta_warmup_epochs=4, lr_factor=0.5, lr_patience=1, patience=3)
+    val = [(ds.tpm[:batch], ds.beta[:batch], ds.site[:batch])]
+
+    def loss_fn(mem, model, b):
+        ra, rb, rc, mu, lv = model(a=b[0], b=b[1], site=b[2])
+        return fused_vae_loss(ra, b[0], rb, b[1], rc, b[2], mu, lv, beta=1e-3, gamma=mem.hyper["gamma"])[0]
+
+    pop.begin_epoch(1)
+    assert pop.members[0].trainer.hyper[2] == pytest.approx(0.25 * SPECS[0][2]["beta_start"])        # beta warm-up
+    pop.step(2)
+    v0 = pop.validate(val, loss_fn)
+    assert all(np.isfinite(v0)) and len(v0) == 2
+    assert pop.end_epoch(v0) == 2
+    snap = pop.members[0].best_state[0].clone()
+    # member 0 stops improving: lr halves after `lr_patience` bad epochs, training stops after `patience`
+    lrs = []
+    for epoch in range(2, 6):
+        pop.begin_epoch(epoch)
+        pop.step(2)
+        alive = pop.end_epoch([v0[0] + 1.0, v0[1] - epoch])                                           # member 1 keeps improving
+        lrs.append(pop.members[0].trainer.hyper[0])
+    assert lrs[0] == pytest.approx(SPECS[0][2]["lr"]) and lrs[1] == pytest.approx(0.5 * SPECS[0][2]["lr"])
+    assert pop.members[0].stopped and not pop.members[1].stopped and alive == 1
+    assert pop.members[1].trainer.hyper[0] == pytest.approx(SPECS[1][2]["lr"])
+    with pytest.raises(ValueError):
+        pop.validate([(torch.zeros(batch + 1, 50, device="cuda"),)], loss_fn)
+    pop.restore_best()
+    assert torch.equal(pop.members[0].trainer.core.arena, snap)
+    pop.step(1)                                                                                       # stopped members are skipped
+    pop.synchronize()
+    assert torch.equal(pop.members[0].trainer.core.arena, snap)
+    pop.close()

@@ -1,0 +1,161 @@
+"""Populations of independent models on one GPU (BASELINE configs[4]).
+
+The reference trains its hyper-parameter trials (`optimize_hyperparameters.py:68-133`) and cross-validation folds
+(`vae_cross_modality_cv.py:113-196, 198-283`) one after the other.  The models are independent -- no data-path
+exchange, "replicas only" -- and each one's train step is a chain of short dependent launches that leaves most SMs idle
+most of the time.  `Population` therefore gives every model its own fused `Trainer` (one CUDA graph
+each) on its own stream and steps them round-robin with no host synchronisation: the graphs of different models overlap on
+the device and fill each other's gaps.  Across GPUs the population is sharded by index (`models[rank::world]`), one
+process per GPU, no collective.
+
+The per-epoch control flow of the reference loops is restated on the host, per model, from ONE device->host read per epoch
+for the whole population: beta warm-up (`train_rna2dna.py:80`), `ReduceLROnPlateau` (torch's own scheduler object on a
+dummy optimizer, so the semantics are exactly the reference's, `vae_cross_modality_cv.py:127`), early stopping with a
+device-side snapshot of the best state (`vae_cross_modality_cv.py:129-196`).
+"""
+import torch
+
+from .engine import Trainer
+
+
+class Member:
+    """One model of the population with its trainer, stream and the host-side training-control state."""
+
+    def __init__(self, model, trainer, stream, hyper):
+        self.model, self.trainer, self.stream, self.hyper = model, trainer, stream, hyper
+        self.best_val = float("inf")
+        self.best_state = None
+        self.bad_epochs = 0
+        self.stopped = False
+        self.history = []
+        self._dummy = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=hyper["lr"])
+        self.scheduler = None
+
+
+class Population:
+    """`specs`: list of dicts with `model` (an un-trained drop-in module on the CPU or the device) and optional `lr`,
+    `weight_decay`, `beta_start`, `gamma`, `seed`, `class_weights`; `datasets`: one DeviceDataset shared by all members or
+    one per member (folds); every member trains at `batch_size`."""
+
+    def __init__(self, specs, datasets, batch_size, device="cuda", beta_warmup_epochs=50, lr_factor=0.5, lr_patience=5,
+                 patience=15, use_graph=True):
+        self.device = torch.device(device)
+        self.batch = int(batch_size)
+        self.beta_warmup_epochs = beta_warmup_epochs
+        self.patience = patience
+        self.members = []
+        shared = not isinstance(datasets, (list, tuple))
+        main = torch.cuda.current_stream(self.device)
+        for i, spec in enumerate(specs):
+            hyper = dict(lr=spec.get("lr", 5e-4), weight_decay=spec.get("weight_decay", 1e-5),
+                         beta_start=spec.get("beta_start", 1e-3), gamma=spec.get("gamma", 1.0), seed=spec.get("seed", i))
+            model = spec["model"].to(self.device).train()
+            ds = datasets if shared else datasets[i]
+            stream = torch.cuda.Stream(device=self.device)
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                tr = Trainer(model, ds, self.batch, lr=hyper["lr"], weight_decay=hyper["weight_decay"],
+                             beta_kl=hyper["beta_start"], gamma=hyper["gamma"], class_weights=spec.get("class_weights"),
+                             seed=hyper["seed"], use_graph=use_graph)
+            mem = Member(model, tr, stream, hyper)
+            mem.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(mem._dummy, mode="min", factor=lr_factor,
+                                                                        patience=lr_patience)
+            self.members.append(mem)
+
+    def __len__(self):
+        return len(self.members)
+
+    # -- stepping ----------------------------------------------------------------------------------------------------
+    def step(self, n=1):
+        """`n` optimizer steps of every active member, round-robin over the members' streams; no host synchronisation."""
+        for _ in range(n):
+            for mem in self.members:
+                if not mem.stopped:
+                    with torch.cuda.stream(mem.stream):
+                        mem.trainer.step()
+
+    def synchronize(self):
+        main = torch.cuda.current_stream(self.device)
+        for mem in self.members:
+            main.wait_stream(mem.stream)
+        torch.cuda.synchronize(self.device)
+
+    def losses(self):
+        """[(total, recon, class, kld)] of every member's last step (synchronises once)."""
+        self.synchronize()
+        stacked = torch.stack([mem.trainer.loss_out for mem in self.members]).tolist()
+        return [tuple(x) for x in stacked]
+
+    # -- the reference's per-epoch control flow ------------------------------------------------------------------------
+    def begin_epoch(self, epoch):
+        """beta warm-up (train_rna2dna.py:80): beta = min(1, epoch / warmup) * beta_start, per member."""
+        w = min(1.0, epoch / self.beta_warmup_epochs) if self.beta_warmup_epochs > 0 else 1.0
+        for mem in self.members:
+            if not mem.stopped:
+                with torch.cuda.stream(mem.stream):
+                    mem.trainer.set_hyper(beta_kl=w * mem.hyper["beta_start"])
+
+    def end_epoch(self, val_losses):
+        """`val_losses`: one validation loss per member (floats).  Steps every member's ReduceLROnPlateau, keeps a device
+        snapshot of the best state and applies early stopping (vae_cross_modality_cv.py:177-190).  Returns the number of
+        members still training."""
+        for mem, v in zip(self.members, val_losses):
+            if mem.stopped:
+                continue
+            v = float(v)
+            mem.history.append(v)
+            mem.scheduler.step(v)
+            lr = mem._dummy.param_groups[0]["lr"]
+            with torch.cuda.stream(mem.stream):
+                mem.trainer.set_hyper(lr=lr)
+                if v < mem.best_val:
+                    mem.best_val, mem.bad_epochs = v, 0
+                    core = mem.trainer.core
+                    mem.best_state = (core.arena.clone(), core.buffers.clone(), core.counters.clone())
+                else:
+                    mem.bad_epochs += 1
+                    if mem.bad_epochs >= self.patience:
+                        mem.stopped = True
+        return sum(not m.stopped for m in self.members)
+
+    def restore_best(self):
+        """Load every member's best snapshot back (vae_cross_modality_cv.py:192-194)."""
+        for mem in self.members:
+            if mem.best_state is not None:
+                with torch.cuda.stream(mem.stream), torch.no_grad():
+                    core = mem.trainer.core
+                    core.arena.copy_(mem.best_state[0])
+                    core.buffers.copy_(mem.best_state[1])
+                    core.counters.copy_(mem.best_state[2])
+                    core.shadow_version = None     # the bf16 operand copies are re-derived before the next step
+        self.synchronize()
+
+    def validate(self, batches, loss_fn):
+        """Validation loss of every member on `batches` (a list of input tuples already on the device) in eval mode, the
+        loops at optimize_hyperparameters.py:113-125 / vae_cross_modality_cv.py:160-173.  `loss_fn(member, model, batch)`
+        returns the loss tensor of one batch; the per-member sums are read back with one synchronisation."""
+        for batch in batches:
+            if batch[0].shape[0] > self.batch:
+                raise ValueError("validation batches must not exceed the training batch size (the captured train-step graphs "
+                                 "hold pointers into a workspace sized for it)")
+        sums = []
+        for mem in self.members:
+            with torch.cuda.stream(mem.stream), torch.no_grad():
+                mem.model.eval()
+                tot = torch.zeros((), device=self.device)
+                for batch in batches:
+                    tot = tot + loss_fn(mem, mem.model, batch).detach()
+                mem.model.train()
+                sums.append(tot / max(len(batches), 1))
+        self.synchronize()
+        return torch.stack(sums).tolist()
+
+    def close(self):
+        self.synchronize()
+        for mem in self.members:
+            mem.trainer.close()
+
+
+def shard(items, rank, world):
+    """Population members of process `rank` out of `world` (one process per GPU; no communication between shards)."""
+    return list(items)[rank::world]
