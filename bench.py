@@ -331,6 +331,42 @@ def population_throughput(dev, B, n_models, steps, warmup):
     return out
 
 
+def metrics_throughput(dev, rows, dim, steps, warmup):
+    """Evaluation metrics of BASELINE configs[3]'s reconstructions (compare_directional_imputation.py:167-210) as one
+    streaming kernel: 8 B of input per element, HBM-bound."""
+    import ctypes as C
+    import torch
+    from vla_b200 import _lib
+    from vla_b200.core import _ptr, _stream
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    t = torch.rand(rows, dim, device=dev, generator=g)
+    p = t + 0.1 * torch.randn(rows, dim, device=dev, generator=g)
+    L = _lib.lib()
+    out = torch.empty(8, dtype=torch.float64, device=dev)
+    ws = torch.zeros(L.vla_metrics_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+    cos, pear = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    args = _lib.MetricsArgs(y_true=_ptr(t), y_pred=_ptr(p), rows=rows, dim=dim, cosine=_ptr(cos), pearson=_ptr(pear), out=_ptr(out),
+                            workspace=_ptr(ws))
+    for _ in range(warmup):
+        _lib.check(L.vla_recon_metrics(C.byref(args), _stream()), "vla_recon_metrics")
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        _lib.check(L.vla_recon_metrics(C.byref(args), _stream()), "vla_recon_metrics")
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    peaks = load_peaks()
+    gbs = 8.0 * rows * dim / (ms * 1e-3) / 1e9
+    res = {"workload": f"reconstruction metrics (MAE/MSE/R2/cosine/Pearson), {rows} x {dim} fp32, one kernel", "value": rows / (ms * 1e-3),
+           "unit": "samples/s", "ms_per_step": ms, "bound": "hbm", "achieved_gb_per_s": gbs, "peak_gb_per_s": peaks["hbm_gbs"],
+           "roofline_frac": gbs / peaks["hbm_gbs"], "l2": f"inputs {8.0 * rows * dim / 1e6:.0f} MB > L2", "mse": out.tolist()[1]}
+    del t, p
+    torch.cuda.empty_cache()
+    return res
+
+
 def inference_throughput(dev, batch, steps, warmup):
     """BASELINE configs[3]: tri-modal cross-modal inference `model(a=x)` in eval mode (BatchNorm running statistics, no
     dropout, epsilon still sampled), all three decoders, fp32 outputs written; vla_forward replayed from a CUDA graph."""
@@ -551,6 +587,7 @@ def run_gpu(args, rank, local_rank, world):
                 continue
             also.append(train_throughput(wl, B, dev, steps=60, warmup=5))
         also.append(inference_throughput(dev, batch=args.infer_batch, steps=10, warmup=3))
+        also.append(metrics_throughput(dev, args.infer_batch, DIMS["A"], steps=10, warmup=3))
         also.append(population_throughput(dev, B, n_models=8, steps=30, warmup=3))
         also.append(population_throughput(dev, 32, n_models=8, steps=100, warmup=5))       # the reference's default batch size
 

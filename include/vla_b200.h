@@ -136,6 +136,23 @@ typedef struct {
 long long vla_loss_workspace_bytes(int batch, int dim_a, int dim_b, int n_sites, int latent);
 int vla_loss(const vla_loss_args_t* a, vla_stream_t stream);
 
+/* Reconstruction metrics of an evaluation pass in one streaming kernel.  Replaces compute_metrics
+ * (compare_directional_imputation.py:167-210), i.e. sklearn's mean_absolute_error / mean_squared_error / r2_score on the
+ * flattened arrays, the diagonal of sklearn's cosine_similarity (the reference builds the full N x N matrix) and
+ * scipy.stats.pearsonr per sample with NaN rows skipped.  out[8] (DEVICE doubles) = {MAE, MSE, RMSE, R2, mean cosine
+ * similarity, Pearson mean, Pearson population std, number of samples with a defined Pearson r}; cosine / pearson are
+ * optional per-sample outputs [rows] (pearson: NaN where a row is constant).  workspace: vla_metrics_workspace_bytes(rows)
+ * bytes, zero-initialised once by the caller. */
+typedef struct {
+  const float* y_true; const float* y_pred;    /* dense fp32 [rows, dim] */
+  long long rows; int dim;
+  float* cosine; float* pearson;
+  double* out;
+  void* workspace;
+} vla_metrics_args_t;
+long long vla_metrics_workspace_bytes(long long rows);
+int vla_recon_metrics(const vla_metrics_args_t* a, vla_stream_t stream);
+
 /* One fused multi-tensor AdamW step over the flat arena (torch.optim.AdamW semantics, the optimizer built at
  * train_rna2dna.py:185-189 and stepped at :94-96); also refreshes the bf16 weight copies. */
 typedef struct {

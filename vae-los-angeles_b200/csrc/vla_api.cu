@@ -1599,6 +1599,25 @@ void vla_dp_destroy(vla_dp_t* d) {
   delete d;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Reconstruction metrics
+// ---------------------------------------------------------------------------------------------
+long long vla_metrics_workspace_bytes(long long rows) {
+  return 256 + static_cast<long long>(metrics_grid(rows)) * 8 * static_cast<long long>(sizeof(double));
+}
+int vla_recon_metrics(const vla_metrics_args_t* a, vla_stream_t stream) {
+  if (!a || !a->y_true || !a->y_pred || !a->out || !a->workspace) return fail(VLA_ERR_INVALID, "null argument");
+  if (a->rows <= 0 || a->dim <= 0) return fail(VLA_ERR_INVALID, "rows and dim must be positive");
+  MetricsArgs m{};
+  m.yt = a->y_true; m.yp = a->y_pred; m.rows = a->rows; m.dim = a->dim;
+  m.cos_out = a->cosine; m.pearson_out = a->pearson;
+  m.counter = reinterpret_cast<unsigned int*>(a->workspace);
+  m.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + 256);
+  m.out = a->out;
+  CK(launch_metrics(m, as_stream(stream)));
+  return VLA_OK;
+}
+
 /* Whole-step kernel timeline: %globaltimer stamps per unit (unit start, dependencies resolved, first operands, MMAs
  * issued, accumulator ready, unit published) written by the next fused steps. */
 int vla_step_timeline(vla_model_t* m, int enable) {

@@ -351,6 +351,20 @@ struct DpArgs {
 cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s, bool pdl);
 cudaError_t launch_dp_adamw(const DpArgs& x, const AdamArgs& a, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+// Reconstruction metrics (metrics.cu)
+// ---------------------------------------------------------------------------------------------
+struct MetricsArgs {
+  const float* yt; const float* yp;     // y_true, y_pred: dense fp32 [rows, dim]
+  long long rows; int dim;
+  float* cos_out; float* pearson_out;   // optional per-sample outputs [rows] (Pearson: NaN where undefined)
+  double* partials;                     // workspace [grid][8]
+  unsigned int* counter;                // zero-initialised ticket (re-armed by the kernel)
+  double* out;                          // [8]: MAE, MSE, RMSE, R2, mean cosine, Pearson mean, Pearson std, Pearson count
+};
+int metrics_grid(long long rows);
+cudaError_t launch_metrics(const MetricsArgs& a, cudaStream_t s);
+
 struct LossGridInfo { int nb_a, nb_b, nb_c, nb_k; };
 LossGridInfo loss_grid_info(const LossArgs& a);
 int bn_rows_per_block(int rows, int m_tiles);

@@ -7,7 +7,8 @@ from .core import VaeModule, Stack, KINDS
 from .dp import Layout, allreduce_gradients
 from .engine import DeviceDataset, FusedAdamW, Trainer
 from .losses import fused_vae_loss
+from .metrics import recon_metrics
 from .population import Population, shard
 
 __all__ = ["VaeModule", "Stack", "KINDS", "DeviceDataset", "FusedAdamW", "Trainer", "fused_vae_loss", "Layout",
-           "allreduce_gradients", "Population", "shard"]
+           "allreduce_gradients", "Population", "shard", "recon_metrics"]

@@ -66,6 +66,11 @@ class TrainArgs(C.Structure):
                 ("dp", C.c_void_p)]
 
 
+class MetricsArgs(C.Structure):
+    _fields_ = [("y_true", C.c_void_p), ("y_pred", C.c_void_p), ("rows", C.c_longlong), ("dim", C.c_int),
+                ("cosine", C.c_void_p), ("pearson", C.c_void_p), ("out", C.c_void_p), ("workspace", C.c_void_p)]
+
+
 class ProfEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("flops", C.c_double), ("bytes", C.c_double)]
 
@@ -88,6 +93,8 @@ EXPORTS = {
     "vla_loss_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vla_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "vla_adamw": (C.c_int, [C.c_void_p, C.POINTER(AdamWArgs), C.c_void_p]),
+    "vla_metrics_workspace_bytes": (C.c_longlong, [C.c_longlong]),
+    "vla_recon_metrics": (C.c_int, [C.POINTER(MetricsArgs), C.c_void_p]),
     "vla_train_step": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "vla_set_hyper": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "vla_set_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
