@@ -85,9 +85,12 @@ class DeviceDataset:
         return len(self.site)
 
     def shuffle_(self, generator=None):
-        """In-place row permutation on the device (DataLoader(shuffle=True) between epochs)."""
+        """In-place row permutation on the device (DataLoader(shuffle=True) between epochs).  The tensors keep their
+        addresses, so a captured train-step graph that reads them stays valid."""
         perm = torch.randperm(len(self), device=self.site.device, generator=generator)
-        self.tpm, self.beta, self.site = self.tpm[perm], self.beta[perm], self.site[perm]
+        self.tpm.copy_(self.tpm[perm])
+        self.beta.copy_(self.beta[perm])
+        self.site.copy_(self.site[perm])
 
     @staticmethod
     def synthetic(n, dim_a, dim_b, n_sites, device, seed=0):
