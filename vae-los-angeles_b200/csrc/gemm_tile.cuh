@@ -28,6 +28,8 @@ constexpr int ONES_BYTES = 2048;
 constexpr int PATCH_LD = 36;                                         // floats; 144-byte rows: 16-byte aligned, conflict-free
 constexpr int CHUNK_OFFSET = 0;                                      // 8 warps x fp32 [32][36] transpose patches: they alias
 constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;                   // pipeline stage 0, which is idle once the accumulator is ready
+constexpr int TGT_OFFSET = STAGE_BYTES;                              // GF_LOSS: per-warp target patches, up to 3 chunks per warp,
+constexpr int TGT_WARP_BYTES = 3 * 32 * PATCH_LD * 4;                // in pipeline stages 1.. (idle once the accumulator is ready)
 constexpr int VEC_OFFSET = ONES_OFFSET + ONES_BYTES;                 // bias | mean | rstd, fp32 [3][192]
 constexpr int VEC_BYTES = 3 * GEMM_BN_MAX_TN * 4;
 constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][6][4][32]
@@ -40,6 +42,8 @@ constexpr int EPI_THREADS = GEMM_THREADS - 64;                       // 8 warps
 
 static_assert(B_STAGE_BYTES >= GEMM_BN_MAX_NT * 128, "B stage too small for NT tiles");
 static_assert(CHUNK_BYTES <= STAGE_BYTES, "epilogue patches must fit in one pipeline stage");
+static_assert(TGT_OFFSET + 8 * TGT_WARP_BYTES <= GEMM_STAGES * STAGE_BYTES, "loss-target patches must fit in the idle stages");
+static_assert((GEMM_BN_MAX_NT / 32 + 1) / 2 <= 3, "a warp stages the targets of at most 3 chunks");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
 static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
@@ -326,8 +330,32 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     const bool bf16_vec = ((reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0) && ((P.ld_bf16 & 7) == 0);
 
     float loss_acc = 0.f;                                // GF_LOSS: this thread's share of the loss value
+    // GF_LOSS (MSE / BCE): stage the targets of ALL this warp's chunks now -- 4-byte asynchronous copies straight into the
+    // transposed position of a per-chunk patch (coalesced: a warp instruction reads 128 contiguous bytes of one row; the
+    // lines were prefetched into L2 during the main loop).  One commit group per chunk: the first chunk waits for an L2
+    // round trip, the later ones find their targets in shared memory; no registers are held.
+    float* tgt_patch = reinterpret_cast<float*>(smem + TGT_OFFSET + (warp - 2) * TGT_WARP_BYTES);
+    int tgt_groups = 0;
+    if ((FEATS & GF_LOSS) && (flags & GF_LOSS) && P.loss_kind != LOSS_CE && !(dbgf & 1)) {
+      for (int c = half; c < n_chunks; c += 2, ++tgt_groups) {
+        const int col0 = n0 + c * 32;
+        const int nvalid = min(32, P.N - col0);
+        if (nvalid > 0) {
+          const float* tp = P.aux0 + (tgt_row0 + rbase) * P.N + col0 + lane;
+          const uint32_t dst = smem_u32(tgt_patch + tgt_groups * (32 * PATCH_LD) + lane);
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = rbase + i < P.M && lane < nvalid;
+            cp_async4_zfill(dst + i * (PATCH_LD * 4), ok ? tp + static_cast<size_t>(i) * P.N : P.aux0, ok ? 4 : 0);
+          }
+        }
+        cp_async_commit();
+      }
+    }
+    int tgt_k = 0;                                       // index of the chunk in flight among this warp's chunks
 
     for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
+      const int my_k = tgt_k++;                         // which of this warp's staged target patches belongs to this chunk
       const int col0 = n0 + c * 32;
       const int nvalid = min(32, P.N - col0);          // <= 0: nothing to store (tile padding)
       const bool full = nvalid == 32;
@@ -432,10 +460,13 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
         continue;
       }
       // ---- this thread's row -> patch; then row-contiguous global accesses ----
+      if (flags & (GF_RED | GF_OUT_F32 | GF_OUT_BF16) && !((FEATS & GF_LOSS) && (flags & GF_LOSS) && !(flags & GF_OUT_F32))) {
+        // (a loss tile that stores no fp32 output writes the patch only once, with the gradient, below)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(patch + lane * PATCH_LD + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      __syncwarp();
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(patch + lane * PATCH_LD + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        __syncwarp();
+      }
       if (flags & GF_RED) {
         // split-K partial sums: one 128-byte red per row
         if (lane < nvalid) {
@@ -484,26 +515,21 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
             }
             if (row_ok) loss_acc += -w * (xt - lse);
           } else {
-            // targets: coalesced row reads (all 32 in flight) -> patch -> this thread's row
+            // targets: staged above by asynchronous copies, one commit group per chunk (oldest first)
             {
-              float tv[32];
-              const float* tp = P.aux0 + (tgt_row0 + rbase) * P.N + col0 + lane;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                tv[i] = 0.f;
-                if (rbase + i < P.M && lane < nvalid) tv[i] = __ldg(tp + static_cast<size_t>(i) * P.N);
-              }
-#pragma unroll
-              for (int i = 0; i < 32; ++i) patch[i * PATCH_LD + lane] = tv[i];
+              const int pending = tgt_groups - 1 - my_k;
+              if (pending >= 2) cp_async_wait<2>(); else if (pending == 1) cp_async_wait<1>(); else cp_async_wait<0>();
             }
             __syncwarp();
             float tg[32];
+            {
+              const float* tp_s = tgt_patch + my_k * (32 * PATCH_LD) + lane * PATCH_LD;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q4 = *reinterpret_cast<const float4*>(patch + lane * PATCH_LD + i * 4);
-              tg[4 * i] = q4.x; tg[4 * i + 1] = q4.y; tg[4 * i + 2] = q4.z; tg[4 * i + 3] = q4.w;
+              for (int i = 0; i < 8; ++i) {
+                const float4 q4 = *reinterpret_cast<const float4*>(tp_s + i * 4);
+                tg[4 * i] = q4.x; tg[4 * i + 1] = q4.y; tg[4 * i + 2] = q4.z; tg[4 * i + 3] = q4.w;
+              }
             }
-            __syncwarp();
             float part = 0.f;
             if (P.loss_kind == LOSS_BCE && !(flags & GF_OUT_F32)) {
 #pragma unroll
@@ -581,21 +607,25 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
       named_bar_sync(3, EPI_THREADS);
       if (*s_flag) {
         __threadfence();
+        // All four terms at once: every thread sums its (fixed) share of each partial array, one shuffle butterfly per
+        // term, then thread 0 adds the eight warp results in order -- deterministic, and one barrier instead of the 36 a
+        // per-term shared-memory tree needs (this runs on the LAST tile of the step: it is pure critical path).
         const int starts[4] = {0, T.n_mse, T.n_mse + T.n_bce, T.n_mse + T.n_bce + T.n_ce};
-        double sums[4] = {0, 0, 0, 0};                             // mse, bce, ce, kl
+        double acc4[4] = {0, 0, 0, 0};                             // mse, bce, ce, kl
+        for (int role = 0; role < 3; ++role)
+          for (int i = starts[role] + et; i < starts[role + 1]; i += EPI_THREADS) acc4[role] += __ldcg(T.partials + i);
+        for (int i = et; i < T.n_kl; i += EPI_THREADS) acc4[3] += __ldcg(T.kl_partials + i);
+#pragma unroll
         for (int role = 0; role < 4; ++role) {
-          double sacc = 0;
-          if (role < 3) { for (int i = starts[role] + et; i < starts[role + 1]; i += EPI_THREADS) sacc += __ldcg(T.partials + i); }
-          else          { for (int i = et; i < T.n_kl; i += EPI_THREADS) sacc += __ldcg(T.kl_partials + i); }
-          dsh[et] = sacc;
-          named_bar_sync(3, EPI_THREADS);
-          for (int o = EPI_THREADS / 2; o > 0; o >>= 1) {
-            if (et < o) dsh[et] += dsh[et + o];
-            named_bar_sync(3, EPI_THREADS);
-          }
-          sums[role] = dsh[0];
-          named_bar_sync(3, EPI_THREADS);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc4[role] += __shfl_xor_sync(0xffffffffu, acc4[role], o);
+          if (lane == 0) dsh[(warp - 2) * 4 + role] = acc4[role];
         }
+        named_bar_sync(3, EPI_THREADS);
+        double sums[4] = {0, 0, 0, 0};
+        if (et == 0)
+          for (int w = 0; w < EPI_THREADS / 32; ++w)
+            for (int role = 0; role < 4; ++role) sums[role] += dsh[w * 4 + role];
         if (et == 0) {
           const double beta = T.dyn->beta_kl, gamma = T.dyn->gamma;
           const double recon = sums[0] + sums[1];

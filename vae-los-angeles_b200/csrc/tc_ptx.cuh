@@ -158,6 +158,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          ((M >> 4) << 24);
 }
 
+// Ampere-style asynchronous copies (LDGSTS, generic proxy): 4 bytes global -> shared without a register round trip;
+// src_bytes = 0 writes zeros and reads nothing.
+__device__ __forceinline__ void cp_async4_zfill(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Programmatic dependent launch: everything before pdl_wait() overlaps the tail of the previous kernel in the stream;
 // nothing before it may touch memory that kernel reads or writes.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
