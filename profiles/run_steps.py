@@ -18,7 +18,13 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = cls(782, 572, 24, 20).to(dev).train()
 ds = DeviceDataset.synthetic(B * 8, 782, 572, 24, dev, seed=1)
-tr = Trainer(model, ds, B, use_graph=False)
+pg = None
+if os.environ.get("VLA_FORCE_DP") == "1":      # world-1 data parallel: the peer-memory exchange + AdamW launch, for ncu
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29544")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    pg = dist.group.WORLD
+tr = Trainer(model, ds, B, use_graph=False, process_group=pg)
 for _ in range(steps):
     tr.step()
 torch.cuda.synchronize()
