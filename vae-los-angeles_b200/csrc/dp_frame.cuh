@@ -23,17 +23,22 @@ __device__ __forceinline__ unsigned long long dp_now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Re-poll one framed word until both halves carry `epoch`; `v` is the first attempt.  A peer that never arrives (crashed
-// rank) traps after 60 s instead of hanging the GPU.
+// Slow path of a poll, kept out of line: the callers are instruction-cache sensitive (an inlined spin loop per polled word
+// made the exchange + AdamW kernel 40 KB of SASS and 10 us slower).  A peer that never arrives (crashed rank) traps after 60 s
+// instead of hanging the GPU.
+static __device__ __noinline__ uint4 spin_framed(const uint4* p, unsigned int epoch) {
+  const unsigned long long t0 = dp_now_ns();
+  int spins = 0;
+  uint4 v;
+  do {
+    if ((++spins & 1023) == 0 && dp_now_ns() - t0 > 60ull * 1000000000ull) __trap();
+    v = ld_framed(p);
+  } while (!framed_ok(v, epoch));
+  return v;
+}
+// Complete a poll: `v` is the first attempt at word `p`; re-polls until both halves carry `epoch`.
 __device__ __forceinline__ float2 finish_framed(const uint4* p, uint4 v, unsigned int epoch) {
-  if (!framed_ok(v, epoch)) {
-    const unsigned long long t0 = dp_now_ns();
-    int spins = 0;
-    do {
-      if ((++spins & 1023) == 0 && dp_now_ns() - t0 > 60ull * 1000000000ull) __trap();
-      v = ld_framed(p);
-    } while (!framed_ok(v, epoch));
-  }
+  if (!framed_ok(v, epoch)) v = spin_framed(p, epoch);
   return make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
 }
 

@@ -666,7 +666,8 @@ __device__ __forceinline__ void loss_body(const LossArgs& a, int block, int grid
 // Fused multi-tensor AdamW over the flat arena + refresh of the bf16 MMA shadows (both orientations)
 // (torch.optim.AdamW semantics; call sites train_rna2dna.py:94-96, 185-189)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid) {
+// g_given: the gradient of this thread's four elements when the caller already holds it (dp_adamw_kernel: shard owner).
+__device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid, const float4* g_given = nullptr) {
   const AdamChunk ch = a.chunks[chunk];
   const int e = 4 * tid;                               // element index inside the chunk
   if (e >= ch.n) return;
@@ -682,7 +683,7 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
   const long long gi = ch.offset + e;                  // multiple of 4: 16-byte aligned in every arena
   const int nv = min(4, ch.n - e);
   float p[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool framed = a.update && a.gframed != nullptr;
+  const bool framed = a.update && a.gframed != nullptr && g_given == nullptr;
   uint4 f0 = make_uint4(0u, 0u, 0u, 0u), f1 = f0;
   unsigned int epoch = 0u;
   if (framed) {               // first attempt at the two framed words of this float4, in flight with the loads below
@@ -693,16 +694,17 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
   if (nv == 4) {
     *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(a.p + gi);
     if (a.update) {
-      if (!framed) *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(a.g + gi);
+      if (!framed && !g_given) *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(a.g + gi);
       *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(a.m + gi);
       *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.v + gi);
     }
   } else {
     for (int k = 0; k < nv; ++k) {
       p[k] = a.p[gi + k];
-      if (a.update) { if (!framed) g[k] = a.g[gi + k]; m[k] = a.m[gi + k]; v[k] = a.v[gi + k]; }
+      if (a.update) { if (!framed && !g_given) g[k] = a.g[gi + k]; m[k] = a.m[gi + k]; v[k] = a.v[gi + k]; }
     }
   }
+  if (g_given) { g[0] = g_given->x; g[1] = g_given->y; g[2] = g_given->z; g[3] = g_given->w; }
   if (framed) {               // (the arena is padded to multiples of 4: both words exist for every chunk tail)
     const float2 lo = finish_framed(a.gframed + (gi >> 1), f0, epoch);
     const float2 hi = finish_framed(a.gframed + (gi >> 1) + 1, f1, epoch);

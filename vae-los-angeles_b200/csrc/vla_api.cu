@@ -141,14 +141,16 @@ struct vla_model {
   int step_grid = 0;
 };
 
-// Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  One allocation per rank:
-// [G n floats | RECV world x per2 framed words | RSUM n / 2 framed words | summed losses | trace], exported / mapped with CUDA IPC.
+// Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  Two allocations per rank:
+//   local (never exported): [G n floats | summed losses | trace] -- only this rank touches them;
+//   base  (exported / mapped with CUDA IPC): [RECV 2 x world x per2 framed words | RSUM n / 2 framed words].
 struct vla_dp {
   int world = 1, rank = 0;
   long long n = 0;                 // floats per buffer (multiple of 4)
   long long per2 = 0;              // float2s per shard
-  char* base = nullptr;            // local allocation
-  size_t off_recv = 0, off_rsum = 0, off_sums = 0, off_trace = 0, bytes = 0;
+  char* base = nullptr;            // exported allocation (RECV | RSUM)
+  char* local = nullptr;           // private allocation (G | sums | trace)
+  size_t off_recv = 0, off_rsum = 0, off_sums = 0, off_trace = 0, bytes = 0, local_bytes = 0;
   char* peer[DP_MAX_WORLD] = {};   // every rank's allocation as mapped here (own: base)
   bool connected = false;
   cudaStream_t side = nullptr;     // the early (decoder) part of the exchange runs here, beside the encoder backward
@@ -887,13 +889,14 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
 DpArgs make_dp_args(vla_model* m, vla_dp* dp, long long first2, long long end2, int part) {
   DpArgs x{};
   x.world = dp->world; x.rank = dp->rank; x.dyn = m->dyn;
-  x.first2 = first2; x.n2 = std::max(0LL, end2 - first2); x.per2 = (x.n2 + dp->world - 1) / dp->world;
-  x.g = reinterpret_cast<float*>(dp->base);
+  x.first2 = first2; x.n2 = std::max(0LL, end2 - first2);
+  x.per2 = ((x.n2 + dp->world - 1) / dp->world + 1) & ~1LL;      // even: a float4 of the arena never straddles two shards
+  x.g = reinterpret_cast<float*>(dp->local);
   for (int r = 0; r < dp->world; ++r) {
     x.recv[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_recv) + static_cast<size_t>(part) * dp->world * dp->per2;
     x.rsum[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_rsum);
   }
-  x.trace = reinterpret_cast<unsigned long long*>(dp->base + dp->off_trace) + 4 * part;
+  x.trace = reinterpret_cast<unsigned long long*>(dp->local + dp->off_trace) + 4 * part;
   return x;
 }
 // Send the decoder gradients early, on the side stream, while the encoder backward runs?  Measured (rna2dna, batch 4096 per
@@ -1269,7 +1272,7 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
   if (dp) {
     a.gframed = reinterpret_cast<const uint4*>(dp->base + dp->off_rsum);
     a.tail2 = m->n_params / 2;
-    a.sums_out = reinterpret_cast<float*>(dp->base + dp->off_sums);
+    a.sums_out = reinterpret_cast<float*>(dp->local + dp->off_sums);
   }
   a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
   a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd;
@@ -1335,7 +1338,7 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
     if (!do_fb || !do_opt) return fail(VLA_ERR_INVALID, "vla_train_step: the peer-memory exchange needs the whole step (phases 0 or 3)");
     if (!dp->connected) return fail(VLA_ERR_STATE, "vla_train_step: vla_dp_connect has not been called");
     if (dp->n != m->n_params + 4) return fail(VLA_ERR_INVALID, "vla_train_step: exchange buffer size != param_count + 4");
-    if (a->grads != reinterpret_cast<float*>(dp->base) || a->loss_out != a->grads + m->n_params)
+    if (a->grads != reinterpret_cast<float*>(dp->local) || a->loss_out != a->grads + m->n_params)
       return fail(VLA_ERR_INVALID, "vla_train_step: grads / loss_out must be vla_dp_grads() and its last 4 floats");
     if (m->rec) m->rec->why = "data-parallel exchange";
   }
@@ -1537,19 +1540,23 @@ int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out) {
   d->world = world; d->rank = rank; d->n = n_floats;
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   const long long n2 = n_floats / 2;
-  d->per2 = (n2 + world - 1) / world;
-  d->off_recv = up(sizeof(float) * n_floats);
-  d->off_rsum = d->off_recv + up(sizeof(uint4) * 2 * static_cast<size_t>(world) * d->per2);   // one RECV region per part
-  d->off_sums = d->off_rsum + up(sizeof(uint4) * static_cast<size_t>(n2));
+  d->per2 = ((n2 + world - 1) / world + 1) & ~1LL;
+  d->off_recv = 0;
+  d->off_rsum = up(sizeof(uint4) * 2 * static_cast<size_t>(world) * d->per2);   // one RECV region per part
+  d->bytes = d->off_rsum + up(sizeof(uint4) * static_cast<size_t>(n2));
+  d->off_sums = up(sizeof(float) * n_floats);
   d->off_trace = d->off_sums + 256;
-  d->bytes = d->off_trace + 256;
+  d->local_bytes = d->off_trace + 256;
+  // G stays in a private allocation: only this rank ever touches its gradients, so nothing of it needs exporting.
   cudaError_t e = cudaMalloc(&d->base, d->bytes);
   if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d->local, d->local_bytes);
+  if (e == cudaSuccess) e = cudaMemset(d->local, 0, d->local_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
-  if (e != cudaSuccess) { cudaFree(d->base); delete d; return fail(VLA_ERR_CUDA, std::string("vla_dp_create: ") + cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(d->base); cudaFree(d->local); delete d; return fail(VLA_ERR_CUDA, std::string("vla_dp_create: ") + cudaGetErrorString(e)); }
   d->peer[rank] = d->base;
   d->connected = world == 1;
   *out = d;
@@ -1583,11 +1590,11 @@ int vla_dp_connect(vla_dp_t* d, const void* handles) {
 }
 int vla_dp_trace(vla_dp_t* d, unsigned long long* out8) {
   if (!d || !out8) return fail(VLA_ERR_INVALID, "null argument");
-  CK(cudaMemcpy(out8, d->base + d->off_trace, 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out8, d->local + d->off_trace, 64, cudaMemcpyDeviceToHost));
   return VLA_OK;
 }
-void* vla_dp_grads(vla_dp_t* d) { return d ? d->base : nullptr; }
-void* vla_dp_losses(vla_dp_t* d) { return d ? d->base + d->off_sums : nullptr; }
+void* vla_dp_grads(vla_dp_t* d) { return d ? d->local : nullptr; }
+void* vla_dp_losses(vla_dp_t* d) { return d ? d->local + d->off_sums : nullptr; }
 void vla_dp_destroy(vla_dp_t* d) {
   if (!d) return;
   for (int r = 0; r < d->world; ++r)
@@ -1596,6 +1603,7 @@ void vla_dp_destroy(vla_dp_t* d) {
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
   cudaFree(d->base);
+  cudaFree(d->local);
   delete d;
 }
 

@@ -288,6 +288,8 @@ class Trainer:
             o = 4 * part
             out[name] = dict(push_us=(t[o + 1] - t[o]) / 1e3, reduce_us=(t[o + 2] - t[o + 1]) / 1e3,
                              total_us=(t[o + 2] - t[o]) / 1e3)
+            if part == 0 and t[o + 3] > t[o + 1]:
+                out[name]["own_gradient_loaded_us"] = (t[o + 3] - t[o + 1]) / 1e3
         out["decoder_part_done_before_encoder_part_starts_us"] = (t[0] - t[6]) / 1e3
         return out
 
