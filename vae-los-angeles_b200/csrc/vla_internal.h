@@ -110,18 +110,6 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   static const bool pdl_on = [] { const char* e = getenv("VLA_NO_PDL"); return !(e && e[0] == '1'); }();
-  // Experiment hook (VLA_CARVEOUT=1): ask for the maximum shared-memory carve-out on every kernel, so that consecutive
-  // launches never differ in their L1 / shared split (a differing split drains the SM before the next CTA can start).
-  static const bool carve_on = [] { const char* e = getenv("VLA_CARVEOUT"); return e && e[0] == '1'; }();
-  if (carve_on) {
-    static thread_local const void* seen[32]; static thread_local int n_seen = 0;
-    bool found = false;
-    for (int i = 0; i < n_seen; ++i) found = found || seen[i] == reinterpret_cast<const void*>(kernel);
-    if (!found) {
-      (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (n_seen < 32) seen[n_seen++] = reinterpret_cast<const void*>(kernel);
-    }
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
