@@ -279,7 +279,6 @@ def population_throughput(dev, B, n_models, steps, warmup):
     import torch
     from src.models import MultiModalVAE
     from vla_b200 import DeviceDataset, Population
-    rng = np.random.default_rng(0)
     ds = DeviceDataset.synthetic(B * 8, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=9)
 
     def specs():
@@ -321,7 +320,6 @@ def population_throughput(dev, B, n_models, steps, warmup):
     ms_seq = timed(pop, one_by_one)
     losses = pop.losses()
     pop.close()
-    del rng
     ok = all(all(x == x and abs(x) < 1e30 for x in l) for l in losses)
     out = {"workload": f"population: {n_models} independent tri-modal VAEs (latent 10..100, embed 16/32/64), batch {B} each, one GPU",
            "value": steps * B * n_models / (ms_conc * 1e-3), "unit": "samples/s (all members)",
