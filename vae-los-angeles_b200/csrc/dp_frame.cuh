@@ -32,6 +32,7 @@ static __device__ __noinline__ uint4 spin_framed(const uint4* p, unsigned int ep
   uint4 v;
   do {
     if ((++spins & 1023) == 0 && dp_now_ns() - t0 > 60ull * 1000000000ull) __trap();
+    __nanosleep(64);                      // back off: thousands of threads polling back to back queue in front of real loads
     v = ld_framed(p);
   } while (!framed_ok(v, epoch));
   return v;
