@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
 
 FULL = dict(A=782, B=572, S=24, L=20, E=32)
 SMALL = dict(A=50, B=36, S=5, L=10, E=16)
+MANY_SITES = dict(A=50, B=36, S=40, L=10, E=16)     # more than 32 classes: the CE term cannot be fused into a 32-column chunk,
+                                                    # the step falls back to the stand-alone loss kernel
 
 
 def _oracle_train(kind, dims, state, data, n_steps, batch, eps, masks, beta, gamma, cw, q):
@@ -30,7 +32,8 @@ def _oracle_train(kind, dims, state, data, n_steps, batch, eps, masks, beta, gam
 
 @pytest.mark.parametrize("kind,dims,batch,use_graph", [("rna2dna", FULL, 64, True), ("multimodal", SMALL, 48, True),
                                                          ("dna2rna", FULL, 40, False), ("multimodal", FULL, 64, True),
-                                                         ("rna2dna_ae", FULL, 64, True), ("dna2rna_ae", SMALL, 40, False)])
+                                                         ("rna2dna_ae", FULL, 64, True), ("dna2rna_ae", SMALL, 40, False),
+                                                         ("multimodal", MANY_SITES, 48, True)])
 def test_fused_train_steps_match_oracle(kind, dims, batch, use_graph):
     from vla_b200 import DeviceDataset, Trainer
     n_steps, n_batches = 4, 3

@@ -117,6 +117,16 @@ def test_autoencoder_dropin_surface():
         rna2dna_ae_loss(torch.rand(4, 36), torch.rand(4, 36))
 
 
+def test_population_shard_partitions_exactly():
+    """vla_b200.shard: every member goes to exactly one rank (replicas only, no communication)."""
+    from vla_b200 import shard
+    items = list(range(23))
+    for world in (1, 2, 4, 8):
+        parts = [shard(items, r, world) for r in range(world)]
+        assert sorted(x for p in parts for x in p) == items
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
 def test_no_cpu_fallback_anywhere():
     from src.models import DNA2RNAVAE
     from src.utils.directional_losses import dna2rna_loss
