@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import vae_oracle as vo
-from parity_util import make_module, rel_l2
+from parity_util import is_pre_bn_bias, make_module, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -41,9 +41,15 @@ def test_concurrent_members_equal_solo_training():
             tr.step()
         solo = tr.losses()
         np.testing.assert_allclose(pop_losses[i], solo, rtol=1e-4)
-        got = pop.members[i].trainer.core.arena.cpu().numpy()
-        ref = tr.core.arena.cpu().numpy()
-        assert rel_l2(got, ref) < 1e-4, (i, rel_l2(got, ref))     # (split-K red.add order is the only non-determinism)
+        # split-K red.add order is the only non-determinism.  It matters only where the true gradient is exactly zero (Linear
+        # biases in front of a train-mode BatchNorm): there the sign of the rounding residue decides Adam's +-lr step.
+        got = dict(pop.members[i].model.named_parameters())
+        for name, p in m.named_parameters():
+            if is_pre_bn_bias(name):
+                assert float((got[name] - p).abs().max()) <= 2.1 * h["lr"] * n_steps, name
+            else:
+                err = rel_l2(got[name].detach().cpu().numpy(), p.detach().cpu().numpy())
+                assert err < 1e-4, (i, name, err)
         tr.close()
     pop.close()
 
