@@ -75,6 +75,11 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
     if (!(used & ~FEATS_FWD_PLAIN)) return launch_one<0, FEATS_FWD_PLAIN>(g, stream, smem);
     if (used & GF_LOSS) {
       if (used & ~FEATS_FWD_LOSS) return cudaErrorInvalidValue;
+      int kinds = 0;
+      for (int i = 0; i < g.nprob; ++i) kinds |= (g.p[i].flags & GF_LOSS) ? 1 << g.p[i].loss_kind : 1 << LOSS_NONE;
+      // uniform groups run the epilogue that contains only their loss kind (about half the code of the generic one)
+      if (kinds == 1 << LOSS_BCE && !(used & ~FEATS_FWD_LOSS_BCE)) return launch_one<0, FEATS_FWD_LOSS_BCE>(g, stream, smem);
+      if (kinds == 1 << LOSS_MSE && !(used & ~FEATS_FWD_LOSS_MSE)) return launch_one<0, FEATS_FWD_LOSS_MSE>(g, stream, smem);
       return launch_one<0, FEATS_FWD_LOSS>(g, stream, smem);
     }
     return launch_one<0, FEATS_FWD_FULL>(g, stream, smem);

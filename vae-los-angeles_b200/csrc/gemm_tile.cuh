@@ -51,7 +51,12 @@ static_assert((2 * GEMM_STAGES + 3) * 8 + 4 <= 128, "barrier block");
 
 constexpr int FEATS_FWD_PLAIN = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;                      // hidden decoder layers, heads
 constexpr int FEATS_FWD_FULL = FEATS_FWD_PLAIN | GF_SIGMOID | GF_COLSTATS;                         // + BatchNorm statistics / sigmoid
-constexpr int FEATS_FWD_LOSS = FEATS_FWD_PLAIN | GF_SIGMOID | GF_LOSS;                             // last decoder layers of a train step
+constexpr int FEATS_FWD_LOSS = FEATS_FWD_PLAIN | GF_SIGMOID | GF_LOSS | GF_LK_MSE | GF_LK_BCE | GF_LK_CE;   // last decoder layers of a
+                                                                                                   // train step, any mix of loss kinds
+// The same epilogue with ONE loss kind and no fp32 output compiled in, for groups that are uniform (rna2dna: BCE, dna2rna:
+// MSE).  The generic instantiation is 84 KB of SASS, the size at which the epilogue is instruction-cache bound.
+constexpr int FEATS_FWD_LOSS_BCE = GF_BIAS | GF_SIGMOID | GF_OUT_BF16 | GF_LOSS | GF_LK_BCE;
+constexpr int FEATS_FWD_LOSS_MSE = GF_BIAS | GF_OUT_BF16 | GF_LOSS | GF_LK_MSE;
 constexpr int FEATS_DGRAD_PLAIN = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;                              // decoder data gradients
 constexpr int FEATS_DGRAD_FULL = FEATS_DGRAD_PLAIN | GF_BNSTATS;                                   // + BatchNorm backward statistics
 constexpr int FEATS_WGRAD = GF_RED | GF_BIASGRAD;
@@ -495,7 +500,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
           // v holds the model output of this row chunk.  Loss value into loss_acc, dL/d(pre-activation) into v (then
           // stored as the bf16 operand of the backward GEMMs).  losses.py:27-42; directional_losses.py:23-24, 48-49.
           __syncwarp();
-          if (P.loss_kind == LOSS_CE) {
+          if ((FEATS & GF_LK_CE) && P.loss_kind == LOSS_CE) {
             // weighted cross-entropy: the whole logit row (N <= 32) is in this thread
             float mx = -FLT_MAX;
 #pragma unroll
@@ -531,7 +536,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
               }
             }
             float part = 0.f;
-            if (P.loss_kind == LOSS_BCE && !(flags & GF_OUT_F32)) {
+            if ((FEATS & GF_LK_BCE) && P.loss_kind == LOSS_BCE && !(flags & GF_OUT_F32)) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {                      // v = pre-sigmoid value
                 float y, g1;
@@ -539,7 +544,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
                 part += (j < nvalid) ? l : 0.f;
                 v[j] = g1;
               }
-            } else if (P.loss_kind == LOSS_BCE) {
+            } else if ((FEATS & GF_LK_BCE) && (FEATS & GF_OUT_F32) && P.loss_kind == LOSS_BCE) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {                      // v = sigmoid output (also stored as fp32 above)
                 float g0, g1;
@@ -547,7 +552,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
                 part += (j < nvalid) ? l : 0.f;
                 v[j] = g1;
               }
-            } else {
+            } else if (FEATS & GF_LK_MSE) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float g0, g1;

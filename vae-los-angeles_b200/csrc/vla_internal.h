@@ -27,6 +27,8 @@ enum GemmFlags : int {
   GF_RED = 1 << 8,        // accumulate into out_f32 with red.global.add (split-K weight gradients)
   GF_BIASGRAD = 1 << 9,   // TN mode: also produce sum_k A[m, k] into bias_grad[m] (ones-MMA)
   GF_LOSS = 1 << 11,      // NT mode, last decoder layer: loss value partials + dL/d(pre-activation) as bf16 (loss_kind)
+  // compile-time only (never set in GemmProblem::flags): which loss kinds an instantiation of the loss epilogue contains
+  GF_LK_MSE = 1 << 12, GF_LK_BCE = 1 << 13, GF_LK_CE = 1 << 14,
 };
 enum LossKind : int { LOSS_NONE = 0, LOSS_MSE = 1, LOSS_BCE = 2, LOSS_CE = 3 };
 
