@@ -180,11 +180,15 @@ class NumaLocal:
 def cpu_arm(workload, batch, steps, warmup, budget_s=25.0):
     import numpy as np
     from oracle import vae_oracle as vo
+    # torchrun exports OMP_NUM_THREADS=1: set the BLAS pool explicitly to every core this process may use and report what
+    # the pool really runs with (round 1's N > 1 lines silently timed one thread).
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
-        threads = os.cpu_count() or 1
+        threads = 1
     state = vo.init_state(workload, DIMS, seed=0)
     opt, step = vo.adamw_init(state)
     tpm, beta, site = vo.synthetic_batch(batch, DIMS, seed=0)

@@ -248,6 +248,11 @@ int vla_profile_pause(vla_model_t* m);
 int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K,
                   int bn, int k_splits, float* bias_grad, vla_stream_t stream);
 
+/* Test hook: device address and row pitch (elements) of a workspace buffer left by the last forward / train step on this
+ * handle.  what 0: the epsilon of reparameterize (src/models/vae.py:13, fp32 [rows, latent]); what 1: the bf16 output of
+ * Dropout(ReLU(BatchNorm(.))) of encoder i, layer j (src/models/encoders.py:14-16, 32-38). */
+int vla_test_workspace(vla_model_t* m, int what, int i, int j, void** ptr, int* ld);
+
 /* Test hook: device buffer [tiles][8] of %globaltimer stamps written by the following vla_test_gemm calls
  * (kernel entry, dependency resolved, setup done, first operands landed, MMAs issued, accumulator ready, epilogue done). */
 int vla_test_set_timeline(unsigned long long* dbg);

@@ -1,8 +1,9 @@
 """torchrun worker of tests/test_gpu_dp.py: 2+ ranks, fused DP train steps vs the per-shard oracle with summed gradients.
 
 DP_EXCHANGE = p2p (the library's peer-memory kernel, default) | nccl (torch.distributed.all_reduce).
-DP_SAME_GPU = 1: every rank uses cuda:0 and the process group is gloo (it only carries the IPC handles and barriers), so
-the peer-memory protocol is exercised between two PROCESSES on a one-GPU box (their kernels time-slice)."""
+One GPU per rank, always: kernels of different ranks wait on one another's stores, and nothing guarantees that two
+processes sharing one GPU run at the same time (B200_PROFILING.md: such runs raised Xid 109).  The index arithmetic of
+the protocol is covered on the CPU by tests/test_dp_protocol_model.py."""
 import os
 import sys
 
@@ -14,21 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "vae-los-angeles_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 from oracle import vae_oracle as vo  # noqa: E402
-from parity_util import is_pre_bn_bias, make_module, rel_l2, to_t  # noqa: E402
+from parity_util import MATCHED_Q, is_pre_bn_bias, make_module, rel_l2, to_t  # noqa: E402
 from vla_b200 import DeviceDataset, Trainer  # noqa: E402
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    same_gpu = os.environ.get("DP_SAME_GPU", "0") == "1"
     exchange = os.environ.get("DP_EXCHANGE", "p2p")
-    if same_gpu:
-        local = 0
-        torch.cuda.set_device(0)
-        dist.init_process_group("gloo")
-    else:
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if torch.cuda.device_count() < world:
+        raise SystemExit("dp_worker needs one GPU per rank")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, dims, per_rank, steps = "rna2dna", dict(A=782, B=572, S=24, L=20, E=32), 64, 3
     state = vo.init_state(kind, dims, seed=31)
     tpm, beta, site = vo.synthetic_batch(per_rank * world, dims, seed=31)
@@ -46,8 +43,6 @@ def main():
     torch.cuda.synchronize()
     # replicas must stay bit-identical
     flat = tr.core.arena.clone()
-    if same_gpu:
-        flat = flat.cpu()
     ref = flat.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(flat, ref), "replicas diverged"
@@ -63,7 +58,7 @@ def main():
                 stc = {k: v.copy() for k, v in st.items()}
                 batch = dict(a=tpm[s2].astype(np.float64), b=beta[s2].astype(np.float64), site=site[s2])
                 out, cache = vo.forward(kind, dims, stc, dict(a=batch["a"], site=batch["site"]), eps[s2].astype(np.float64),
-                                        {k: v[s2] for k, v in masks.items()}, train=True, q=vo.round_bf16)
+                                        {k: v[s2] for k, v in masks.items()}, train=True, q=MATCHED_Q)
                 scal, og = vo.loss_and_output_grads(kind, out, batch, 1e-3, 1.0, None)
                 g = vo.backward(kind, dims, stc, cache, og, train=True)
                 total = g if total is None else {k: total[k] + g[k] for k in g}

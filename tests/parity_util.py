@@ -1,5 +1,6 @@
 """Shared helpers of the GPU parity tests: build the CUDA module from an oracle state, run the oracle,
 compare with the tolerances BASELINE.json states."""
+import os
 import re
 
 import numpy as np
@@ -11,14 +12,20 @@ from oracle import vae_oracle as vo
 # gradients; argmax site predictions exact.  "relative" is measured as ||x - ref||_2 / ||ref||_2 per tensor.
 TOL_FP32 = 1e-5
 TOL_BF16 = 2e-2
-# Parameter gradients against the EXACT (fp64) arithmetic: bf16 operand rounding (relative step 2^-9) flips the
-# ReLU decision of pre-activations that lie within that distance of zero; each flip switches one (sample, unit)
-# gradient contribution on or off, so the error scales like sqrt(fraction flipped) ~ sqrt(2^-9) ~ 5-10 %, not
-# like 2^-9 (measured in numpy with no GPU involved: DESIGN.md "Precision").  The implementation itself is held
-# to TOL_BF16 against the oracle evaluated at the same operand precision; against the exact arithmetic the
-# gradients must stay within this looser, documented envelope and point the same way.
-TOL_GRAD_VS_EXACT = 0.25
-MIN_COSINE_VS_EXACT = 0.97
+# Parameter gradients against the EXACT (fp64) arithmetic and against the reference fixtures: the same 2e-2.
+# Round 1 needed 0.25 here: with every GEMM operand rounded to bf16 once, pre-activations within 2^-9 (relative) of zero
+# flip their ReLU decision and each flip switches a whole (sample, unit) gradient contribution on or off (7-9 % at
+# batch 4096, measured in numpy with no GPU involved).  The CUDA path now carries the operands of every forward GEMM
+# upstream of a ReLU as hi + lo bf16 pairs (three MMA passes, DESIGN.md "Precision"), which removes the flips:
+# measured <= 1.8e-2 (typically 3e-3 .. 9e-3) for all five model kinds at batch 8 .. 4096.
+TOL_GRAD_VS_EXACT = 2e-2
+MIN_COSINE_VS_EXACT = 0.9995
+# Same algorithm at the CUDA path's declared operand precision (oracle/vae_oracle.py header); VLA_SPLIT=0 selects the
+# single-rounding variant in the library and here.
+SPLIT = os.environ.get("VLA_SPLIT", "1") != "0"
+MATCHED_Q = vo.SPLIT_BF16 if SPLIT else vo.round_bf16
+if not SPLIT:                      # documented envelope of the single-rounding variant (round 1)
+    TOL_GRAD_VS_EXACT, MIN_COSINE_VS_EXACT = 0.25, 0.97
 
 
 def rel_l2(x, ref):
@@ -102,7 +109,7 @@ def to_t(x, device="cuda"):
 
 def oracle_step(kind, dims, state, batch, present, eps, masks, beta, gamma, cw, train=True, dtype=np.float64, q=None):
     """Oracle forward + loss + backward on a private fp64 copy of `state`.
-    q=None: exact reference arithmetic; q=vo.round_bf16: same algorithm at the CUDA path's declared GEMM-operand
+    q=None: exact reference arithmetic; q=MATCHED_Q: same algorithm at the CUDA path's declared GEMM-operand
     precision (oracle/vae_oracle.py header)."""
     st = {k: (v.astype(dtype) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
     bt = {k: (v.astype(dtype) if v.dtype.kind == "f" else v) for k, v in batch.items()}
@@ -127,3 +134,23 @@ def cosine(x, ref):
     x = np.asarray(x, dtype=np.float64).reshape(-1)
     ref = np.asarray(ref, dtype=np.float64).reshape(-1)
     return float(x @ ref / max(np.linalg.norm(x) * np.linalg.norm(ref), 1e-300))
+
+
+def grads_by_name(core, flat):
+    """{state_dict name: numpy gradient} from a flat gradient arena laid out like the parameter arena."""
+    from vla_b200 import _lib
+    out = {}
+    host = flat.detach().cpu().numpy()
+    for name, kind, off, shape in core.infos:
+        if kind == _lib.TENSOR_PARAM:
+            n = int(np.prod(shape)) if shape else 1
+            out[name] = host[off:off + n].reshape(shape)
+    return out
+
+
+def out_dir():
+    """Where GPU tests leave their measured tables (merged back by gpurun; the summaries are copied to profiles/)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    return d

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import vae_oracle as vo
-from parity_util import TOL_BF16, TOL_FP32, assert_close, is_pre_bn_bias, make_module, rel_l2, to_t
+from parity_util import MATCHED_Q, TOL_BF16, TOL_FP32, assert_close, is_pre_bn_bias, make_module, rel_l2, to_t
 
 pytestmark = pytest.mark.gpu
 
@@ -43,7 +43,7 @@ def test_fused_train_steps_match_oracle(kind, dims, batch, use_graph):
     eps, masks = vo.synthetic_noise(batch, dims, kind, seed=21)
     cw = vo.balanced_class_weights(site, dims["S"]) if kind == "multimodal" else None
     beta, gamma = 2e-3, 1.5
-    ref_state, ref_losses = _oracle_train(kind, dims, state, data, n_steps, batch, eps, masks, beta, gamma, cw, vo.round_bf16)
+    ref_state, ref_losses = _oracle_train(kind, dims, state, data, n_steps, batch, eps, masks, beta, gamma, cw, MATCHED_Q)
 
     m = make_module(kind, dims, state).train()
     ds = DeviceDataset(tpm, beta_v, site, "cuda")

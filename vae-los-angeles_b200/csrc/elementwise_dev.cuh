@@ -53,6 +53,16 @@ __device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
   return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
+// hi = bf16(x, y) packed; lo = bf16 of what the rounding dropped (split-bf16 operands, DESIGN.md "Precision")
+__device__ __forceinline__ uint32_t pack_bf16x2_hi_lo(float x, float y, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ bf16 bf16_lo_of(float x, bf16 h) { return __float2bfloat16(x - __bfloat162float(h)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -87,7 +97,16 @@ __device__ __forceinline__ void ingest_site(const IngestArgs& a, int r_begin, in
   for (int i = t; i < n_h; i += nthreads) {
     const int r = i / a.ld_hsite, c = i - r * a.ld_hsite;
     const long long s = __ldg(a.site + row0 + r_begin + r);
-    a.h_site[static_cast<size_t>(r_begin + r) * a.ld_hsite + c] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
+    if (a.hsite_lo > 0) {                       // split layout: hi in [0, embed), lo in [hsite_lo, hsite_lo + embed), rest stays zero
+      const int cc = c >= a.hsite_lo ? c - a.hsite_lo : c;
+      if (cc < a.embed) {
+        const float x = a.emb[s * a.embed + cc];
+        const bf16 h = __float2bfloat16(x);
+        a.h_site[static_cast<size_t>(r_begin + r) * a.ld_hsite + c] = c >= a.hsite_lo ? bf16_lo_of(x, h) : h;
+      }
+    } else {
+      a.h_site[static_cast<size_t>(r_begin + r) * a.ld_hsite + c] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
+    }
   }
 #pragma unroll 4
   for (int i = t; i < n_o; i += nthreads) {
@@ -108,7 +127,9 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
   }
   const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
   for (int e = 0; e < a.n; ++e) {
-    const int quads = a.ld_dst[e] >> 2;                        // ld_dst is a multiple of 8
+    const int lo_off = a.lo_off[e];
+    // split layout [hi: 0 .. w | zeros | lo: lo_off .. lo_off + w | zeros]: only the quads that hold data are written
+    const int quads = lo_off > 0 ? (a.width[e] + 3) >> 2 : a.ld_dst[e] >> 2;   // ld_dst is a multiple of 8
     const float* __restrict__ src = a.src[e];
     const int w = a.width[e];
     const bool vec_ok = (w % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
@@ -135,11 +156,11 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
         for (int k = 0; k < 4; ++k) {
           const int qd = base + 32 * k;
           if (qd < quads) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(x[k][0], x[k][1]), hi = __floats2bfloat162_rn(x[k][2], x[k][3]);
-            uint2 o;
-            o.x = *reinterpret_cast<uint32_t*>(&lo);
-            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            uint2 o, ol;
+            o.x = pack_bf16x2_hi_lo(x[k][0], x[k][1], ol.x);
+            o.y = pack_bf16x2_hi_lo(x[k][2], x[k][3], ol.y);
             dp[qd] = o;
+            if (lo_off > 0) dp[(lo_off >> 2) + qd] = ol;
           }
         }
       }
@@ -167,7 +188,7 @@ __device__ __forceinline__ void ingest_body_bulk(const IngestArgs& a, int r_begi
     total += (bytes + 127u) & ~127u;
     ok = ok && (bytes % 16u == 0u) && (src % 16u == 0u);
   }
-  ok = ok && total <= stage_bytes && a.n > 0;
+  ok = ok && total <= stage_bytes && a.n > 0 && a.lo_off[0] == 0 && a.lo_off[1] == 0;
   if (!ok) {
     if (tid == 0) mbar_arrive(bar);        // keep the barrier's phase in step with the caller's parity
     ingest_body(a, r_begin, r_end, tid >> 5, EW_THREADS / 32, tid & 31, first_unit && tid == 0);
@@ -340,7 +361,11 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
       y0 = k0 ? y0 * keep_scale : 0.f;
       y1 = k1 ? y1 * keep_scale : 0.f;
     }
-    *reinterpret_cast<__nv_bfloat162*>(a.out + static_cast<size_t>(row) * a.ld_out + col) = __floats2bfloat162_rn(y0, y1);
+    uint32_t lo;
+    const uint32_t hi = pack_bf16x2_hi_lo(y0, y1, lo);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(a.out + static_cast<size_t>(row) * a.ld_out + col);
+    *dst = hi;
+    if (a.out_lo > 0) dst[a.out_lo >> 1] = lo;
   };
 #pragma unroll
   for (int i = 0; i < PF; ++i) {
@@ -444,7 +469,9 @@ __device__ __forceinline__ void latent_fwd_body(const LatentFwdArgs& a, int b, i
       a.mu[idx] = mu;
       a.logvar[idx] = 0.f;
       a.eps_save[idx] = 0.f;
-      a.z[static_cast<size_t>(r) * a.ld_z + j] = __float2bfloat16(mu);
+      { const bf16 h = __float2bfloat16(mu);
+        a.z[static_cast<size_t>(r) * a.ld_z + j] = h;
+        if (a.z_lo > 0) a.z[static_cast<size_t>(r) * a.ld_z + a.z_lo + j] = bf16_lo_of(mu, h); }
       eps = 0.f;
     } else {
     if (a.eps_in) {
@@ -461,7 +488,9 @@ __device__ __forceinline__ void latent_fwd_body(const LatentFwdArgs& a, int b, i
     a.mu[idx] = mu;
     a.logvar[idx] = lv;
     a.eps_save[idx] = eps;
-    a.z[static_cast<size_t>(r) * a.ld_z + j] = __float2bfloat16(z);
+    { const bf16 h = __float2bfloat16(z);
+      a.z[static_cast<size_t>(r) * a.ld_z + j] = h;
+      if (a.z_lo > 0) a.z[static_cast<size_t>(r) * a.ld_z + a.z_lo + j] = bf16_lo_of(z, h); }
     kl = 1.0f + lv - mu * mu - expf(lv);
     }
   }
@@ -736,7 +765,10 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
     int r = static_cast<int>(idx / static_cast<unsigned>(ch.cols));
     int c = static_cast<int>(idx - static_cast<unsigned>(r) * ch.cols);
     for (int k = 0; k < nv; ++k) {
-      a.shadow[ch.shadow_off + static_cast<long long>(r) * ch.ld_shadow + c] = __float2bfloat16(p[k]);
+      const bf16 h = __float2bfloat16(p[k]);
+      bf16* dst = a.shadow + ch.shadow_off + static_cast<long long>(r) * ch.ld_shadow + c;
+      *dst = h;
+      if (ch.sh_lo > 0) dst[ch.sh_lo] = bf16_lo_of(p[k], h);
       if (++c == ch.cols) { c = 0; ++r; }
     }
   }
@@ -799,7 +831,10 @@ __device__ __forceinline__ void adamw_unit(const AdamArgs& a, int c0, int c1, in
           int c = static_cast<int>(idx - static_cast<unsigned>(r) * ch[k].cols);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            a.shadow[ch[k].shadow_off + static_cast<long long>(r) * ch[k].ld_shadow + c] = __float2bfloat16(p[j]);
+            const bf16 h = __float2bfloat16(p[j]);
+            bf16* dst = a.shadow + ch[k].shadow_off + static_cast<long long>(r) * ch[k].ld_shadow + c;
+            *dst = h;
+            if (ch[k].sh_lo > 0) dst[ch[k].sh_lo] = bf16_lo_of(p[j], h);
             if (++c == ch[k].cols) { c = 0; ++r; }
           }
         }

@@ -182,10 +182,12 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     const float* rstd; float* stats; float* bias_grad;
     const float* aux0; const float* aux1; const long long* aux_site; float* aux_partials; const DynParams* dyn;
     int aux_n, loss_kind; float aux_scale;
+    int a_lo, b_lo, out_lo;
   } P;
   P.M = Pd.M; P.N = Pd.N; P.K = Pd.K; P.BN = Pd.BN; P.m_tiles = Pd.m_tiles; P.n_tiles = Pd.n_tiles;
   P.kb_per_split = Pd.kb_per_split; P.flags = Pd.flags; P.ld_f32 = Pd.ld_f32; P.ld_bf16 = Pd.ld_bf16; P.ld_mask = Pd.ld_mask;
   P.ld_pre = Pd.ld_pre; P.mask_scale = Pd.mask_scale; P.bias = Pd.bias; P.out_f32 = Pd.out_f32; P.out_bf16 = Pd.out_bf16;
+  P.a_lo = (MODE == 0) ? Pd.a_lo : 0; P.b_lo = (MODE == 0) ? Pd.b_lo : 0; P.out_lo = (MODE == 0) ? Pd.out_lo : 0;
   P.mask_src = Pd.mask_src; P.pre = Pd.pre; P.mean = Pd.mean; P.rstd = Pd.rstd; P.stats = Pd.stats; P.bias_grad = Pd.bias_grad;
   if (FEATS & GF_LOSS) {
     P.aux0 = Pd.aux0; P.aux1 = Pd.aux1; P.aux_site = Pd.aux_site; P.aux_partials = Pd.aux_partials; P.dyn = Pd.dyn;
@@ -202,6 +204,9 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
   const int kb_total = (P.K + GEMM_BK - 1) / GEMM_BK;
   const int kb0 = k_split * P.kb_per_split;
   const int kb1 = min(kb0 + P.kb_per_split, kb_total);
+  // split-bf16 operands (NT only): every k-block occupies TWO consecutive ring slots -- (A_hi, B_hi) then (A_lo, B_lo) --
+  // and the tile accumulates A_hi B_hi + A_lo B_hi + A_hi B_lo (the lo x lo term is below fp32 rounding).
+  const bool split = (MODE == 0) && P.a_lo > 0;
   const bool bias_mma = (MODE == 1) && (FEATS & GF_BIASGRAD) && (P.flags & GF_BIASGRAD) && n_tile == 0;
   const int dbgf = MEGA ? 0 : ctx.dbg_flags;      // test hooks exist only in the stand-alone kernel
   const uint32_t tmem_base = ctx.tmem_base;
@@ -222,7 +227,9 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     if (lane == 0) {
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kv = (split ? 2 : 1) * kb0; kv < (split ? 2 : 1) * kb1; ++kv) {
+        const int kb = split ? (kv >> 1) : kv;
+        const int lo = split ? (kv & 1) : 0;                                   // second slot of a split k-block: the lo copies
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
@@ -232,10 +239,10 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
           tma_load_2d(sa, tmA, &full_bar[stage], m0, kb * GEMM_BK);           // box 64 (M) x 64 (K)
           tma_load_2d(sa + 8192, tmA, &full_bar[stage], m0 + 64, kb * GEMM_BK);
         } else {
-          tma_load_2d(sa, tmA, &full_bar[stage], kb * GEMM_BK, m0);           // box 64 (K) x 128 (M)
+          tma_load_2d(sa, tmA, &full_bar[stage], kb * GEMM_BK + (lo ? P.a_lo : 0), m0);   // box 64 (K) x 128 (M)
         }
         if (MODE == 0) {
-          tma_load_2d(sb, tmB, &full_bar[stage], kb * GEMM_BK, n0);           // box 64 (K) x BN (N)
+          tma_load_2d(sb, tmB, &full_bar[stage], kb * GEMM_BK + (lo ? P.b_lo : 0), n0);   // box 64 (K) x BN (N)
         } else {
           for (int i = 0; i < nb; ++i)
             tma_load_2d(sb + i * 8192, tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);   // box 64 (N) x 64 (K)
@@ -252,6 +259,30 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (split) {
+          // two ring slots per k-block: slot s0 = (A_hi, B_hi), slot s1 = (A_lo, B_lo); three passes of four MMAs
+          const int s0 = stage;
+          mbar_wait(&full_bar[s0], phase);
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          const int s1 = stage;
+          mbar_wait(&full_bar[s1], phase);
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          if (kb == kb0) VLA_STAMP(3);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s0 * STAGE_BYTES), b_hi = a_hi + A_STAGE_BYTES;
+          const uint32_t a_lo = smem_u32(smem + s1 * STAGE_BYTES), b_lo = a_lo + A_STAGE_BYTES;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t pa = pass == 1 ? a_lo : a_hi, pb = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_bf16(tmem_base, make_smem_desc(pa + k * 32, 16, 1024), make_smem_desc(pb + k * 32, 16, 1024), idesc,
+                        (kb > kb0 || k > 0 || pass > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s0]);
+          umma_commit(&empty_bar[s1]);
+          continue;
+        }
         mbar_wait(&full_bar[stage], phase);
         if (kb == kb0) VLA_STAMP(3);                               // first operands landed
         tc_fence_after();
@@ -582,13 +613,27 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
                 o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
                 o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
                 reinterpret_cast<uint4*>(P.out_bf16 + static_cast<size_t>(rbase + rr) * P.ld_bf16 + col0)[lane & 3] = o;
+                if (MODE == 0 && !(FEATS & GF_LOSS) && P.out_lo > 0) {      // lo copy: what bf16 rounding dropped
+                  const float2 f0 = __bfloat1622float2(b0), f1 = __bfloat1622float2(b1);
+                  const float2 f2 = __bfloat1622float2(b2), f3 = __bfloat1622float2(b3);
+                  b0 = __floats2bfloat162_rn(lo.x - f0.x, lo.y - f0.y); b1 = __floats2bfloat162_rn(lo.z - f1.x, lo.w - f1.y);
+                  b2 = __floats2bfloat162_rn(hi.x - f2.x, hi.y - f2.y); b3 = __floats2bfloat162_rn(hi.z - f3.x, hi.w - f3.y);
+                  o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+                  o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+                  reinterpret_cast<uint4*>(P.out_bf16 + static_cast<size_t>(rbase + rr) * P.ld_bf16 + P.out_lo + col0)[lane & 3] = o;
+                }
               }
             }
           } else if (lane < nvalid) {
 #pragma unroll 4
             for (int i = 0; i < 32; ++i)
-              if (rbase + i < P.M)
-                P.out_bf16[static_cast<size_t>(rbase + i) * P.ld_bf16 + col0 + lane] = __float2bfloat16(patch[i * PATCH_LD + lane]);
+              if (rbase + i < P.M) {
+                const float x = patch[i * PATCH_LD + lane];
+                const bf16 h = __float2bfloat16(x);
+                bf16* dst = P.out_bf16 + static_cast<size_t>(rbase + i) * P.ld_bf16 + col0 + lane;
+                *dst = h;
+                if (MODE == 0 && !(FEATS & GF_LOSS) && P.out_lo > 0) dst[P.out_lo] = __float2bfloat16(x - __bfloat162float(h));
+              }
           }
         }
       }
@@ -664,7 +709,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
 
   // ---- every thread: advance the ring position and the tile parity ----
   if (!(!MEGA && (dbgf & 2))) {
-    const int s = ctx.stage + (kb1 - kb0);
+    const int s = ctx.stage + (split ? 2 : 1) * (kb1 - kb0);
     ctx.phase ^= static_cast<uint32_t>(s / GEMM_STAGES) & 1u;
     ctx.stage = s % GEMM_STAGES;
     ctx.tile_parity ^= 1u;

@@ -28,6 +28,12 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 constexpr int FEATS_FWD_PLAIN_HOST = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;     // must match gemm_tile.cuh
 constexpr int FEATS_DGRAD_PLAIN_HOST = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;
 inline int pad8(int x) { return (x + 7) & ~7; }
+inline int pad64(int x) { return (x + 63) & ~63; }
+// Row pitch / lo offset of a bf16 GEMM operand of logical width w.  Split layout (DESIGN.md "Precision"):
+// [hi: 0 .. w | zeros up to pad64(w) | lo: pad64(w) .. pad64(w) + w | zeros]; the pad columns are never written (the
+// workspace and the weight copies are zero-filled once), so whole 64-column k-blocks can be read from either half.
+inline int op_ld(bool split, int w) { return split ? 2 * pad64(w) : pad8(w); }
+inline int op_lo(bool split, int w) { return split ? pad64(w) : 0; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 struct Lin {
@@ -35,6 +41,7 @@ struct Lin {
   long long w_off = -1, b_off = -1;
   long long sh_off = -1; int sh_ld = 0;      // bf16 copy [out, sh_ld]: K-major B operand of the forward GEMM and
                                              // MN-major B operand of the data-gradient GEMM
+  int sh_lo = 0;                             // > 0: split copy, lo part sh_lo elements further along the row
 };
 struct Bn { int n = 0; long long g_off = -1, b_off = -1, rm_off = -1, rv_off = -1; int counter = -1; };
 struct Enc {
@@ -49,15 +56,17 @@ struct Dec {
 };
 
 struct EncWS {
-  bf16* x = nullptr; int ldx = 0;                         // bf16 input (dense) / gathered embedding (site)
+  bf16* x = nullptr; int ldx = 0, x_lo = 0;               // bf16 input (dense) / gathered embedding (site)
   bf16* onehot = nullptr; int ld_onehot = 0;
-  bf16* g_x = nullptr;                                    // site: gradient w.r.t. the gathered embedding
+  bf16* g_x = nullptr; int ld_gx = 0;                     // site: gradient w.r.t. the gathered embedding
   std::vector<float*> pre, stats, bstats, mean, rstd;
   std::vector<bf16*> act, gy, gpre;
+  std::vector<int> ld_act, act_lo;
   float* ml = nullptr;
 };
 struct DecWS {
   std::vector<bf16*> act, gact;                           // hidden activations after the fused first layer
+  std::vector<int> ld_act, act_lo;
   bf16* g_out = nullptr; int ld_gout = 0;                 // bf16 gradient w.r.t. the last layer's pre-activation
   float* recon = nullptr;                                 // fp32 output when the caller passes none
 };
@@ -106,6 +115,7 @@ struct vla_model {
   std::vector<ProfEntry> prof;
   vla_config_t cfg{};
   int L = 0, E = 0, S = 0;
+  bool split = true;                 // split-bf16 operands for every forward GEMM that feeds a ReLU (VLA_SPLIT=0: plain bf16)
   bool ae = false; int HW = 0;       // autoencoder kinds: one head of width L per encoder (HW = L), else fused mu | logvar (HW = 2L)
   std::vector<Enc> encs;
   std::vector<Dec> decs;
@@ -128,7 +138,7 @@ struct vla_model {
   std::vector<DecWS> dws;
   float *mu = nullptr, *logvar = nullptr, *eps = nullptr, *kl_partials = nullptr, *gz = nullptr;
   bf16 *z = nullptr, *gml = nullptr, *d0 = nullptr, *g_d0 = nullptr;
-  int ldz = 0, ldgml = 0;
+  int ldz = 0, z_lo = 0, ldgml = 0, ld_d0 = 0, d0_lo = 0;
   std::map<TmapKey, CUtensorMap> tmaps;
   // what the last forward left in the workspace
   bool saved = false; int saved_batch = 0, saved_present = 0, saved_train = 0, kl_grid = 0;
@@ -241,8 +251,12 @@ void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
     const GemmProblem& p = g.p[i];
     *flops += 2.0 * p.M * p.N * p.K;
     const double out_b = (p.flags & (GF_OUT_F32 | GF_RED)) ? 4.0 : 0.0;
-    *bytes += 2.0 * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K) +
-              (out_b + ((p.flags & GF_OUT_BF16) ? 2.0 : 0.0)) * p.M * p.N;
+    // operands (hi + lo copies when split), results, and the fp32 targets a loss-fused tile reads (MSE / BCE)
+    const double tgt_b = ((p.flags & GF_LOSS) && p.loss_kind != LOSS_CE) ? 4.0 : 0.0;
+    const double opw = p.a_lo > 0 ? 4.0 : 2.0;
+    *bytes += opw * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K) +
+              (out_b + tgt_b + ((p.flags & GF_OUT_BF16) ? (p.out_lo > 0 ? 4.0 : 2.0) : 0.0)) * p.M * p.N;
+    if (p.a_lo > 0) *flops += 4.0 * p.M * p.N * p.K;      // three MMA passes
   }
 }
 int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStream_t st, bool finalized = false) {
@@ -287,23 +301,24 @@ struct ArenaBuilder {
     t.shape[0] = d0 < 0 ? 0 : d0; t.shape[1] = d1 < 0 ? 0 : d1;
     m->infos.push_back(t);
   }
-  void seg(long long off, int rows, int cols, long long sh_off, int sh_ld) {
+  void seg(long long off, int rows, int cols, long long sh_off, int sh_ld, int sh_lo = 0) {
     const long long n = static_cast<long long>(rows) * cols;
     for (long long st = 0; st < n; st += ADAM_CHUNK) {
       AdamChunk c{};
       c.offset = off + st; c.shadow_off = sh_off; c.n = static_cast<int>(std::min<long long>(ADAM_CHUNK, n - st));
-      c.first = static_cast<int>(st); c.cols = cols; c.ld_shadow = sh_ld;
+      c.first = static_cast<int>(st); c.cols = cols; c.ld_shadow = sh_ld; c.sh_lo = sh_lo;
       m->chunks_h.push_back(c);
     }
   }
   // A Linear whose weight rows may be exposed under several state_dict names (fused groups).
-  Lin linear(int out, int in) {
+  // split: this layer's forward GEMM runs on split-bf16 operands (its result reaches a ReLU)
+  Lin linear(int out, int in, bool split) {
     Lin l; l.out = out; l.in = in;
     l.w_off = take_p(static_cast<long long>(out) * in);
     l.b_off = take_p(out);
-    l.sh_ld = pad8(in);
+    l.sh_ld = op_ld(split, in); l.sh_lo = op_lo(split, in);
     l.sh_off = take_sh(static_cast<long long>(out) * l.sh_ld);
-    seg(l.w_off, out, in, l.sh_off, l.sh_ld);
+    seg(l.w_off, out, in, l.sh_off, l.sh_ld, l.sh_lo);
     seg(l.b_off, out, 1, -1, 0);
     return l;
   }
@@ -355,7 +370,7 @@ int build_layout(vla_model* m) {
       last = e.in_dim;
       for (size_t i = 0; i < hidden.size(); ++i) {
         const int h = hidden[i];
-        Lin l = ab.linear(h, last);
+        Lin l = ab.linear(h, last, m->split);
         Bn bn; bn.n = h;
         bn.g_off = ab.take_p(h); ab.seg(bn.g_off, h, 1, -1, 0);
         bn.b_off = ab.take_p(h); ab.seg(bn.b_off, h, 1, -1, 0);
@@ -378,7 +393,7 @@ int build_layout(vla_model* m) {
       }
     }
     // fused heads: rows [0, L) = fc_mu, rows [L, 2L) = fc_logvar
-    e.heads = ab.linear(m->HW, last);
+    e.heads = ab.linear(m->HW, last, m->split);
     if (ae) {
       // one head: the last Linear of the encoder Sequential, or site_projection (directional_ae.py:26, 30, 89, 93)
       const std::string head = s.type == 'C' ? std::string("site_projection") : e.prefix + "." + std::to_string(4 * e.fc.size());
@@ -395,7 +410,7 @@ int build_layout(vla_model* m) {
   // fused first decoder layers: one [sum of first hidden widths, L] matrix
   int cat_w = 0;
   for (const auto& s : ds) cat_w += s.type == 'A' ? 128 : (s.type == 'B' ? 256 : 64);
-  m->cat = ab.linear(cat_w, L);
+  m->cat = ab.linear(cat_w, L, m->split);
   int off = 0;
   for (const auto& s : ds) {
     Dec d; d.type = s.type; d.prefix = s.prefix;
@@ -407,7 +422,9 @@ int build_layout(vla_model* m) {
     std::vector<int> widths = s.type == 'B' ? std::vector<int>{512, d.out_dim} : std::vector<int>{d.out_dim};
     int last = d.cat_w;
     for (size_t i = 0; i < widths.size(); ++i) {
-      Lin l = ab.linear(widths[i], last);
+      // The output layers feed no ReLU: plain bf16 -- except the site classifier's (64 x n_sites, negligible work), whose
+      // argmax must agree with the reference's row by row (BASELINE.json north_star).
+      Lin l = ab.linear(widths[i], last, m->split && (i + 1 < widths.size() || s.type == 'C'));
       const std::string fc = d.prefix + ".fc." + std::to_string(2 * (i + 1));
       ab.info(fc + ".weight", VLA_TENSOR_PARAM, l.w_off, widths[i], last);
       ab.info(fc + ".bias", VLA_TENSOR_PARAM, l.b_off, widths[i]);
@@ -440,18 +457,19 @@ void carve(vla_model* m, Bump& b, int cap) {
   for (size_t i = 0; i < m->encs.size(); ++i) {
     const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
     if (e.type == 'C') {
-      w.ldx = pad8(m->E); w.x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
-      w.g_x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
+      w.ldx = op_ld(m->split, m->E); w.x_lo = op_lo(m->split, m->E); w.x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
+      w.ld_gx = pad8(m->E); w.g_x = b.take<bf16>(static_cast<size_t>(cap) * w.ld_gx);
       w.ld_onehot = pad8(m->S); w.onehot = b.take<bf16>(static_cast<size_t>(cap) * w.ld_onehot);
     } else {
-      w.ldx = pad8(e.in_dim); w.x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
+      w.ldx = op_ld(m->split, e.in_dim); w.x_lo = op_lo(m->split, e.in_dim); w.x = b.take<bf16>(static_cast<size_t>(cap) * w.ldx);
       for (const Lin& l : e.fc) {
+        w.ld_act.push_back(op_ld(m->split, l.out)); w.act_lo.push_back(op_lo(m->split, l.out));
         w.pre.push_back(b.take<float>(static_cast<size_t>(cap) * l.out));
         w.stats.push_back(b.take<float>(static_cast<size_t>(mt) * 2 * l.out));
         w.bstats.push_back(b.take<float>(static_cast<size_t>(mt) * 2 * l.out));
         w.mean.push_back(b.take<float>(l.out));
         w.rstd.push_back(b.take<float>(l.out));
-        w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
+        w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * w.ld_act.back()));
         w.gy.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
         w.gpre.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
       }
@@ -463,15 +481,19 @@ void carve(vla_model* m, Bump& b, int cap) {
   m->eps = b.take<float>(static_cast<size_t>(cap) * L);
   m->gz = b.take<float>(static_cast<size_t>(cap) * L);
   m->kl_partials = b.take<float>(ceil_div(cap * L, 256) + 1);
-  m->ldz = pad8(L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
+  m->ldz = op_ld(m->split, L); m->z_lo = op_lo(m->split, L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
   m->ldgml = pad8(m->HW); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
-  m->d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
+  m->ld_d0 = op_ld(m->split, m->cat.out); m->d0_lo = op_lo(m->split, m->cat.out);
+  m->d0 = b.take<bf16>(static_cast<size_t>(cap) * m->ld_d0);
   m->g_d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
   m->dws.assign(m->decs.size(), DecWS{});
   for (size_t i = 0; i < m->decs.size(); ++i) {
     const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
     for (size_t r = 0; r + 1 < d.rest.size(); ++r) {
-      w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * d.rest[r].out));
+      // hidden activation r feeds layer r + 1: split only when that layer is itself followed by a ReLU
+      const bool sp = m->split && (r + 2 < d.rest.size() || d.type == 'C');
+      w.ld_act.push_back(op_ld(sp, d.rest[r].out)); w.act_lo.push_back(op_lo(sp, d.rest[r].out));
+      w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * w.ld_act.back()));
       w.gact.push_back(b.take<bf16>(static_cast<size_t>(cap) * d.rest[r].out));
     }
     w.ld_gout = pad8(d.out_dim);
@@ -534,9 +556,11 @@ int choose_bn_tn(int N) {
 thread_local PendingB g_pending[GEMM_MAX_PROBLEMS];
 
 // C[M,N] = A[M,K] * W[N,K]^T ; A bf16 [M, lda], W bf16 [N, ldw]
+// a_lo / b_lo > 0 (both or neither): split-bf16 operands, the lo copies sit a_lo / b_lo elements further along each row
 int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int flags,
-           GemmProblem** out, int force_bn = 0) {
+           GemmProblem** out, int force_bn = 0, int a_lo = 0, int b_lo = 0) {
   if (g.nprob >= GEMM_MAX_PROBLEMS) return fail(VLA_ERR_STATE, "too many problems in one GEMM group");
+  if ((a_lo > 0) != (b_lo > 0) || (a_lo & 63) || (b_lo & 63)) return fail(VLA_ERR_STATE, "split GEMM operands need both lo copies at 64-element offsets");
   GemmProblem& p = g.p[g.nprob];
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
@@ -544,9 +568,10 @@ int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, in
   p.m_tiles = ceil_div(M, GEMM_BM);
   p.k_splits = 1; p.kb_per_split = ceil_div(K, GEMM_BK);
   p.flags = flags;
+  p.a_lo = a_lo; p.b_lo = b_lo;
   int rc;
-  if ((rc = get_tmap(m, &p.tmA, A, K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
-  g_pending[g.nprob] = PendingB{W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, 0, K, force_bn != 0};
+  if ((rc = get_tmap(m, &p.tmA, A, a_lo > 0 ? a_lo + K : K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
+  g_pending[g.nprob] = PendingB{W, static_cast<uint64_t>(b_lo > 0 ? b_lo + K : K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, 0, K, force_bn != 0};
   g.nprob++;
   *out = &p;
   return VLA_OK;
@@ -592,7 +617,7 @@ int finalize_group(vla_model* m, GemmGroup& g, int mode) {
     for (int i = 0; i < n; ++i) {
       const int bn = cand[i][pk[i]];
       tiles += g.p[i].m_tiles * ceil_div(g.p[i].N, bn);
-      const double t = 5.0 + ceil_div(g.p[i].K, GEMM_BK) * (16384.0 + bn * 128.0) / 150e3 + 0.4 * ceil_div(bn, 64);
+      const double t = 5.0 + (g.p[i].a_lo > 0 ? 2 : 1) * ceil_div(g.p[i].K, GEMM_BK) * (16384.0 + bn * 128.0) / 150e3 + 0.4 * ceil_div(bn, 64);
       slow = std::max(slow, t);
     }
     return ceil_div(tiles, 148) * slow + 1e-3 * tiles;
@@ -724,14 +749,14 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       if (!(present >> i & 1)) continue;
       const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
       if (e.type == 'C') {
-        a.site = io.site; a.emb = P + e.emb_off; a.h_site = w.x; a.ld_hsite = w.ldx;
+        a.site = io.site; a.emb = P + e.emb_off; a.h_site = w.x; a.ld_hsite = w.ldx; a.hsite_lo = w.x_lo;
         a.onehot = w.onehot; a.ld_onehot = w.ld_onehot; a.n_sites = m->S; a.embed = m->E;
       } else {
-        a.src[a.n] = io.x[e.slot]; a.dst[a.n] = w.x; a.width[a.n] = e.in_dim; a.ld_dst[a.n] = w.ldx; a.n++;
+        a.src[a.n] = io.x[e.slot]; a.dst[a.n] = w.x; a.width[a.n] = e.in_dim; a.ld_dst[a.n] = w.ldx; a.lo_off[a.n] = w.x_lo; a.n++;
       }
     }
     a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches; a.beta1 = io.beta1; a.beta2 = io.beta2;
-    { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * (4.0 * a.width[e] + 2.0 * a.ld_dst[e]);
+    { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * a.width[e] * (4.0 + (a.lo_off[e] > 0 ? 4.0 : 2.0));
       if (m->rec) {
         const char* env_rpb = getenv("VLA_INGEST_RPB");           // experiment hook: rows per ingest unit
         const int rpu = env_rpb ? std::max(1, atoi(env_rpb)) : 32;
@@ -752,15 +777,17 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       if (r < e.fc.size()) {
         const Lin& l = e.fc[r];
         const bf16* A = r == 0 ? w.x : w.act[r - 1];
-        const int lda = r == 0 ? w.ldx : e.fc[r - 1].out;
+        const int lda = r == 0 ? w.ldx : w.ld_act[r - 1];
+        const int a_lo = r == 0 ? w.x_lo : w.act_lo[r - 1];
         const int flags = GF_BIAS | GF_OUT_F32 | (io.train ? GF_COLSTATS : 0);
-        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_f32 = w.pre[r]; p->ld_f32 = l.out; p->stats = w.stats[r];
       } else if (r == e.fc.size()) {
         const Lin& l = e.heads;
         const bf16* A = r == 0 ? w.x : w.act[r - 1];
-        const int lda = r == 0 ? w.ldx : e.fc[r - 1].out;
-        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_OUT_F32, &p))) return rc;
+        const int lda = r == 0 ? w.ldx : w.ld_act[r - 1];
+        const int a_lo = r == 0 ? w.x_lo : w.act_lo[r - 1];
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_OUT_F32, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_f32 = w.ml; p->ld_f32 = m->HW;
       }
     }
@@ -776,7 +803,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.running_mean = io.buffers + bn.rm_off; a.running_var = io.buffers + bn.rv_off;
       a.num_batches_tracked = io.counters ? io.counters + bn.counter : nullptr;
       a.save_mean = w.mean[r]; a.save_rstd = w.rstd[r];
-      a.out = w.act[r]; a.ld_out = bn.n;
+      a.out = w.act[r]; a.ld_out = w.ld_act[r]; a.out_lo = w.act_lo[r];
       a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
@@ -794,7 +821,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     for (size_t i = 0; i < m->encs.size(); ++i)
       if (present >> i & 1) { a.ml[a.n_enc] = m->ews[i].ml; a.ld_ml[a.n_enc] = m->HW; a.n_enc++; }
     a.eps_in = io.eps; a.seed = io.seed; a.offset = io.offset * 16; a.dyn = io.engine ? m->dyn : nullptr;
-    a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz;
+    a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz; a.z_lo = m->z_lo;
     a.kl_partials = m->kl_partials; a.rows = B; a.L = L; a.ae = m->ae ? 1 : 0;
     if (m->rec) {
       const int nb = ceil_div(B * L, 256), sub = 4;
@@ -813,8 +840,8 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
   {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
-    if ((rc = add_nt(m, g, m->z, m->ldz, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p))) return rc;
-    p->bias = P + l.b_off; p->out_bf16 = m->d0; p->ld_bf16 = l.out;
+    if ((rc = add_nt(m, g, m->z, m->ldz, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p, 0, m->z_lo, l.sh_lo))) return rc;
+    p->bias = P + l.b_off; p->out_bf16 = m->d0; p->ld_bf16 = m->ld_d0; p->out_lo = m->d0_lo;
     if ((rc = timed_gemm(m, g, 0, "gemm_dec_l0", st))) return rc;
   }
   size_t max_rest = 0;
@@ -827,7 +854,9 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       if (r >= d.rest.size()) continue;
       const Lin& l = d.rest[r];
       const bf16* A = r == 0 ? m->d0 + d.cat_off : w.act[r - 1];
-      const int lda = r == 0 ? m->cat.out : d.rest[r - 1].out;
+      const int lda = r == 0 ? m->ld_d0 : w.ld_act[r - 1];
+      // split operands for the hidden layers (their result feeds a ReLU); the output layer runs plain bf16
+      const int a_lo = l.sh_lo > 0 ? (r == 0 ? m->d0_lo : w.act_lo[r - 1]) : 0;
       GemmProblem* p;
       const bool last = r + 1 == d.rest.size();
       if (last) {
@@ -835,7 +864,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         if (io.fuse_loss) {
           // output -> loss partials + bf16 dL/d(pre-activation); the fp32 output is written only if the caller wants it
           const int flags = GF_BIAS | GF_LOSS | GF_OUT_BF16 | (io.recon[slot] ? GF_OUT_F32 : 0) | (d.type == 'B' ? GF_SIGMOID : 0);
-          if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+          if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p, 0, a_lo, l.sh_lo))) return rc;
           p->bias = P + l.b_off; p->out_f32 = io.recon[slot]; p->ld_f32 = l.out;
           p->out_bf16 = w.g_out; p->ld_bf16 = w.ld_gout;
           p->loss_kind = d.type == 'A' ? LOSS_MSE : (d.type == 'B' ? LOSS_BCE : LOSS_CE);
@@ -846,12 +875,12 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         } else {
           float* dst = io.recon[slot] ? io.recon[slot] : w.recon;
           const int flags = GF_BIAS | GF_OUT_F32 | (d.type == 'B' ? GF_SIGMOID : 0);
-          if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p))) return rc;
+          if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p, 0, a_lo, l.sh_lo))) return rc;
           p->bias = P + l.b_off; p->out_f32 = dst; p->ld_f32 = l.out;
         }
       } else {
-        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p))) return rc;
-        p->bias = P + l.b_off; p->out_bf16 = w.act[r]; p->ld_bf16 = l.out;
+        if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p, 0, a_lo, l.sh_lo))) return rc;
+        p->bias = P + l.b_off; p->out_bf16 = w.act[r]; p->ld_bf16 = w.ld_act[r]; p->out_lo = w.act_lo[r];
       }
     }
     if (g.nprob) {
@@ -969,10 +998,10 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       // dX[B, in] = dY[B, out] * W[out, in]  ->  A K-major, B = forward weight copy read MN-major
       if ((rc = add_nn(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_MASK | GF_OUT_BF16, &p))) return rc;
       if (rr == 0) {
-        p->mask_src = m->d0 + d.cat_off; p->ld_mask = m->cat.out;
+        p->mask_src = m->d0 + d.cat_off; p->ld_mask = m->ld_d0;
         p->out_bf16 = m->g_d0 + d.cat_off; p->ld_bf16 = m->cat.out;
       } else {
-        p->mask_src = w.act[rr - 1]; p->ld_mask = l.in;
+        p->mask_src = w.act[rr - 1]; p->ld_mask = w.ld_act[rr - 1];
         p->out_bf16 = w.gact[rr - 1]; p->ld_bf16 = l.in;
       }
       p->mask_scale = 1.0f;
@@ -996,15 +1025,15 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
         for (size_t r = 0; r < e.fc.size(); ++r) {
           const Lin& l = e.fc[r];
           const bf16* X = r == 0 ? w.x : w.act[r - 1];
-          const int ldx = r == 0 ? w.ldx : e.fc[r - 1].out;
+          const int ldx = r == 0 ? w.ldx : w.ld_act[r - 1];
           if ((rc2 = add_tn(m, g, w.gpre[r], l.out, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc2;
         }
         const Lin& h = e.heads;
         const bf16* X = e.fc.empty() ? w.x : w.act.back();
-        const int ldx = e.fc.empty() ? w.ldx : e.fc.back().out;
+        const int ldx = e.fc.empty() ? w.ldx : w.ld_act.back();
         if ((rc2 = add_tn(m, g, m->gml, m->ldgml, X, ldx, h.out, h.in, B, G + h.w_off, h.in, G + h.b_off))) return rc2;
         if (e.type == 'C')
-          if ((rc2 = add_tn(m, g, w.onehot, w.ld_onehot, w.g_x, w.ldx, m->S, m->E, B, G + e.emb_off, m->E, nullptr))) return rc2;
+          if ((rc2 = add_tn(m, g, w.onehot, w.ld_onehot, w.g_x, w.ld_gx, m->S, m->E, B, G + e.emb_off, m->E, nullptr))) return rc2;
       }
     }
     if (dec && any_dec) {
@@ -1020,7 +1049,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
           const bf16* Gr = last ? w.g_out : w.gact[r];
           const int ldg = last ? w.ld_gout : l.out;
           const bf16* X = r == 0 ? m->d0 + d.cat_off : w.act[r - 1];
-          const int ldx = r == 0 ? m->cat.out : d.rest[r - 1].out;
+          const int ldx = r == 0 ? m->ld_d0 : w.ld_act[r - 1];
           if ((rc2 = add_tn(m, g, Gr, ldg, X, ldx, l.out, l.in, B, G + l.w_off, l.in, G + l.b_off))) return rc2;
         }
       }
@@ -1079,7 +1108,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
         if (site_done) continue;
         const Lin& l = e.heads;
         if ((rc = add_nn(m, g, m->gml, m->ldgml, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
-        p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
+        p->out_bf16 = w.g_x; p->ld_bf16 = w.ld_gx;
         site_done = true;
         continue;
       }
@@ -1090,7 +1119,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const int lda = r == depth ? m->ldgml : l.out;
       const size_t tgt = r - 1;                       // gradient w.r.t. act[tgt]
       if ((rc = add_nn(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_MASK | GF_BNSTATS | GF_OUT_BF16, &p))) return rc;
-      p->mask_src = w.act[tgt]; p->ld_mask = l.in; p->mask_scale = train ? 1.0f / 0.9f : 1.0f;
+      p->mask_src = w.act[tgt]; p->ld_mask = w.ld_act[tgt]; p->mask_scale = train ? 1.0f / 0.9f : 1.0f;
       p->pre = w.pre[tgt]; p->ld_pre = l.in; p->mean = w.mean[tgt]; p->rstd = w.rstd[tgt];
       p->stats = w.bstats[tgt];
       p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;
@@ -1119,7 +1148,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       GemmGroup g; init_group(g); GemmProblem* p;
       const Lin& l = m->encs[i].heads; EncWS& w = m->ews[i];
       if ((rc = add_nn(m, g, m->gml, m->ldgml, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
-      p->out_bf16 = w.g_x; p->ld_bf16 = w.ldx;
+      p->out_bf16 = w.g_x; p->ld_bf16 = w.ld_gx;
       if ((rc = timed_gemm(m, g, 2, "dgrad_site", st))) return rc;
     }
   }
@@ -1154,6 +1183,7 @@ int vla_model_create(const vla_config_t* cfg, vla_model_t** out) {
                                   std::to_string(prop.major) + std::to_string(prop.minor));
   vla_model* m = new vla_model();
   m->cfg = *cfg;
+  { const char* e = getenv("VLA_SPLIT"); m->split = !(e && e[0] == '0'); }
   int rc = build_layout(m);
   if (rc) { delete m; return rc; }
   auto bail = [&](cudaError_t e, const char* what) {
@@ -1700,6 +1730,18 @@ int vla_profile_collect(vla_model_t* m, vla_prof_entry_t* out, int max_entries) 
   }
   m->prof.clear();
   return n;
+}
+
+/* Test hook: device address of a workspace buffer of the last forward on this handle (tests/test_gpu_philox.py reads the
+ * epsilon the kernels drew and the post-dropout activations).  what 0: eps fp32 [rows, latent] (ld = latent);
+ * what 1: activation bf16 of encoder `i`, BatchNorm layer `j` (ld = row pitch in elements).  Returns VLA_ERR_INVALID if absent. */
+int vla_test_workspace(vla_model_t* m, int what, int i, int j, void** ptr, int* ld) {
+  if (!m || !ptr || !ld || !m->ws) return fail(VLA_ERR_INVALID, "vla_test_workspace: no workspace");
+  if (what == 0) { *ptr = m->eps; *ld = m->L; return VLA_OK; }
+  if (what == 1 && i >= 0 && i < static_cast<int>(m->ews.size()) && j >= 0 && j < static_cast<int>(m->ews[i].act.size())) {
+    *ptr = m->ews[i].act[j]; *ld = m->ews[i].ld_act[j]; return VLA_OK;
+  }
+  return fail(VLA_ERR_INVALID, "vla_test_workspace: no such buffer");
 }
 
 static unsigned long long* g_test_dbg = nullptr;

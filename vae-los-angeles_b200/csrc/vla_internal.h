@@ -72,6 +72,12 @@ struct alignas(64) GemmProblem {
   const struct DynParams* dyn;
   int aux_n, loss_kind;
   float aux_scale;                   // CE: gamma when dyn == nullptr
+  // ---- split-bf16 operands (NT mode) ----
+  // a_lo > 0: both operands carry a second bf16 copy ("lo" = bf16(x - bf16(x))) a_lo / b_lo elements further along K in the
+  // same rows; the tile then accumulates A_hi B_hi + A_lo B_hi + A_hi B_lo, i.e. operands of ~16 mantissa bits.  Used by
+  // every forward GEMM whose result reaches a ReLU (DESIGN.md "Precision").
+  int a_lo, b_lo;
+  int out_lo;                        // > 0: GF_OUT_BF16 also stores the lo copy of the result out_lo elements further
   int pad1;
 };
 
@@ -147,11 +153,13 @@ struct IngestArgs {           // fp32 [rows, width] (dense) -> bf16 [rows, ld_ds
   bf16* dst[2];
   int width[2];
   int ld_dst[2];
+  int lo_off[2];              // > 0: also write the lo copy bf16(x - bf16(x)) lo_off elements further along the row
   int n;                      // number of active entries (0..2)
   int rows;
   // site encoder input: h_site[r, :] = bf16(emb[site[r], :]) and onehot[r, s] = (site[r] == s)
   const long long* site; const float* emb; bf16* h_site; int ld_hsite; bf16* onehot; int ld_onehot;
   int n_sites, embed;
+  int hsite_lo;               // > 0: lo copy of the gathered embedding rows
   // train step bookkeeping: dyn->step += 1 (first kernel of a train step)
   struct DynParams* dyn; int bump_step;
   float beta1, beta2;         // Adam betas, to advance dyn->b1pow / b2pow with the step
@@ -166,6 +174,7 @@ struct BnActArgs {
   float* running_mean; float* running_var; long long* num_batches_tracked;
   float* save_mean; float* save_rstd;   // [n]
   bf16* out; int ld_out;
+  int out_lo;                           // > 0: lo copy of the activation out_lo elements further along the row
   const unsigned char* keep_mask;       // optional injected keep mask [rows, n]
   int rows, n;
   int train;                            // batch statistics + dropout
@@ -194,6 +203,7 @@ struct LatentFwdArgs {
   float* mu; float* logvar;                       // outputs [rows, L] dense
   float* eps_save;                                // [rows, L]
   bf16* z; int ld_z;                              // [rows, ld_z]
+  int z_lo;                                       // > 0: lo copy of z
   float* kl_partials;                             // [grid]
   int rows, L;
   int ae;                                         // autoencoder: heads are [rows, L]; z = mu = mean, no sampling, KL = 0
@@ -258,6 +268,8 @@ struct alignas(16) AdamChunk {
   int first;              // element index of the chunk's first element inside its tensor
   int cols;               // tensor columns (vectors: 1)
   int ld_shadow;
+  int sh_lo;              // > 0: the bf16 copy carries a lo part sh_lo elements further along the row
+  int pad[3];
 };
 constexpr int ADAM_CHUNK = 1024;   // one float4 per thread
 struct AdamArgs {

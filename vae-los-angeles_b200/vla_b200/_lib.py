@@ -115,6 +115,7 @@ EXPORTS = {
     "vla_step_phase_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "vla_step_timeline_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
+    "vla_test_workspace": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "vla_test_set_timeline": (C.c_int, [C.c_void_p]),
     "vla_test_set_flags": (C.c_int, [C.c_int]),
     "vla_test_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,

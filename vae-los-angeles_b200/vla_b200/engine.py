@@ -242,6 +242,28 @@ class Trainer:
         self.steps += 1
         core.generation += 1
 
+    def _refresh_shadows_if_needed(self):
+        core = self.core
+        if core.shadow_version != core.param_version():
+            _lib.check(_lib.lib().vla_refresh_shadows(core.handle, _ptr(core.arena), _stream()), "vla_refresh_shadows")
+            core.shadow_version = core.param_version()
+
+    def forward_backward(self, which=0):
+        """First half of a step (vla_train_step phases = 1): forward + loss + backward; the gradients stay in `self.grads`
+        (loss.backward() at train_rna2dna.py:95) until `apply_optimizer()`.  Not available with the peer-memory exchange."""
+        if self.dp is not None:
+            raise RuntimeError("forward_backward(): the peer-memory exchange runs the whole step")
+        with torch.cuda.device(self.core.device):
+            self._refresh_shadows_if_needed()
+            self._call(self.datasets[which], 1)
+        self.core.generation += 1
+
+    def apply_optimizer(self, which=0):
+        """Second half (phases = 2): fused AdamW on `self.grads`, which it clears (optimizer.step() at train_rna2dna.py:96)."""
+        with torch.cuda.device(self.core.device):
+            self._call(self.datasets[which], 2)
+        self.steps += 1
+
     def _first_step_and_capture(self, which, ds):
         # The first step runs eagerly on a side stream (it also loads the kernels and sizes the workspace);
         # the same call sequence is then captured, without executing, for every later step.
@@ -362,3 +384,20 @@ class Trainer:
             L.vla_profile_collect(self.core.handle, buf, 512)   # releases the events
             del g
         return out
+
+
+class _DeviceInt16:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i2", "data": (int(ptr), False), "version": 3}
+
+
+def workspace_view(core, what, rows, i=0, j=0):
+    """Test hook (vla_test_workspace): zero-copy view of a workspace buffer left by the last forward / train step.
+    what = "eps": fp32 [rows, latent]; what = "act": bf16 [rows, row pitch] of encoder i, BatchNorm layer j."""
+    ptr, ld = C.c_void_p(), C.c_int()
+    code = {"eps": 0, "act": 1}[what]
+    _lib.check(_lib.lib().vla_test_workspace(core.handle, code, i, j, C.byref(ptr), C.byref(ld)), "vla_test_workspace")
+    n = int(rows) * ld.value
+    if what == "eps":
+        return _wrap_device_floats(ptr.value, n, core.device).view(rows, ld.value)
+    return torch.as_tensor(_DeviceInt16(ptr.value, n), device=core.device).view(torch.bfloat16).view(rows, ld.value)
