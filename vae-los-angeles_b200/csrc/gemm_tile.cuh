@@ -345,8 +345,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
       if (P.loss_kind != LOSS_CE && row_ok) {
         const float* trow = P.aux0 + (tgt_row0 + row) * P.N;
         for (int c = half; c < n_chunks; c += 2) {
-          const int c_lo = n0 + c * 32, c_hi = min(c_lo + 31, P.N - 1);
-          if (c_lo < P.N) {
+          const int c_lo = n0 + c * 32, c_hi = min(c_lo + 31, min(P.N, n0 + BN) - 1);
+          if (c_lo <= c_hi) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(trow + c_lo));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(trow + c_hi));
           }
@@ -375,7 +375,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     if ((FEATS & GF_LOSS) && (flags & GF_LOSS) && P.loss_kind != LOSS_CE && !(dbgf & 1)) {
       for (int c = half; c < n_chunks; c += 2, ++tgt_groups) {
         const int col0 = n0 + c * 32;
-        const int nvalid = min(32, P.N - col0);
+        const int nvalid = min(32, min(P.N, n0 + BN) - col0);
         if (nvalid > 0) {
           const float* tp = P.aux0 + (tgt_row0 + rbase) * P.N + col0 + lane;
           const uint32_t dst = smem_u32(tgt_patch + tgt_groups * (32 * PATCH_LD) + lane);
@@ -393,7 +393,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
       const int my_k = tgt_k++;                         // which of this warp's staged target patches belongs to this chunk
       const int col0 = n0 + c * 32;
-      const int nvalid = min(32, P.N - col0);          // <= 0: nothing to store (tile padding)
+      const int nvalid = min(32, min(P.N, n0 + BN) - col0);   // <= 0: nothing to store (tile padding); a tile never touches
+                                                              // columns of its right-hand neighbour (BN % 32 may be 16)
       const bool full = nvalid == 32;
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32);
@@ -696,7 +697,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     }
     if (want_stats) {
       named_bar_sync(3, EPI_THREADS);
-      for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+      for (int i = et; i < 2 * BN; i += EPI_THREADS) {       // (cc < BN: only this tile's own columns)
         const int which = i / BN, cc = i - which * BN;
         const int col = n0 + cc;
         if (col < P.N) {
