@@ -548,12 +548,6 @@ def run_gpu(args, rank, local_rank, world):
                             frac=max(t_t, t_h) / (avg_ms * 1e-3) if avg_ms > 0 else None))
     top = kernels[0]
     w = WORK[args.workload]
-    if top["name"] == "train_step_fused":
-        # the whole step is one kernel: its algorithmic work is SURVEY section 8d's per-sample figure x batch (+ 32 B per parameter)
-        top["flops"], top["bytes"] = float(w["flop"] * B), float(w["bytes"] * B + 32 * w["params"])
-        t_t, t_h = top["flops"] / (peaks["bf16_tflops"] * 1e12), top["bytes"] / (peaks["hbm_gbs"] * 1e9)
-        top["bound"] = "tensor" if t_t > t_h else "hbm"
-        top["frac"] = max(t_t, t_h) / (top["avg_us"] * 1e-6)
     if top["bound"] == "tensor":
         ach, peak, unit = top["flops"] / (top["avg_us"] * 1e-6) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
     else:
@@ -569,10 +563,14 @@ def run_gpu(args, rank, local_rank, world):
                 "how": "CUDA event pair around each launch, recorded as nodes of the captured step graph, 10 replays; the duration of "
                        "an empty event pair is subtracted (vla_profile_*); achieved = algorithmic flops or bytes of the launch / that time"}
     phases = None
-    if world == 1 and top["name"] == "train_step_fused":
-        # inside the whole-step kernel: per-phase spans from the %globaltimer stamps every unit writes (one replayed step)
-        tl_us, tl = trainer.timeline()
-        phases = {"step_us": tl_us, "phases": [{k: (round(v, 2) if isinstance(v, float) else v) for k, v in ph.items()} for ph in tl]}
+    if world == 1:
+        # inside the chain launches: per-phase spans from the %globaltimer stamps every CTA writes (one eager step)
+        try:
+            phases = [{"chain": c["name"], "ctas": c["ctas"], "span_us": round(c["span_us"], 2),
+                       "phases": [{k: (round(v, 2) if isinstance(v, float) else v) for k, v in ph.items()} for ph in c["phases"]]}
+                      for c in trainer.timeline()]
+        except Exception as e:                       # a diagnostic, never fatal to the measurement
+            phases = {"error": f"{type(e).__name__}: {e}"}
     t_tensor = w["flop"] * B / (peaks["bf16_tflops"] * 1e12)
     t_hbm = (w["bytes"] * B + 32 * w["params"]) / (peaks["hbm_gbs"] * 1e9)
     step_s = ms * 1e-3 / args.steps

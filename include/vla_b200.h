@@ -213,18 +213,23 @@ void* vla_dp_losses(vla_dp_t* d);                            /* device: float[4]
 int vla_dp_trace(vla_dp_t* d, unsigned long long* out8);
 void vla_dp_destroy(vla_dp_t* d);
 
-/* Whole-step kernel.  vla_train_step (phases 0 / 1 / 3) can run as ONE persistent cooperative kernel: the launches of the
- * step become phases whose units (GEMM tiles, element-wise blocks) wait on per-row-block completion counters instead of
- * kernel boundaries (csrc/step_kernel.cu).  The first call for a new argument set builds the plan (device allocation +
- * upload, not capturable); later calls and CUDA-graph replays only launch.  Selected with VLA_FUSED_STEP=1 in the
- * environment; the default issues the same phases as separate launches (same device code per phase).
- * Timeline: when enabled, every unit writes %globaltimer stamps [8]: 0 unit start, 1 dependencies resolved, 3 first
- * operands landed, 4 MMAs issued, 5 accumulator ready, 6 unit published, 7 (phase << 32 | SM id). */
-int vla_step_timeline(vla_model_t* m, int enable);
-int vla_step_timeline_phases(vla_model_t* m);
-int vla_step_timeline_units(vla_model_t* m);
-int vla_step_phase_info(vla_model_t* m, int phase, char* name48, int* n_units, int* unit_base, double* flops, double* bytes);
-int vla_step_timeline_read(vla_model_t* m, unsigned long long* out, int max_units);   /* out[max_units][8]; returns units */
+/* Chain kernel.  The row-local stretches of a call -- consecutive launches in which a 128-row block of the batch depends
+ * only on the same rows of the previous launch, i.e. everything between two BatchNorm-statistics boundaries; in eval mode
+ * the whole forward -- run as ONE launch each (csrc/chain_kernel.cu): a 4-CTA cluster per row block walks the phases with
+ * cluster barriers instead of kernel boundaries.  Used by vla_train_step and by vla_forward / vla_backward from batch 1024.
+ * The first call for a new argument set builds the plan (device allocation + upload, not capturable); later calls and
+ * CUDA-graph replays only launch.  VLA_CHAIN=0 in the environment issues the same phases as separate launches.
+ * Timeline: when enabled, every CTA writes %globaltimer stamps (phase start, phase end) for every phase. */
+int vla_chain_timeline(vla_model_t* m, int enable);
+int vla_chain_count(vla_model_t* m);                     /* chain launches made by the last call on this handle */
+int vla_chain_info(vla_model_t* m, int which, char* name48, int* n_phases, int* n_ctas, double* flops, double* bytes);
+int vla_chain_phase_name(vla_model_t* m, int which, int phase, char* name48);
+int vla_chain_timeline_read(vla_model_t* m, int which, unsigned long long* out);   /* out[n_ctas][24][2]; returns n_ctas */
+
+/* A caller that captures calls on this handle into CUDA graphs (vla_b200.Trainer) pins the handle (+1) for as long as the
+ * graphs live (-1 afterwards): while pinned, a call that would have to grow -- i.e. free and reallocate -- the workspace the
+ * graphs reference fails with VLA_ERR_STATE instead of leaving them replaying against freed memory. */
+int vla_model_pin(vla_model_t* m, int delta);
 
 /* Per-launch device timing (CUDA events on `stream`, recorded around every kernel launch the library makes between
  * vla_profile_begin and vla_profile_collect).  flops / bytes are the ALGORITHMIC work of the launch.

@@ -1,6 +1,6 @@
 // Stand-alone launches of the element-wise / reduction steps (bodies in elementwise_dev.cuh): used by the per-call
-// autograd path (vla_forward / vla_backward / vla_loss / vla_adamw) and by the inference forward; the fused train step
-// runs the same bodies inside the whole-step kernel (step_kernel.cu).
+// autograd path (vla_forward / vla_backward / vla_loss / vla_adamw) and for the phases with a grid-wide dependency; the
+// row-local phases of large batches run the same bodies inside the chain kernel (chain_kernel.cu).
 #include "elementwise_dev.cuh"
 
 #include <algorithm>
@@ -37,6 +37,15 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(LatentFwdArgs a) {
   pdl_launch_dependents();
   __shared__ __align__(16) unsigned char scratch[256];
   latent_fwd_body<false>(a, blockIdx.x, threadIdx.x, scratch);
+}
+
+__global__ void __launch_bounds__(256) latent_fwd_rows_kernel(LatentFwdArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[256];
+  constexpr int RPB = CHAIN_ROWS / CHAIN_CLUSTER;
+  const int r0 = blockIdx.x * RPB;
+  latent_fwd_rows<false>(a, r0, min(a.rows, r0 + RPB), blockIdx.x, threadIdx.x, scratch);
 }
 
 __global__ void __launch_bounds__(256) latent_bwd_kernel(LatentBwdArgs a) {
@@ -126,6 +135,11 @@ cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_
   const int grid = static_cast<int>((total + 255) / 256);
   if (grid_out) *grid_out = grid;
   return launch_pdl(latent_fwd_kernel, dim3(grid), dim3(256), 0, s, a);
+}
+
+cudaError_t launch_latent_fwd_rows(const LatentFwdArgs& a, cudaStream_t s) {
+  const int blocks = CHAIN_CLUSTER * ((a.rows + CHAIN_ROWS - 1) / CHAIN_ROWS);      // (slices past the last row write a zero partial)
+  return launch_pdl(latent_fwd_rows_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {

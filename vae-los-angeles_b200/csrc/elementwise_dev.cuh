@@ -2,7 +2,7 @@
 // MMA operands, embedding gather), BatchNorm apply + ReLU + dropout, the fused latent step (modality mean,
 // reparameterisation, per-sample KL), the fused loss (MSE + BCE + weighted CE + KL with their gradients), BatchNorm
 // backward, the latent backward and the fused multi-tensor AdamW.  Each body is one 256-thread block's worth of work; it
-// is called by the stand-alone kernels (elementwise.cu) and by the whole-step kernel (step_kernel.cu, MEGA = true, where
+// is called by the stand-alone kernels (elementwise.cu) and by the chain kernel (chain_kernel.cu, MEGA = true, where
 // the eight epilogue warps of the CTA form the block and synchronise on a named barrier).
 // All arithmetic is fp32; reductions are deterministic (fixed-order partials, no float atomics).
 #pragma once
@@ -167,74 +167,6 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
     }
   }
   ingest_site(a, r_begin, r_end, gwarp * 32 + lane, nwarps * 32, row0);
-}
-
-// Whole-step kernel: rows [r_begin, r_end) of every dense modality arrive in shared memory as ONE bulk copy each (the
-// rows of a unit are contiguous in the source), then are converted from there -- the unit keeps ~100 KB in flight with
-// a single issuing thread instead of a few hundred bytes per warp.  Falls back to ingest_body when the source block is
-// not 16-byte aligned or does not fit `stage_bytes`.  `bar` / `parity`: a CTA-local mbarrier used only here.
-template <bool MEGA>
-__device__ __forceinline__ void ingest_body_bulk(const IngestArgs& a, int r_begin, int r_end, int tid, bool first_unit,
-                                                 uint8_t* stage, uint32_t stage_bytes, uint64_t* bar, uint32_t parity,
-                                                 unsigned long long* dbg_row = nullptr) {
-  const int nrows = r_end - r_begin;
-  const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
-  uint32_t off[2] = {0u, 0u}, total = 0u;
-  bool ok = nrows > 0;
-  for (int e = 0; e < a.n; ++e) {
-    const uint32_t bytes = static_cast<uint32_t>(nrows) * a.width[e] * 4u;
-    const uintptr_t src = reinterpret_cast<uintptr_t>(a.src[e] + (row0 + r_begin) * a.width[e]);
-    off[e] = total;
-    total += (bytes + 127u) & ~127u;
-    ok = ok && (bytes % 16u == 0u) && (src % 16u == 0u);
-  }
-  ok = ok && total <= stage_bytes && a.n > 0 && a.lo_off[0] == 0 && a.lo_off[1] == 0;
-  if (!ok) {
-    if (tid == 0) mbar_arrive(bar);        // keep the barrier's phase in step with the caller's parity
-    ingest_body(a, r_begin, r_end, tid >> 5, EW_THREADS / 32, tid & 31, first_unit && tid == 0);
-    return;
-  }
-  if (tid == 0) {
-    uint32_t tx = 0;
-    for (int e = 0; e < a.n; ++e) tx += static_cast<uint32_t>(nrows) * a.width[e] * 4u;
-    mbar_expect_tx(bar, tx);
-    for (int e = 0; e < a.n; ++e)
-      bulk_load_1d(stage + off[e], a.src[e] + (row0 + r_begin) * a.width[e], static_cast<uint32_t>(nrows) * a.width[e] * 4u, bar);
-    if (a.bump_step && first_unit) {
-      a.dyn->step += 1;
-      a.dyn->b1pow *= static_cast<double>(a.beta1);
-      a.dyn->b2pow *= static_cast<double>(a.beta2);
-    }
-  }
-  ew_stamp(dbg_row, 2, tid);
-  ingest_site(a, r_begin, r_end, tid, EW_THREADS, row0);      // independent of the bulk copies: overlaps their latency
-  ew_stamp(dbg_row, 3, tid);
-  mbar_wait(bar, parity);
-  ew_stamp(dbg_row, 4, tid);
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int e = 0; e < a.n; ++e) {
-    const int w = a.width[e];
-    const int octs = a.ld_dst[e] >> 3;                         // ld_dst is a multiple of 8: 16-byte bf16 stores
-    const float* sbase = reinterpret_cast<const float*>(stage + off[e]);
-    for (int r = warp; r < nrows; r += EW_THREADS / 32) {
-      const float* sp = sbase + static_cast<size_t>(r) * w;
-      uint4* dp = reinterpret_cast<uint4*>(a.dst[e] + static_cast<size_t>(r_begin + r) * a.ld_dst[e]);
-#pragma unroll 4
-      for (int o = lane; o < octs; o += 32) {
-        const int c = o * 8;
-        float x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (c + k < w) ? sp[c + k] : 0.f;
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]), b1 = __floats2bfloat162_rn(x[2], x[3]);
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(x[4], x[5]), b3 = __floats2bfloat162_rn(x[6], x[7]);
-        uint4 v;
-        v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
-        v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
-        dp[o] = v;
-      }
-    }
-  }
-  ew_stamp(dbg_row, 5, tid);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,65 +378,82 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdArgs& a, int rows_per_blo
 // Latent: mean over present encoders' (mu | logvar) heads, z = mu + eps * exp(logvar / 2), KL partials
 // (vae.py:11-15, 64-73; losses.py:42)
 // ---------------------------------------------------------------------------------------------
+// Element (r, j) of the latent step; returns its KL summand 1 + logvar - mu^2 - exp(logvar) (0 for the autoencoders).
+__device__ __forceinline__ float latent_fwd_elem(const LatentFwdArgs& a, int r, int j, unsigned long long offset) {
+  const unsigned idx = static_cast<unsigned>(r) * a.L + j;             // rows * L < 2^31 (checked by the launcher)
+  float mu = 0.f, lv = 0.f;
+  for (int e = 0; e < a.n_enc; ++e) {
+    const float* p = a.ml[e] + static_cast<size_t>(r) * a.ld_ml[e];
+    mu += p[j];
+    if (!a.ae) lv += p[a.L + j];
+  }
+  if (a.n_enc > 1) { mu /= a.n_enc; lv /= a.n_enc; }
+  if (a.ae) {
+    // directional autoencoders (directional_ae.py:46-59): the mean of the encoder outputs IS the decoder input
+    a.mu[idx] = mu;
+    a.logvar[idx] = 0.f;
+    a.eps_save[idx] = 0.f;
+    const bf16 h = __float2bfloat16(mu);
+    a.z[static_cast<size_t>(r) * a.ld_z + j] = h;
+    if (a.z_lo > 0) a.z[static_cast<size_t>(r) * a.ld_z + a.z_lo + j] = bf16_lo_of(mu, h);
+    return 0.f;
+  }
+  float eps;
+  if (a.eps_in) {
+    eps = a.eps_in[idx];
+  } else {
+    const uint4 rnd = philox4x32_10(make_uint4(idx, 0u, static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32) ^ 0x5EEDu),
+                                    make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
+    eps = normal_from(rnd.x, rnd.y);
+  }
+  const float sd = expf(0.5f * lv);
+  const float z = mu + eps * sd;
+  a.mu[idx] = mu;
+  a.logvar[idx] = lv;
+  a.eps_save[idx] = eps;
+  const bf16 h = __float2bfloat16(z);
+  a.z[static_cast<size_t>(r) * a.ld_z + j] = h;
+  if (a.z_lo > 0) a.z[static_cast<size_t>(r) * a.ld_z + a.z_lo + j] = bf16_lo_of(z, h);
+  return 1.0f + lv - mu * mu - expf(lv);
+}
+__device__ __forceinline__ unsigned long long latent_offset(const LatentFwdArgs& a) {
+  unsigned long long offset = a.offset;
+  if (a.dyn && !a.eps_in) offset += static_cast<unsigned long long>(__ldcg(&a.dyn->step)) << 20;   // bumped by an earlier launch of the step
+  return offset;
+}
+
 // Block b covers elements [256 b, 256 b + 256) of the [rows, L] latent.
 template <bool MEGA>
 __device__ __forceinline__ void latent_fwd_body(const LatentFwdArgs& a, int b, int tid, void* scratch) {
   float* sh = reinterpret_cast<float*>(scratch);
-  const unsigned idx = static_cast<unsigned>(b) * EW_THREADS + tid;  // rows * L < 2^31 (checked by the launcher)
+  const unsigned idx = static_cast<unsigned>(b) * EW_THREADS + tid;
   const unsigned total = static_cast<unsigned>(a.rows) * a.L;
   float kl = 0.f;
   if (idx < total) {
     const int r = static_cast<int>(idx / static_cast<unsigned>(a.L));
-    const int j = static_cast<int>(idx - static_cast<unsigned>(r) * a.L);
-    float mu = 0.f, lv = 0.f;
-    for (int e = 0; e < a.n_enc; ++e) {
-      const float* p = a.ml[e] + static_cast<size_t>(r) * a.ld_ml[e];
-      mu += p[j];
-      if (!a.ae) lv += p[a.L + j];
-    }
-    if (a.n_enc > 1) { mu /= a.n_enc; lv /= a.n_enc; }
-    float eps;
-    if (a.ae) {
-      // directional autoencoders (directional_ae.py:46-59): the mean of the encoder outputs IS the decoder input
-      a.mu[idx] = mu;
-      a.logvar[idx] = 0.f;
-      a.eps_save[idx] = 0.f;
-      { const bf16 h = __float2bfloat16(mu);
-        a.z[static_cast<size_t>(r) * a.ld_z + j] = h;
-        if (a.z_lo > 0) a.z[static_cast<size_t>(r) * a.ld_z + a.z_lo + j] = bf16_lo_of(mu, h); }
-      eps = 0.f;
-    } else {
-    if (a.eps_in) {
-      eps = a.eps_in[idx];
-    } else {
-      unsigned long long offset = a.offset;
-      if (a.dyn) offset += static_cast<unsigned long long>(__ldcg(&a.dyn->step)) << 20;   // bumped earlier in the same launch: bypass L1
-      const uint4 rnd = philox4x32_10(make_uint4(idx, 0u, static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32) ^ 0x5EEDu),
-                                      make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
-      eps = normal_from(rnd.x, rnd.y);
-    }
-    const float sd = expf(0.5f * lv);
-    const float z = mu + eps * sd;
-    a.mu[idx] = mu;
-    a.logvar[idx] = lv;
-    a.eps_save[idx] = eps;
-    { const bf16 h = __float2bfloat16(z);
-      a.z[static_cast<size_t>(r) * a.ld_z + j] = h;
-      if (a.z_lo > 0) a.z[static_cast<size_t>(r) * a.ld_z + a.z_lo + j] = bf16_lo_of(z, h); }
-    kl = 1.0f + lv - mu * mu - expf(lv);
-    }
+    kl = latent_fwd_elem(a, r, static_cast<int>(idx - static_cast<unsigned>(r) * a.L), latent_offset(a));
   }
   const float t = block_sum<MEGA>(kl, sh, tid);
   if (tid == 0) a.kl_partials[b] = -0.5f * t;
 }
 
-__device__ __forceinline__ void latent_bwd_body(const LatentBwdArgs& a, int b, int tid) {
-  const unsigned idx = static_cast<unsigned>(b) * EW_THREADS + tid;
-  const unsigned total = static_cast<unsigned>(a.rows) * a.L;
-  if (idx >= total) return;
-  const int r = static_cast<int>(idx / static_cast<unsigned>(a.L));
-  const int j = static_cast<int>(idx - static_cast<unsigned>(r) * a.L);
-  const float beta = a.dyn ? a.dyn->beta_kl : a.beta;
+// Chain kernel: rows [r0, r1) by the 256 element-wise threads of one CTA; one KL partial (index `part`).
+template <bool MEGA>
+__device__ __forceinline__ void latent_fwd_rows(const LatentFwdArgs& a, int r0, int r1, int part, int tid, void* scratch) {
+  float* sh = reinterpret_cast<float*>(scratch);
+  const unsigned long long offset = latent_offset(a);
+  float kl = 0.f;
+  const int n = (r1 - r0) * a.L;
+  for (int i = tid; i < n; i += EW_THREADS) {
+    const int rr = i / a.L;
+    kl += latent_fwd_elem(a, r0 + rr, i - rr * a.L, offset);
+  }
+  const float t = block_sum<MEGA>(kl, sh, tid);
+  if (tid == 0) a.kl_partials[part] = -0.5f * t;
+}
+
+__device__ __forceinline__ void latent_bwd_elem(const LatentBwdArgs& a, int r, int j, float beta) {
+  const unsigned idx = static_cast<unsigned>(r) * a.L + j;
   const float gz = a.gz ? a.gz[static_cast<size_t>(r) * a.ld_gz + j] : 0.f;
   if (a.ae) {
     float g = gz + (a.gmu_in ? a.gmu_in[idx] : 0.f);
@@ -520,6 +469,23 @@ __device__ __forceinline__ void latent_bwd_body(const LatentBwdArgs& a, int b, i
   if (a.n_modalities > 1) { gmu /= a.n_modalities; glv /= a.n_modalities; }
   a.gml[static_cast<size_t>(r) * a.ld_gml + j] = __float2bfloat16(gmu);
   a.gml[static_cast<size_t>(r) * a.ld_gml + a.L + j] = __float2bfloat16(glv);
+}
+
+__device__ __forceinline__ void latent_bwd_body(const LatentBwdArgs& a, int b, int tid) {
+  const unsigned idx = static_cast<unsigned>(b) * EW_THREADS + tid;
+  const unsigned total = static_cast<unsigned>(a.rows) * a.L;
+  if (idx >= total) return;
+  const int r = static_cast<int>(idx / static_cast<unsigned>(a.L));
+  latent_bwd_elem(a, r, static_cast<int>(idx - static_cast<unsigned>(r) * a.L), a.dyn ? a.dyn->beta_kl : a.beta);
+}
+
+__device__ __forceinline__ void latent_bwd_rows(const LatentBwdArgs& a, int r0, int r1, int tid) {
+  const float beta = a.dyn ? a.dyn->beta_kl : a.beta;
+  const int n = (r1 - r0) * a.L;
+  for (int i = tid; i < n; i += EW_THREADS) {
+    const int rr = i / a.L;
+    latent_bwd_elem(a, r0 + rr, i - rr * a.L, beta);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -771,79 +737,6 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
       if (ch.sh_lo > 0) dst[ch.sh_lo] = bf16_lo_of(p[k], h);
       if (++c == ch.cols) { c = 0; ++r; }
     }
-  }
-}
-
-// Whole-step kernel: chunks [c0, c1) of the table in batches of four, so that a thread has 16 independent 128-bit loads
-// in flight (the unit runs alone on its SM: memory-level parallelism has to come from the thread itself).
-__device__ __forceinline__ void adamw_unit(const AdamArgs& a, int c0, int c1, int tid, unsigned long long* dbg_row = nullptr) {
-  float lr = a.lr, wd = a.weight_decay, bc1 = a.bc1, inv_bc2s = a.inv_bc2_sqrt;
-  if (a.dyn) {
-    lr = a.dyn->lr; wd = a.dyn->weight_decay;
-    bc1 = static_cast<float>(1.0 - __ldcg(&a.dyn->b1pow));
-    inv_bc2s = static_cast<float>(1.0 / sqrt(1.0 - __ldcg(&a.dyn->b2pow)));
-  }
-  const float step_size = lr / bc1;
-  const float decay = 1.0f - lr * wd;
-  const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
-  const int e = 4 * tid;
-  for (int base = c0; base < c1; base += 4) {
-    AdamChunk ch[4];
-    bool fast[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool valid = base + k < c1;
-      ch[k] = a.chunks[valid ? base + k : c0];
-      fast[k] = valid && a.update && !a.gframed && (ch[k].n - e >= 4);
-    }
-    float4 P[4], Gr[4], M[4], V[4];
-    ew_stamp(dbg_row, 2, tid);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (fast[k]) {
-        const long long gi = ch[k].offset + e;
-        P[k] = *reinterpret_cast<const float4*>(a.p + gi);
-        Gr[k] = *reinterpret_cast<const float4*>(a.g + gi);
-        M[k] = *reinterpret_cast<const float4*>(a.m + gi);
-        V[k] = *reinterpret_cast<const float4*>(a.v + gi);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (fast[k]) {
-        const long long gi = ch[k].offset + e;
-        float p[4] = {P[k].x, P[k].y, P[k].z, P[k].w}, g[4] = {Gr[k].x, Gr[k].y, Gr[k].z, Gr[k].w};
-        float m[4] = {M[k].x, M[k].y, M[k].z, M[k].w}, v[4] = {V[k].x, V[k].y, V[k].z, V[k].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          p[j] *= decay;
-          m[j] = b1 * m[j] + (1.0f - b1) * g[j];
-          v[j] = b2 * v[j] + (1.0f - b2) * g[j] * g[j];
-          p[j] -= step_size * __fdividef(m[j], sqrtf(v[j]) * inv_bc2s + eps);
-        }
-        *reinterpret_cast<float4*>(a.p + gi) = make_float4(p[0], p[1], p[2], p[3]);
-        *reinterpret_cast<float4*>(a.m + gi) = make_float4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<float4*>(a.v + gi) = make_float4(v[0], v[1], v[2], v[3]);
-        if (a.zero_grad) *reinterpret_cast<float4*>(a.gclear + gi) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ch[k].shadow_off >= 0) {
-          const unsigned idx = static_cast<unsigned>(ch[k].first + e);
-          int r = static_cast<int>(idx / static_cast<unsigned>(ch[k].cols));
-          int c = static_cast<int>(idx - static_cast<unsigned>(r) * ch[k].cols);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bf16 h = __float2bfloat16(p[j]);
-            bf16* dst = a.shadow + ch[k].shadow_off + static_cast<long long>(r) * ch[k].ld_shadow + c;
-            *dst = h;
-            if (ch[k].sh_lo > 0) dst[ch[k].sh_lo] = bf16_lo_of(p[j], h);
-            if (++c == ch[k].cols) { c = 0; ++r; }
-          }
-        }
-      } else if (base + k < c1) {
-        adamw_body(a, base + k, tid);                 // chunk tails and the refresh-only mode
-      }
-      if (k == 0) ew_stamp(dbg_row, 3, tid);
-    }
-    ew_stamp(dbg_row, 4, tid);
   }
 }
 

@@ -1,7 +1,7 @@
 // One 128 x BN output tile of the grouped bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulator in
 // TMEM), operands staged by TMA into 128-byte-swizzled shared memory.  The body is shared by the stand-alone grouped
-// GEMM kernel (gemm_tc.cu: one tile per CTA) and the persistent whole-step kernel (step_kernel.cu: a CTA walks a list
-// of tiles and element-wise units, the shared-memory ring, the barriers and the TMEM allocation live across tiles).
+// GEMM kernel (gemm_tc.cu: one tile per CTA) and the chain kernel (chain_kernel.cu: a CTA of a 4-CTA cluster walks the
+// row-local layers of one 128-row block; the shared-memory ring, the barriers and the TMEM allocation live across tiles).
 //
 //   mode 0 NT: C[M,N] = A[M,K] * B[N,K]^T   both operands K-major       (Linear forward)
 //   mode 1 TN: C[M,N] = A[K,M]^T * B[K,N]   both operands MN-major      (weight gradients, split-K + red.add)
@@ -152,27 +152,19 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
 
 #define VLA_STAMP(slot) do { if (ctx.dbg) ctx.dbg[static_cast<size_t>(ctx.dbg_row) * 8 + (slot)] = gtime(); } while (0)
 
-struct NoDeps {
-  __device__ __forceinline__ void wait(int /*lane*/) const {}
-};
-
 // FEATS: compile-time superset of the epilogue flags that may occur; everything else is compiled out (smaller code:
-// the epilogue is instruction-fetch sensitive).  MEGA: called from the whole-step kernel -- warp 0 resolves the tile's
-// dependencies (deps.wait, all 32 lanes) before the first load of an activation operand and releases the epilogue
-// warps' reads of BatchNorm statistics through dep_bar.  All threads of the CTA call this; on return the tile's global
-// writes have been issued by the epilogue threads (the caller orders them: barrier + fence) and ctx has advanced.
-template <int MODE, int FEATS, bool MEGA, class Deps>
-__device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc, int local, const Deps& deps,
-                                          const LossTail* tail_desc = nullptr) {
+// the epilogue is instruction-fetch sensitive).  All threads of the CTA call this; on return the tile's global writes
+// have been issued by the epilogue threads (the caller orders them: barrier + fence) and ctx has advanced.
+template <int MODE, int FEATS>
+__device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc, int local, const LossTail* tail_desc = nullptr) {
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
   uint64_t* acc_bar = empty_bar + GEMM_STAGES;
-  uint64_t* dep_bar = acc_bar + 1;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // Snapshot of the descriptor's scalar fields: in the whole-step kernel the descriptor lives in global memory and the
+  // Snapshot of the descriptor's scalar fields: in the chain kernel the descriptor lives in global memory and the
   // epilogue's global stores could alias it, which would force a reload after every store.
   const GemmProblem& Pd = Pdesc;
   struct {
@@ -208,22 +200,13 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
   // and the tile accumulates A_hi B_hi + A_lo B_hi + A_hi B_lo (the lo x lo term is below fp32 rounding).
   const bool split = (MODE == 0) && P.a_lo > 0;
   const bool bias_mma = (MODE == 1) && (FEATS & GF_BIASGRAD) && (P.flags & GF_BIASGRAD) && n_tile == 0;
-  const int dbgf = MEGA ? 0 : ctx.dbg_flags;      // test hooks exist only in the stand-alone kernel
+  const int dbgf = ctx.dbg_flags;                 // test hooks (0 outside vla_test_gemm)
   const uint32_t tmem_base = ctx.tmem_base;
 
-  if (!MEGA && (dbgf & 2)) {
+  if (dbgf & 2) {
     // test hook: no main loop, no epilogue
   } else if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (MEGA) {
-      if (lane == 0) { tma_prefetch_desc(tmA); tma_prefetch_desc(tmB); }
-      deps.wait(lane);
-      if (lane == 0) {
-        VLA_STAMP(1);                                              // dependencies resolved
-        asm volatile("fence.proxy.async.global;" ::: "memory");   // other CTAs' generic-proxy stores -> this CTA's TMA reads
-        mbar_arrive(dep_bar);
-      }
-    }
     if (lane == 0) {
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
@@ -325,7 +308,6 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     const bool want_stats = (flags & (GF_COLSTATS | GF_BNSTATS)) != 0;
 
     // per-column epilogue vectors of this tile (BatchNorm statistics come from an earlier unit of the step)
-    if (MEGA && (FEATS & GF_BNSTATS)) mbar_wait(dep_bar, ctx.tile_parity);
     for (int i = et; i < BN; i += EPI_THREADS) {
       const int col = n0 + i;
       const bool ok = col < P.N;
@@ -640,7 +622,6 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
       }
       __syncwarp();
     }
-    if (MEGA && et == 0) VLA_STAMP(2);                             // first epilogue warp: chunks stored
     if ((FEATS & GF_LOSS) && (flags & GF_LOSS)) {
       // ---- loss partials of this tile, ticket, and (last tile of the step) the fixed-order final reduction ----
 #pragma unroll
@@ -709,7 +690,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
   }
 
   // ---- every thread: advance the ring position and the tile parity ----
-  if (!(!MEGA && (dbgf & 2))) {
+  if (!(dbgf & 2)) {
     const int s = ctx.stage + (split ? 2 : 1) * (kb1 - kb0);
     ctx.phase ^= static_cast<uint32_t>(s / GEMM_STAGES) & 1u;
     ctx.stage = s % GEMM_STAGES;

@@ -27,6 +27,8 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 constexpr int FEATS_FWD_PLAIN_HOST = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;     // must match gemm_tile.cuh
 constexpr int FEATS_DGRAD_PLAIN_HOST = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;
+constexpr int FEATS_FWD_LOSS_BCE_HOST = GF_BIAS | GF_SIGMOID | GF_OUT_BF16 | GF_LOSS;
+constexpr int FEATS_FWD_LOSS_MSE_HOST = GF_BIAS | GF_OUT_BF16 | GF_LOSS;
 inline int pad8(int x) { return (x + 7) & ~7; }
 inline int pad64(int x) { return (x + 63) & ~63; }
 // Row pitch / lo offset of a bf16 GEMM operand of logical width w.  Split layout (DESIGN.md "Precision"):
@@ -84,29 +86,24 @@ struct TmapKey {
 
 struct ProfEntry { char name[48]; cudaEvent_t e0, e1; double flops, bytes; };
 
-// Records the launches of one train step as phases of the whole-step kernel (step_kernel.cu) instead of issuing them.
-struct StepRecorder {
-  StepPlan plan{};
-  std::vector<char> args;                 // argument structs, 64-byte aligned, offsets relative to the start of this vector
-  std::vector<std::string> names;
-  std::vector<double> flops, bytes;
-  std::vector<int> frontier, siblings;    // phases a new phase must wait for (ROW); BatchNorm siblings pending promotion
-  int last_gemm = -1, ph_ingest = -1;
-  int rows = 0;
-  std::string why;                        // non-empty: this step cannot be fused (caller falls back to separate launches)
+// One recorded launch of a row-local stretch (chain_kernel.cu): its argument struct by value.
+struct ChainOp {
+  int kind;                               // ChainKind
+  int gemm_mode;                          // GEMM ops: 0 NT / 2 NN
+  std::vector<char> args;
+  std::string name;
+  double flops, bytes;
 };
-enum { DEP_CHAIN = 0, DEP_BN_SIBLING = 1, DEP_ALL = 2 };
-
-struct CachedStep {
-  std::vector<char> key;
-  char* dev = nullptr;                    // [StepPlan | args | counters | targets | finish | timeline]
-  StepPlan plan{};                        // host copy of the header (device pointers)
-  std::vector<std::string> names;
-  std::vector<double> ph_flops, ph_bytes;
-  int units_total = 0;
+// Device image of one stretch, built on its first (eager) execution and reused by every later call / graph replay with
+// the same arguments.  Never freed before the model (captured graphs hold the address).
+struct ChainPlanCached {
+  std::vector<char> key;                  // the host image [ChainPlan | argument structs] (dbg pointer cleared)
+  char* dev = nullptr;
+  size_t dbg_off = 0;
+  int n_clusters = 0, n_phases = 0;
   double flops = 0, bytes = 0;
-  int saved_batch = 0, saved_present = 0, kl_grid = 0;
-  size_t timeline_off = 0;
+  std::string name;
+  std::vector<std::string> phase_names;
 };
 
 struct vla_model {
@@ -143,12 +140,14 @@ struct vla_model {
   // what the last forward left in the workspace
   bool saved = false; int saved_batch = 0, saved_present = 0, saved_train = 0, kl_grid = 0;
   unsigned long long generation = 0;
-  // whole-step kernel
-  StepRecorder* rec = nullptr;
-  std::vector<CachedStep*> steps;
-  CachedStep* last_step = nullptr;
-  bool timeline_on = false;
-  int step_grid = 0;
+  // chain kernel: row-local stretches of a call as one launch each
+  bool chain_on = false;                  // set by the entry point for the duration of a call that may chain
+  std::vector<ChainOp> seg;               // the open stretch
+  std::vector<ChainPlanCached*> plans;
+  ChainPlanCached* last_plans[8] = {}; int n_last_plans = 0;   // plans launched by the last call (timeline)
+  bool chain_dbg = false;
+  int chain_clusters = 0;                 // 4-CTA clusters of the chain kernel the device runs at once
+  int pinned = 0;                         // > 0: captured graphs reference the workspace / plans (vla_model_pin)
 };
 
 // Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  Two allocations per rank:
@@ -175,7 +174,7 @@ namespace {
 struct ProfScope {
   vla_model* m; cudaStream_t st; int idx = -1;
   ProfScope(vla_model* m_, cudaStream_t st_, const char* name, double flops, double bytes) : m(m_), st(st_) {
-    if (!m->prof_on || m->rec) return;
+    if (!m->prof_on) return;
     ProfEntry e{};
     snprintf(e.name, sizeof(e.name), "%s", name);
     e.flops = flops; e.bytes = bytes;
@@ -193,57 +192,16 @@ struct ProfScope {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Whole-step recording
+// Chain recording
 // ---------------------------------------------------------------------------------------------
-void free_steps(vla_model* m) {
-  for (CachedStep* c : m->steps) { cudaFree(c->dev); delete c; }
-  m->steps.clear();
-  m->last_step = nullptr;
+void free_plans(vla_model* m) {
+  for (ChainPlanCached* c : m->plans) { cudaFree(c->dev); delete c; }
+  m->plans.clear();
+  m->n_last_plans = 0;
 }
-
-// BatchNorm units of the whole-step kernel: one round over the grid (<= 148 units), at least the stand-alone block height.
-int fused_bn_rpb(int rows, int gx, int base_rpb) {
-  const int gy_max = std::max(1, 148 / std::max(gx, 1));
-  const int rpb = std::max(base_rpb, ceil_div(rows, gy_max));
-  return (rpb + 7) & ~7;
-}
-
-// Adds one phase.  dep_mode: DEP_CHAIN = wait (ROW) for the frontier and become the frontier; DEP_BN_SIBLING = wait for ALL
-// units of the latest GEMM phase, join the siblings that replace the frontier once the next ordinary phase arrives;
-// DEP_ALL = wait for ALL units of every frontier phase.  extra_all >= 0 adds an ALL dependency on that phase.
-StepPhase* rec_phase(vla_model* m, int kind, const char* name, const void* args, size_t args_size, int n_units,
-                     int dep_mode, double flops, double bytes, int extra_all = -1) {
-  StepRecorder* r = m->rec;
-  if (!r->why.empty()) return nullptr;
-  if (r->plan.n_phases >= STEP_MAX_PHASES) { r->why = "too many phases"; return nullptr; }
-  if (dep_mode != DEP_BN_SIBLING && !r->siblings.empty()) { r->frontier = r->siblings; r->siblings.clear(); }
-  const int id = r->plan.n_phases++;
-  StepPhase& ph = r->plan.ph[id];
-  memset(&ph, 0, sizeof(ph));
-  ph.kind = kind; ph.n_units = n_units; ph.rows = r->rows; ph.sub = 1; ph.n_blocks = n_units; ph.gx = 1; ph.rpb = 1; ph.L = 1;
-  if (dep_mode == DEP_BN_SIBLING) {
-    if (r->last_gemm < 0) { r->why = "BatchNorm phase without a preceding GEMM"; return nullptr; }
-    ph.dep_phase[ph.n_deps] = r->last_gemm; ph.dep_all[ph.n_deps] = 1; ph.n_deps++;
-    r->siblings.push_back(id);
-  } else {
-    for (int f : r->frontier) {
-      if (ph.n_deps >= STEP_MAX_DEPS) { r->why = "too many dependencies"; return nullptr; }
-      ph.dep_phase[ph.n_deps] = f; ph.dep_all[ph.n_deps] = dep_mode == DEP_ALL ? 1 : 0; ph.n_deps++;
-    }
-    r->frontier.assign(1, id);
-  }
-  if (extra_all >= 0) {
-    if (ph.n_deps >= STEP_MAX_DEPS) { r->why = "too many dependencies"; return nullptr; }
-    ph.dep_phase[ph.n_deps] = extra_all; ph.dep_all[ph.n_deps] = 1; ph.n_deps++;
-  }
-  if (kind <= SK_GEMM_TN) r->last_gemm = id;
-  size_t off = (r->args.size() + 63) & ~size_t(63);
-  r->args.resize(off + args_size);
-  memcpy(r->args.data() + off, args, args_size);
-  ph.args_off = static_cast<long long>(off);
-  r->names.push_back(name); r->flops.push_back(flops); r->bytes.push_back(bytes);
-  return &ph;
-}
+int chain_flush(vla_model* m, cudaStream_t st);
+int chain_add(vla_model* m, cudaStream_t st, int kind, int gemm_mode, const void* args, size_t size, const char* name,
+              double flops, double bytes, bool needs_all);
 int finalize_group(vla_model* m, GemmGroup& g, int mode);
 void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
   *flops = 0; *bytes = 0;
@@ -269,15 +227,28 @@ int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStrea
       return fail(VLA_ERR_STATE, std::string(name) + ": BatchNorm-statistics epilogue needs N % 32 == 0 and 16-byte aligned rows");
   }
   double fl, by; gemm_work(g, &fl, &by);
-  if (m->rec) {
-    int used = 0;
-    for (int i = 0; i < g.nprob; ++i) used |= g.p[i].flags;
-    int kind = SK_GEMM_TN;
-    if (mode == 0) kind = (used & GF_LOSS) ? SK_GEMM_NT_LOSS : ((used & ~FEATS_FWD_PLAIN_HOST) ? SK_GEMM_NT_FULL : SK_GEMM_NT_PLAIN);
-    if (mode == 2) kind = (used & ~FEATS_DGRAD_PLAIN_HOST) ? SK_GEMM_NN_FULL : SK_GEMM_NN_PLAIN;
-    rec_phase(m, kind, name, &g, sizeof(g), g.total_tiles, DEP_CHAIN, fl, by);
-    return VLA_OK;
+  if (m->chain_on && mode != 1) {
+    // which instantiation of the tile body (the same choice launch_gemm_group makes)
+    int used = 0, kinds = 0;
+    for (int i = 0; i < g.nprob; ++i) {
+      used |= g.p[i].flags;
+      kinds |= (g.p[i].flags & GF_LOSS) ? 1 << g.p[i].loss_kind : 1 << LOSS_NONE;
+    }
+    int kind;
+    if (mode == 0) {
+      if (used & GF_LOSS) {
+        kind = CK_GEMM_NT_LOSS;
+        if (kinds == 1 << LOSS_BCE && !(used & ~FEATS_FWD_LOSS_BCE_HOST)) kind = CK_GEMM_NT_LOSS_BCE;
+        if (kinds == 1 << LOSS_MSE && !(used & ~FEATS_FWD_LOSS_MSE_HOST)) kind = CK_GEMM_NT_LOSS_MSE;
+      } else {
+        kind = (used & ~FEATS_FWD_PLAIN_HOST) ? CK_GEMM_NT_FULL : CK_GEMM_NT_PLAIN;
+      }
+    } else {
+      kind = (used & ~FEATS_DGRAD_PLAIN_HOST) ? CK_GEMM_NN_FULL : CK_GEMM_NN_PLAIN;
+    }
+    return chain_add(m, st, kind, mode, &g, sizeof(g), name, fl, by, false);
   }
+  { int rcf = chain_flush(m, st); if (rcf) return rcf; }
   ProfScope ps(m, st, name, fl, by);
   cudaError_t e = launch_gemm_group(g, mode, st);
   if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("gemm launch (") + name + "): " + cudaGetErrorString(e));
@@ -480,7 +451,7 @@ void carve(vla_model* m, Bump& b, int cap) {
   m->logvar = b.take<float>(static_cast<size_t>(cap) * L);
   m->eps = b.take<float>(static_cast<size_t>(cap) * L);
   m->gz = b.take<float>(static_cast<size_t>(cap) * L);
-  m->kl_partials = b.take<float>(ceil_div(cap * L, 256) + 1);
+  m->kl_partials = b.take<float>(std::max(ceil_div(cap * L, 256), CHAIN_CLUSTER * mt) + 1);
   m->ldz = op_ld(m->split, L); m->z_lo = op_lo(m->split, L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
   m->ldgml = pad8(m->HW); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
   m->ld_d0 = op_ld(m->split, m->cat.out); m->d0_lo = op_lo(m->split, m->cat.out);
@@ -511,10 +482,16 @@ int reserve(vla_model* m, int batch) {
   if (m->layout_only) return fail(VLA_ERR_STATE, "layout-only handle: no device state");
   if (batch <= m->cap) return VLA_OK;
   int cap = std::max(batch, 32);
-  if (m->rec) return fail(VLA_ERR_STATE, "workspace growth while recording a fused step");
+  if (!m->seg.empty()) return fail(VLA_ERR_STATE, "workspace growth while recording a chain");
+  // Captured CUDA graphs (vla_b200.Trainer) bake workspace addresses and tensor maps into their kernel arguments: growing
+  // the workspace under them would leave the graphs replaying against freed memory.
+  if (m->pinned > 0 && m->ws)
+    return fail(VLA_ERR_STATE, "this handle's workspace is pinned by a live Trainer (captured CUDA graphs reference it) and holds " +
+                                   std::to_string(m->cap) + " rows; a call with " + std::to_string(batch) +
+                                   " rows would reallocate it.  Use a separate module / handle for the larger batch, or close the Trainer first");
   if (m->ws) { CK(cudaDeviceSynchronize()); CK(cudaFree(m->ws)); m->ws = nullptr; m->cap = 0; }
   m->tmaps.clear();
-  free_steps(m);
+  free_plans(m);
   m->saved = false;
   Bump dry; carve(m, dry, cap);
   const size_t bytes = dry.off + 256;
@@ -598,7 +575,83 @@ int add_nn(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, in
 
 // Joint tile-width choice for an NT / NN group: minimise waves x slowest tile (exhaustive over <= 5 widths per problem,
 // greedy coordinate descent when the group is large), then build the B tensor maps and the tile index ranges.
+// Cost of one tile in the chain kernel (us-like units): fixed part (first operands, epilogue drain, boundary) + operand
+// traffic of the main loop + epilogue columns.
+double chain_tile_cost(const GemmProblem& p, int bn) {
+  return 1.5 + (p.a_lo > 0 ? 2 : 1) * ceil_div(p.K, GEMM_BK) * (16384.0 + bn * 128.0) / 150e3 + 0.4 * ceil_div(bn, 64);
+}
+// Longest-processing-time assignment of the tiles of ONE row block to the four CTAs of a cluster.  units: (problem << 8) |
+// n_tile per rank.  Returns the makespan, or a negative value when a rank would get more than CHAIN_MAX_UNITS tiles.
+double chain_assign(const GemmGroup& g, const int* bn_of, std::vector<int> (*units)[CHAIN_CLUSTER]) {
+  struct U { double c; int code; };
+  std::vector<U> all;
+  for (int i = 0; i < g.nprob; ++i) {
+    const int bn = bn_of ? bn_of[i] : g.p[i].BN;
+    const int nt = ceil_div(g.p[i].N, bn);
+    for (int t = 0; t < nt; ++t) all.push_back(U{chain_tile_cost(g.p[i], bn), (i << 8) | t});
+  }
+  std::stable_sort(all.begin(), all.end(), [](const U& a, const U& b) { return a.c > b.c; });
+  double load[CHAIN_CLUSTER] = {0, 0, 0, 0};
+  int cnt[CHAIN_CLUSTER] = {0, 0, 0, 0};
+  for (const U& u : all) {
+    int r = 0;
+    for (int k = 1; k < CHAIN_CLUSTER; ++k) if (load[k] < load[r]) r = k;
+    load[r] += u.c; cnt[r]++;
+    if (units) (*units)[r].push_back(u.code);
+  }
+  double mk = 0;
+  for (int k = 0; k < CHAIN_CLUSTER; ++k) { mk = std::max(mk, load[k]); if (cnt[k] > CHAIN_MAX_UNITS) return -1.0; }
+  return mk;
+}
+
+// Tile widths for the chain kernel: the tiles of one 128-row block are shared by the four CTAs of a cluster, so the widths
+// minimise the busiest CTA's load (coordinate descent over the candidate widths of each problem, LPT assignment).
+int finalize_chain(vla_model* m, GemmGroup& g, int mode) {
+  const int n = g.nprob;
+  int cand[GEMM_MAX_PROBLEMS][16], nc[GEMM_MAX_PROBLEMS], pick[GEMM_MAX_PROBLEMS], bn_of[GEMM_MAX_PROBLEMS];
+  for (int i = 0; i < n; ++i) {
+    const GemmProblem& p = g.p[i];
+    nc[i] = 0;
+    // full 32-column chunks wherever the epilogue reads or reduces per-column side inputs; CE needs the whole row in one chunk
+    const bool chunky = (p.flags & (GF_COLSTATS | GF_BNSTATS | GF_MASK)) != 0 || ((p.flags & GF_LOSS) && p.loss_kind == LOSS_CE);
+    const int step = mode == 0 ? (chunky ? 32 : 16) : 64;
+    const int cap = mode == 0 ? GEMM_BN_MAX_NT : GEMM_BN_MAX_TN;
+    if (g_pending[i].fixed) cand[i][nc[i]++] = p.BN;
+    else for (int bn = step; bn <= cap && nc[i] < 16; bn += step) { cand[i][nc[i]++] = bn; if (bn >= p.N) break; }
+    pick[i] = nc[i] - 1;                                  // start from the widest tiles
+    bn_of[i] = cand[i][pick[i]];
+  }
+  double best = chain_assign(g, bn_of, nullptr);
+  if (best < 0) best = 1e30;
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    bool moved = false;
+    for (int i = 0; i < n; ++i) {
+      int keep = pick[i];
+      for (int c = 0; c < nc[i]; ++c) {
+        bn_of[i] = cand[i][c];
+        const double v = chain_assign(g, bn_of, nullptr);
+        if (v >= 0 && v < best - 1e-9) { best = v; keep = c; moved = true; }
+      }
+      pick[i] = keep; bn_of[i] = cand[i][keep];
+    }
+    if (!moved) break;
+  }
+  g.total_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    GemmProblem& p = g.p[i];
+    p.BN = bn_of[i];
+    p.n_tiles = ceil_div(p.N, p.BN);
+    const PendingB& b = g_pending[i];
+    int rc;
+    if ((rc = get_tmap(m, &p.tmB, b.base, b.inner, b.outer, b.pitch, mode == 0 ? static_cast<uint32_t>(p.BN) : 64u))) return rc;
+    p.tile_begin = g.total_tiles;
+    g.total_tiles += p.m_tiles * p.n_tiles;
+  }
+  return VLA_OK;
+}
+
 int finalize_group(vla_model* m, GemmGroup& g, int mode) {
+  if (m->chain_on) return finalize_chain(m, g, mode);
   const int n = g.nprob;
   int cand[GEMM_MAX_PROBLEMS][8], nc[GEMM_MAX_PROBLEMS], pick[GEMM_MAX_PROBLEMS];
   for (int i = 0; i < n; ++i) {
@@ -757,12 +810,8 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     }
     a.dyn = m->dyn; a.bump_step = io.engine ? 1 : 0; a.n_batches = io.n_batches; a.beta1 = io.beta1; a.beta2 = io.beta2;
     { double by = 0; for (int e = 0; e < a.n; ++e) by += static_cast<double>(B) * a.width[e] * (4.0 + (a.lo_off[e] > 0 ? 4.0 : 2.0));
-      if (m->rec) {
-        const char* env_rpb = getenv("VLA_INGEST_RPB");           // experiment hook: rows per ingest unit
-        const int rpu = env_rpb ? std::max(1, atoi(env_rpb)) : 32;
-        StepPhase* ph = rec_phase(m, SK_INGEST, "ingest", &a, sizeof(a), ceil_div(B, rpu), DEP_CHAIN, 0, by);
-        if (ph) { ph->rpb = rpu; m->rec->ph_ingest = m->rec->plan.n_phases - 1; }
-      } else { ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); } }
+      if (m->chain_on) { if ((rc = chain_add(m, st, CK_INGEST, -1, &a, sizeof(a), "ingest", 0, by, false))) return rc; }
+      else { ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); } }
   }
   const int mt = ceil_div(B, GEMM_BM);
   // ---- encoders, round by round ----
@@ -807,12 +856,9 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
-      if (m->rec) {
-        const int gx = ceil_div(a.n, 64), rpb = fused_bn_rpb(a.rows, gx, bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0));
-        const int gy = ceil_div(a.rows, rpb);
-        StepPhase* ph = rec_phase(m, SK_BN_ACT, "bn_act", &a, sizeof(a), gx * gy, DEP_BN_SIBLING, 0, 6.0 * B * bn.n);
-        if (ph) { ph->rpb = rpb; ph->gx = gx; }
-      } else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
+      // train mode needs the statistics of the WHOLE batch: a grid-wide dependency, the stretch ends in front of it
+      if (m->chain_on) { if ((rc = chain_add(m, st, CK_BN_ACT, -1, &a, sizeof(a), "bn_act", 0, 6.0 * B * bn.n, a.train != 0))) return rc; }
+      else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
     }
   }
   // ---- latent ----
@@ -823,15 +869,15 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     a.eps_in = io.eps; a.seed = io.seed; a.offset = io.offset * 16; a.dyn = io.engine ? m->dyn : nullptr;
     a.mu = m->mu; a.logvar = m->logvar; a.eps_save = m->eps; a.z = m->z; a.ld_z = m->ldz; a.z_lo = m->z_lo;
     a.kl_partials = m->kl_partials; a.rows = B; a.L = L; a.ae = m->ae ? 1 : 0;
-    if (m->rec) {
-      const int nb = ceil_div(B * L, 256), sub = 4;
-      m->kl_grid = nb;
-      StepPhase* ph = rec_phase(m, SK_LATENT_FWD, "latent_fwd", &a, sizeof(a), ceil_div(nb, sub), DEP_CHAIN,
-                                0, static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0), m->rec->ph_ingest);
-      if (ph) { ph->sub = sub; ph->n_blocks = nb; ph->L = L; }
-      if (io.mu || io.logvar) m->rec->why = "optional mu / logvar outputs";
+    const double lat_by = static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0);
+    if (m->chain_on) {
+      m->kl_grid = CHAIN_CLUSTER * mt;               // one KL partial per (row block, cluster rank)
+      if ((rc = chain_add(m, st, CK_LATENT_FWD, -1, &a, sizeof(a), "latent_fwd", 0, lat_by, false))) return rc;
     } else {
-      { ProfScope ps(m, st, "latent_fwd", 0, static_cast<double>(B) * L * (8.0 * a.n_enc + 14.0)); CK(launch_latent_fwd(a, &m->kl_grid, st)); }
+      ProfScope ps(m, st, "latent_fwd", 0, lat_by); CK(launch_latent_fwd(a, &m->kl_grid, st));
+    }
+    if (io.mu || io.logvar) {
+      if ((rc = chain_flush(m, st))) return rc;
       if (io.mu) CK(cudaMemcpyAsync(io.mu, m->mu, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
       if (io.logvar) CK(cudaMemcpyAsync(io.logvar, m->logvar, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
     }
@@ -942,6 +988,7 @@ double dp_bytes(const DpArgs& x) { return 16.0 * x.n2 * (x.world - 1) / x.world;
 int run_exchange(vla_model* m, vla_dp* dp, long long first2, long long end2, int part, cudaStream_t st, bool pdl) {
   const DpArgs x = make_dp_args(m, dp, first2, end2, part);
   if (x.n2 <= 0) return VLA_OK;
+  { int rcf = chain_flush(m, st); if (rcf) return rcf; }
   ProfScope ps(m, st, part ? "dp_exchange_dec" : "dp_exchange_enc", 0, dp_bytes(x));
   CK(launch_dp_exchange(x, st, pdl));
   return VLA_OK;
@@ -962,7 +1009,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   const int B = m->saved_batch, L = m->L, present = m->saved_present, train = m->saved_train;
   const float* P = io.params; const bf16* SH = m->shadow; float* G = io.grads;
   int rc;
-  if (io.zero_grads) { if (m->rec) m->rec->why = "gradient clear"; else CK(cudaMemsetAsync(G, 0, sizeof(float) * m->n_params, st)); }
+  if (io.zero_grads) { if ((rc = chain_flush(m, st))) return rc; CK(cudaMemsetAsync(G, 0, sizeof(float) * m->n_params, st)); }
   // which decoders carry a gradient
   std::vector<bool> active(m->decs.size(), false);
   if (!io.engine) {
@@ -976,6 +1023,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       og[n].dst = w.g_out; og[n].ld_dst = w.ld_gout; og[n].rows = B; n++;
       active[i] = true;
     }
+    if ((rc = chain_flush(m, st))) return rc;
     { ProfScope ps(m, st, "out_grad", 0, 0); CK(launch_out_grad(og, n, st)); }
   } else {
     for (size_t i = 0; i < m->decs.size(); ++i) active[i] = true;
@@ -1011,7 +1059,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   // inactive decoders contribute zero to dL/dz: clear their slice of g_d0
   if (any_dec)
     for (size_t i = 0; i < m->decs.size(); ++i)
-      if (!active[i] && m->rec) m->rec->why = "inactive decoder";
+      if (!active[i] && (rc = chain_flush(m, st))) return rc;
       else if (!active[i])
         CK(cudaMemset2DAsync(m->g_d0 + m->decs[i].cat_off, sizeof(bf16) * m->cat.out, 0, sizeof(bf16) * m->decs[i].cat_w, B, st));
   // Weight-gradient group over the encoder and / or decoder layers (dW = dY^T X, bias gradients by the ones-MMA).
@@ -1060,7 +1108,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   };
   // Data parallel: the decoder weight gradients need nothing from the encoder backward.  Compute them now and send them
   // (with the loss scalars, which sit behind them in the flat buffer) on the side stream while the encoder backward runs.
-  const bool early_dec = io.dp != nullptr && any_dec && !m->rec && dp_overlap(io.dp);
+  // (with the chain kernel the decoder data gradients sit in the middle of one launch: no fork point, no early exchange)
+  const bool early_dec = io.dp != nullptr && any_dec && !m->chain_on && dp_overlap(io.dp);
   if (early_dec) {
     vla_dp* dp = io.dp;
     CK(cudaEventRecord(dp->ev_fork, st));
@@ -1086,11 +1135,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     a.mu = m->mu; a.logvar = m->logvar; a.eps = m->eps;
     a.beta = 0.f; a.dyn = io.engine ? m->dyn : nullptr;
     a.n_modalities = n_present; a.gml = m->gml; a.ld_gml = m->ldgml; a.rows = B; a.L = L; a.ae = m->ae ? 1 : 0;
-    if (m->rec) {
-      const int nb = ceil_div(B * L, 256), sub = 4;
-      StepPhase* ph = rec_phase(m, SK_LATENT_BWD, "latent_bwd", &a, sizeof(a), ceil_div(nb, sub), DEP_CHAIN, 0, static_cast<double>(B) * L * 20.0);
-      if (ph) { ph->sub = sub; ph->n_blocks = nb; ph->L = L; }
-    } else { ProfScope ps(m, st, "latent_bwd", 0, static_cast<double>(B) * L * 20.0); CK(launch_latent_bwd(a, st)); }
+    if (m->chain_on) { if ((rc = chain_add(m, st, CK_LATENT_BWD, -1, &a, sizeof(a), "latent_bwd", 0, static_cast<double>(B) * L * 20.0, false))) return rc; }
+    else { ProfScope ps(m, st, "latent_bwd", 0, static_cast<double>(B) * L * 20.0); CK(launch_latent_bwd(a, st)); }
   }
   const int mt = ceil_div(B, GEMM_BM);
   // ---- encoder data gradients ----
@@ -1134,12 +1180,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       a.mean = w.mean[it.second]; a.rstd = w.rstd[it.second]; a.gamma = P + bn.g_off;
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
-      if (m->rec) {
-        const int gx = ceil_div(a.n, 64), rpb = fused_bn_rpb(a.rows, gx, bn_rows_per_block(a.rows, a.m_tiles));
-        const int gy = ceil_div(a.rows, rpb);
-        StepPhase* ph = rec_phase(m, SK_BN_BWD, "bn_bwd", &a, sizeof(a), gx * gy, DEP_BN_SIBLING, 0, 8.0 * B * bn.n);
-        if (ph) { ph->rpb = rpb; ph->gx = gx; }
-      } else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
+      if (m->chain_on) { if ((rc = chain_add(m, st, CK_BN_BWD, -1, &a, sizeof(a), "bn_bwd", 0, 8.0 * B * bn.n, train != 0))) return rc; }
+      else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
     }
   }
   if (!site_done) {
@@ -1156,6 +1198,162 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   if (early_dec) return emit_wgrad(true, false, "wgrad_enc", st);
   return emit_wgrad(true, true, "wgrad_all", st);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Chain: collect the row-local launches of a call, issue each stretch as one chain_kernel launch
+// ---------------------------------------------------------------------------------------------
+int chain_add(vla_model* m, cudaStream_t st, int kind, int gemm_mode, const void* args, size_t size, const char* name,
+              double flops, double bytes, bool needs_all) {
+  int rc;
+  if (needs_all && (rc = chain_flush(m, st))) return rc;
+  if (static_cast<int>(m->seg.size()) >= CHAIN_MAX_PHASES && (rc = chain_flush(m, st))) return rc;
+  if (kind == CK_LATENT_FWD && static_cast<const LatentFwdArgs*>(args)->dyn && !static_cast<const LatentFwdArgs*>(args)->eps_in)
+    for (const ChainOp& o : m->seg)      // the Philox offset reads dyn->step: never in the launch whose ingest phase bumps it
+      if (o.kind == CK_INGEST && reinterpret_cast<const IngestArgs*>(o.args.data())->bump_step) { if ((rc = chain_flush(m, st))) return rc; break; }
+  ChainOp op;
+  op.kind = kind; op.gemm_mode = gemm_mode; op.name = name; op.flops = flops; op.bytes = bytes;
+  op.args.assign(static_cast<const char*>(args), static_cast<const char*>(args) + size);
+  m->seg.push_back(std::move(op));
+  return VLA_OK;
+}
+
+int launch_op(vla_model* m, const ChainOp& op, cudaStream_t st) {
+  ProfScope ps(m, st, op.name.c_str(), op.flops, op.bytes);
+  cudaError_t e = cudaSuccess;
+  switch (op.kind) {
+    case CK_INGEST: e = launch_ingest(*reinterpret_cast<const IngestArgs*>(op.args.data()), st); break;
+    case CK_BN_ACT: e = launch_bn_act(*reinterpret_cast<const BnActArgs*>(op.args.data()), st); break;
+    case CK_BN_BWD: e = launch_bn_bwd(*reinterpret_cast<const BnBwdArgs*>(op.args.data()), st); break;
+    // (KL partials in the chain's layout: one per 32-row slice -- the loss tail was sized for that)
+    case CK_LATENT_FWD: e = launch_latent_fwd_rows(*reinterpret_cast<const LatentFwdArgs*>(op.args.data()), st); break;
+    case CK_LATENT_BWD: e = launch_latent_bwd(*reinterpret_cast<const LatentBwdArgs*>(op.args.data()), st); break;
+    default: {
+      // GemmGroup holds tensor maps (64-byte alignment): copy out of the byte vector
+      GemmGroup g;
+      memcpy(&g, op.args.data(), sizeof(g));
+      e = launch_gemm_group(g, op.gemm_mode, st);
+    }
+  }
+  if (e != cudaSuccess) return fail(VLA_ERR_CUDA, "launch (" + op.name + "): " + cudaGetErrorString(e));
+  return VLA_OK;
+}
+
+int op_rows(const ChainOp& op) {
+  switch (op.kind) {
+    case CK_INGEST: return reinterpret_cast<const IngestArgs*>(op.args.data())->rows;
+    case CK_BN_ACT: return reinterpret_cast<const BnActArgs*>(op.args.data())->rows;
+    case CK_BN_BWD: return reinterpret_cast<const BnBwdArgs*>(op.args.data())->rows;
+    case CK_LATENT_FWD: return reinterpret_cast<const LatentFwdArgs*>(op.args.data())->rows;
+    case CK_LATENT_BWD: return reinterpret_cast<const LatentBwdArgs*>(op.args.data())->rows;
+    default: return reinterpret_cast<const GemmGroup*>(op.args.data())->p[0].M;
+  }
+}
+
+// Returns 1 when this stretch cannot run as a chain (the caller issues the separate launches), 0 on success, < 0 on error.
+int launch_stretch(vla_model* m, cudaStream_t st, const std::vector<ChainOp>& ops) {
+  auto up64 = [](size_t x) { return (x + 63) & ~size_t(63); };
+  ChainPlan pl{};
+  pl.n_phases = static_cast<int>(ops.size());
+  pl.rows = op_rows(ops[0]);
+  pl.m_blocks = ceil_div(pl.rows, CHAIN_ROWS);
+  std::vector<char> img(up64(sizeof(ChainPlan)), 0);
+  double flops = 0, bytes = 0;
+  bool has_ingest = false, has_latent = false, has_loss = false, has_bwd = false;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const ChainOp& op = ops[i];
+    if (op_rows(op) != pl.rows) return 1;
+    ChainPhase& ph = pl.ph[i];
+    ph.kind = op.kind;
+    ph.args_off = static_cast<long long>(img.size());
+    img.resize(up64(img.size() + op.args.size()), 0);
+    memcpy(img.data() + ph.args_off, op.args.data(), op.args.size());
+    if (op.kind <= CK_GEMM_LAST) {
+      GemmGroup g;
+      memcpy(&g, op.args.data(), sizeof(g));
+      std::vector<int> units[CHAIN_CLUSTER];
+      if (chain_assign(g, nullptr, &units) < 0) return 1;
+      for (int r = 0; r < CHAIN_CLUSTER; ++r) {
+        ph.n_units[r] = static_cast<int>(units[r].size());
+        for (size_t u = 0; u < units[r].size(); ++u) ph.units[r][u] = static_cast<unsigned short>(units[r][u]);
+      }
+      for (int k = 0; k < g.nprob; ++k) if (g.p[k].flags & GF_LOSS) has_loss = true;
+      if (op.gemm_mode == 2) has_bwd = true;
+    }
+    has_ingest = has_ingest || op.kind == CK_INGEST;
+    has_latent = has_latent || op.kind == CK_LATENT_FWD;
+    has_bwd = has_bwd || op.kind == CK_BN_BWD || op.kind == CK_LATENT_BWD;
+    flops += op.flops; bytes += op.bytes;
+  }
+  memcpy(img.data(), &pl, sizeof(pl));
+  ChainPlanCached* c = nullptr;
+  for (ChainPlanCached* q : m->plans) if (q->key == img) { c = q; break; }
+  if (!c) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(VLA_ERR_STATE, "the first call for a new argument set builds the chain plan (device allocation + upload) and "
+                                 "cannot run inside a stream capture; make the same call once outside the capture");
+    if (m->plans.size() >= 64) return 1;       // callers with ever-changing buffers: separate launches from here on
+    if (m->chain_clusters == 0) {
+      cudaError_t e = cudaSuccess;
+      m->chain_clusters = chain_max_clusters(&e);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); m->chain_clusters = -1; }
+    }
+    if (m->chain_clusters <= 0) return 1;
+    c = new ChainPlanCached();
+    c->key = img;
+    c->dbg_off = (img.size() + 255) & ~size_t(255);
+    const size_t dbg_bytes = sizeof(unsigned long long) * 2 * CHAIN_MAX_PHASES * CHAIN_CLUSTER * static_cast<size_t>(m->chain_clusters);
+    cudaError_t e = cudaMalloc(&c->dev, c->dbg_off + dbg_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->dev + c->dbg_off, 0, dbg_bytes);
+    if (e == cudaSuccess) {
+      ChainPlan up = pl;
+      up.dbg = m->chain_dbg ? reinterpret_cast<unsigned long long*>(c->dev + c->dbg_off) : nullptr;
+      std::vector<char> img2 = img;
+      memcpy(img2.data(), &up, sizeof(up));
+      e = cudaMemcpy(c->dev, img2.data(), img2.size(), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) { cudaFree(c->dev); delete c; return fail(VLA_ERR_CUDA, std::string("chain plan upload: ") + cudaGetErrorString(e)); }
+    c->n_clusters = std::min(pl.m_blocks, m->chain_clusters);
+    c->n_phases = pl.n_phases;
+    c->flops = flops; c->bytes = bytes;
+    c->name = has_ingest && !has_latent ? "chain_ingest_enc"
+              : (has_latent ? (has_loss ? "chain_fwd_bwd" : (has_ingest ? "chain_forward" : "chain_enc_dec")) : (has_bwd ? "chain_bwd_" : "chain_") + ops[0].name);
+    for (const ChainOp& op : ops) c->phase_names.push_back(op.name);
+    m->plans.push_back(c);
+  }
+  if (m->n_last_plans < 8) m->last_plans[m->n_last_plans++] = c;
+  ProfScope ps(m, st, c->name.c_str(), c->flops, c->bytes);
+  cudaError_t e = launch_chain(reinterpret_cast<const ChainPlan*>(c->dev), c->n_clusters, st);
+  if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("chain kernel launch (") + c->name + "): " + cudaGetErrorString(e));
+  return VLA_OK;
+}
+
+int chain_flush(vla_model* m, cudaStream_t st) {
+  if (m->seg.empty()) return VLA_OK;
+  std::vector<ChainOp> ops;
+  ops.swap(m->seg);
+  if (ops.size() >= 2) {
+    const int rc = launch_stretch(m, st, ops);
+    if (rc <= 0) return rc;
+  }
+  for (const ChainOp& op : ops) { const int rc = launch_op(m, op, st); if (rc) return rc; }
+  return VLA_OK;
+}
+
+// When the row-local stretches of a call run as chain launches (chain_kernel.cu).  The chain plans are device images keyed
+// by the argument structs, built on a stretch's first eager execution: callers whose buffers keep their addresses (the
+// Trainer, graph-captured inference) hit the cache from the second call on.  VLA_CHAIN=0 switches it off everywhere.
+bool chain_enabled() {      // read per call: a host-side switch, not on the replay path
+  const char* e = getenv("VLA_CHAIN");
+  return !(e && e[0] == '0');
+}
+struct ChainScope {      // sets m->chain_on for one entry-point call; the stretch still open at the end is issued by finish()
+  vla_model* m; bool prev;
+  ChainScope(vla_model* m_, bool on) : m(m_), prev(m_->chain_on) { m->chain_on = on; if (on) m->n_last_plans = 0; }
+  int finish(cudaStream_t st) { const int rc = chain_flush(m, st); m->chain_on = prev; return rc; }
+  ~ChainScope() { m->seg.clear(); m->chain_on = prev; }
+};
 
 cudaStream_t as_stream(vla_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -1222,7 +1420,7 @@ int vla_model_create_layout_only(const vla_config_t* cfg, vla_model_t** out) {
 void vla_model_destroy(vla_model_t* m) {
   if (!m) return;
   if (m->layout_only) { delete m; return; }
-  free_steps(m);
+  free_plans(m);
   cudaFree(m->shadow); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
   cudaFree(m->ws);
   delete m;
@@ -1251,7 +1449,12 @@ int vla_forward(vla_model_t* m, const vla_forward_args_t* a, vla_stream_t stream
   io.eps = a->eps; io.keep_masks = a->keep_masks; io.seed = a->seed; io.offset = a->offset;
   io.recon[0] = a->recon_a; io.recon[1] = a->recon_b; io.recon[2] = a->recon_c;
   io.mu = a->mu; io.logvar = a->logvar; io.engine = false;
-  return run_forward(m, io, st);
+  // Large batches (inference sweeps, BASELINE configs[3]): row-local stretches as chain launches -- in eval mode the whole
+  // forward is ONE launch.  Small per-call batches (the scripts' batch 32) keep the separate launches: their output tensors
+  // change address from call to call, which would rebuild the chain plan every time.
+  ChainScope cs(m, chain_enabled() && a->batch >= 1024);
+  if ((rc = run_forward(m, io, st))) return rc;
+  return cs.finish(st);
 }
 
 int vla_refresh_shadows(vla_model_t* m, const float* params, vla_stream_t stream) {
@@ -1266,7 +1469,10 @@ int vla_backward(vla_model_t* m, const vla_backward_args_t* a, vla_stream_t stre
   io.g_recon[0] = a->g_recon_a; io.g_recon[1] = a->g_recon_b; io.g_recon[2] = a->g_recon_c;
   io.recon_b = a->recon_b; io.g_mu = a->g_mu; io.g_logvar = a->g_logvar;
   io.grads = a->grads; io.engine = false; io.zero_grads = true;
-  return run_backward(m, io, as_stream(stream));
+  ChainScope cs(m, chain_enabled() && m->saved_batch >= 1024);
+  int rc = run_backward(m, io, as_stream(stream));
+  if (rc) return rc;
+  return cs.finish(as_stream(stream));
 }
 
 long long vla_loss_workspace_bytes(int batch, int dim_a, int dim_b, int n_sites, int latent) {
@@ -1311,12 +1517,7 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
     a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), step)));
   }
   a.dyn = dyn ? m->dyn : nullptr; a.update = 1; a.zero_grad = zero_grad ? 1 : 0;
-  if (m->rec) {
-    const int sub = std::max(1, ceil_div(a.n_chunks, 148));
-    StepPhase* ph = rec_phase(m, SK_ADAMW, "adamw", &a, sizeof(a), ceil_div(a.n_chunks, sub), DEP_ALL, 0, 34.0 * m->n_params);
-    if (ph) { ph->sub = sub; ph->n_blocks = a.n_chunks; }
-    return VLA_OK;
-  }
+  { int rcf = chain_flush(m, st); if (rcf) return rcf; }
   if (fused) {      // exchange of `fused`'s range + AdamW as one launch (dp_exchange.cu)
     ProfScope ps(m, st, "dp_exchange_adamw", 0, 34.0 * m->n_params + dp_bytes(*fused)); CK(launch_dp_adamw(*fused, a, st));
     return VLA_OK;
@@ -1347,7 +1548,7 @@ int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float bet
   return VLA_OK;
 }
 
-// The launches of one train step, in order (issued on `st`, or recorded when m->rec is set).
+// The launches of one train step, in order (row-local stretches are collected and issued as chain launches when m->chain_on).
 static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaStream_t st) {
   FwdIO io{};
   io.params = a->params; io.buffers = a->buffers; io.counters = a->counters;
@@ -1370,7 +1571,6 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
     if (dp->n != m->n_params + 4) return fail(VLA_ERR_INVALID, "vla_train_step: exchange buffer size != param_count + 4");
     if (a->grads != reinterpret_cast<float*>(dp->local) || a->loss_out != a->grads + m->n_params)
       return fail(VLA_ERR_INVALID, "vla_train_step: grads / loss_out must be vla_dp_grads() and its last 4 floats");
-    if (m->rec) m->rec->why = "data-parallel exchange";
   }
   if (!do_fb)
     return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
@@ -1413,19 +1613,15 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
       if (l.recon_a) by += static_cast<double>(l.rows) * l.width_a * 10.0;
       if (l.recon_b) by += static_cast<double>(l.rows) * l.width_b * 10.0;
       if (l.logits) by += static_cast<double>(l.rows) * l.n_sites * 6.0;
-      if (m->rec) {
-        const LossGridInfo lg = loss_grid_info(l);
-        const int nb = std::max(1, lg.nb_a + lg.nb_b + lg.nb_c + lg.nb_k), sub = 4;
-        StepPhase* ph = rec_phase(m, SK_LOSS, "loss", &l, sizeof(l), ceil_div(nb, sub), DEP_CHAIN, 0, by);
-        if (ph) { ph->sub = sub; ph->n_blocks = nb; }
-      } else { ProfScope ps(m, st, "loss", 0, by); CK(launch_loss(l, st)); } }
+      if ((rc = chain_flush(m, st))) return rc;
+      { ProfScope ps(m, st, "loss", 0, by); CK(launch_loss(l, st)); } }
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
   bo.dp = dp;
   if ((rc = run_backward(m, bo, st))) return rc;
   if (!do_opt) return VLA_OK;
-  if (dp && !m->rec) {
+  if (dp) {
     // ---- the step's one collective, second part: the encoder gradients (the decoder part left from run_backward on the
     // side stream, or goes now if there was no decoder gradient); then AdamW, which polls the framed sums of both parts ----
     // (an engine step carries every decoder gradient, so run_backward took the early path when VLA_DP_OVERLAP=1)
@@ -1447,116 +1643,21 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
 }
 
 
-// Builds (first call for these arguments) and launches the whole-step kernel.  Returns 1 when this step cannot be fused
-// (the caller then issues the separate launches), 0 on success, < 0 on error.
-static int train_step_fused(vla_model_t* m, const vla_train_args_t* a, cudaStream_t st) {
-  std::vector<char> key(sizeof(*a) + sizeof(void*) * (1 + m->n_drop));
-  memcpy(key.data(), a, sizeof(*a));
-  for (int i = 0; i < m->n_drop; ++i) {
-    const void* p = a->keep_masks ? a->keep_masks[i] : nullptr;
-    memcpy(key.data() + sizeof(*a) + sizeof(void*) * i, &p, sizeof(void*));
-  }
-  CachedStep* cs = nullptr;
-  for (CachedStep* c : m->steps) if (c->key == key) { cs = c; break; }
-  if (!cs) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    CK(cudaStreamIsCapturing(st, &cap));
-    if (cap != cudaStreamCaptureStatusNone)
-      return fail(VLA_ERR_STATE, "vla_train_step: the first call for a new argument set builds the fused step plan "
-                                 "(device allocation + upload) and cannot run inside a stream capture; call it once outside");
-    if (m->step_grid == 0) {
-      cudaError_t e = cudaSuccess;
-      m->step_grid = step_max_grid(&e);
-      if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("whole-step kernel setup: ") + cudaGetErrorString(e));
-      if (m->step_grid <= 0) return fail(VLA_ERR_CUDA, "whole-step kernel does not fit on this device");
-    }
-    int rc;
-    if ((rc = reserve(m, a->batch))) return rc;       // before recording: the plan holds workspace pointers
-    StepRecorder rec;
-    rec.rows = a->batch;
-    m->rec = &rec;
-    rc = train_step_sequence(m, a, st);
-    m->rec = nullptr;
-    if (rc) return rc;
-    if (!rec.why.empty()) return 1;
-    // ---- finalize: CTA assignment, counters, targets ----
-    StepPlan& pl = rec.plan;
-    const int G = m->step_grid;
-    pl.grid = G;
-    pl.mt = ceil_div(a->batch, STEP_ROW_BLOCK);
-    pl.n_counters = pl.n_phases * (pl.mt + 1);
-    std::vector<unsigned int> targets(pl.n_counters, 0u);
-    int units = 0;
-    for (int p = 0; p < pl.n_phases; ++p) {
-      StepPhase& ph = pl.ph[p];
-      ph.unit_base = units; ph.unit_rot = units % G; ph.cbase = p * (pl.mt + 1);
-      const void* args = rec.args.data() + ph.args_off;
-      for (int u = 0; u < ph.n_units; ++u) {
-        int r0, r1;
-        step_unit_rows_host(ph, args, u, &r0, &r1);
-        if (r1 > r0) {
-          if (r1 > a->batch) return fail(VLA_ERR_STATE, "fused step: unit rows out of range");
-          for (int b = r0 / STEP_ROW_BLOCK; b <= (r1 - 1) / STEP_ROW_BLOCK; ++b) targets[ph.cbase + b]++;
-        }
-      }
-      targets[ph.cbase + pl.mt] = static_cast<unsigned int>(ph.n_units);
-      units += ph.n_units;
-    }
-    // ---- device image: [StepPlan | args | counters | targets | finish | timeline] ----
-    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t off_args = up(sizeof(StepPlan));
-    const size_t off_cnt = up(off_args + rec.args.size());
-    const size_t off_tgt = up(off_cnt + sizeof(unsigned int) * pl.n_counters);
-    const size_t off_fin = up(off_tgt + sizeof(unsigned int) * pl.n_counters);
-    const size_t off_tl = up(off_fin + 64);
-    const size_t total = off_tl + sizeof(unsigned long long) * 8 * units;
-    cs = new CachedStep();
-    cudaError_t e = cudaMalloc(&cs->dev, total);
-    if (e != cudaSuccess) { delete cs; return fail(VLA_ERR_CUDA, std::string("cudaMalloc fused step: ") + cudaGetErrorString(e)); }
-    for (int p = 0; p < pl.n_phases; ++p) pl.ph[p].args_off += static_cast<long long>(off_args);
-    pl.counters = reinterpret_cast<unsigned int*>(cs->dev + off_cnt);
-    pl.targets = reinterpret_cast<const unsigned int*>(cs->dev + off_tgt);
-    pl.finish = reinterpret_cast<unsigned int*>(cs->dev + off_fin);
-    pl.dbg = m->timeline_on ? reinterpret_cast<unsigned long long*>(cs->dev + off_tl) : nullptr;
-    std::vector<char> img(total, 0);
-    memcpy(img.data(), &pl, sizeof(pl));
-    memcpy(img.data() + off_args, rec.args.data(), rec.args.size());
-    memcpy(img.data() + off_tgt, targets.data(), sizeof(unsigned int) * pl.n_counters);
-    e = cudaMemcpy(cs->dev, img.data(), total, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(cs->dev); delete cs; return fail(VLA_ERR_CUDA, std::string("upload fused step: ") + cudaGetErrorString(e)); }
-    cs->key = key; cs->plan = pl; cs->names = rec.names; cs->ph_flops = rec.flops; cs->ph_bytes = rec.bytes;
-    cs->units_total = units; cs->timeline_off = off_tl;
-    for (double f : rec.flops) cs->flops += f;
-    for (double b : rec.bytes) cs->bytes += b;
-    cs->saved_batch = m->saved_batch; cs->saved_present = m->saved_present; cs->kl_grid = m->kl_grid;
-    m->steps.push_back(cs);
-  }
-  m->saved = true; m->saved_batch = cs->saved_batch; m->saved_present = cs->saved_present; m->saved_train = 1;
-  m->kl_grid = cs->kl_grid; m->generation++;
-  m->last_step = cs;
-  if (m->prof_on) { ProfScope calib(m, st, "_empty_pair", 0, 0); }   // event-pair overhead, subtracted by the reader
-  {
-    ProfScope ps(m, st, "train_step_fused", cs->flops, cs->bytes);
-    cudaError_t e = launch_step(reinterpret_cast<const StepPlan*>(cs->dev), cs->plan.grid, st);
-    if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("whole-step kernel launch: ") + cudaGetErrorString(e));
-  }
-  return VLA_OK;
-}
-
 int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream) {
   if (!m || !a || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->buffers || !a->loss_out)
     return fail(VLA_ERR_INVALID, "null argument");
   if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
   cudaStream_t st = as_stream(stream);
-  // Read per call (a host-side switch, not on the replay path).  Default: separate launches -- at one CTA per SM the
-  // element-wise phases of the whole-step kernel are latency-bound (DESIGN.md section 5 has the measured timeline).
-  const char* env = getenv("VLA_FUSED_STEP");
-  const bool fused_on = env && env[0] == '1';
-  if (fused_on && a->phases != 2) {
-    const int rc = train_step_fused(m, a, st);
-    if (rc <= 0) return rc;
-  }
-  return train_step_sequence(m, a, st);
+  ChainScope cs(m, chain_enabled() && a->phases != 2);
+  int rc = train_step_sequence(m, a, st);
+  if (rc) return rc;
+  return cs.finish(st);
+}
+
+int vla_model_pin(vla_model_t* m, int delta) {
+  if (!m) return fail(VLA_ERR_INVALID, "null model");
+  m->pinned = std::max(0, m->pinned + delta);
+  return VLA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1656,37 +1757,43 @@ int vla_recon_metrics(const vla_metrics_args_t* a, vla_stream_t stream) {
   return VLA_OK;
 }
 
-/* Whole-step kernel timeline: %globaltimer stamps per unit (unit start, dependencies resolved, first operands, MMAs
- * issued, accumulator ready, unit published) written by the next fused steps. */
-int vla_step_timeline(vla_model_t* m, int enable) {
+/* Chain kernel timeline: per (CTA, phase) %globaltimer stamps (phase start, phase end before the cluster barrier) written by
+ * the chain launches of the following calls. */
+int vla_chain_timeline(vla_model_t* m, int enable) {
   if (!m) return fail(VLA_ERR_INVALID, "null model");
   CK(cudaDeviceSynchronize());
-  m->timeline_on = enable != 0;
-  for (CachedStep* c : m->steps) {
-    c->plan.dbg = enable ? reinterpret_cast<unsigned long long*>(c->dev + c->timeline_off) : nullptr;
-    CK(cudaMemcpy(c->dev + offsetof(StepPlan, dbg), &c->plan.dbg, sizeof(c->plan.dbg), cudaMemcpyHostToDevice));
+  m->chain_dbg = enable != 0;
+  for (ChainPlanCached* c : m->plans) {
+    unsigned long long* dbg = enable ? reinterpret_cast<unsigned long long*>(c->dev + c->dbg_off) : nullptr;
+    CK(cudaMemcpy(c->dev + offsetof(ChainPlan, dbg), &dbg, sizeof(dbg), cudaMemcpyHostToDevice));
   }
   return VLA_OK;
 }
-int vla_step_timeline_phases(vla_model_t* m) { return (m && m->last_step) ? m->last_step->plan.n_phases : 0; }
-int vla_step_timeline_units(vla_model_t* m) { return (m && m->last_step) ? m->last_step->units_total : 0; }
-int vla_step_phase_info(vla_model_t* m, int phase, char* name48, int* n_units, int* unit_base, double* flops, double* bytes) {
-  if (!m || !m->last_step || phase < 0 || phase >= m->last_step->plan.n_phases) return fail(VLA_ERR_INVALID, "bad phase index");
-  const CachedStep* c = m->last_step;
-  if (name48) snprintf(name48, 48, "%s", c->names[phase].c_str());
-  if (n_units) *n_units = c->plan.ph[phase].n_units;
-  if (unit_base) *unit_base = c->plan.ph[phase].unit_base;
-  if (flops) *flops = c->ph_flops[phase];
-  if (bytes) *bytes = c->ph_bytes[phase];
+int vla_chain_count(vla_model_t* m) { return m ? m->n_last_plans : 0; }
+int vla_chain_info(vla_model_t* m, int which, char* name48, int* n_phases, int* n_ctas, double* flops, double* bytes) {
+  if (!m || which < 0 || which >= m->n_last_plans) return fail(VLA_ERR_INVALID, "bad chain index");
+  const ChainPlanCached* c = m->last_plans[which];
+  if (name48) snprintf(name48, 48, "%s", c->name.c_str());
+  if (n_phases) *n_phases = c->n_phases;
+  if (n_ctas) *n_ctas = c->n_clusters * CHAIN_CLUSTER;
+  if (flops) *flops = c->flops;
+  if (bytes) *bytes = c->bytes;
   return VLA_OK;
 }
-int vla_step_timeline_read(vla_model_t* m, unsigned long long* out, int max_units) {
-  if (!m || !out || !m->last_step) return fail(VLA_ERR_INVALID, "no fused step has run");
-  const CachedStep* c = m->last_step;
-  const int n = std::min(max_units, c->units_total);
+int vla_chain_phase_name(vla_model_t* m, int which, int phase, char* name48) {
+  if (!m || which < 0 || which >= m->n_last_plans || !name48) return fail(VLA_ERR_INVALID, "bad chain index");
+  const ChainPlanCached* c = m->last_plans[which];
+  if (phase < 0 || phase >= c->n_phases) return fail(VLA_ERR_INVALID, "bad phase index");
+  snprintf(name48, 48, "%s", c->phase_names[phase].c_str());
+  return VLA_OK;
+}
+/* out[n_ctas][CHAIN_MAX_PHASES = 24][2] */
+int vla_chain_timeline_read(vla_model_t* m, int which, unsigned long long* out) {
+  if (!m || !out || which < 0 || which >= m->n_last_plans) return fail(VLA_ERR_INVALID, "bad chain index");
+  const ChainPlanCached* c = m->last_plans[which];
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, c->dev + c->timeline_off, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost));
-  return n;
+  CK(cudaMemcpy(out, c->dev + c->dbg_off, sizeof(unsigned long long) * 2 * CHAIN_MAX_PHASES * c->n_clusters * CHAIN_CLUSTER, cudaMemcpyDeviceToHost));
+  return c->n_clusters * CHAIN_CLUSTER;
 }
 
 int vla_profile_begin(vla_model_t* m) {

@@ -209,6 +209,8 @@ struct LatentFwdArgs {
   int ae;                                         // autoencoder: heads are [rows, L]; z = mu = mean, no sampling, KL = 0
 };
 cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_t s);
+// Same step with the chain kernel's partial layout: one block and one KL partial per 32-row slice.
+cudaError_t launch_latent_fwd_rows(const LatentFwdArgs& a, cudaStream_t s);
 
 struct LatentBwdArgs {
   const float* gz; int ld_gz;                     // [rows, L] (may be nullptr -> 0)
@@ -292,48 +294,43 @@ struct AdamArgs {
 cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
-// Whole-step kernel (step_kernel.cu): one persistent cooperative launch executes the train step as a list of PHASES
-// (the launches of the per-call path), each split into UNITS (one GEMM tile, or a few element-wise blocks).  Units of
-// phase p go to CTA (u + rot_p) mod grid; a unit waits on per-row-block completion counters of the phases it depends
-// on (ROW: the 128-row blocks it reads; ALL: every unit of that phase) instead of a kernel boundary.
+// Chain kernel (chain_kernel.cu): the ROW-LOCAL stretches of a step -- consecutive launches in which a 128-row block of
+// the batch only ever depends on the same rows of the previous launch (everything between two BatchNorm statistics
+// boundaries: BN apply -> heads -> latent -> decoders + loss -> data gradients -> latent backward -> encoder data
+// gradients) -- run as ONE launch.  One 4-CTA thread-block cluster owns a 128-row block and walks the phases; each phase's
+// tiles (N split over the cluster) or rows (element-wise phases, 32 per CTA) are spread over the four CTAs; a cluster
+// barrier replaces the kernel boundary.  Activations travel through L2 (they are needed in global memory by the
+// weight-gradient GEMMs anyway); TMEM, the mbarrier ring and the tensor-map prefetches are set up once per launch.
 // ---------------------------------------------------------------------------------------------
-enum StepKind : int {
-  SK_GEMM_NT_PLAIN = 0, SK_GEMM_NT_FULL, SK_GEMM_NT_LOSS, SK_GEMM_NN_PLAIN, SK_GEMM_NN_FULL, SK_GEMM_TN,
-  SK_INGEST, SK_BN_ACT, SK_LATENT_FWD, SK_LOSS, SK_LATENT_BWD, SK_BN_BWD, SK_ADAMW,
+enum ChainKind : int {
+  CK_GEMM_NT_PLAIN = 0, CK_GEMM_NT_FULL, CK_GEMM_NT_LOSS, CK_GEMM_NT_LOSS_BCE, CK_GEMM_NT_LOSS_MSE, CK_GEMM_NN_PLAIN,
+  CK_GEMM_NN_FULL, CK_GEMM_LAST = CK_GEMM_NN_FULL,
+  CK_INGEST, CK_BN_ACT, CK_BN_BWD, CK_LATENT_FWD, CK_LATENT_BWD,
 };
-constexpr int STEP_MAX_PHASES = 40;
-constexpr int STEP_MAX_DEPS = 3;
-constexpr int STEP_ROW_BLOCK = GEMM_BM;     // dependency granularity: 128 rows
+constexpr int CHAIN_CLUSTER = 4;
+constexpr int CHAIN_MAX_PHASES = 24;
+constexpr int CHAIN_MAX_UNITS = 12;       // tiles of one row block one CTA may be given in one phase
+constexpr int CHAIN_ROWS = GEMM_BM;       // rows per cluster iteration
 
-struct StepPhase {
+struct ChainPhase {
   int kind;
-  int n_units;
-  int unit_rot;            // unit u runs on CTA (u + unit_rot) % grid
-  int unit_base;           // index of unit 0 in the timeline buffer
-  int sub;                 // element-wise: stand-alone blocks per unit
-  int n_blocks;            // element-wise: number of stand-alone blocks (BatchNorm: gx * gy, block = bx + gx * by)
-  int gx;                  // BatchNorm: column blocks
-  int rpb;                 // ingest: rows per unit; BatchNorm: rows per block
-  int L;                   // latent width
-  int rows;                // batch rows
-  int cbase;               // counters [cbase, cbase + mt): per row block; [cbase + mt]: all units
-  int n_deps;
-  int dep_phase[STEP_MAX_DEPS];
-  int dep_all[STEP_MAX_DEPS];
-  long long args_off;      // byte offset of the argument struct (GemmGroup, IngestArgs, ...) from the plan base
+  int n_units[CHAIN_CLUSTER];                              // GEMM phases: tiles per cluster rank
+  unsigned short units[CHAIN_CLUSTER][CHAIN_MAX_UNITS];    // (problem << 8) | n_tile
+  long long args_off;                                      // byte offset of the argument struct from the plan base
 };
-
-struct StepPlan {
+struct ChainPlan {
   int n_phases;
-  int mt;                  // number of 128-row blocks
-  int n_counters;
-  int grid;
-  unsigned int* counters;  // [n_counters], zero between launches (the last CTA to finish re-arms them)
-  const unsigned int* targets;   // [n_counters]
-  unsigned int* finish;    // CTA exit ticket
-  unsigned long long* dbg; // optional [total units][8] globaltimer stamps
-  StepPhase ph[STEP_MAX_PHASES];
+  int rows;
+  int m_blocks;                 // 128-row blocks
+  int pad;
+  unsigned long long* dbg;      // optional [clusters * 4][CHAIN_MAX_PHASES][2] %globaltimer stamps (phase start / end)
+  ChainPhase ph[CHAIN_MAX_PHASES];
 };
+size_t chain_smem_bytes();
+int chain_max_clusters(cudaError_t* err);
+cudaError_t launch_chain(const ChainPlan* plan_dev, int n_clusters, cudaStream_t s);
+
+int bn_rows_per_block(int rows, int m_tiles);
 
 // ---------------------------------------------------------------------------------------------
 // Data-parallel gradient exchange over NVLink peer memory (dp_exchange.cu)
@@ -366,15 +363,5 @@ struct MetricsArgs {
 };
 int metrics_grid(long long rows);
 cudaError_t launch_metrics(const MetricsArgs& a, cudaStream_t s);
-
-struct LossGridInfo { int nb_a, nb_b, nb_c, nb_k; };
-LossGridInfo loss_grid_info(const LossArgs& a);
-int bn_rows_per_block(int rows, int m_tiles);
-size_t step_smem_bytes();
-// Rows [r0, r1) a unit reads / writes (empty for AdamW); shared by the host (targets) and the kernel (signals, waits).
-// `args` points at the phase's argument struct.
-void step_unit_rows_host(const StepPhase& ph, const void* args, int u, int* r0, int* r1);
-cudaError_t launch_step(const StepPlan* plan_dev, int grid, cudaStream_t s);
-int step_max_grid(cudaError_t* err);
 
 }  // namespace vla

@@ -109,12 +109,13 @@ EXPORTS = {
     "vla_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
     "vla_profile_read": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
     "vla_profile_pause": (C.c_int, [C.c_void_p]),
-    "vla_step_timeline": (C.c_int, [C.c_void_p, C.c_int]),
-    "vla_step_timeline_phases": (C.c_int, [C.c_void_p]),
-    "vla_step_timeline_units": (C.c_int, [C.c_void_p]),
-    "vla_step_phase_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-    "vla_step_timeline_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
+    "vla_chain_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "vla_chain_count": (C.c_int, [C.c_void_p]),
+    "vla_chain_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "vla_chain_phase_name": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "vla_chain_timeline_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),
+    "vla_model_pin": (C.c_int, [C.c_void_p, C.c_int]),
     "vla_test_workspace": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "vla_test_set_timeline": (C.c_int, [C.c_void_p]),
     "vla_test_set_flags": (C.c_int, [C.c_int]),

@@ -152,6 +152,10 @@ class Trainer:
         self.injected = None
         self._mask_arr = None
         _lib.check(_lib.lib().vla_model_reserve(self.core.handle, self.batch), "vla_model_reserve")
+        # the graphs captured below bake workspace addresses into their kernel arguments: while this trainer lives, a call on
+        # the same handle that would have to reallocate the workspace (a larger batch) fails instead of corrupting them
+        _lib.check(_lib.lib().vla_model_pin(self.core.handle, 1), "vla_model_pin")
+        self._pinned = True
         self.reset_counters(0, 0)
 
     def _connect_peers(self, n_floats):
@@ -283,6 +287,9 @@ class Trainer:
         """Release the captured graphs (do this before destroying a process group whose collectives they contain)."""
         torch.cuda.synchronize(self.core.device)
         self.graphs.clear()
+        if getattr(self, "_pinned", False):
+            _lib.lib().vla_model_pin(self.core.handle, -1)
+            self._pinned = False
         if self.dp is not None:
             import torch.distributed as dist
             dist.barrier(group=self.pg)       # no peer may still be reading or writing this rank's buffers
@@ -290,6 +297,14 @@ class Trainer:
             self.flat = self.reduced = self.grads = self.loss_out = self._loss_local = None
             _lib.lib().vla_dp_destroy(self.dp)
             self.dp = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pinned", False) and self.core.handle:
+                _lib.lib().vla_model_pin(self.core.handle, -1)
+                self._pinned = False
+        except Exception:
+            pass
 
     def losses(self):
         """(total, recon, class, kld) of the last completed step -- one 16-byte device->host read.
@@ -316,44 +331,50 @@ class Trainer:
         return out
 
     def timeline(self, which=0):
-        """Per-phase timing of the whole-step kernel for ONE replayed step, from the %globaltimer stamps every unit writes
-        (vla_step_timeline).  Returns (step_us, phases): phases is a list of dicts with the phase's name, number of units,
-        first unit start / last unit published relative to the first stamp of the step (us), the mean unit duration and the
-        mean time a unit spent waiting for its dependencies, plus the phase's algorithmic flops / bytes."""
+        """Per-phase timing inside the chain launches of ONE replayed step, from the %globaltimer stamps every CTA writes
+        (vla_chain_timeline).  Returns a list with one entry per chain launch: dict(name, ctas, span_us, flops, bytes,
+        phases=[dict(name, start_us, work_us (mean over CTAs that had work), wait_us (mean time a CTA then waited at the
+        cluster barrier), span_us (first start to last end))])."""
         import numpy as np
         L = _lib.lib()
         dev = self.core.device
+        out = []
         with torch.cuda.device(dev):
-            torch.cuda.synchronize(dev)
-            self.step(which)                               # make sure the plan exists
-            torch.cuda.synchronize(dev)
-            _lib.check(L.vla_step_timeline(self.core.handle, 1), "vla_step_timeline")
             self.step(which)
             torch.cuda.synchronize(dev)
-            n_units = L.vla_step_timeline_units(self.core.handle)
-            n_ph = L.vla_step_timeline_phases(self.core.handle)
-            buf = (C.c_ulonglong * (8 * max(n_units, 1)))()
-            got = L.vla_step_timeline_read(self.core.handle, buf, n_units)
-            _lib.check(L.vla_step_timeline(self.core.handle, 0), "vla_step_timeline")
-        if got <= 0:
-            return 0.0, []
-        t = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 8)[:got].astype(np.int64)
-        t0 = int(t[:, 0].min())
-        out = []
-        for p in range(n_ph):
-            name = C.create_string_buffer(48)
-            nu, ub, fl, by = C.c_int(), C.c_int(), C.c_double(), C.c_double()
-            _lib.check(L.vla_step_phase_info(self.core.handle, p, name, C.byref(nu), C.byref(ub), C.byref(fl), C.byref(by)),
-                       "vla_step_phase_info")
-            rows = t[ub.value:ub.value + nu.value]
-            out.append(dict(name=name.value.decode(), units=nu.value,
-                            start_us=(int(rows[:, 0].min()) - t0) / 1e3, ready_us=(int(rows[:, 1].min()) - t0) / 1e3,
-                            end_us=(int(rows[:, 6].max()) - t0) / 1e3,
-                            unit_us=float((rows[:, 6] - rows[:, 0]).mean()) / 1e3,
-                            wait_us=float((rows[:, 1] - rows[:, 0]).mean()) / 1e3,
-                            work_us=float((rows[:, 6] - rows[:, 1]).mean()) / 1e3,
-                            flops=fl.value, bytes=by.value))
-        return (int(t[:, 6].max()) - t0) / 1e3, out
+            _lib.check(L.vla_chain_timeline(self.core.handle, 1), "vla_chain_timeline")
+            self.step(which)
+            torch.cuda.synchronize(dev)
+            if which in self.graphs:
+                # a graph replay does not pass through the library: ask it which plans an eager step launches
+                self._enqueue(self.datasets[which])
+                self.steps += 1
+                torch.cuda.synchronize(dev)
+            n = L.vla_chain_count(self.core.handle)
+            for w in range(n):
+                name = C.create_string_buffer(48)
+                nph, nct, fl, by = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+                _lib.check(L.vla_chain_info(self.core.handle, w, name, C.byref(nph), C.byref(nct), C.byref(fl), C.byref(by)), "vla_chain_info")
+                buf = (C.c_ulonglong * (nct.value * 24 * 2))()
+                _lib.check(min(L.vla_chain_timeline_read(self.core.handle, w, buf), 0), "vla_chain_timeline_read")
+                t = np.frombuffer(buf, dtype=np.uint64).reshape(nct.value, 24, 2)[:, :nph.value].astype(np.int64)
+                t0 = int(t[:, 0, 0].min())
+                phases = []
+                for p in range(nph.value):
+                    pn = C.create_string_buffer(48)
+                    _lib.check(L.vla_chain_phase_name(self.core.handle, w, p, pn), "vla_chain_phase_name")
+                    s, e = t[:, p, 0], t[:, p, 1]
+                    nxt = t[:, p + 1, 0] if p + 1 < nph.value else e
+                    work = (e - s)
+                    busy = work > 200                        # CTAs without a tile in this phase pass straight through
+                    phases.append(dict(name=pn.value.decode(), start_us=(int(s.min()) - t0) / 1e3,
+                                       work_us=float(work[busy].mean()) / 1e3 if busy.any() else 0.0,
+                                       work_max_us=float(work.max()) / 1e3, busy_ctas=int(busy.sum()),
+                                       wait_us=float((nxt - e).mean()) / 1e3, span_us=(int(e.max()) - int(s.min())) / 1e3))
+                out.append(dict(name=name.value.decode(), ctas=nct.value, span_us=(int(t[:, :, 1].max()) - t0) / 1e3,
+                                flops=fl.value, bytes=by.value, phases=phases))
+            _lib.check(L.vla_chain_timeline(self.core.handle, 0), "vla_chain_timeline")
+        return out
 
     def profile(self, steps=3, which=0):
         """Per-launch device times inside a replayed CUDA graph: the step is captured once with an event pair around every
