@@ -219,12 +219,15 @@ void vla_dp_destroy(vla_dp_t* d);
  * cluster barriers instead of kernel boundaries.  Used by vla_train_step and by vla_forward / vla_backward from batch 1024.
  * The first call for a new argument set builds the plan (device allocation + upload, not capturable); later calls and
  * CUDA-graph replays only launch.  VLA_CHAIN=0 in the environment issues the same phases as separate launches.
- * Timeline: when enabled, every CTA writes %globaltimer stamps (phase start, phase end) for every phase. */
+ * Timeline: when enabled, every CTA writes eight %globaltimer stamps per phase: 0 phase start, 1 phase end (thread 0, in front of the
+ * cluster barrier), 2 barrier passed, 3 first operands landed, 4 all MMAs issued, 5 accumulator ready (element-wise phases: start),
+ * 6 first epilogue warp done, 7 last epilogue warp done. */
 int vla_chain_timeline(vla_model_t* m, int enable);
 int vla_chain_count(vla_model_t* m);                     /* chain launches made by the last call on this handle */
+int vla_chain_cached_plans(vla_model_t* m);              /* plan images built so far on this handle (a repeated call must not add one) */
 int vla_chain_info(vla_model_t* m, int which, char* name48, int* n_phases, int* n_ctas, double* flops, double* bytes);
 int vla_chain_phase_name(vla_model_t* m, int which, int phase, char* name48);
-int vla_chain_timeline_read(vla_model_t* m, int which, unsigned long long* out);   /* out[n_ctas][24][2]; returns n_ctas */
+int vla_chain_timeline_read(vla_model_t* m, int which, unsigned long long* out);   /* out[n_ctas][24][8]; returns n_ctas */
 
 /* A caller that captures calls on this handle into CUDA graphs (vla_b200.Trainer) pins the handle (+1) for as long as the
  * graphs live (-1 afterwards): while pinned, a call that would have to grow -- i.e. free and reallocate -- the workspace the

@@ -25,6 +25,7 @@ for rep in range(2):
     chains = tr.timeline()
 for c in chains:
     print(f"== {c['name']}: {c['ctas']} CTAs, {c['span_us']:.1f} us, {c['flops'] / 1e9:.2f} GFLOP, {c['bytes'] / 1e6:.1f} MB")
-    print(f"   {'phase':16s} {'start':>7s} {'work(mean)':>10s} {'work(max)':>9s} {'busy':>5s} {'wait':>7s} {'span':>7s}   (us)")
+    print(f"   {'phase':16s} {'start':>7s} {'busy':>5s} {'operands':>8s} {'mma_iss':>8s} {'acc_rdy':>8s} {'epi_1st':>8s} {'epi_last':>8s} {'bar_in':>7s} {'bar_out':>7s} {'span':>7s}   (us, relative to the CTA's phase start)")
     for p in c["phases"]:
-        print(f"   {p['name']:16s} {p['start_us']:7.2f} {p['work_us']:10.2f} {p['work_max_us']:9.2f} {p['busy_ctas']:5d} {p['wait_us']:7.2f} {p['span_us']:7.2f}")
+        print(f"   {p['name']:16s} {p['start_us']:7.2f} {p['busy_ctas']:5d} {p['operands_us']:8.2f} {p['mma_issued_us']:8.2f} {p['acc_ready_us']:8.2f} "
+              f"{p['epi_first_us']:8.2f} {p['epi_last_us']:8.2f} {p['barrier_in_us']:7.2f} {p['barrier_out_us']:7.2f} {p['span_us']:7.2f}")

@@ -62,8 +62,12 @@ def test_chained_steps_equal_separate_launches(kind, batch):
     for k, v in sd_sep.items():
         if k.endswith("num_batches_tracked"):
             assert int(sd_fus[k]) == int(v) == 5
-        elif k.endswith(("running_mean", "running_var")):
-            np.testing.assert_allclose(sd_fus[k], v, rtol=1e-3, atol=1e-4)
+        elif k.endswith("running_mean"):
+            # the running mean contains the pre-BatchNorm bias, whose true gradient is exactly zero: Adam moves it by +-lr per
+            # step on rounding noise, differently for the two orders of summation
+            np.testing.assert_allclose(sd_fus[k], v, rtol=1e-3, atol=2 * 5e-4 * 5)
+        elif k.endswith("running_var"):
+            np.testing.assert_allclose(sd_fus[k], v, rtol=5e-3, atol=1e-4)
         else:
             # Adam turns rounding-level gradient differences of near-zero gradients into +-lr steps
             assert np.abs(sd_fus[k] - v).max() <= 2 * 5e-4 * 5 + 1e-6, k
@@ -71,7 +75,12 @@ def test_chained_steps_equal_separate_launches(kind, batch):
                 assert rel_l2(sd_fus[k], v) < 1e-2, (k, rel_l2(sd_fus[k], v))
 
 
-def test_chain_graph_replay_and_timeline():
+@pytest.fixture
+def chain_on(monkeypatch):
+    monkeypatch.setenv("VLA_CHAIN", "1")
+
+
+def test_chain_graph_replay_and_timeline(chain_on):
     """CUDA-graph replays of the chained step walk the resident batches; the step is a handful of launches; the per-phase
     timeline of the chain launches is complete."""
     from vla_b200 import DeviceDataset, Trainer
@@ -101,6 +110,21 @@ def test_chain_graph_replay_and_timeline():
         launches[name] = launches.get(name, 0) + 1
     launches.pop("_empty_pair", None)
     assert sum(launches.values()) <= 6, launches                # ingest+enc | middle | bn_bwd | wgrad | adamw
+
+
+def test_repeated_eager_steps_reuse_their_plans(chain_on):
+    """The plan cache is keyed by the argument image: identical calls must hit it (an uninitialised byte in a group once made
+    every call build a new plan and the captured call fail)."""
+    from vla_b200 import DeviceDataset, Trainer, _lib
+    m = make_module("multimodal", FULL, vo.init_state("multimodal", FULL, seed=4)).train()
+    ds = DeviceDataset.synthetic(1024, FULL["A"], FULL["B"], FULL["S"], "cuda", seed=1)
+    tr = Trainer(m, ds, 512, use_graph=False)
+    tr.step()
+    n1 = _lib.lib().vla_chain_cached_plans(m._ensure_core().handle)
+    for _ in range(5):
+        tr.step()
+    torch.cuda.synchronize()
+    assert n1 >= 2 and _lib.lib().vla_chain_cached_plans(m._ensure_core().handle) == n1
 
 
 def test_pinned_workspace_refuses_to_grow():

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chain_kernel(const ChainPlan*
       const ChainPhase& ph = plan->ph[p];
       const int kind = ph.kind;
       const void* args = base + ph.args_off;
-      if (dbg && threadIdx.x == 0) dbg[(static_cast<size_t>(cid * CHAIN_CLUSTER + rank) * CHAIN_MAX_PHASES + p) * 2] = gtime();
+      const size_t drow = static_cast<size_t>(cid * CHAIN_CLUSTER + rank) * CHAIN_MAX_PHASES + p;
+      ctx.dbg = dbg; ctx.dbg_row = static_cast<int>(drow);
+      if (dbg && threadIdx.x == 0) dbg[drow * 8] = gtime();
       if (kind <= CK_GEMM_LAST) {
         const GemmGroup* grp = static_cast<const GemmGroup*>(args);
         const LossTail* tail = &grp->tail;
@@ -147,10 +149,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chain_kernel(const ChainPlan*
           }
         }
       } else if (warp >= 2 && r1 > r0) {
+        if (dbg && threadIdx.x == 64) dbg[drow * 8 + 5] = gtime();
         ew_phase(kind, args, mb, rank, r0, r1, static_cast<int>(threadIdx.x) - 64);
+        if (dbg && threadIdx.x == 64) dbg[drow * 8 + 6] = gtime();
+        if (dbg && threadIdx.x == GEMM_THREADS - 32) dbg[drow * 8 + 7] = gtime();
       }
-      if (dbg && threadIdx.x == 0) dbg[(static_cast<size_t>(cid * CHAIN_CLUSTER + rank) * CHAIN_MAX_PHASES + p) * 2 + 1] = gtime();
+      if (dbg && threadIdx.x == 0) dbg[drow * 8 + 1] = gtime();
       phase_barrier();
+      if (dbg && threadIdx.x == 0) dbg[drow * 8 + 2] = gtime();
     }
   }
 

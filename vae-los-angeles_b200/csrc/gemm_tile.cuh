@@ -670,6 +670,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
         }
       }
     }
+    if (et == 0) VLA_STAMP(6);                                     // this thread's chunks are done
+    if (et == EPI_THREADS - 32) VLA_STAMP(7);                      // ... and the last epilogue warp's
     if (bias_mma && half == 0) {
       uint32_t r1[1];
       tmem_ld1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + GEMM_BIAS_TMEM_COL, r1);

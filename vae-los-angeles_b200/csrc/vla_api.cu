@@ -738,7 +738,8 @@ void finalize_tn(GemmGroup& g, int Kb, int force_splits = 0) {
   }
 }
 
-void init_group(GemmGroup& g) { g.nprob = 0; g.total_tiles = 0; g.dbg = nullptr; g.dbg_flags = 0; }
+// Zero everything: the chain plan cache compares whole argument images, so no byte of a group may be stack garbage.
+void init_group(GemmGroup& g) { memset(static_cast<void*>(&g), 0, sizeof(g)); }
 
 // ---------------------------------------------------------------------------------------------
 // Sequencing
@@ -1303,7 +1304,7 @@ int launch_stretch(vla_model* m, cudaStream_t st, const std::vector<ChainOp>& op
     c = new ChainPlanCached();
     c->key = img;
     c->dbg_off = (img.size() + 255) & ~size_t(255);
-    const size_t dbg_bytes = sizeof(unsigned long long) * 2 * CHAIN_MAX_PHASES * CHAIN_CLUSTER * static_cast<size_t>(m->chain_clusters);
+    const size_t dbg_bytes = sizeof(unsigned long long) * 8 * CHAIN_MAX_PHASES * CHAIN_CLUSTER * static_cast<size_t>(m->chain_clusters);
     cudaError_t e = cudaMalloc(&c->dev, c->dbg_off + dbg_bytes);
     if (e == cudaSuccess) e = cudaMemset(c->dev + c->dbg_off, 0, dbg_bytes);
     if (e == cudaSuccess) {
@@ -1345,8 +1346,11 @@ int chain_flush(vla_model* m, cudaStream_t st) {
 // by the argument structs, built on a stretch's first eager execution: callers whose buffers keep their addresses (the
 // Trainer, graph-captured inference) hit the cache from the second call on.  VLA_CHAIN=0 switches it off everywhere.
 bool chain_enabled() {      // read per call: a host-side switch, not on the replay path
+  // Measured (profiles/r2_chain_timeline_v1.log, rna2dna batch 4096): 192 us / step chained vs 123 us as separate launches --
+  // every phase pays ~3 us until its first operands land, 2-16 us of epilogue and ~1.4 us of barrier.  Opt-in until the
+  // per-phase latency work lands (VLA_CHAIN=1).
   const char* e = getenv("VLA_CHAIN");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 struct ChainScope {      // sets m->chain_on for one entry-point call; the stretch still open at the end is issued by finish()
   vla_model* m; bool prev;
@@ -1770,6 +1774,7 @@ int vla_chain_timeline(vla_model_t* m, int enable) {
   return VLA_OK;
 }
 int vla_chain_count(vla_model_t* m) { return m ? m->n_last_plans : 0; }
+int vla_chain_cached_plans(vla_model_t* m) { return m ? static_cast<int>(m->plans.size()) : 0; }
 int vla_chain_info(vla_model_t* m, int which, char* name48, int* n_phases, int* n_ctas, double* flops, double* bytes) {
   if (!m || which < 0 || which >= m->n_last_plans) return fail(VLA_ERR_INVALID, "bad chain index");
   const ChainPlanCached* c = m->last_plans[which];
@@ -1787,12 +1792,12 @@ int vla_chain_phase_name(vla_model_t* m, int which, int phase, char* name48) {
   snprintf(name48, 48, "%s", c->phase_names[phase].c_str());
   return VLA_OK;
 }
-/* out[n_ctas][CHAIN_MAX_PHASES = 24][2] */
+/* out[n_ctas][CHAIN_MAX_PHASES = 24][8] */
 int vla_chain_timeline_read(vla_model_t* m, int which, unsigned long long* out) {
   if (!m || !out || which < 0 || which >= m->n_last_plans) return fail(VLA_ERR_INVALID, "bad chain index");
   const ChainPlanCached* c = m->last_plans[which];
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, c->dev + c->dbg_off, sizeof(unsigned long long) * 2 * CHAIN_MAX_PHASES * c->n_clusters * CHAIN_CLUSTER, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, c->dev + c->dbg_off, sizeof(unsigned long long) * 8 * CHAIN_MAX_PHASES * c->n_clusters * CHAIN_CLUSTER, cudaMemcpyDeviceToHost));
   return c->n_clusters * CHAIN_CLUSTER;
 }
 

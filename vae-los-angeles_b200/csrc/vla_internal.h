@@ -323,7 +323,7 @@ struct ChainPlan {
   int rows;
   int m_blocks;                 // 128-row blocks
   int pad;
-  unsigned long long* dbg;      // optional [clusters * 4][CHAIN_MAX_PHASES][2] %globaltimer stamps (phase start / end)
+  unsigned long long* dbg;      // optional [clusters * 4][CHAIN_MAX_PHASES][8] %globaltimer stamps (include/vla_b200.h)
   ChainPhase ph[CHAIN_MAX_PHASES];
 };
 size_t chain_smem_bytes();

@@ -334,7 +334,9 @@ class Trainer:
         """Per-phase timing inside the chain launches of ONE replayed step, from the %globaltimer stamps every CTA writes
         (vla_chain_timeline).  Returns a list with one entry per chain launch: dict(name, ctas, span_us, flops, bytes,
         phases=[dict(name, start_us, work_us (mean over CTAs that had work), wait_us (mean time a CTA then waited at the
-        cluster barrier), span_us (first start to last end))])."""
+        cluster barrier), span_us (first start to last end))]).  Per phase, relative to the CTA's phase start and averaged over
+        the CTAs that had work: operands_us (first operands in shared memory), mma_issued_us, acc_ready_us, epi_first_us /
+        epi_last_us (first / last epilogue warp done), barrier_in_us (thread 0 reaches the cluster barrier), barrier_out_us."""
         import numpy as np
         L = _lib.lib()
         dev = self.core.device
@@ -355,23 +357,25 @@ class Trainer:
                 name = C.create_string_buffer(48)
                 nph, nct, fl, by = C.c_int(), C.c_int(), C.c_double(), C.c_double()
                 _lib.check(L.vla_chain_info(self.core.handle, w, name, C.byref(nph), C.byref(nct), C.byref(fl), C.byref(by)), "vla_chain_info")
-                buf = (C.c_ulonglong * (nct.value * 24 * 2))()
+                buf = (C.c_ulonglong * (nct.value * 24 * 8))()
                 _lib.check(min(L.vla_chain_timeline_read(self.core.handle, w, buf), 0), "vla_chain_timeline_read")
-                t = np.frombuffer(buf, dtype=np.uint64).reshape(nct.value, 24, 2)[:, :nph.value].astype(np.int64)
+                t = np.frombuffer(buf, dtype=np.uint64).reshape(nct.value, 24, 8)[:, :nph.value].astype(np.int64)
                 t0 = int(t[:, 0, 0].min())
                 phases = []
                 for p in range(nph.value):
                     pn = C.create_string_buffer(48)
                     _lib.check(L.vla_chain_phase_name(self.core.handle, w, p, pn), "vla_chain_phase_name")
-                    s, e = t[:, p, 0], t[:, p, 1]
-                    nxt = t[:, p + 1, 0] if p + 1 < nph.value else e
-                    work = (e - s)
-                    busy = work > 200                        # CTAs without a tile in this phase pass straight through
-                    phases.append(dict(name=pn.value.decode(), start_us=(int(s.min()) - t0) / 1e3,
-                                       work_us=float(work[busy].mean()) / 1e3 if busy.any() else 0.0,
-                                       work_max_us=float(work.max()) / 1e3, busy_ctas=int(busy.sum()),
-                                       wait_us=float((nxt - e).mean()) / 1e3, span_us=(int(e.max()) - int(s.min())) / 1e3))
-                out.append(dict(name=name.value.decode(), ctas=nct.value, span_us=(int(t[:, :, 1].max()) - t0) / 1e3,
+                    s, e, b = t[:, p, 0], t[:, p, 1], t[:, p, 2]
+                    busy = t[:, p, 7] > s                      # CTAs whose epilogue / element-wise warps ran in this phase
+
+                    def rel(slot):                             # mean over the busy CTAs of (stamp - phase start), us
+                        v = (t[:, p, slot] - s)[busy & (t[:, p, slot] > s)]
+                        return float(v.mean()) / 1e3 if v.size else 0.0
+                    phases.append(dict(name=pn.value.decode(), start_us=(int(s.min()) - t0) / 1e3, busy_ctas=int(busy.sum()),
+                                       operands_us=rel(3), mma_issued_us=rel(4), acc_ready_us=rel(5), epi_first_us=rel(6),
+                                       epi_last_us=rel(7), barrier_in_us=float((e - s).mean()) / 1e3,
+                                       barrier_out_us=float((b - s).mean()) / 1e3, span_us=(int(b.max()) - int(s.min())) / 1e3))
+                out.append(dict(name=name.value.decode(), ctas=nct.value, span_us=(int(t[:, :, 2].max()) - t0) / 1e3,
                                 flops=fl.value, bytes=by.value, phases=phases))
             _lib.check(L.vla_chain_timeline(self.core.handle, 0), "vla_chain_timeline")
         return out
