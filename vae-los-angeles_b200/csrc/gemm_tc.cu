@@ -43,7 +43,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   pdl_wait();
   pdl_launch_dependents();
   if (threadIdx.x == 0 && grp.dbg) grp.dbg[static_cast<size_t>(blockIdx.x) * 8 + 2] = gtime();  // setup done, dependency resolved
-  gemm_tile<MODE, FEATS>(ctx, P, static_cast<int>(blockIdx.x) - P.tile_begin, &grp.tail);
+  {
+    const int local = static_cast<int>(blockIdx.x) - P.tile_begin;
+    const int n_tile = local % P.n_tiles, rest = local / P.n_tiles;
+    gemm_tile<MODE, FEATS>(ctx, P, &P.tmA, &P.tmB, rest % P.m_tiles, n_tile, rest / P.m_tiles, &grp.tail);
+  }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();

@@ -156,7 +156,8 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
 // the epilogue is instruction-fetch sensitive).  All threads of the CTA call this; on return the tile's global writes
 // have been issued by the epilogue threads (the caller orders them: barrier + fence) and ctx has advanced.
 template <int MODE, int FEATS>
-__device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc, int local, const LossTail* tail_desc = nullptr) {
+__device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                          int m_tile, int n_tile, int k_split, const LossTail* tail_desc = nullptr) {
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
@@ -164,9 +165,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // Snapshot of the descriptor's scalar fields: in the chain kernel the descriptor lives in global memory and the
-  // epilogue's global stores could alias it, which would force a reload after every store.
-  const GemmProblem& Pd = Pdesc;
+  // Snapshot of the descriptor's scalar fields (kernel parameter space, or the chain kernel's shared-memory phase image):
+  // the epilogue's stores could alias the descriptor, which would force a reload after every store.
   struct {
     int M, N, K, BN, m_tiles, n_tiles, kb_per_split, flags, ld_f32, ld_bf16, ld_mask, ld_pre;
     float mask_scale;
@@ -175,21 +175,19 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmProblem& Pdesc
     const float* aux0; const float* aux1; const long long* aux_site; float* aux_partials; const DynParams* dyn;
     int aux_n, loss_kind; float aux_scale;
     int a_lo, b_lo, out_lo;
+    unsigned int* mask_bits_out; const unsigned int* mask_bits_in;
   } P;
   P.M = Pd.M; P.N = Pd.N; P.K = Pd.K; P.BN = Pd.BN; P.m_tiles = Pd.m_tiles; P.n_tiles = Pd.n_tiles;
   P.kb_per_split = Pd.kb_per_split; P.flags = Pd.flags; P.ld_f32 = Pd.ld_f32; P.ld_bf16 = Pd.ld_bf16; P.ld_mask = Pd.ld_mask;
   P.ld_pre = Pd.ld_pre; P.mask_scale = Pd.mask_scale; P.bias = Pd.bias; P.out_f32 = Pd.out_f32; P.out_bf16 = Pd.out_bf16;
   P.a_lo = (MODE == 0) ? Pd.a_lo : 0; P.b_lo = (MODE == 0) ? Pd.b_lo : 0; P.out_lo = (MODE == 0) ? Pd.out_lo : 0;
+  P.mask_bits_out = Pd.mask_bits_out; P.mask_bits_in = Pd.mask_bits_in;
   P.mask_src = Pd.mask_src; P.pre = Pd.pre; P.mean = Pd.mean; P.rstd = Pd.rstd; P.stats = Pd.stats; P.bias_grad = Pd.bias_grad;
   if (FEATS & GF_LOSS) {
     P.aux0 = Pd.aux0; P.aux1 = Pd.aux1; P.aux_site = Pd.aux_site; P.aux_partials = Pd.aux_partials; P.dyn = Pd.dyn;
     P.aux_n = Pd.aux_n; P.loss_kind = Pd.loss_kind; P.aux_scale = Pd.aux_scale;
   }
-  const CUtensorMap* tmA = &Pd.tmA;
-  const CUtensorMap* tmB = &Pd.tmB;
-  const int n_tile = local % P.n_tiles;
-  const int m_tile = (local / P.n_tiles) % P.m_tiles;
-  const int k_split = local / (P.n_tiles * P.m_tiles);
+  const int local = (k_split * P.m_tiles + m_tile) * P.n_tiles + n_tile;      // index of the tile inside its problem
   const int m0 = m_tile * GEMM_BM;
   const int n0 = n_tile * P.BN;
   const int BN = P.BN;

@@ -42,9 +42,8 @@ constexpr int GEMM_THREADS = 320;     // warp 0: TMA producer, warp 1: MMA issue
 constexpr int GEMM_TMEM_COLS = 256;
 constexpr int GEMM_BIAS_TMEM_COL = 224;
 
-struct alignas(64) GemmProblem {
-  CUtensorMap tmA;
-  CUtensorMap tmB;
+// Everything a tile needs besides its two tensor maps (the chain kernel stages these in shared memory, phase by phase).
+struct GemmScalars {
   int M, N, K;
   int BN;
   int m_tiles, n_tiles, k_splits, kb_per_split;
@@ -78,7 +77,18 @@ struct alignas(64) GemmProblem {
   // every forward GEMM whose result reaches a ReLU (DESIGN.md "Precision").
   int a_lo, b_lo;
   int out_lo;                        // > 0: GF_OUT_BF16 also stores the lo copy of the result out_lo elements further
-  int pad1;
+  // ---- ReLU / dropout masks as bits (one 32-bit word per row and 32-column chunk, [chunk][M] words) ----
+  // GF_OUT_BF16 forward tiles with mask_bits_out != nullptr record (value > 0) per element; GF_MASK tiles with
+  // mask_bits_in != nullptr read the bits instead of the bf16 activation (one coalesced word per thread and chunk).
+  unsigned int* mask_bits_out;
+  const unsigned int* mask_bits_in;
+  int pad1[2];
+};
+static_assert(sizeof(GemmScalars) % 16 == 0 && sizeof(GemmScalars) <= 224, "GemmScalars is copied in 16-byte pieces into a 224-byte slot");
+
+struct alignas(64) GemmProblem : GemmScalars {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
 };
 
 // Final reduction of the fused loss: the epilogue of the tile that takes the last ticket sums every partial in a fixed
