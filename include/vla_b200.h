@@ -223,6 +223,10 @@ void vla_dp_destroy(vla_dp_t* d);
  * cluster barrier), 2 barrier passed, 3 first operands landed, 4 all MMAs issued, 5 accumulator ready (element-wise phases: start),
  * 6 first epilogue warp done, 7 last epilogue warp done. */
 int vla_chain_timeline(vla_model_t* m, int enable);
+/* Row-chain kernel (csrc/rowchain.cu: the row-local middle of a directional model's step, activations on chip).  With
+ * VLA_RC_TIMELINE=1 in the environment every CTA stamps %globaltimer per op: out[148][32][4] = GEMM issue start, all MMAs
+ * issued, accumulator ready (element-wise ops: start), epilogue done; kinds / subs[32] name the ops.  Returns the op count. */
+int vla_rowchain_timeline(vla_model_t* m, unsigned long long* out, int* kinds, int* subs);
 int vla_chain_count(vla_model_t* m);                     /* chain launches made by the last call on this handle */
 int vla_chain_cached_plans(vla_model_t* m);              /* plan images built so far on this handle (a repeated call must not add one) */
 int vla_chain_info(vla_model_t* m, int which, char* name48, int* n_phases, int* n_ctas, double* flops, double* bytes);

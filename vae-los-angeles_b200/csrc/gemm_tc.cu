@@ -144,4 +144,25 @@ bool make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
   return true;
 }
 
+bool make_tmap_f32_tile(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_bytes & 15) || inner == 0 || outer == 0) {
+    if (err) *err = "make_tmap_f32_tile: base and row pitch must be 16-byte aligned";
+    return false;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled (fp32 tile) failed with CUresult " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
 }  // namespace vla

@@ -63,11 +63,13 @@ struct EncWS {
   bf16* g_x = nullptr; int ld_gx = 0;                     // site: gradient w.r.t. the gathered embedding
   std::vector<float*> pre, stats, bstats, mean, rstd;
   std::vector<bf16*> act, gy, gpre;
+  std::vector<unsigned short*> bits;                      // row-chain kernel: (activation > 0) per element, [rows][n / 16] halfwords
   std::vector<int> ld_act, act_lo;
   float* ml = nullptr;
 };
 struct DecWS {
   std::vector<bf16*> act, gact;                           // hidden activations after the fused first layer
+  std::vector<unsigned short*> bits;                      // row-chain kernel: ReLU masks of the hidden activations
   std::vector<int> ld_act, act_lo;
   bf16* g_out = nullptr; int ld_gout = 0;                 // bf16 gradient w.r.t. the last layer's pre-activation
   float* recon = nullptr;                                 // fp32 output when the caller passes none
@@ -135,6 +137,7 @@ struct vla_model {
   std::vector<DecWS> dws;
   float *mu = nullptr, *logvar = nullptr, *eps = nullptr, *kl_partials = nullptr, *gz = nullptr;
   bf16 *z = nullptr, *gml = nullptr, *d0 = nullptr, *g_d0 = nullptr;
+  unsigned short* d0_bits = nullptr;
   int ldz = 0, z_lo = 0, ldgml = 0, ld_d0 = 0, d0_lo = 0;
   std::map<TmapKey, CUtensorMap> tmaps;
   // what the last forward left in the workspace
@@ -146,6 +149,8 @@ struct vla_model {
   std::vector<ChainPlanCached*> plans;
   ChainPlanCached* last_plans[8] = {}; int n_last_plans = 0;   // plans launched by the last call (timeline)
   bool chain_dbg = false;
+  unsigned long long* rc_dbg = nullptr;   // row-chain timeline buffer [148][RC_MAX_OPS][4] (VLA_RC_TIMELINE=1)
+  RcPlan* rc_last = nullptr;              // host copy of the last row-chain plan (timeline labels)
   int chain_clusters = 0;                 // 4-CTA clusters of the chain kernel the device runs at once
   int pinned = 0;                         // > 0: captured graphs reference the workspace / plans (vla_model_pin)
 };
@@ -443,6 +448,7 @@ void carve(vla_model* m, Bump& b, int cap) {
         w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * w.ld_act.back()));
         w.gy.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
         w.gpre.push_back(b.take<bf16>(static_cast<size_t>(cap) * l.out));
+        w.bits.push_back(b.take<unsigned short>(static_cast<size_t>(cap) * ((l.out + 15) / 16)));
       }
     }
     w.ml = b.take<float>(static_cast<size_t>(cap) * m->HW);
@@ -451,12 +457,13 @@ void carve(vla_model* m, Bump& b, int cap) {
   m->logvar = b.take<float>(static_cast<size_t>(cap) * L);
   m->eps = b.take<float>(static_cast<size_t>(cap) * L);
   m->gz = b.take<float>(static_cast<size_t>(cap) * L);
-  m->kl_partials = b.take<float>(std::max(ceil_div(cap * L, 256), CHAIN_CLUSTER * mt) + 1);
+  m->kl_partials = b.take<float>(std::max(ceil_div(cap * L, 256), 8 * mt) + 1);
   m->ldz = op_ld(m->split, L); m->z_lo = op_lo(m->split, L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
   m->ldgml = pad8(m->HW); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
   m->ld_d0 = op_ld(m->split, m->cat.out); m->d0_lo = op_lo(m->split, m->cat.out);
   m->d0 = b.take<bf16>(static_cast<size_t>(cap) * m->ld_d0);
   m->g_d0 = b.take<bf16>(static_cast<size_t>(cap) * m->cat.out);
+  m->d0_bits = b.take<unsigned short>(static_cast<size_t>(cap) * ((m->cat.out + 15) / 16));
   m->dws.assign(m->decs.size(), DecWS{});
   for (size_t i = 0; i < m->decs.size(); ++i) {
     const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
@@ -466,6 +473,7 @@ void carve(vla_model* m, Bump& b, int cap) {
       w.ld_act.push_back(op_ld(sp, d.rest[r].out)); w.act_lo.push_back(op_lo(sp, d.rest[r].out));
       w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * w.ld_act.back()));
       w.gact.push_back(b.take<bf16>(static_cast<size_t>(cap) * d.rest[r].out));
+      w.bits.push_back(b.take<unsigned short>(static_cast<size_t>(cap) * ((d.rest[r].out + 15) / 16)));
     }
     w.ld_gout = pad8(d.out_dim);
     w.g_out = b.take<bf16>(static_cast<size_t>(cap) * w.ld_gout);
@@ -475,7 +483,7 @@ void carve(vla_model* m, Bump& b, int cap) {
   m->loss_partials = b.take<float>(lg);
   size_t ep = 0;
   for (const Dec& d : m->decs) ep += static_cast<size_t>(mt) * ceil_div(d.out_dim, 32) * 8;
-  m->eloss_partials = b.take<float>(ep + 8);
+  m->eloss_partials = b.take<float>(std::max(ep, static_cast<size_t>(16) * mt) + 8);
 }
 
 int reserve(vla_model* m, int batch) {
@@ -759,6 +767,7 @@ struct FwdIO {
   bool fuse_loss = false;
   const float* tgt_a = nullptr; const float* tgt_b = nullptr; const long long* tgt_site = nullptr;
   const float* class_w = nullptr; float* loss_out = nullptr;
+  bool rc_prefix = false;   // row-chain step: only ingest + the first encoder layer (the row-chain kernel takes over behind it)
 };
 
 int present_mask(const vla_model* m, const FwdIO& io) {
@@ -832,7 +841,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         const int flags = GF_BIAS | GF_OUT_F32 | (io.train ? GF_COLSTATS : 0);
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_f32 = w.pre[r]; p->ld_f32 = l.out; p->stats = w.stats[r];
-      } else if (r == e.fc.size()) {
+      } else if (r == e.fc.size() && !io.rc_prefix) {
         const Lin& l = e.heads;
         const bf16* A = r == 0 ? w.x : w.act[r - 1];
         const int lda = r == 0 ? w.ldx : w.ld_act[r - 1];
@@ -842,6 +851,11 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       }
     }
     if (g.nprob && (rc = timed_gemm(m, g, 0, r == 0 ? "gemm_enc_l0" : (r == 1 ? "gemm_enc_l1" : "gemm_enc_l2"), st))) return rc;
+    if (io.rc_prefix) {
+      m->saved = true; m->saved_batch = B; m->saved_present = present; m->saved_train = io.train;
+      m->generation++;
+      return VLA_OK;
+    }
     for (size_t i = 0; i < m->encs.size(); ++i) {
       if (!(present >> i & 1)) continue;
       const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
@@ -1003,6 +1017,7 @@ struct BwdIO {
   bool engine;                                     // bf16 output gradients already written by the loss kernel
   bool zero_grads;
   vla_dp* dp = nullptr;                            // data parallel: the decoder weight gradients are computed and sent early
+  bool rc_suffix = false;                          // row-chain step: only BatchNorm backward of the first layers + weight gradients
 };
 
 int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
@@ -1013,7 +1028,10 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   if (io.zero_grads) { if ((rc = chain_flush(m, st))) return rc; CK(cudaMemsetAsync(G, 0, sizeof(float) * m->n_params, st)); }
   // which decoders carry a gradient
   std::vector<bool> active(m->decs.size(), false);
-  if (!io.engine) {
+  const bool sfx = io.rc_suffix;
+  if (sfx) {
+    for (size_t i = 0; i < m->decs.size(); ++i) active[i] = true;
+  } else if (!io.engine) {
     OutGradArgs og[3]; int n = 0;
     for (size_t i = 0; i < m->decs.size(); ++i) {
       const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
@@ -1034,7 +1052,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   // ---- decoder data gradients, last layer first ----
   size_t max_rest = 0;
   for (const Dec& d : m->decs) max_rest = std::max(max_rest, d.rest.size());
-  for (size_t rr = max_rest; rr-- > 0;) {
+  for (size_t rr = max_rest; rr-- > 0 && !sfx;) {
     GemmGroup g; init_group(g);
     for (size_t i = 0; i < m->decs.size(); ++i) {
       const Dec& d = m->decs[i]; DecWS& w = m->dws[i];
@@ -1121,7 +1139,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   }
   int n_present = 0;
   for (size_t i = 0; i < m->encs.size(); ++i) n_present += present >> i & 1;
-  if (any_dec) {
+  if (any_dec && !sfx) {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
     if ((rc = add_nn(m, g, m->g_d0, l.out, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
@@ -1129,7 +1147,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     if ((rc = timed_gemm(m, g, 2, "dgrad_dec_l0", st))) return rc;
   }
   // ---- latent ----
-  {
+  if (!sfx) {
     LatentBwdArgs a{};
     a.gz = any_dec ? m->gz : nullptr; a.ld_gz = L;
     a.gmu_in = io.g_mu; a.glv_in = io.g_logvar;
@@ -1172,7 +1190,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;
       bn_todo.emplace_back(i, tgt);
     }
-    if (g.nprob && (rc = timed_gemm(m, g, 2, r == 1 ? "dgrad_enc_l1" : "dgrad_enc_l2", st))) return rc;
+    if (g.nprob && !sfx && (rc = timed_gemm(m, g, 2, r == 1 ? "dgrad_enc_l1" : "dgrad_enc_l2", st))) return rc;
     for (auto& it : bn_todo) {
       const Enc& e = m->encs[it.first]; EncWS& w = m->ews[it.first]; const Bn& bn = e.bn[it.second];
       BnBwdArgs a{};
@@ -1185,7 +1203,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
     }
   }
-  if (!site_done) {
+  if (!site_done && !sfx) {
     for (size_t i = 0; i < m->encs.size(); ++i) {
       if (!(present >> i & 1) || m->encs[i].type != 'C') continue;
       GemmGroup g; init_group(g); GemmProblem* p;
@@ -1425,6 +1443,7 @@ void vla_model_destroy(vla_model_t* m) {
   if (!m) return;
   if (m->layout_only) { delete m; return; }
   free_plans(m);
+  cudaFree(m->rc_dbg); delete m->rc_last;
   cudaFree(m->shadow); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
   cudaFree(m->ws);
   delete m;
@@ -1552,6 +1571,161 @@ int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float bet
   return VLA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-chain step (rowchain.cu): plan of the on-chip middle of a directional model's train step
+// ---------------------------------------------------------------------------------------------
+// Which steps qualify: one dense encoder with ONE BatchNorm layer of at most 128 columns, the site encoder, one decoder
+// with two layers behind the fused first one (RNA2DNAVAE / RNA2DNAAE: encoders.py:8-24, 46-61; decoders.py:21-35), latent
+// <= 64, hidden widths <= 512, output <= 576 columns, loss fused (MSE or BCE).  Everything else keeps the separate launches.
+// Opt-in (VLA_ROWCHAIN=1).  Measured at batch 4096 (profiles/r2_rowchain_timeline_*.log): parity with the separate launches
+// (tests/test_gpu_rowchain.py) but 160 us for what the separate launches do in ~75 us -- one CTA per row block leaves 32 SMs
+// doing 11 layers strictly one after the other: 47 us of issue loops that run at 0.33 us per 16 KB weight tile whatever the
+// tile's work (producer <-> MMA mbarrier hand-shake + tcgen05.commit; with neither loads nor MMAs still 0.2 us) and ~100 us of
+// epilogues at 8 warps per SM.  The separate launches spread the same layers over 128 CTAs each.
+bool rowchain_enabled() {
+  const char* e = getenv("VLA_ROWCHAIN");
+  return e && e[0] == '1';
+}
+bool rowchain_fits(const vla_model* m, int present) {
+  if (m->encs.size() != 2 || m->decs.size() != 1) return false;
+  const Enc& ea = m->encs[0]; const Enc& es = m->encs[1]; const Dec& d = m->decs[0];
+  if (ea.type == 'C' || es.type != 'C' || present != 3) return false;
+  if (ea.fc.size() != 1 || ea.fc[0].out > 128 || (ea.fc[0].out & 31)) return false;
+  if (d.type == 'C' || d.rest.size() != 2) return false;
+  if (m->L > 64 || m->E > 64 || m->HW > 128) return false;
+  if (m->cat.out > 256 || (m->cat.out & 63) || d.rest[0].out > 512 || (d.rest[0].out & 63) || d.rest[1].out > 576) return false;
+  return true;
+}
+
+struct RcBuilder {
+  vla_model* m; RcPlan* pl; int rc = VLA_OK;
+  int tm_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer) {
+    if (rc || pl->n_tm >= RC_MAX_TMAPS) { if (!rc) rc = fail(VLA_ERR_STATE, "row-chain plan: too many tensor maps"); return 0; }
+    rc = get_tmap(m, &pl->tm[pl->n_tm], base, inner, outer, pitch_bytes, box_outer);
+    return pl->n_tm++;
+  }
+  int tm_f32(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes) {
+    if (rc || pl->n_tm >= RC_MAX_TMAPS) { if (!rc) rc = fail(VLA_ERR_STATE, "row-chain plan: too many tensor maps"); return 0; }
+    std::string err;
+    if (!make_tmap_f32_tile(&pl->tm[pl->n_tm], base, inner, outer, pitch_bytes, &err)) rc = fail(VLA_ERR_CUDA, err);
+    return pl->n_tm++;
+  }
+  RcOp& op(int kind, int sub = 0) {
+    static RcOp dummy;
+    if (pl->n_ops >= RC_MAX_OPS) { if (!rc) rc = fail(VLA_ERR_STATE, "row-chain plan: too many ops"); return dummy; }
+    RcOp& o = pl->ops[pl->n_ops++];
+    memset(&o, 0, sizeof(o));
+    o.kind = kind; o.sub = sub; o.a_lo_slot = -1; o.out_lo_slot = -1; o.tm_side = -1; o.fscale = 1.0f;
+    return o;
+  }
+  // weight of a Linear as the K-major B operand of its forward GEMM (box 64 x 128) / the MN-major one of its data gradient
+  int w_nt(const Lin& l) { return tm_bf16(m->shadow + l.sh_off, static_cast<uint64_t>(l.sh_lo > 0 ? l.sh_lo + l.in : l.in), l.out, static_cast<uint64_t>(l.sh_ld) * 2, 128); }
+  int w_nn(const Lin& l) { return tm_bf16(m->shadow + l.sh_off, l.in, l.out, static_cast<uint64_t>(l.sh_ld) * 2, 64); }
+  // activation [B, width] as a store / load target in blocks of [128 x 64]
+  int act(const void* base, int width, int ld, int B) { return tm_bf16(base, width, B, static_cast<uint64_t>(ld) * 2, 128); }
+};
+
+int build_rowchain_plan(vla_model* m, const FwdIO& io, RcPlan* pl) {
+  memset(static_cast<void*>(pl), 0, sizeof(*pl));
+  const int B = io.batch, L = m->L, HW = m->HW, E = m->E;
+  const float* P = io.params;
+  const Enc& ea = m->encs[0]; const Enc& es = m->encs[1]; const Dec& d = m->decs[0];
+  EncWS& wa = m->ews[0]; EncWS& wsx = m->ews[1]; DecWS& wd = m->dws[0];
+  const Lin& l1 = d.rest[0]; const Lin& l2 = d.rest[1];
+  const int H = ea.fc[0].out;                     // BatchNorm width (<= 128)
+  const int hk = ceil_div(H, 64);                 // k-blocks of the encoder activation
+  const bool sp = m->split;
+  RcBuilder b{m, pl};
+  pl->rows = B; pl->m_blocks = ceil_div(B, GEMM_BM); pl->n_batches = io.n_batches; pl->L = L; pl->ae = m->ae ? 1 : 0; pl->n_enc = 2;
+  pl->dyn = m->dyn; pl->dyn_bump = m->dyn;
+  const Bn& bn = ea.bn[0];
+  pl->bn_stats = wa.stats[0]; pl->bn_gamma = P + bn.g_off; pl->bn_beta = P + bn.b_off;
+  pl->bn_running_mean = io.buffers + bn.rm_off; pl->bn_running_var = io.buffers + bn.rv_off;
+  pl->bn_nbt = io.counters ? io.counters + bn.counter : nullptr;
+  pl->bn_save_mean = wa.mean[0]; pl->bn_save_rstd = wa.rstd[0];
+  pl->bn_keep = io.keep_masks ? io.keep_masks[ea.first_drop] : nullptr;
+  pl->bn_n = H; pl->bn_m_tiles = pl->m_blocks; pl->train = io.train; pl->p_drop = 0.1f;
+  pl->seed = io.seed; pl->bn_offset = io.offset * 16 + 1 + ea.first_drop; pl->lat_offset = io.offset * 16;
+  pl->loss_partials = m->eloss_partials; pl->kl_partials = m->kl_partials; pl->counter = m->loss_counter; pl->loss_out = io.loss_out;
+  pl->loss_kind = d.type == 'A' ? LOSS_MSE : LOSS_BCE;
+  const float* tgt = d.type == 'A' ? io.tgt_a : io.tgt_b;
+  const long long tgt_rows = static_cast<long long>(B) * std::max(io.n_batches, 1);
+
+  const int tm_pre = b.tm_f32(wa.pre[0], H, B, static_cast<uint64_t>(H) * 4);
+  const int tm_tgt = b.tm_f32(tgt, d.out_dim, tgt_rows, static_cast<uint64_t>(d.out_dim) * 4);
+  // slot map (nine [128 x 64] blocks): 0.. encoder activation hi, hk.. lo | 4, 5 gathered embedding hi, lo | 6, 7 z hi, lo
+  const int S_H = 0, S_HLO = sp ? 2 : -1, S_X = 4, S_XLO = sp ? 5 : -1, S_Z = 6, S_ZLO = sp ? 7 : -1;
+  { RcOp& o = b.op(RC_LOADA);      // the gathered embedding rows (written by the ingest launch)
+    o.tm_b = b.act(wsx.x, sp ? wsx.x_lo + E : E, wsx.ldx, B); o.kb = 1; o.a_slot = S_X; o.a_lo_slot = S_XLO; o.b_lo = wsx.x_lo; }
+  { RcOp& o = b.op(RC_BNACT);
+    o.tm_side = tm_pre; o.side_tiles = H / 32; o.out_slot = S_H; o.out_lo_slot = S_HLO; o.n_total = H;
+    o.p[1] = wa.bits[0];
+    o.st[0] = RcStore{static_cast<short>(b.act(wa.act[0], H, wa.ld_act[0], B)), static_cast<short>(S_H), static_cast<short>(hk), 0}; }
+  { RcOp& o = b.op(RC_GEMM);       // heads of the dense encoder
+    o.tm_b = b.w_nt(ea.heads); o.n = HW; o.kb = hk; o.a_slot = S_H; o.a_lo_slot = S_HLO; o.b_lo = ea.heads.sh_lo; o.tmem_col = 0; }
+  { RcOp& o = b.op(RC_GEMM);       // heads of the site encoder
+    o.tm_b = b.w_nt(es.heads); o.n = HW; o.kb = 1; o.a_slot = S_X; o.a_lo_slot = S_XLO; o.b_lo = es.heads.sh_lo; o.tmem_col = 256;
+    o.commit = 1; o.wait_lda = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_LATENT);
+    o.e_tmem = 0; o.e_tmem2 = 256; o.out_slot = S_Z; o.out_lo_slot = S_ZLO;
+    o.p[0] = P + ea.heads.b_off; o.p[1] = P + es.heads.b_off; o.p[2] = m->mu; o.p[3] = m->logvar; o.p[4] = m->eps; o.p[5] = io.eps;
+    o.st[0] = RcStore{static_cast<short>(b.act(m->z, L, m->ldz, B)), static_cast<short>(S_Z), 1, 0}; }
+  const Lin& c = m->cat;
+  const int ck = c.out / 64, k1 = l1.out / 64, k2 = ceil_div(l2.out, 64);
+  { RcOp& o = b.op(RC_GEMM);       // fused first decoder layer
+    o.tm_b = b.w_nt(c); o.n = c.out; o.kb = 1; o.a_slot = S_Z; o.a_lo_slot = S_ZLO; o.b_lo = c.sh_lo; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_RELU);
+    o.e_n = c.out; o.n_total = c.out; o.relu = 1; o.out_slot = 0; o.out_lo_slot = sp ? ck : -1;
+    o.p[0] = P + c.b_off; o.p[1] = m->d0_bits;
+    o.st[0] = RcStore{static_cast<short>(b.act(m->d0, c.out, m->ld_d0, B)), 0, static_cast<short>(ck), 0}; }
+  { RcOp& o = b.op(RC_GEMM);       // hidden decoder layer
+    o.tm_b = b.w_nt(l1); o.n = l1.out; o.kb = ck; o.a_slot = 0; o.a_lo_slot = sp ? ck : -1; o.b_lo = l1.sh_lo; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_RELU);
+    o.e_n = l1.out; o.n_total = l1.out; o.relu = 1; o.out_slot = 0;
+    o.p[0] = P + l1.b_off; o.p[1] = wd.bits[0];
+    o.st[0] = RcStore{static_cast<short>(b.act(wd.act[0], l1.out, wd.ld_act[0], B)), 0, static_cast<short>(k1), 0}; }
+  // output layer + loss: at most 512 accumulator columns at a time; the columns beyond 512 go FIRST (their gradient block
+  // lands in the slot behind the hidden activation, which the second round still reads)
+  const int tm_w2 = b.w_nt(l2);
+  const int tail_n = l2.out > 512 ? l2.out - 512 : 0;
+  if (tail_n) {
+    { RcOp& o = b.op(RC_GEMM); o.tm_b = tm_w2; o.n0 = 512; o.n = tail_n; o.kb = k1; o.a_slot = 0; o.commit = 1; }
+    { RcOp& o = b.op(RC_EPI, EP_LOSS);
+      o.e_n = tail_n; o.e_col0 = 512; o.n_total = l2.out; o.out_slot = 0; o.tm_side = tm_tgt; o.side_tiles = ceil_div(tail_n, 32);
+      o.p[0] = P + l2.b_off; }
+  }
+  { RcOp& o = b.op(RC_GEMM); o.tm_b = tm_w2; o.n0 = 0; o.n = std::min(l2.out, 512); o.kb = k1; o.a_slot = 0; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_LOSS);
+    o.e_n = std::min(l2.out, 512); o.e_col0 = 0; o.n_total = l2.out; o.out_slot = 0; o.tm_side = tm_tgt; o.side_tiles = ceil_div(std::min(l2.out, 512), 32);
+    o.last_loss = 1; o.p[0] = P + l2.b_off;
+    o.st[0] = RcStore{static_cast<short>(b.act(wd.g_out, l2.out, wd.ld_gout, B)), 0, static_cast<short>(k2), 0}; }
+  // ---- backward ----
+  { RcOp& o = b.op(RC_GEMM); o.tm_b = b.w_nn(l2); o.nn = 1; o.n = l2.in; o.kb = k2; o.a_slot = 0; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_MASK);
+    o.e_n = l2.in; o.n_total = l2.in; o.out_slot = 0; o.p[1] = wd.bits[0];
+    o.st[0] = RcStore{static_cast<short>(b.act(wd.gact[0], l2.in, l2.in, B)), 0, static_cast<short>(k1), 0}; }
+  { RcOp& o = b.op(RC_GEMM); o.tm_b = b.w_nn(l1); o.nn = 1; o.n = l1.in; o.kb = k1; o.a_slot = 0; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_MASK);
+    o.e_n = l1.in; o.n_total = l1.in; o.out_slot = 0; o.p[1] = m->d0_bits;
+    o.st[0] = RcStore{static_cast<short>(b.act(m->g_d0, c.out, c.out, B)), 0, static_cast<short>(ck), 0}; }
+  { RcOp& o = b.op(RC_GEMM); o.tm_b = b.w_nn(c); o.nn = 1; o.n = L; o.kb = ck; o.a_slot = 0; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_LATENT_BWD);
+    o.e_tmem = 0; o.out_slot = 4; o.out_slot2 = 4 + ceil_div(HW, 64); o.p[2] = m->mu;
+    // scratch behind the operand: dL/dz [128][L + 1] and, if they fit in the free slots, mu / logvar / eps [3][128 x L]
+    o.e_n2 = (static_cast<size_t>(GEMM_BM) * (L + 1) + 3u * GEMM_BM * L) * 4 <= static_cast<size_t>(9 - o.out_slot2) * 16384 ? 1 : 0; o.p[3] = m->logvar; o.p[4] = m->eps;
+    o.st[0] = RcStore{static_cast<short>(b.act(m->gml, HW, m->ldgml, B)), 4, static_cast<short>(ceil_div(HW, 64)), 0}; }
+  const int gk = ceil_div(HW, 64);
+  { RcOp& o = b.op(RC_GEMM); o.tm_b = b.w_nn(ea.heads); o.nn = 1; o.n = H; o.kb = gk; o.a_slot = 4; o.tmem_col = 0; }
+  { RcOp& o = b.op(RC_GEMM); o.tm_b = b.w_nn(es.heads); o.nn = 1; o.n = E; o.kb = gk; o.a_slot = 4; o.tmem_col = 256; o.commit = 1; }
+  { RcOp& o = b.op(RC_EPI, EP_DGRAD_ENC);
+    o.e_tmem = 0; o.e_n = H; o.e_tmem2 = 256; o.e_n2 = E; o.out_slot = 0; o.out_slot2 = 8; o.tm_side = tm_pre; o.side_tiles = H / 32;
+    o.n_total = H; o.fscale = io.train ? 1.0f / 0.9f : 1.0f;
+    o.p[0] = wa.bstats[0]; o.p[1] = wa.bits[0];
+    o.st[0] = RcStore{static_cast<short>(b.act(wa.gy[0], H, H, B)), 0, static_cast<short>(hk), 0};
+    o.st[1] = RcStore{static_cast<short>(b.act(wsx.g_x, E, wsx.ld_gx, B)), 2, 1, 0}; }
+  return b.rc;
+}
+
 // The launches of one train step, in order (row-local stretches are collected and issued as chain launches when m->chain_on).
 static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaStream_t st) {
   FwdIO io{};
@@ -1590,6 +1764,44 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   }
   io.tgt_a = a->x_a; io.tgt_b = a->x_b; io.tgt_site = a->site; io.class_w = a->class_weights; io.loss_out = a->loss_out;
   int rc;
+  // ---- row-chain step: ingest + first encoder layer | the on-chip middle | BatchNorm backward + weight gradients | AdamW ----
+  const bool rowchain = rowchain_enabled() && io.fuse_loss && rowchain_fits(m, present_mask(m, io)) && !a->recon_a && !a->recon_b &&
+                        !a->recon_c && !a->mu && !a->logvar && a->batch >= 2;
+  if (rowchain) {
+    io.rc_prefix = true;
+    const bool chain_prev = m->chain_on;
+    m->chain_on = false;                       // the prefix and the suffix are plain launches
+    if ((rc = run_forward(m, io, st))) { m->chain_on = chain_prev; return rc; }
+    RcPlan pl;
+    if ((rc = build_rowchain_plan(m, io, &pl))) { m->chain_on = chain_prev; return rc; }
+    {
+      const char* tl = getenv("VLA_RC_TIMELINE");
+      if (tl && tl[0] == '1') {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (!m->rc_dbg && cap == cudaStreamCaptureStatusNone) {
+          if (cudaMalloc(&m->rc_dbg, sizeof(unsigned long long) * 148 * RC_MAX_OPS * 4) == cudaSuccess)
+            cudaMemset(m->rc_dbg, 0, sizeof(unsigned long long) * 148 * RC_MAX_OPS * 4);
+          else { m->rc_dbg = nullptr; (void)cudaGetLastError(); }
+        }
+        pl.dbg = m->rc_dbg;
+        { const char* ex = getenv("VLA_RC_EXPERIMENT"); pl.pad2 = ex ? atoi(ex) : 0; }   // 1: no MMAs, 2: no weight loads (timing only)
+        if (!m->rc_last) m->rc_last = new RcPlan();
+        *m->rc_last = pl;
+      }
+    }
+    {
+      double fl = 0, by = 0;
+      ProfScope ps(m, st, "rowchain_fwd_bwd", fl, by);
+      cudaError_t e = launch_rowchain(pl, std::min(pl.m_blocks, 148), st);
+      if (e != cudaSuccess) { m->chain_on = chain_prev; return fail(VLA_ERR_CUDA, std::string("row-chain launch: ") + cudaGetErrorString(e)); }
+    }
+    BwdIO bo{};
+    bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false; bo.dp = dp; bo.rc_suffix = true;
+    rc = run_backward(m, bo, st);
+    m->chain_on = chain_prev;
+    if (rc) return rc;
+  } else {
   if ((rc = run_forward(m, io, st))) return rc;
   // ---- loss: values + bf16 gradients for the backward GEMMs (only when it could not be fused) ----
   if (!io.fuse_loss) {
@@ -1624,6 +1836,7 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
   bo.dp = dp;
   if ((rc = run_backward(m, bo, st))) return rc;
+  }
   if (!do_opt) return VLA_OK;
   if (dp) {
     // ---- the step's one collective, second part: the encoder gradients (the decoder part left from run_backward on the
@@ -1799,6 +2012,19 @@ int vla_chain_timeline_read(vla_model_t* m, int which, unsigned long long* out) 
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, c->dev + c->dbg_off, sizeof(unsigned long long) * 8 * CHAIN_MAX_PHASES * c->n_clusters * CHAIN_CLUSTER, cudaMemcpyDeviceToHost));
   return c->n_clusters * CHAIN_CLUSTER;
+}
+
+/* Row-chain timeline (VLA_RC_TIMELINE=1): out[148][32][4] %globaltimer stamps of the last row-chain launch -- per op: GEMM
+ * issue start, all MMAs issued, accumulator ready (element-wise ops: start), epilogue done; kinds[32] / subs[32] = the ops. */
+int vla_rowchain_timeline(vla_model_t* m, unsigned long long* out, int* kinds, int* subs) {
+  if (!m || !out || !m->rc_dbg || !m->rc_last) return fail(VLA_ERR_STATE, "no row-chain timeline (set VLA_RC_TIMELINE=1 before the step)");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, m->rc_dbg, sizeof(unsigned long long) * 148 * RC_MAX_OPS * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < RC_MAX_OPS; ++i) {
+    if (kinds) kinds[i] = i < m->rc_last->n_ops ? m->rc_last->ops[i].kind : 0;
+    if (subs) subs[i] = i < m->rc_last->n_ops ? m->rc_last->ops[i].sub : 0;
+  }
+  return m->rc_last->n_ops;
 }
 
 int vla_profile_begin(vla_model_t* m) {

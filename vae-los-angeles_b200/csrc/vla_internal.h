@@ -340,6 +340,55 @@ size_t chain_smem_bytes();
 int chain_max_clusters(cudaError_t* err);
 cudaError_t launch_chain(const ChainPlan* plan_dev, int n_clusters, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------
+// Row-chain kernel (rowchain.cu): the row-local middle of a directional model's train step with every activation ON CHIP.
+// One CTA owns a 128-row block and runs BatchNorm apply -> heads -> latent -> decoder -> loss -> decoder data gradients ->
+// latent backward -> encoder data gradients as one launch: A operands live in shared memory in the UMMA layout (nine
+// [128 x 64] bf16 slots, written by the epilogue threads themselves), weights stream through a five-slot TMA ring that runs
+// ahead across layers, accumulators live in TMEM (all 512 columns), ReLU / dropout masks travel as bits, the fp32 side
+// inputs (loss targets, BatchNorm pre-activations) arrive as TMA tiles through the same ring, and every tensor the
+// weight-gradient GEMMs need goes to global memory by TMA stores straight from the operand slots.  The plan is a list of ops
+// (kernel parameter); producer, MMA issuer and epilogue warps walk it in lockstep through mbarriers -- no kernel boundary,
+// no cluster barrier, no dependent global load between two layers.
+// ---------------------------------------------------------------------------------------------
+constexpr int RC_MAX_TMAPS = 28;
+constexpr int RC_MAX_OPS = 32;
+enum RcKind : int { RC_LOADA = 1, RC_BNACT, RC_GEMM, RC_EPI };
+enum RcEpiKind : int { EP_LATENT = 1, EP_RELU, EP_LOSS, EP_MASK, EP_LATENT_BWD, EP_DGRAD_ENC };
+struct RcStore { short tm, slot, kb, pad; };   // after the op: TMA-store kb [128 x 64] blocks, slot.. -> tensor map tm, columns 0..
+struct RcOp {
+  int kind, sub;
+  // RC_GEMM / RC_LOADA: B (or the loaded A) = tensor map tm_b; nn = 1: B is MN-major (data gradients read the forward
+  // weight copy); output columns [n0, n0 + n) of the layer in chunks of 128 into TMEM columns tmem_col..; kb k-blocks;
+  // A = slots a_slot.. (hi) and a_lo_slot.. (lo, -1: plain bf16); b_lo = element offset of the lo copy along K.
+  short tm_b, nn, n0, n, kb, a_slot, a_lo_slot, b_lo, tmem_col, commit, wait_lda, pad0;
+  // RC_EPI / RC_BNACT: accumulator columns e_tmem.. (e_n valid), second accumulator e_tmem2 (e_n2); global column of
+  // accumulator column 0 = e_col0; output slots (slot of global column 0): out_slot (hi), out_lo_slot (lo, -1 none),
+  // out_slot2 (second output); side-input tiles [128 x 32] fp32 through the ring: tensor map tm_side, side_tiles of them.
+  short e_tmem, e_tmem2, e_n, e_n2, e_col0, out_slot, out_lo_slot, out_slot2, tm_side, side_tiles, last_loss, relu;
+  RcStore st[3];
+  float fscale; int n_total;               // n_total: width of the whole tensor (mask pitch, validity of the last columns)
+  const void* p[6];
+};
+struct alignas(64) RcPlan {
+  CUtensorMap tm[RC_MAX_TMAPS];
+  RcOp ops[RC_MAX_OPS];
+  int n_ops, n_tm, rows, m_blocks;
+  int n_batches, L, ae, n_enc;
+  const DynParams* dyn; DynParams* dyn_bump;
+  // the BatchNorm layer in front of the heads (RC_BNACT applies it, EP_DGRAD_ENC takes its backward statistics)
+  const float* bn_stats; const float* bn_gamma; const float* bn_beta; float* bn_running_mean; float* bn_running_var;
+  long long* bn_nbt; float* bn_save_mean; float* bn_save_rstd; const unsigned char* bn_keep;
+  int bn_n, bn_m_tiles, train, pad0; float p_drop; int pad1;
+  unsigned long long seed, bn_offset, lat_offset;
+  // loss
+  float* loss_partials; float* kl_partials; unsigned int* counter; float* loss_out; int loss_kind; int pad2;
+  unsigned long long* dbg;                 // optional [CTAs][RC_MAX_OPS][4] %globaltimer stamps
+};
+cudaError_t launch_rowchain(const RcPlan& plan, int n_ctas, cudaStream_t s);
+// fp32 tile map, box [32 columns x 128 rows], 128-byte swizzle (loss targets, BatchNorm pre-activations)
+bool make_tmap_f32_tile(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, std::string* err);
+
 int bn_rows_per_block(int rows, int m_tiles);
 
 // ---------------------------------------------------------------------------------------------

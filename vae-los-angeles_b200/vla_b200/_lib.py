@@ -110,6 +110,7 @@ EXPORTS = {
     "vla_profile_read": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),
     "vla_profile_pause": (C.c_int, [C.c_void_p]),
     "vla_chain_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "vla_rowchain_timeline": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vla_chain_count": (C.c_int, [C.c_void_p]),
     "vla_chain_cached_plans": (C.c_int, [C.c_void_p]),
     "vla_chain_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
