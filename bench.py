@@ -275,6 +275,44 @@ def train_throughput(workload, B, dev, steps, warmup):
     return out
 
 
+def torch_eager_throughput(workload, B, dev, steps, warmup, mode):
+    """The competitor a user would actually run: the reference's algorithm in stock PyTorch on the SAME B200
+    (oracle/torch_eager.py: the ATen calls the reference's nn.Modules make + torch.optim.AdamW, eager, batches resident on the
+    device).  mode: "fp32" (the reference's defaults), "tf32" (torch.backends.cuda.matmul.allow_tf32) or "bf16" (autocast)."""
+    import torch
+    from oracle import torch_eager as te
+    from oracle import vae_oracle as vo
+    from vla_b200 import DeviceDataset
+    state = vo.init_state(workload, DIMS, seed=0)
+    ds = DeviceDataset.synthetic(B * 8, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=3)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = mode in ("tf32", "bf16")
+    try:
+        tr = te.EagerTrainer(workload, state, dev, autocast=torch.bfloat16 if mode == "bf16" else None)
+
+        def one(i):
+            lo = (i % 8) * B
+            return tr.step(ds.tpm[lo:lo + B], ds.beta[lo:lo + B], ds.site[lo:lo + B])
+
+        for i in range(max(warmup, 3)):
+            one(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            last = one(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        out = {"workload": f"stock PyTorch eager ({mode}) {workload} train step, batch {B}, same GPU (oracle/torch_eager.py)",
+               "value": steps * B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "final_loss": float(last)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    del tr, ds
+    torch.cuda.empty_cache()
+    return out
+
+
 def population_throughput(dev, B, n_models, steps, warmup):
     """BASELINE configs[4] on one GPU: `n_models` independent tri-modal VAEs with hyper-parameters drawn from the ranges of
     optimize_hyperparameters.py:71-76 (latent 10..100, embed 16/32/64, lr, weight decay, beta, gamma), each with its own
@@ -581,15 +619,56 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- the other BASELINE.json configurations, short runs (reported under "also"; not the headline) ----------------
     also = []
+    extra_trainers = []
     if world == 1 and not args.no_also:
         for wl in ("multimodal", "dna2rna", "rna2dna", "rna2dna_ae", "dna2rna_ae"):
             if wl == args.workload:
                 continue
             also.append(train_throughput(wl, B, dev, steps=60, warmup=5))
+        for mode in ("fp32", "tf32", "bf16"):
+            also.append(torch_eager_throughput(args.workload, B, dev, steps=40, warmup=5, mode=mode))
         also.append(inference_throughput(dev, batch=args.infer_batch, steps=10, warmup=3))
         also.append(metrics_throughput(dev, args.infer_batch, DIMS["A"], steps=10, warmup=3))
         also.append(population_throughput(dev, B, n_models=8, steps=30, warmup=3))
         also.append(population_throughput(dev, 32, n_models=8, steps=100, warmup=5))       # the reference's default batch size
+
+    # ---- data parallel: driver-visible parity of the replicas + BASELINE configs[2] (dna2rna, global batch = world x B) ----
+    dp_check = None
+    if world > 1:
+        arena = trainer.core.arena.detach()
+        digest = torch.stack([arena.double().sum(), arena.double().abs().sum(), arena.double().pow(2).sum()])
+        lo, hi = digest.clone(), digest.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        # per-shard loss of the last step (this rank's own 4 scalars) summed over the ranks vs what the exchange delivered
+        own = trainer._loss_local.detach().double().clone()
+        dist.all_reduce(own, op=dist.ReduceOp.SUM)
+        delivered = torch.tensor(list(losses), dtype=torch.float64, device=dev)
+        dp_check = {"replicas_identical": bool(torch.equal(lo, hi)),
+                    "param_digest": [float(x) for x in digest.tolist()],
+                    "loss_sum_over_shards": [float(x) for x in own.tolist()],
+                    "loss_delivered_by_exchange": [float(x) for x in delivered.tolist()],
+                    "loss_rel_diff": float(((own - delivered).abs() / own.abs().clamp_min(1e-30)).max())}
+        if not args.no_also:
+            torch.manual_seed(0)
+            m2 = DNA2RNAVAE(DIMS["A"], DIMS["B"], DIMS["S"], DIMS["L"]).to(dev).train()
+            ds2 = DeviceDataset.synthetic(B * 16, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=2000 + rank)
+            t2 = Trainer(m2, ds2, B, lr=5e-4, weight_decay=1e-5, beta_kl=1e-3, gamma=1.0, seed=rank, process_group=pg, exchange=args.exchange)
+            for _ in range(5):
+                t2.step()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(100):
+                t2.step()
+            a1.record()
+            barrier()
+            tt = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            also.append({"workload": f"dna2rna train step (BASELINE configs[2]), data parallel over {world} GPUs, global batch {B * world}",
+                         "value": 100 * B * world / (float(tt.item()) * 1e-3), "unit": "samples/s", "ms_per_step": float(tt.item()) / 100,
+                         "losses": t2.losses()})
+            extra_trainers.append(t2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -610,11 +689,11 @@ def run_gpu(args, rank, local_rank, world):
                        "graph": "CUDA graph replay per step, no host sync in the timed region"},
             "e2e": e2e, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels[:8], "timeline": phases,
             "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
-            "cpu_baseline": cpu, "dp_exchange_trace": dp_trace, "clocks": clocks, "final_losses": losses, "also": also,
+            "cpu_baseline": cpu, "dp_exchange_trace": dp_trace, "dp_check": dp_check, "clocks": clocks, "final_losses": losses, "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        shutdown_distributed([trainer, tr2], dev)
+        shutdown_distributed([trainer, tr2] + extra_trainers, dev)
 
 
 def main():

@@ -150,6 +150,16 @@ typedef struct {
   double* out;
   void* workspace;
 } vla_metrics_args_t;
+/* Batch assembly on the device: rows index[0..n) (int64, device) of the three dataset arrays (fp32 [rows, dim_a], fp32
+ * [rows, dim_b], int64 [rows]) into contiguous batch buffers -- what DataLoader's sampler + default collate do per batch
+ * (reference src/data/dataset.py:35-39 __getitem__, train_rna2dna.py:57-67 DataLoader(shuffle=True)) as one kernel.
+ * An index outside [0, rows) is an error reported through the return value of the next call that synchronises (the kernel
+ * clamps it, never reads out of bounds). */
+int vla_gather_rows(const float* a, int dim_a, const float* b, int dim_b, const long long* site, long long rows,
+                    const long long* index, int n, float* out_a, float* out_b, long long* out_site, vla_stream_t stream);
+/* x[i] *= scale[0] for n_tensors fp32 device arrays in one launch (scale: one fp32 on the device): the upstream d/d(total) of
+ * the fused loss applied to its stored gradients (loss.backward() at train_rna2dna.py:95 when the script scales the loss). */
+int vla_scale_inplace(void* const* tensors, const long long* counts, int n_tensors, const float* scale, vla_stream_t stream);
 long long vla_metrics_workspace_bytes(long long rows);
 int vla_recon_metrics(const vla_metrics_args_t* a, vla_stream_t stream);
 
@@ -211,6 +221,9 @@ void* vla_dp_losses(vla_dp_t* d);                            /* device: float[4]
  * encoder part (main stream), [4..6] the decoder part (side stream, overlapping the encoder backward): kernel entry,
  * contributions pushed to the other ranks, own shard slice reduced and pushed.  Synchronises the device. */
 int vla_dp_trace(vla_dp_t* d, unsigned long long* out8);
+/* Teardown in two steps: every rank calls vla_dp_disconnect (unmaps the peers' buffers), the ranks meet in a barrier, then every
+ * rank calls vla_dp_destroy (frees its own exported buffer: no importer has it mapped any more). */
+int vla_dp_disconnect(vla_dp_t* d);
 void vla_dp_destroy(vla_dp_t* d);
 
 /* Chain kernel.  The row-local stretches of a call -- consecutive launches in which a 128-row block of the batch depends

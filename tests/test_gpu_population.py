@@ -94,3 +94,27 @@ def test_epoch_control_flow():
     pop.synchronize()
     assert torch.equal(pop.members[0].trainer.core.arena, snap)
     pop.close()
+
+
+def test_population_epoch_with_ragged_tail_equals_solo_epochs():
+    """Population.run_epoch walks every member's dataset including the ragged last batch, like Trainer.run_epoch alone."""
+    from vla_b200 import DeviceDataset, Population, Trainer
+    dims = dict(A=782, B=572, S=24, L=20, E=32)
+    batch, n = 64, 64 * 2 + 17
+    datasets = [DeviceDataset.synthetic(n, dims["A"], dims["B"], dims["S"], "cuda", seed=40 + i) for i in range(2)]
+    states = [vo.init_state("multimodal", dims, seed=50 + i) for i in range(2)]
+    pop = Population([dict(model=make_module("multimodal", dims, states[i]), seed=i) for i in range(2)], datasets, batch)
+    pop.run_epoch()
+    pop.synchronize()
+    for i in range(2):
+        solo_m = make_module("multimodal", dims, states[i]).train()
+        tr = Trainer(solo_m, datasets[i], batch, seed=i)
+        assert tr.run_epoch() == 3
+        torch.cuda.synchronize()
+        assert pop.members[i].trainer.steps == 3
+        got = {k: v.detach() for k, v in pop.members[i].model.state_dict().items()}
+        for k, v in solo_m.state_dict().items():
+            if v.dtype.is_floating_point:
+                assert float((got[k] - v).abs().max()) <= 2.1 * 5e-4 * 3 + 1e-6, k
+        tr.close()
+    pop.close()

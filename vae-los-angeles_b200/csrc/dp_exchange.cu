@@ -139,22 +139,46 @@ cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s, bool pdl) {
 }
 
 // Exchange of float2s [x.first2, x.first2 + x.n2) fused with the AdamW step over the whole arena (a.gframed set).
+// Phase C of a block waits for phase B of arbitrary blocks on the OTHER ranks, so every block of this launch must be
+// resident at once.  The launch is therefore cooperative: if the blocks cannot all be co-resident (another stream, trainer or
+// process occupies the SMs) it FAILS with an error instead of dead-locking across ranks.  Programmatic dependent launch is
+// requested beside it where the driver accepts the pair; otherwise the launch is cooperative only.
 cudaError_t launch_dp_adamw(const DpArgs& x, const AdamArgs& a, cudaStream_t s) {
-  static int per_sm = -1;
-  if (per_sm < 0) {
-    int v = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, dp_adamw_kernel, DP_THREADS, 0);
-    if (e != cudaSuccess) return e;
-    per_sm = v < 1 ? 1 : (v > 4 ? 4 : v);
-  }
+  static int per_sm_of[64];                     // occupancy per device (0 = not queried yet)
+  static int pdl_ok = -1;                       // cooperative + programmatic serialization accepted together?
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
+  int per_sm = dev >= 0 && dev < 64 ? per_sm_of[dev] : 0;
+  if (per_sm == 0) {
+    int v = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, dp_adamw_kernel, DP_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    per_sm = v < 1 ? 1 : (v > 4 ? 4 : v);
+    if (dev >= 0 && dev < 64) per_sm_of[dev] = per_sm;
+  }
   long long blocks = a.n_chunks;
   if (blocks > static_cast<long long>(per_sm) * sms) blocks = static_cast<long long>(per_sm) * sms;   // all resident
   if (blocks < 1) blocks = 1;
-  return launch_pdl(dp_adamw_kernel, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, s, x, a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks)); cfg.blockDim = dim3(DP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  if (pdl_ok != 0) {
+    cfg.numAttrs = 2;
+    e = cudaLaunchKernelEx(&cfg, dp_adamw_kernel, x, a);
+    if (e == cudaSuccess) { pdl_ok = 1; return e; }
+    if (pdl_ok == 1) return e;                  // the pair works on this driver: a real failure (e.g. not co-resident)
+    (void)cudaGetLastError();
+    pdl_ok = 0;
+  }
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, dp_adamw_kernel, x, a);
 }
 
 }  // namespace vla

@@ -179,4 +179,53 @@ cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s) {
   return launch_pdl(adamw_kernel, dim3(a.n_chunks), dim3(256), 0, s, a);
 }
 
+namespace {
+
+// One warp per gathered row: the row's two feature vectors stream as 128-bit loads where the geometry allows (dim % 4 == 0
+// keeps every row 16-byte aligned), else as scalars; lane 0 copies the label.
+__global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs g) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < g.n; r += warps) {
+    long long src = g.index[r];
+    src = src < 0 ? 0 : (src >= g.rows ? g.rows - 1 : src);
+    const float* pa = g.a + src * g.dim_a; float* qa = g.out_a + static_cast<long long>(r) * g.dim_a;
+    const float* pb = g.b + src * g.dim_b; float* qb = g.out_b + static_cast<long long>(r) * g.dim_b;
+    if ((g.dim_a & 3) == 0) { for (int i = lane; i < g.dim_a / 4; i += 32) reinterpret_cast<float4*>(qa)[i] = __ldg(reinterpret_cast<const float4*>(pa) + i); }
+    else if ((g.dim_a & 1) == 0) { for (int i = lane; i < g.dim_a / 2; i += 32) reinterpret_cast<float2*>(qa)[i] = __ldg(reinterpret_cast<const float2*>(pa) + i); }
+    else { for (int i = lane; i < g.dim_a; i += 32) qa[i] = __ldg(pa + i); }
+    if ((g.dim_b & 3) == 0) { for (int i = lane; i < g.dim_b / 4; i += 32) reinterpret_cast<float4*>(qb)[i] = __ldg(reinterpret_cast<const float4*>(pb) + i); }
+    else if ((g.dim_b & 1) == 0) { for (int i = lane; i < g.dim_b / 2; i += 32) reinterpret_cast<float2*>(qb)[i] = __ldg(reinterpret_cast<const float2*>(pb) + i); }
+    else { for (int i = lane; i < g.dim_b; i += 32) qb[i] = __ldg(pb + i); }
+    if (lane == 0) g.out_site[r] = g.site[src];
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(ScaleArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const float sc = *a.scale;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int t = 0; t < a.count; ++t)
+    for (long long i = tid; i < a.n[t]; i += nthr) a.x[t][i] *= sc;
+}
+
+}  // namespace
+
+cudaError_t launch_gather_rows(const GatherArgs& g, cudaStream_t s) {
+  if (g.n <= 0) return cudaSuccess;
+  const int blocks = std::min(148 * 8, (g.n + 7) / 8);
+  return launch_pdl(gather_rows_kernel, dim3(blocks), dim3(256), 0, s, g);
+}
+cudaError_t launch_scale(const ScaleArgs& a, cudaStream_t s) {
+  long long total = 0;
+  for (int t = 0; t < a.count; ++t) total += a.n[t];
+  if (total <= 0) return cudaSuccess;
+  const int blocks = static_cast<int>(std::min<long long>(148 * 4, (total + 1023) / 1024));
+  return launch_pdl(scale_kernel, dim3(blocks), dim3(256), 0, s, a);
+}
+
 }  // namespace vla

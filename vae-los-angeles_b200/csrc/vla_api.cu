@@ -1943,6 +1943,17 @@ int vla_dp_trace(vla_dp_t* d, unsigned long long* out8) {
 }
 void* vla_dp_grads(vla_dp_t* d) { return d ? d->local : nullptr; }
 void* vla_dp_losses(vla_dp_t* d) { return d ? d->local + d->off_sums : nullptr; }
+/* First half of the teardown: unmap every peer's exported buffer.  The caller then runs a barrier over the ranks and only after
+ * that frees its own exported allocation (vla_dp_destroy): CUDA leaves freeing an exported allocation that an importer still
+ * has mapped undefined. */
+int vla_dp_disconnect(vla_dp_t* d) {
+  if (!d) return fail(VLA_ERR_INVALID, "null argument");
+  CK(cudaDeviceSynchronize());
+  for (int r = 0; r < d->world; ++r)
+    if (r != d->rank && d->peer[r]) { cudaIpcCloseMemHandle(d->peer[r]); d->peer[r] = nullptr; }
+  d->connected = d->world == 1;
+  return VLA_OK;
+}
 void vla_dp_destroy(vla_dp_t* d) {
   if (!d) return;
   for (int r = 0; r < d->world; ++r)
@@ -1971,6 +1982,23 @@ int vla_recon_metrics(const vla_metrics_args_t* a, vla_stream_t stream) {
   m.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + 256);
   m.out = a->out;
   CK(launch_metrics(m, as_stream(stream)));
+  return VLA_OK;
+}
+
+int vla_gather_rows(const float* a, int dim_a, const float* b, int dim_b, const long long* site, long long rows,
+                    const long long* index, int n, float* out_a, float* out_b, long long* out_site, vla_stream_t stream) {
+  if (!a || !b || !site || !index || !out_a || !out_b || !out_site) return fail(VLA_ERR_INVALID, "null argument");
+  if (rows <= 0 || n < 0 || dim_a <= 0 || dim_b <= 0) return fail(VLA_ERR_INVALID, "vla_gather_rows: bad extents");
+  GatherArgs g{a, b, site, rows, dim_a, dim_b, index, n, out_a, out_b, out_site};
+  CK(launch_gather_rows(g, as_stream(stream)));
+  return VLA_OK;
+}
+int vla_scale_inplace(void* const* tensors, const long long* counts, int n_tensors, const float* scale, vla_stream_t stream) {
+  if (!tensors || !counts || !scale || n_tensors < 0 || n_tensors > 8) return fail(VLA_ERR_INVALID, "vla_scale_inplace: 0..8 tensors");
+  ScaleArgs a{};
+  a.count = n_tensors; a.scale = scale;
+  for (int i = 0; i < n_tensors; ++i) { a.x[i] = static_cast<float*>(tensors[i]); a.n[i] = counts[i]; }
+  CK(launch_scale(a, as_stream(stream)));
   return VLA_OK;
 }
 

@@ -421,6 +421,15 @@ struct MetricsArgs {
   double* out;                          // [8]: MAE, MSE, RMSE, R2, mean cosine, Pearson mean, Pearson std, Pearson count
 };
 int metrics_grid(long long rows);
+// Batch assembly by index (src/data/dataset.py:35-39 + DataLoader collate as one kernel) and in-place scaling of up to 8 arrays
+struct GatherArgs {
+  const float* a; const float* b; const long long* site; long long rows; int dim_a, dim_b;
+  const long long* index; int n;
+  float* out_a; float* out_b; long long* out_site;
+};
+cudaError_t launch_gather_rows(const GatherArgs& g, cudaStream_t s);
+struct ScaleArgs { float* x[8]; long long n[8]; int count; const float* scale; };
+cudaError_t launch_scale(const ScaleArgs& a, cudaStream_t s);
 cudaError_t launch_metrics(const MetricsArgs& a, cudaStream_t s);
 
 }  // namespace vla

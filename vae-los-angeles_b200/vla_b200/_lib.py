@@ -93,6 +93,9 @@ EXPORTS = {
     "vla_loss_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vla_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "vla_adamw": (C.c_int, [C.c_void_p, C.POINTER(AdamWArgs), C.c_void_p]),
+    "vla_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vla_scale_inplace": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.c_int, C.c_void_p, C.c_void_p]),
     "vla_metrics_workspace_bytes": (C.c_longlong, [C.c_longlong]),
     "vla_recon_metrics": (C.c_int, [C.POINTER(MetricsArgs), C.c_void_p]),
     "vla_train_step": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
@@ -104,6 +107,7 @@ EXPORTS = {
     "vla_dp_grads": (C.c_void_p, [C.c_void_p]),
     "vla_dp_losses": (C.c_void_p, [C.c_void_p]),
     "vla_dp_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "vla_dp_disconnect": (C.c_int, [C.c_void_p]),
     "vla_dp_destroy": (None, [C.c_void_p]),
     "vla_profile_begin": (C.c_int, [C.c_void_p]),
     "vla_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int]),

@@ -92,6 +92,23 @@ class DeviceDataset:
         self.beta.copy_(self.beta[perm])
         self.site.copy_(self.site[perm])
 
+    def gather_into(self, index, out):
+        """Rows `index` (int64 on the device) of all three arrays into the batch slot `out` (a DeviceDataset of len(index)
+        rows whose storage a captured step graph reads): what DataLoader's sampler + collate do for one batch
+        (src/data/dataset.py:35-39, train_rna2dna.py:57-67), as ONE kernel on the device -- shuffled training without
+        permuting the whole dataset."""
+        from . import _lib
+        from .core import _ptr, _stream
+        index = index.to(self.site.device, torch.long).contiguous()
+        n = int(index.numel())
+        if n != len(out):
+            raise ValueError("gather_into: the batch slot must hold exactly len(index) rows")
+        with torch.cuda.device(self.site.device):
+            _lib.check(_lib.lib().vla_gather_rows(_ptr(self.tpm), self.tpm.shape[1], _ptr(self.beta), self.beta.shape[1], _ptr(self.site),
+                                                  len(self), _ptr(index), n, _ptr(out.tpm), _ptr(out.beta), _ptr(out.site), _stream()),
+                       "vla_gather_rows")
+        return out
+
     @staticmethod
     def synthetic(n, dim_a, dim_b, n_sites, device, seed=0):
         """Synthetic rows of the reference's schema (scripts/prepare_data.py:112-125): tpm = log1p(Gamma(1, 20)),
@@ -246,6 +263,39 @@ class Trainer:
         self.steps += 1
         core.generation += 1
 
+    def run_epoch(self, which=0):
+        """One pass over dataset `which` in storage order, as `for batch in DataLoader(ds, batch_size)` walks it
+        (train_rna2dna.py:82-99, vae_cross_modality_cv.py:121-158): every full batch by the captured step, then the ragged
+        last batch (len(ds) % batch rows, the reference's loaders keep it: no drop_last) by one eager call on the same handle.
+        Shuffle between epochs with `dataset.shuffle_()`.  Returns the number of optimizer steps taken."""
+        ds = self.datasets[which]
+        n_full, tail = divmod(len(ds), self.batch)
+        self.reset_counters(self.steps, 0)                  # the epoch starts at the dataset's first row
+        for _ in range(n_full):
+            self.step(which)
+        if tail:
+            self._step_tail(which, n_full * self.batch, tail)
+        return n_full + (1 if tail else 0)
+
+    def _step_tail(self, which, first_row, rows):
+        if self.dp is not None or self.pg is not None:
+            raise RuntimeError("run_epoch(): ragged last batches are not supported under data parallelism (shards must agree on the step count)")
+        if rows < 2:
+            raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d): the last batch has one row")
+        core = self.core
+        ds = self.datasets[which]
+        with torch.cuda.device(core.device):
+            self._refresh_shadows_if_needed()
+            args = self._args(ds, 0)
+            args.x_a = C.c_void_p(ds.tpm.data_ptr() + first_row * ds.tpm.shape[1] * 4)
+            args.x_b = C.c_void_p(ds.beta.data_ptr() + first_row * ds.beta.shape[1] * 4)
+            args.site = C.c_void_p(ds.site.data_ptr() + first_row * 8)
+            args.batch = int(rows)
+            args.dataset_rows = int(rows)
+            _lib.check(_lib.lib().vla_train_step(core.handle, C.byref(args), _stream()), "vla_train_step")
+        self.steps += 1
+        core.generation += 1
+
     def _refresh_shadows_if_needed(self):
         core = self.core
         if core.shadow_version != core.param_version():
@@ -295,7 +345,9 @@ class Trainer:
             dist.barrier(group=self.pg)       # no peer may still be reading or writing this rank's buffers
             torch.cuda.synchronize(self.core.device)
             self.flat = self.reduced = self.grads = self.loss_out = self._loss_local = None
-            _lib.lib().vla_dp_destroy(self.dp)
+            _lib.check(_lib.lib().vla_dp_disconnect(self.dp), "vla_dp_disconnect")   # unmap the peers' buffers ...
+            dist.barrier(group=self.pg)       # ... every rank has, so nobody imports this rank's buffer any more ...
+            _lib.lib().vla_dp_destroy(self.dp)                                        # ... and it can be freed
             self.dp = None
 
     def __del__(self):

@@ -82,8 +82,17 @@ class _LossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        g = gout[0]                     # only d/d(total) flows; recon/class/kld entries are reported values
-        gs = [None if t is None else t * g for t in ctx.grads]
+        # only d/d(total) flows (the recon / class / kld entries are reported values): every stored gradient is scaled by it
+        # in place, all tensors in ONE launch of the library (vla_scale_inplace) instead of one ATen multiply per tensor
+        live = [t for t in ctx.grads if t is not None]
+        if live:
+            g = gout.contiguous()
+            L = _lib.lib()
+            ptrs = (C.c_void_p * len(live))(*[t.data_ptr() for t in live])
+            counts = (C.c_longlong * len(live))(*[t.numel() for t in live])
+            with torch.cuda.device(g.device):
+                _lib.check(L.vla_scale_inplace(ptrs, counts, len(live), _ptr(g), _stream()), "vla_scale_inplace")
+        gs = ctx.grads
         return (gs[0], None, gs[1], None, gs[2], None, gs[3], gs[4], None, None, None)
 
 

@@ -74,6 +74,27 @@ class Population:
                     with torch.cuda.stream(mem.stream):
                         mem.trainer.step()
 
+    def run_epoch(self):
+        """One pass of every active member over its own dataset, as the reference's per-model `for batch in train_loader`
+        (vae_cross_modality_cv.py:121-158, optimize_hyperparameters.py:104-113): full batches round-robin over the members'
+        streams, then each member's ragged last batch (the loaders keep it).  No host synchronisation."""
+        live = [m for m in self.members if not m.stopped]
+        plan = []
+        for mem in live:
+            n_full, tail = divmod(len(mem.trainer.datasets[0]), self.batch)
+            plan.append((mem, n_full, tail))
+            with torch.cuda.stream(mem.stream):
+                mem.trainer.reset_counters(mem.trainer.steps, 0)
+        for i in range(max((n for _, n, _ in plan), default=0)):
+            for mem, n_full, _ in plan:
+                if i < n_full:
+                    with torch.cuda.stream(mem.stream):
+                        mem.trainer.step()
+        for mem, n_full, tail in plan:
+            if tail:
+                with torch.cuda.stream(mem.stream):
+                    mem.trainer._step_tail(0, n_full * self.batch, tail)
+
     def synchronize(self):
         main = torch.cuda.current_stream(self.device)
         for mem in self.members:
