@@ -171,3 +171,54 @@ def test_eval_is_stochastic_and_none_inputs():
     assert not torch.equal(o1[0], o2[0])                                  # decoders see a fresh epsilon
     assert o1[0].shape == (16, 50) and o1[1].shape == (16, 36) and o1[2].shape == (16, 5)
     assert float(o1[1].min()) >= 0.0 and float(o1[1].max()) <= 1.0
+
+
+def test_saturated_logits_fused_vs_functional():
+    """for logits beyond +16.6 fp32 sigmoid rounds to exactly 1 and the reference's
+    F.binary_cross_entropy(sigmoid(x), t) clamps log(1 - y) at -100 (loss 100 (1 - t), gradient 0 through the sigmoid); the
+    loss fused into the last decoder layer works on the logit (loss (1 - t) x, gradient y - t).  The functional path follows
+    ATen; this test pins the size of the deliberate difference on columns whose bias is pushed to +30 / -30 (below -27.6
+    ATen's backward floor 1e-12 on y (1 - y) shrinks the reference's gradient), and that nothing else differs."""
+    from src.utils.directional_losses import rna2dna_loss
+    from vla_b200 import DeviceDataset, Trainer
+    kind, dims, n = "rna2dna", dict(A=782, B=572, S=24, L=20, E=32), 64
+    state = vo.init_state(kind, dims, seed=31)
+    bias = state["decoder_dna.fc.4.bias"].copy()
+    bias[:5] = 30.0            # saturated positive
+    bias[5:10] = -30.0         # saturated negative: the loss values agree, the reference's gradient is floored
+    state["decoder_dna.fc.4.bias"] = bias
+    tpm, beta_v, site = vo.synthetic_batch(n, dims, seed=31)
+    eps, masks = vo.synthetic_noise(n, dims, kind, seed=31)
+    inj = dict(eps=to_t(eps), keep_masks=[to_t(v) for v in masks.values()])
+    # fused engine path
+    m1 = make_module(kind, dims, state).train()
+    tr = Trainer(m1, DeviceDataset(tpm, beta_v, site, "cuda"), n, beta_kl=1e-3, use_graph=False)
+    tr.injected = inj
+    tr.forward_backward()
+    torch.cuda.synchronize()
+    fused_total = tr.losses()[0]
+    named = {name: (off, int(np.prod(shape))) for (name, k_, off, shape) in m1._ensure_core().infos if name == "decoder_dna.fc.4.bias"}
+    off, cnt = named["decoder_dna.fc.4.bias"]
+    g_fused = tr.grads[off:off + cnt].cpu().numpy()
+    tr.close()
+    # functional (autograd) path = the reference's arithmetic
+    m2 = make_module(kind, dims, state).train()
+    with m2.inject(**inj):
+        recon, mu, lv = m2(rna=to_t(tpm), site=to_t(site))
+    total, _, _ = rna2dna_loss(recon, to_t(beta_v), mu, lv, beta=1e-3)
+    total.backward()
+    g_func = dict(m2.named_parameters())["decoder_dna.fc.4.bias"].grad.cpu().numpy()
+    t = beta_v[:, :5].astype(np.float64)
+    x = 30.0                                                       # the logit is the bias up to O(1)
+    # functional: 100 (1 - t) and zero gradient; fused: (1 - t) x and gradient sum(1 - t)
+    assert np.all(np.abs(g_func[:5]) < 1e-3)
+    np.testing.assert_allclose(g_fused[:5], (1 - t).sum(0), rtol=2e-2)
+    expected_gap = ((1 - t) * (100.0 - x)).sum()
+    assert abs((float(total) - fused_total) - expected_gap) <= 0.1 * expected_gap
+    # negative saturation (x = -30): y (1 - y) = 9e-14 falls below ATen's backward floor 1e-12, so the reference scales the
+    # gradient by y (1 - y) / 1e-12 = 0.09; the fused path keeps y - t = -t
+    tn = beta_v[:, 5:10].astype(np.float64)
+    np.testing.assert_allclose(g_fused[5:10], -tn.sum(0), rtol=2e-2)
+    assert np.all(np.abs(g_func[5:10]) < 0.2 * np.abs(g_fused[5:10]))
+    # everything that is not saturated agrees
+    np.testing.assert_allclose(g_fused[10:], g_func[10:], rtol=2e-2, atol=2e-2 * np.abs(g_func[10:]).max())
