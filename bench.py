@@ -714,6 +714,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    # stdout carries ONE line (the JSON result): NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) would precede it
+    os.environ["NCCL_DEBUG"] = os.environ.get("VLA_NCCL_DEBUG", "WARN")
     if args.impl == "reference":
         reference_main(args, rank)
         return

@@ -30,7 +30,7 @@ struct PhaseRow {                      // 40 bytes
   long long args_off;
   unsigned short code[CHAIN_MAX_UNITS];
 };
-constexpr int EW_ARG_BYTES = 160;
+constexpr int EW_ARG_BYTES = 176;
 static_assert(sizeof(IngestArgs) <= EW_ARG_BYTES && sizeof(BnActArgs) <= EW_ARG_BYTES && sizeof(BnBwdArgs) <= EW_ARG_BYTES &&
               sizeof(LatentFwdArgs) <= EW_ARG_BYTES && sizeof(LatentBwdArgs) <= EW_ARG_BYTES, "element-wise argument staging");
 struct alignas(16) PhaseImg {

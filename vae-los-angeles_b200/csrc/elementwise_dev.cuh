@@ -213,6 +213,15 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ stats,
 // One block = 64 columns x rows_per_block rows.  scratch: EW_SCRATCH_BYTES of shared memory.
 // MEGA (whole-step kernel): every block stores the saved mean / rstd (identical values), so that a later unit only needs
 // the blocks of its own rows to have finished.
+// bit i of x -> bit 2 i (x < 2^16)
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
 template <bool MEGA>
 __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_block, int bx, int by, int tid, void* scratch) {
   double (*sh)[BN_COLS][2] = reinterpret_cast<double (*)[BN_COLS][2]>(scratch);
@@ -298,6 +307,14 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
     uint32_t* dst = reinterpret_cast<uint32_t*>(a.out + static_cast<size_t>(row) * a.ld_out + col);
     *dst = hi;
     if (a.out_lo > 0) dst[a.out_lo >> 1] = lo;
+    if (a.mask_bits) {
+      // the warp holds 64 consecutive columns of this row (lane = column pair): two 32-bit words of (value > 0) bits
+      const uint32_t be = __ballot_sync(0xffffffffu, y0 > 0.f), bo = __ballot_sync(0xffffffffu, y1 > 0.f);
+      if (lane < 2) {
+        const uint32_t e16 = lane ? (be >> 16) : (be & 0xFFFFu), o16 = lane ? (bo >> 16) : (bo & 0xFFFFu);
+        a.mask_bits[static_cast<size_t>((bx * BN_COLS >> 5) + lane) * a.rows + row] = spread16(e16) | (spread16(o16) << 1);
+      }
+    }
   };
 #pragma unroll
   for (int i = 0; i < PF; ++i) {

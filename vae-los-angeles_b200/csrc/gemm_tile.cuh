@@ -334,6 +334,17 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       }
     }
 
+    // GF_MASK with bit masks: this warp's words (one per chunk, at most 3) travel while the main loop runs
+    uint32_t mbits[3] = {0u, 0u, 0u};
+    const bool bit_mask = (FEATS & GF_MASK) && (P.flags & GF_MASK) && P.mask_bits_in != nullptr;
+    if (bit_mask && row_ok) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int c = half + 2 * k;
+        if (c < n_chunks && n0 + c * 32 < P.N) mbits[k] = __ldcg(P.mask_bits_in + static_cast<size_t>((n0 >> 5) + c) * P.M + row);
+      }
+    }
+
     mbar_wait(acc_bar, ctx.tile_parity);
     tc_fence_after();
     if (et == 0) VLA_STAMP(5);                                     // accumulator ready
@@ -388,7 +399,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       // ---- per-row operands: coalesced loads -> patch -> this thread's row ----
       uint4 mk[4];
       float4 pr[8];
-      const bool mask_fast = (flags & GF_MASK) != 0;     // host side guarantees N % 32 == 0 and 16-byte aligned rows
+      const bool mask_fast = (flags & GF_MASK) != 0 && !bit_mask;     // host side guarantees N % 32 == 0 and 16-byte aligned rows
       const bool pre_fast = (flags & GF_BNSTATS) != 0;
       if (mask_fast) {
 #pragma unroll
@@ -427,7 +438,12 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
         v[j] = __uint_as_float(r[j]) + bv.x;         v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
         v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
       }
-      if (flags & GF_MASK) {                           // ReLU / dropout backward: keep where the saved activation is > 0
+      if (bit_mask) {                                  // ReLU / dropout backward from the forward's (activation > 0) bits
+        const float sc = P.mask_scale;
+        const uint32_t word = my_k == 0 ? mbits[0] : (my_k == 1 ? mbits[1] : mbits[2]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] * sc : 0.f;
+      } else if (flags & GF_MASK) {                    // ... or from the saved bf16 activation itself
         const float sc = P.mask_scale;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -462,6 +478,13 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       if ((flags & GF_RELU) && !(dbgf & 32)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        if (MODE == 0 && P.mask_bits_out != nullptr && nvalid > 0 && row_ok) {
+          // (value > 0) per element as one word per row and 32-column chunk, [chunk][M]: the ReLU mask of the backward
+          uint32_t bits = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f && j < nvalid ? 1u : 0u) << j;
+          P.mask_bits_out[static_cast<size_t>(col0 >> 5) * P.M + row] = bits;
+        }
       }
       const bool bce_fused = (FEATS & GF_LOSS) && (flags & GF_LOSS) && P.loss_kind == LOSS_BCE;
       if ((flags & GF_SIGMOID) && !(dbgf & 32) && !(bce_fused && !(flags & GF_OUT_F32))) {

@@ -621,7 +621,8 @@ int finalize_chain(vla_model* m, GemmGroup& g, int mode) {
     const GemmProblem& p = g.p[i];
     nc[i] = 0;
     // full 32-column chunks wherever the epilogue reads or reduces per-column side inputs; CE needs the whole row in one chunk
-    const bool chunky = (p.flags & (GF_COLSTATS | GF_BNSTATS | GF_MASK)) != 0 || ((p.flags & GF_LOSS) && p.loss_kind == LOSS_CE);
+    const bool chunky = (p.flags & (GF_COLSTATS | GF_BNSTATS | GF_MASK)) != 0 || ((p.flags & GF_LOSS) && p.loss_kind == LOSS_CE) ||
+                        p.mask_bits_out != nullptr;      // (mask words cover whole 32-column chunks)
     const int step = mode == 0 ? (chunky ? 32 : 16) : 64;
     const int cap = mode == 0 ? GEMM_BN_MAX_NT : GEMM_BN_MAX_TN;
     if (g_pending[i].fixed) cand[i][nc[i]++] = p.BN;
@@ -871,6 +872,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
+      a.mask_bits = (bn.n % 64 == 0) ? reinterpret_cast<unsigned int*>(w.bits[r]) : nullptr;
       // train mode needs the statistics of the WHOLE batch: a grid-wide dependency, the stretch ends in front of it
       if (m->chain_on) { if ((rc = chain_add(m, st, CK_BN_ACT, -1, &a, sizeof(a), "bn_act", 0, 6.0 * B * bn.n, a.train != 0))) return rc; }
       else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
@@ -903,6 +905,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     const Lin& l = m->cat;
     if ((rc = add_nt(m, g, m->z, m->ldz, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p, 0, m->z_lo, l.sh_lo))) return rc;
     p->bias = P + l.b_off; p->out_bf16 = m->d0; p->ld_bf16 = m->ld_d0; p->out_lo = m->d0_lo;
+    if (l.out % 32 == 0) p->mask_bits_out = reinterpret_cast<unsigned int*>(m->d0_bits);
     if ((rc = timed_gemm(m, g, 0, "gemm_dec_l0", st))) return rc;
   }
   size_t max_rest = 0;
@@ -942,6 +945,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       } else {
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_bf16 = w.act[r]; p->ld_bf16 = w.ld_act[r]; p->out_lo = w.act_lo[r];
+        if (l.out % 32 == 0) p->mask_bits_out = reinterpret_cast<unsigned int*>(w.bits[r]);
       }
     }
     if (g.nprob) {
@@ -1067,9 +1071,12 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       if (rr == 0) {
         p->mask_src = m->d0 + d.cat_off; p->ld_mask = m->ld_d0;
         p->out_bf16 = m->g_d0 + d.cat_off; p->ld_bf16 = m->cat.out;
+        if (m->cat.out % 32 == 0 && d.cat_off % 32 == 0)       // the forward left (activation > 0) bits, [chunk][B] words
+          p->mask_bits_in = reinterpret_cast<const unsigned int*>(m->d0_bits) + static_cast<size_t>(d.cat_off / 32) * B;
       } else {
         p->mask_src = w.act[rr - 1]; p->ld_mask = w.ld_act[rr - 1];
         p->out_bf16 = w.gact[rr - 1]; p->ld_bf16 = l.in;
+        if (l.in % 32 == 0) p->mask_bits_in = reinterpret_cast<const unsigned int*>(w.bits[rr - 1]);
       }
       p->mask_scale = 1.0f;
     }
@@ -1185,6 +1192,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const size_t tgt = r - 1;                       // gradient w.r.t. act[tgt]
       if ((rc = add_nn(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_MASK | GF_BNSTATS | GF_OUT_BF16, &p))) return rc;
       p->mask_src = w.act[tgt]; p->ld_mask = w.ld_act[tgt]; p->mask_scale = train ? 1.0f / 0.9f : 1.0f;
+      if (l.in % 64 == 0) p->mask_bits_in = reinterpret_cast<const unsigned int*>(w.bits[tgt]);
       p->pre = w.pre[tgt]; p->ld_pre = l.in; p->mean = w.mean[tgt]; p->rstd = w.rstd[tgt];
       p->stats = w.bstats[tgt];
       p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;

@@ -192,6 +192,8 @@ struct BnActArgs {
   float p_drop;
   unsigned long long seed, offset;      // Philox stream for dropout when keep_mask == nullptr
   const struct DynParams* dyn;          // if set, the Philox offset also mixes in dyn->step
+  unsigned int* mask_bits;              // optional: (output > 0) per element as bits, [n / 32][rows] words (needs n % 64 == 0):
+                                        // what the backward's ReLU / dropout mask reads instead of the bf16 activation
 };
 cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s);
 
