@@ -19,6 +19,7 @@ FULL = dict(A=782, B=572, S=24, L=20, E=32)
 def _run(kind, batch, fused, n_steps, phases_only_fb):
     from vla_b200 import DeviceDataset, Trainer
     os.environ["VLA_CHAIN"] = "1" if fused else "0"
+    os.environ["VLA_HEADBLOCK"] = "0"            # like with like: the chain runs these layers as tensor-core tiles too
     try:
         state = vo.init_state(kind, FULL, seed=3)
         tpm, beta_v, site = vo.synthetic_batch(batch * 2, FULL, seed=3)
@@ -41,6 +42,7 @@ def _run(kind, batch, fused, n_steps, phases_only_fb):
         return None, np.array(losses), sd
     finally:
         os.environ.pop("VLA_CHAIN", None)
+        os.environ.pop("VLA_HEADBLOCK", None)
 
 
 @pytest.mark.parametrize("kind,batch", [("rna2dna", 4096), ("rna2dna", 1000), ("dna2rna", 333), ("multimodal", 1500),

@@ -19,6 +19,7 @@ FULL = dict(A=782, B=572, S=24, L=20, E=32)
 def _run(kind, batch, rowchain, n_steps, only_fb, dims=FULL, inject=True):
     from vla_b200 import DeviceDataset, Trainer
     os.environ["VLA_ROWCHAIN"] = "1" if rowchain else "0"      # (opt-in: the default path is the separate launches)
+    os.environ["VLA_HEADBLOCK"] = "0"            # like with like: the row chain runs these layers on the tensor cores too
     try:
         state = vo.init_state(kind, dims, seed=3)
         tpm, beta_v, site = vo.synthetic_batch(batch * 2, dims, seed=3)
@@ -41,6 +42,7 @@ def _run(kind, batch, rowchain, n_steps, only_fb, dims=FULL, inject=True):
         return None, np.array(losses), sd
     finally:
         os.environ.pop("VLA_ROWCHAIN", None)
+        os.environ.pop("VLA_HEADBLOCK", None)
 
 
 @pytest.mark.parametrize("kind,batch,inject", [("rna2dna", 4096, True), ("rna2dna", 1000, True), ("rna2dna", 130, True),

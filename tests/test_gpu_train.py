@@ -78,6 +78,24 @@ def test_fused_train_steps_match_oracle(kind, dims, batch, use_graph):
             assert_close(name, got, ref, 1e-2, atol=1e-6)
 
 
+@pytest.mark.parametrize("kind,dims,batch", [("rna2dna", FULL, 64), ("multimodal", FULL, 200), ("dna2rna", FULL, 40), ("rna2dna_ae", FULL, 64)])
+def test_head_block_train_steps_match_oracle(kind, dims, batch, monkeypatch):
+    """The opt-in head block (VLA_HEADBLOCK=1: BatchNorm apply + heads + latent + first decoder layer, and their backward, as
+    one CUDA-core launch each way, fp32) against the same oracle at the same tolerances."""
+    monkeypatch.setenv("VLA_HEADBLOCK", "1")
+    test_fused_train_steps_match_oracle(kind, dims, batch, False)
+    launches = {}
+    from vla_b200 import DeviceDataset, Trainer
+    m = make_module(kind, dims, vo.init_state(kind, dims, seed=2)).train()
+    ds = DeviceDataset.synthetic(batch * 2, dims["A"], dims["B"], dims["S"], "cuda", seed=1)
+    tr = Trainer(m, ds, batch, use_graph=True)
+    tr.step()
+    for name, ms, fl, by in tr.profile(1):
+        launches[name] = launches.get(name, 0) + 1
+    assert launches.get("head_block_fwd") == 1 and launches.get("head_block_bwd") == 1, launches
+    tr.close()
+
+
 def test_adamw_kernel_fp32():
     """vla_adamw alone (fp32 arithmetic) against the oracle's AdamW: 1e-5 relative on p, and on m, v."""
     from vla_b200 import _lib

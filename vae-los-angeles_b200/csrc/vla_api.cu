@@ -153,6 +153,7 @@ struct vla_model {
   RcPlan* rc_last = nullptr;              // host copy of the last row-chain plan (timeline labels)
   int chain_clusters = 0;                 // 4-CTA clusters of the chain kernel the device runs at once
   int pinned = 0;                         // > 0: captured graphs reference the workspace / plans (vla_model_pin)
+  bool hb_used = false;                   // the last forward ran the head-block kernel (the backward must mirror it)
 };
 
 // Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  Two allocations per rank:
@@ -442,7 +443,7 @@ void carve(vla_model* m, Bump& b, int cap) {
         w.ld_act.push_back(op_ld(m->split, l.out)); w.act_lo.push_back(op_lo(m->split, l.out));
         w.pre.push_back(b.take<float>(static_cast<size_t>(cap) * l.out));
         w.stats.push_back(b.take<float>(static_cast<size_t>(mt) * 2 * l.out));
-        w.bstats.push_back(b.take<float>(static_cast<size_t>(mt) * 2 * l.out));
+        w.bstats.push_back(b.take<float>(static_cast<size_t>(ceil_div(cap, HB_ROWS)) * 2 * l.out));   // (head block: one partial per 32 rows)
         w.mean.push_back(b.take<float>(l.out));
         w.rstd.push_back(b.take<float>(l.out));
         w.act.push_back(b.take<bf16>(static_cast<size_t>(cap) * w.ld_act.back()));
@@ -457,7 +458,7 @@ void carve(vla_model* m, Bump& b, int cap) {
   m->logvar = b.take<float>(static_cast<size_t>(cap) * L);
   m->eps = b.take<float>(static_cast<size_t>(cap) * L);
   m->gz = b.take<float>(static_cast<size_t>(cap) * L);
-  m->kl_partials = b.take<float>(std::max(ceil_div(cap * L, 256), 8 * mt) + 1);
+  m->kl_partials = b.take<float>(std::max(std::max(ceil_div(cap * L, 256), 8 * mt), ceil_div(cap, HB_ROWS)) + 1);
   m->ldz = op_ld(m->split, L); m->z_lo = op_lo(m->split, L); m->z = b.take<bf16>(static_cast<size_t>(cap) * m->ldz);
   m->ldgml = pad8(m->HW); m->gml = b.take<bf16>(static_cast<size_t>(cap) * m->ldgml);
   m->ld_d0 = op_ld(m->split, m->cat.out); m->d0_lo = op_lo(m->split, m->cat.out);
@@ -790,6 +791,64 @@ int run_shadow_refresh(vla_model* m, const float* params, cudaStream_t st) {
   return VLA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head block (headblock.cu): BatchNorm apply of the last hidden layers + heads + latent + fused first decoder layer as one
+// CUDA-core launch (and the mirror-image backward) instead of four / three tensor-core and element-wise launches.
+// ---------------------------------------------------------------------------------------------
+// Opt-in (VLA_HEADBLOCK=1).  Measured (rna2dna, batch 4096, profiles/r2_headblock.md): 11 launches instead of 16, results
+// within the oracle tolerances (fp32 instead of split-bf16 for these layers), but 23 us + 21 us for the two launches against
+// ~30 us of step time for the seven launches they replace: the step takes 135 us instead of 122 us.
+bool headblock_enabled() {
+  const char* e = getenv("VLA_HEADBLOCK");
+  return e && e[0] == '1';
+}
+bool headblock_fits(const vla_model* m, int present) {
+  if (m->HW > 64 || m->L > 64 || (m->E & 3) || m->cat.out > 512 || (m->cat.out & 31)) return false;
+  for (size_t i = 0; i < m->encs.size(); ++i) {
+    if (!(present >> i & 1)) continue;
+    const Enc& e = m->encs[i];
+    if (e.type == 'C') continue;
+    if (e.fc.empty() || e.fc.back().out > 256 || (e.fc.back().out & 63)) return false;
+  }
+  return true;
+}
+int fill_headblock(vla_model* m, HbArgs* a, int B, int present, const float* P, float* buffers, long long* counters, int train,
+                   const unsigned char* const* keep_masks, unsigned long long seed, unsigned long long offset, bool engine,
+                   int n_batches, const long long* site) {
+  memset(static_cast<void*>(a), 0, sizeof(*a));
+  a->rows = B; a->L = m->L; a->HW = m->HW; a->ae = m->ae ? 1 : 0; a->C = m->cat.out; a->n_batches = n_batches; a->p_drop = 0.1f;
+  a->seed = seed; a->lat_offset = offset * 16; a->dyn = m->dyn;
+  (void)engine;
+  const int mt = ceil_div(B, GEMM_BM);
+  for (size_t i = 0; i < m->encs.size(); ++i) {
+    if (!(present >> i & 1)) continue;
+    const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
+    HbEnc& E = a->enc[a->n_enc++];
+    E.Wh = P + e.heads.w_off; E.bh = P + e.heads.b_off;
+    if (e.type == 'C') {
+      E.kind = 1; E.in_dim = m->E; E.site = site; E.emb = P + e.emb_off; E.g_x = w.g_x; E.ld_gx = w.ld_gx;
+    } else {
+      const size_t r = e.fc.size() - 1;
+      const Bn& bn = e.bn[r];
+      E.kind = 0; E.in_dim = bn.n; E.pre = w.pre[r]; E.stats = w.stats[r]; E.m_tiles = mt; E.train = train;
+      E.gamma = P + bn.g_off; E.beta = P + bn.b_off;
+      E.running_mean = buffers ? buffers + bn.rm_off : nullptr; E.running_var = buffers ? buffers + bn.rv_off : nullptr;
+      E.nbt = counters ? counters + bn.counter : nullptr;
+      E.save_mean = w.mean[r]; E.save_rstd = w.rstd[r];
+      E.keep_mask = keep_masks ? keep_masks[e.first_drop + r] : nullptr;
+      E.drop_offset = offset * 16 + 1 + e.first_drop + r;
+      E.act = w.act[r]; E.ld_act = w.ld_act[r]; E.bits = reinterpret_cast<unsigned int*>(w.bits[r]);
+      E.gy = w.gy[r]; E.bstats = w.bstats[r]; E.mask_scale = train ? 1.0f / 0.9f : 1.0f;
+    }
+  }
+  a->mu = m->mu; a->logvar = m->logvar; a->eps_save = m->eps; a->z = m->z; a->ld_z = m->ldz; a->kl_partials = m->kl_partials;
+  a->W0 = P + m->cat.w_off; a->b0 = P + m->cat.b_off; a->d0 = m->d0; a->ld_d0 = m->ld_d0; a->d0_lo = m->d0_lo;
+  a->d0_bits = reinterpret_cast<unsigned int*>(m->d0_bits);
+  a->g_d0 = m->g_d0; a->ld_gd0 = m->cat.out; a->gml = m->gml; a->ld_gml = m->ldgml;
+  if (hb_smem_bytes(*a, false) > 227 * 1024 || hb_smem_bytes(*a, true) > 227 * 1024) return 1;
+  return 0;
+}
+
 int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
   const int B = io.batch, L = m->L;
   if (B <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
@@ -825,6 +884,12 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       else { ProfScope ps(m, st, "ingest", 0, by); CK(launch_ingest(a, st)); } }
   }
   const int mt = ceil_div(B, GEMM_BM);
+  // the small layers around the latent as one CUDA-core launch (headblock.cu)?
+  HbArgs hb;
+  const bool use_hb = headblock_enabled() && !m->chain_on && !io.rc_prefix && headblock_fits(m, present) &&
+                      fill_headblock(m, &hb, B, present, P, io.buffers, io.counters, io.train, io.keep_masks, io.seed, io.offset,
+                                     io.engine, io.n_batches, io.site) == 0;
+  m->hb_used = use_hb;
   // ---- encoders, round by round ----
   size_t max_depth = 0;
   for (size_t i = 0; i < m->encs.size(); ++i) if (present >> i & 1) max_depth = std::max(max_depth, m->encs[i].fc.size());
@@ -842,7 +907,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         const int flags = GF_BIAS | GF_OUT_F32 | (io.train ? GF_COLSTATS : 0);
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_f32 = w.pre[r]; p->ld_f32 = l.out; p->stats = w.stats[r];
-      } else if (r == e.fc.size() && !io.rc_prefix) {
+      } else if (r == e.fc.size() && !io.rc_prefix && !use_hb) {
         const Lin& l = e.heads;
         const bf16* A = r == 0 ? w.x : w.act[r - 1];
         const int lda = r == 0 ? w.ldx : w.ld_act[r - 1];
@@ -861,6 +926,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       if (!(present >> i & 1)) continue;
       const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
       if (r >= e.fc.size()) continue;
+      if (use_hb && r + 1 == e.fc.size()) continue;      // the last hidden layer's BatchNorm apply belongs to the head block
       const Bn& bn = e.bn[r];
       BnActArgs a{};
       a.pre = w.pre[r]; a.ld_pre = bn.n; a.stats = w.stats[r]; a.m_tiles = mt;
@@ -879,7 +945,19 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     }
   }
   // ---- latent ----
-  {
+  if (use_hb) {
+    hb.eps_in = io.eps;
+    if (!io.engine) hb.dyn = nullptr;                    // per-call path: Philox offsets come from the caller, no step counter
+    hb.n_batches = io.engine ? io.n_batches : 1;
+    const double by = static_cast<double>(B) * (m->L * 16.0 + m->cat.out * 4.0);
+    double fl = 0;
+    for (int e = 0; e < hb.n_enc; ++e) fl += 2.0 * B * hb.enc[e].in_dim * m->HW;
+    fl += 2.0 * B * m->L * m->cat.out;
+    { ProfScope ps(m, st, "head_block_fwd", fl, by); CK(launch_head_block_fwd(hb, st)); }
+    m->kl_grid = ceil_div(B, HB_ROWS);
+    if (io.mu) CK(cudaMemcpyAsync(io.mu, m->mu, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+    if (io.logvar) CK(cudaMemcpyAsync(io.logvar, m->logvar, sizeof(float) * B * L, cudaMemcpyDeviceToDevice, st));
+  } else {
     LatentFwdArgs a{};
     for (size_t i = 0; i < m->encs.size(); ++i)
       if (present >> i & 1) { a.ml[a.n_enc] = m->ews[i].ml; a.ld_ml[a.n_enc] = m->HW; a.n_enc++; }
@@ -900,7 +978,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     }
   }
   // ---- decoders ----
-  {
+  if (!use_hb) {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
     if ((rc = add_nt(m, g, m->z, m->ldz, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_RELU | GF_OUT_BF16, &p, 0, m->z_lo, l.sh_lo))) return rc;
@@ -1146,7 +1224,20 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   }
   int n_present = 0;
   for (size_t i = 0; i < m->encs.size(); ++i) n_present += present >> i & 1;
-  if (any_dec && !sfx) {
+  const bool use_hb = m->hb_used && !sfx;
+  if (use_hb) {
+    // ---- head block backward: d(first decoder layer) -> d(mu | logvar) -> d(heads) incl. BatchNorm statistics, one launch ----
+    HbArgs hb;
+    if (fill_headblock(m, &hb, B, present, P, nullptr, nullptr, train, nullptr, 0, 0, io.engine, 1, nullptr))
+      return fail(VLA_ERR_STATE, "head block backward: plan does not fit");
+    hb.has_dec = any_dec ? 1 : 0;
+    hb.gmu_in = io.g_mu; hb.glv_in = io.g_logvar;
+    if (!io.engine) hb.dyn = nullptr;
+    double fl = 2.0 * B * m->L * m->cat.out;
+    for (int e = 0; e < hb.n_enc; ++e) fl += 2.0 * B * hb.enc[e].in_dim * m->HW;
+    { ProfScope ps(m, st, "head_block_bwd", fl, static_cast<double>(B) * (m->cat.out * 2.0 + m->L * 12.0)); CK(launch_head_block_bwd(hb, st)); }
+  }
+  if (any_dec && !sfx && !use_hb) {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
     if ((rc = add_nn(m, g, m->g_d0, l.out, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
@@ -1154,7 +1245,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     if ((rc = timed_gemm(m, g, 2, "dgrad_dec_l0", st))) return rc;
   }
   // ---- latent ----
-  if (!sfx) {
+  if (!sfx && !use_hb) {
     LatentBwdArgs a{};
     a.gz = any_dec ? m->gz : nullptr; a.ld_gz = L;
     a.gmu_in = io.g_mu; a.glv_in = io.g_logvar;
@@ -1177,7 +1268,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
       GemmProblem* p;
       if (e.type == 'C') {
-        if (site_done) continue;
+        if (site_done || use_hb) { site_done = true; continue; }
         const Lin& l = e.heads;
         if ((rc = add_nn(m, g, m->gml, m->ldgml, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_BF16, &p))) return rc;
         p->out_bf16 = w.g_x; p->ld_bf16 = w.ld_gx;
@@ -1186,6 +1277,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       }
       const size_t depth = e.fc.size();
       if (r > depth) continue;
+      if (use_hb && r == depth) { bn_todo.emplace_back(i, r - 1); continue; }      // (the head block wrote gy and the statistics)
       const Lin& l = r == depth ? e.heads : e.fc[r];
       const bf16* A = r == depth ? m->gml : w.gpre[r];
       const int lda = r == depth ? m->ldgml : l.out;
@@ -1203,7 +1295,8 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const Enc& e = m->encs[it.first]; EncWS& w = m->ews[it.first]; const Bn& bn = e.bn[it.second];
       BnBwdArgs a{};
       a.gy = w.gy[it.second]; a.ld_gy = bn.n; a.pre = w.pre[it.second]; a.ld_pre = bn.n;
-      a.stats = w.bstats[it.second]; a.m_tiles = mt;
+      // partial statistics per 128-row GEMM tile, or per 32-row block when the head block produced them
+      a.stats = w.bstats[it.second]; a.m_tiles = (use_hb && it.second + 1 == e.fc.size()) ? ceil_div(B, HB_ROWS) : mt;
       a.mean = w.mean[it.second]; a.rstd = w.rstd[it.second]; a.gamma = P + bn.g_off;
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
@@ -1211,7 +1304,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
     }
   }
-  if (!site_done && !sfx) {
+  if (!site_done && !sfx && !use_hb) {
     for (size_t i = 0; i < m->encs.size(); ++i) {
       if (!(present >> i & 1) || m->encs[i].type != 'C') continue;
       GemmGroup g; init_group(g); GemmProblem* p;

@@ -391,6 +391,49 @@ cudaError_t launch_rowchain(const RcPlan& plan, int n_ctas, cudaStream_t s);
 // fp32 tile map, box [32 columns x 128 rows], 128-byte swizzle (loss targets, BatchNorm pre-activations)
 bool make_tmap_f32_tile(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, std::string* err);
 
+// ---------------------------------------------------------------------------------------------
+// Head block (headblock.cu): the small layers around the latent as ONE launch each way, on the CUDA cores.
+// Forward:  BatchNorm apply + ReLU + dropout of every encoder's last hidden layer -> mu / logvar heads -> mean over the
+//           encoders -> z = mu + eps * exp(logvar / 2), KL partial -> fused first decoder layer (+ ReLU).
+// Backward: first decoder layer's data gradient -> d(mu | logvar) incl. beta * dKL -> heads' data gradients (ReLU / dropout
+//           mask, BatchNorm backward statistics of the row block), site encoder's gradient w.r.t. the embedding rows.
+// These layers have K or N <= 2 * latent: 6-12 k FMA per row.  As tensor-core launches they cost 5-10 us EACH of fixed
+// latency (first operands, accumulator hand-over, epilogue) for 0.1 us of math; here a 32-row block keeps everything in
+// shared memory and registers, fp32 throughout (master weights, no bf16 staging).
+// ---------------------------------------------------------------------------------------------
+constexpr int HB_ROWS = 32;
+constexpr int HB_THREADS = 512;            // 16 warps per 32-row block: the small dot products need the latency hiding
+struct HbEnc {
+  int kind;                       // 0: dense encoder (last hidden layer behind a BatchNorm), 1: site embedding
+  int in_dim;                     // BatchNorm width / embedding dimension (multiple of 4)
+  // kind 0 -- forward
+  const float* pre; const float* stats; int m_tiles; int train;
+  const float* gamma; const float* beta; float* running_mean; float* running_var; long long* nbt;
+  float* save_mean; float* save_rstd; const unsigned char* keep_mask; unsigned long long drop_offset;
+  bf16* act; int ld_act; int pad0; unsigned int* bits;
+  // kind 0 -- backward
+  bf16* gy; float* bstats; float mask_scale; int pad1;
+  // kind 1
+  const long long* site; const float* emb; bf16* g_x; int ld_gx; int pad2;
+  // heads (both kinds): W [HW, in_dim], b [HW] fp32
+  const float* Wh; const float* bh;
+};
+struct HbArgs {
+  HbEnc enc[3];
+  int n_enc, rows, L, HW, ae, C, n_batches, pad0;
+  float p_drop; int pad1;
+  const float* eps_in; unsigned long long seed, lat_offset; const DynParams* dyn;
+  float* mu; float* logvar; float* eps_save; bf16* z; int ld_z; int pad2; float* kl_partials;
+  // fused first decoder layer: W0 [C, L], b0 [C]; forward output d0 (hi | lo) + bits, backward input g_d0 [rows, C]
+  const float* W0; const float* b0; bf16* d0; int ld_d0, d0_lo; unsigned int* d0_bits;
+  const bf16* g_d0; int ld_gd0; int pad3;
+  // backward: upstream d/dmu, d/dlogvar (autograd path, optional), output d(mu | logvar) as bf16 [rows, ld_gml]
+  const float* gmu_in; const float* glv_in; bf16* gml; int ld_gml; int has_dec;
+};
+size_t hb_smem_bytes(const HbArgs& a, bool backward);
+cudaError_t launch_head_block_fwd(const HbArgs& a, cudaStream_t s);
+cudaError_t launch_head_block_bwd(const HbArgs& a, cudaStream_t s);
+
 int bn_rows_per_block(int rows, int m_tiles);
 
 // ---------------------------------------------------------------------------------------------

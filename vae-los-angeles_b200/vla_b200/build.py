@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
-SOURCES = ["gemm_tc.cu", "elementwise.cu", "chain_kernel.cu", "rowchain.cu", "dp_exchange.cu", "metrics.cu", "vla_api.cu"]
+SOURCES = ["gemm_tc.cu", "elementwise.cu", "chain_kernel.cu", "rowchain.cu", "headblock.cu", "dp_exchange.cu", "metrics.cu", "vla_api.cu"]
 OUT = os.path.join(HERE, "libvla_b200.so")
 
 
