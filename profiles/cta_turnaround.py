@@ -45,9 +45,9 @@ def run(M, N, K, bn, flags=0, label=""):
 
 
 if __name__ == "__main__":
-    run(16384, 572, 512, 160, 0, "full kernel")
-    run(16384, 572, 512, 160, 8, "no patch/stores")
-    run(16384, 572, 512, 160, 8 | 16, "no stores, no TMEM loads")
-    run(16384, 572, 512, 160, 1, "no epilogue at all")
-    run(16384, 576, 512, 160, 0, "full kernel, N=576 (no partial chunk)")
+    run(16384, 572, 512, 144, 0, "full kernel")
+    run(16384, 572, 512, 144, 8, "no patch/stores")
+    run(16384, 572, 512, 144, 8 | 16, "no stores, no TMEM loads")
+    run(16384, 572, 512, 144, 1, "no epilogue at all")
+    run(16384, 576, 512, 144, 0, "full kernel, N=576 (no partial chunk)")
     run(16384, 512, 512, 128, 0, "full kernel, N=512 bn=128")

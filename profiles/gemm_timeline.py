@@ -43,8 +43,8 @@ def run(mode, M, N, K, bn, splits=1, reps=5):
 
 if __name__ == "__main__":
     run(0, 4096, 512, 256, 128)
-    run(0, 4096, 572, 512, 160)
+    run(0, 4096, 572, 512, 144)
     run(0, 4096, 128, 782, 32)
     run(0, 4096, 40, 128, 64)
     run(2, 4096, 512, 572, 128)
-    run(1, 572, 512, 4096, 192, 7)
+    run(1, 572, 512, 4096, 128, 7)

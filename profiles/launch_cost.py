@@ -55,12 +55,12 @@ if __name__ == "__main__":
     gemm(0, 128, 32, 64, 32)          # one CTA: fixed cost
     gemm(0, 4096, 32, 64, 32)         # 32 CTAs, trivial work
     gemm(0, 4096, 512, 256, 128)
-    gemm(0, 4096, 572, 512, 160)
+    gemm(0, 4096, 572, 512, 144)
     gemm(0, 4096, 128, 782, 32)
     gemm(0, 4096, 128, 782, 128)
     gemm(2, 4096, 512, 572, 128)
-    gemm(1, 572, 512, 4096, 192, 7)
-    gemm(0, 16384, 572, 512, 160)
-    gemm(0, 65536, 572, 512, 160)
+    gemm(1, 572, 512, 4096, 128, 7)
+    gemm(0, 16384, 572, 512, 144)
+    gemm(0, 65536, 572, 512, 144)
     a = torch.randn(8192, 8192, device="cuda").bfloat16()
     print(f"torch bf16 matmul 4096x512x572-ish: {graph_time(lambda: torch.matmul(a[:4096, :512], a[:512, :576])):.2f} us/launch")

@@ -28,8 +28,8 @@ def _padded(rows, cols, seed):
     return buf, buf[:, :cols]
 
 
-NT_CASES = [(128, 128, 64, 128), (256, 64, 782, 32), (4096, 572, 512, 160), (33, 40, 128, 32), (4096, 128, 782, 32),
-            (100, 448, 20, 64), (4096, 20, 448, 32), (515, 160, 200, 160), (4096, 782, 128, 96), (4096, 572, 512, 128)]
+NT_CASES = [(128, 128, 64, 128), (256, 64, 782, 32), (4096, 572, 512, 144), (33, 40, 128, 32), (4096, 128, 782, 32),
+            (100, 448, 20, 64), (4096, 20, 448, 32), (515, 160, 200, 144), (4096, 782, 128, 96), (4096, 572, 512, 128)]
 
 
 @pytest.mark.parametrize("M,N,K,bn", NT_CASES)
@@ -43,7 +43,7 @@ def test_gemm_nt(M, N, K, bn):
     assert (out - ref).abs().max() < 2e-3 * ref.abs().max() + 1e-3
 
 
-TN_CASES = [(128, 128, 64, 128, 1), (572, 512, 4096, 192, 8), (40, 128, 4096, 128, 4), (448, 20, 4096, 64, 8),
+TN_CASES = [(128, 128, 64, 128, 1), (572, 512, 4096, 128, 8), (40, 128, 4096, 128, 4), (448, 20, 4096, 64, 8),
             (24, 32, 100, 64, 1), (128, 782, 4096, 128, 7), (512, 257, 1000, 128, 3)]
 
 
@@ -60,7 +60,7 @@ def test_gemm_tn_with_bias_grad(M, N, Kb, bn, splits):
     assert berr < 2e-3, float(berr)
 
 
-NN_CASES = [(128, 64, 64, 64), (4096, 128, 40, 128), (4096, 512, 572, 128), (4096, 20, 448, 64), (300, 256, 512, 192),
+NN_CASES = [(128, 64, 64, 64), (4096, 128, 40, 128), (4096, 512, 572, 128), (4096, 20, 448, 64), (300, 256, 512, 128),
             (4096, 32, 40, 64)]
 
 

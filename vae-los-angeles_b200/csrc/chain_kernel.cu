@@ -48,8 +48,9 @@ static_assert(sizeof(LossTail) % 16 == 0 && sizeof(PhaseRow) == 40, "staging cop
 
 constexpr int CH_TABLE_OFFSET = SMEM_USED;
 constexpr int CH_IMG_OFFSET = CH_TABLE_OFFSET + ((CHAIN_MAX_PHASES * static_cast<int>(sizeof(PhaseRow)) + 15) & ~15);
-constexpr int CH_SCRATCH_OFFSET = CH_IMG_OFFSET + 2 * static_cast<int>(sizeof(PhaseImg));   // element-wise scratch behind the images
-constexpr int CH_SMEM_USED = CH_SCRATCH_OFFSET + ((EW_SCRATCH_BYTES + 127) & ~127);
+constexpr int CH_SCRATCH_OFFSET = 0;       // element-wise scratch aliases the first operand slot (no GEMM tile runs in an element-wise phase)
+constexpr int CH_SMEM_USED = CH_IMG_OFFSET + 2 * static_cast<int>(sizeof(PhaseImg));
+static_assert(EW_SCRATCH_BYTES <= STAGE_BYTES, "element-wise scratch aliases one operand slot");
 constexpr int CH_SMEM_BYTES = CH_SMEM_USED + 1024;
 static_assert(CH_SMEM_BYTES <= 227 * 1024, "chain kernel shared memory budget");
 static_assert(CH_IMG_OFFSET % 16 == 0 && sizeof(PhaseImg) % 16 == 0, "phase images are filled by 16-byte asynchronous copies");

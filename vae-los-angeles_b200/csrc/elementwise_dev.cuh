@@ -307,14 +307,6 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
     uint32_t* dst = reinterpret_cast<uint32_t*>(a.out + static_cast<size_t>(row) * a.ld_out + col);
     *dst = hi;
     if (a.out_lo > 0) dst[a.out_lo >> 1] = lo;
-    if (a.mask_bits) {
-      // the warp holds 64 consecutive columns of this row (lane = column pair): two 32-bit words of (value > 0) bits
-      const uint32_t be = __ballot_sync(0xffffffffu, y0 > 0.f), bo = __ballot_sync(0xffffffffu, y1 > 0.f);
-      if (lane < 2) {
-        const uint32_t e16 = lane ? (be >> 16) : (be & 0xFFFFu), o16 = lane ? (bo >> 16) : (bo & 0xFFFFu);
-        a.mask_bits[static_cast<size_t>((bx * BN_COLS >> 5) + lane) * a.rows + row] = spread16(e16) | (spread16(o16) << 1);
-      }
-    }
   };
 #pragma unroll
   for (int i = 0; i < PF; ++i) {

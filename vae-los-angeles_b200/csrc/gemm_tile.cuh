@@ -21,32 +21,33 @@
 namespace vla {
 
 constexpr int A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;                 // 16 KiB
-constexpr int B_STAGE_BYTES = GEMM_BN_MAX_TN * GEMM_BK * 2;          // 24 KiB (>= 160 * 128 B)
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 40 KiB
-constexpr int ONES_OFFSET = GEMM_STAGES * STAGE_BYTES;               // 2 KiB of bf16 1.0
+constexpr int B_STAGE_BYTES = GEMM_BN_MAX_NT * 128;                  // 18 KiB (>= 2 x 8 KiB boxes of the MN-major modes)
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 34 KiB: one SLOT = one k-block of A and B
+constexpr int ONES_OFFSET = GEMM_SLOTS * STAGE_BYTES;                // 2 KiB of bf16 1.0
 constexpr int ONES_BYTES = 2048;
 constexpr int PATCH_LD = 36;                                         // floats; 144-byte rows: 16-byte aligned, conflict-free
 constexpr int CHUNK_OFFSET = 0;                                      // 8 warps x fp32 [32][36] transpose patches: they alias
-constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;                   // pipeline stage 0, which is idle once the accumulator is ready
-constexpr int TGT_OFFSET = STAGE_BYTES;                              // GF_LOSS: per-warp target patches, up to 3 chunks per warp,
-constexpr int TGT_WARP_BYTES = 3 * 32 * PATCH_LD * 4;                // in pipeline stages 1.. (idle once the accumulator is ready)
-constexpr int VEC_OFFSET = ONES_OFFSET + ONES_BYTES;                 // bias | mean | rstd, fp32 [3][192]
-constexpr int VEC_BYTES = 3 * GEMM_BN_MAX_TN * 4;
-constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][6][4][32]
-constexpr int MAX_CHUNKS = GEMM_BN_MAX_TN / 32;
+constexpr int CHUNK_BYTES = 8 * 32 * PATCH_LD * 4;                   // the first slots, idle once the accumulator is ready
+constexpr int TGT_OFFSET = 2 * STAGE_BYTES;                          // GF_LOSS: per-warp target patches, up to 3 chunks per warp,
+constexpr int TGT_WARP_BYTES = 3 * 32 * PATCH_LD * 4;                // in the later slots (idle once the accumulator is ready)
+constexpr int VEC_LD = GEMM_BN_MAX_NT;                               // widest tile of any mode
+constexpr int VEC_OFFSET = ONES_OFFSET + ONES_BYTES;                 // bias | mean | rstd, fp32 [3][VEC_LD]
+constexpr int VEC_BYTES = 3 * VEC_LD * 4;
+constexpr int PART_OFFSET = VEC_OFFSET + VEC_BYTES;                  // column-stat partials fp32 [2][5][4][32]
+constexpr int MAX_CHUNKS = (GEMM_BN_MAX_NT + 31) / 32;
 constexpr int PART_BYTES = 2 * MAX_CHUNKS * 4 * 32 * 4;
-constexpr int BAR_OFFSET = PART_OFFSET + PART_BYTES;                 // mbarriers: full[S] | empty[S] | acc | dep | tmem slot
-constexpr int SMEM_USED = BAR_OFFSET + 128;            // barrier block: 13 mbarriers (the last one: element-wise bulk loads) + slot
+constexpr int BAR_OFFSET = PART_OFFSET + PART_BYTES;                 // mbarriers: full[S] | empty[S] | acc | dep | ew | tmem slot
+constexpr int SMEM_USED = BAR_OFFSET + 128;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                         // slack for manual 1 KiB alignment
 constexpr int EPI_THREADS = GEMM_THREADS - 64;                       // 8 warps
 
-static_assert(B_STAGE_BYTES >= GEMM_BN_MAX_NT * 128, "B stage too small for NT tiles");
-static_assert(CHUNK_BYTES <= STAGE_BYTES, "epilogue patches must fit in one pipeline stage");
-static_assert(TGT_OFFSET + 8 * TGT_WARP_BYTES <= GEMM_STAGES * STAGE_BYTES, "loss-target patches must fit in the idle stages");
-static_assert((GEMM_BN_MAX_NT / 32 + 1) / 2 <= 3, "a warp stages the targets of at most 3 chunks");
+static_assert(GEMM_BN_MAX_TN <= GEMM_BN_MAX_NT && B_STAGE_BYTES >= (GEMM_BN_MAX_TN / 64) * 8192, "B slot too small for the MN-major tiles");
+static_assert(CHUNK_BYTES <= TGT_OFFSET, "epilogue patches and loss-target patches must not overlap");
+static_assert(TGT_OFFSET + 8 * TGT_WARP_BYTES <= GEMM_SLOTS * STAGE_BYTES, "loss-target patches must fit in the idle slots");
+static_assert((GEMM_BN_MAX_NT / 32 + 1 + 1) / 2 <= 3, "a warp stages the targets of at most 3 chunks");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
-static_assert(GEMM_BN_MAX_NT % 32 == 0 && GEMM_BN_MAX_NT <= GEMM_BN_MAX_TN, "tile limits");
+static_assert(GEMM_BN_MAX_NT % 16 == 0 && GEMM_BN_MAX_TN % 64 == 0, "tile limits");
 static_assert((2 * GEMM_STAGES + 3) * 8 + 4 <= 128, "barrier block");
 
 constexpr int FEATS_FWD_PLAIN = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;                      // hidden decoder layers, heads
@@ -205,28 +206,36 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
     // test hook: no main loop, no epilogue
   } else if (warp == 0) {
     // =========================== TMA producer ===========================
+    // A load unit = one k-block of A and B (split operands: the hi or the lo copy of a k-block) = one shared-memory slot.
+    // GEMM_GROUP consecutive units share ONE full / empty barrier pair (one hand-shake).
     if (lane == 0) {
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
-      for (int kv = (split ? 2 : 1) * kb0; kv < (split ? 2 : 1) * kb1; ++kv) {
-        const int kb = split ? (kv >> 1) : kv;
-        const int lo = split ? (kv & 1) : 0;                                   // second slot of a split k-block: the lo copies
+      const int u0 = (split ? 2 : 1) * kb0, u1 = (split ? 2 : 1) * kb1;
+      const int nb = BN >> 6;
+      const uint32_t unit_bytes = A_STAGE_BYTES + (MODE == 0 ? BN * 128 : nb * 8192);
+      for (int ug = u0; ug < u1; ug += GEMM_GROUP) {
+        const int cnt = min(GEMM_GROUP, u1 - ug);
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        const int nb = BN >> 6;
-        mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (MODE == 0 ? BN * 128 : nb * 8192));
-        if (MODE == 1) {
-          tma_load_2d(sa, tmA, &full_bar[stage], m0, kb * GEMM_BK);           // box 64 (M) x 64 (K)
-          tma_load_2d(sa + 8192, tmA, &full_bar[stage], m0 + 64, kb * GEMM_BK);
-        } else {
-          tma_load_2d(sa, tmA, &full_bar[stage], kb * GEMM_BK + (lo ? P.a_lo : 0), m0);   // box 64 (K) x 128 (M)
-        }
-        if (MODE == 0) {
-          tma_load_2d(sb, tmB, &full_bar[stage], kb * GEMM_BK + (lo ? P.b_lo : 0), n0);   // box 64 (K) x BN (N)
-        } else {
-          for (int i = 0; i < nb; ++i)
-            tma_load_2d(sb + i * 8192, tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);   // box 64 (N) x 64 (K)
+        mbar_expect_tx(&full_bar[stage], cnt * unit_bytes);
+        for (int j = 0; j < cnt; ++j) {
+          const int kv = ug + j;
+          const int kb = split ? (kv >> 1) : kv;
+          const int lo = split ? (kv & 1) : 0;                                   // second unit of a split k-block: the lo copies
+          uint8_t* sa = smem + (stage * GEMM_GROUP + j) * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (MODE == 1) {
+            tma_load_2d(sa, tmA, &full_bar[stage], m0, kb * GEMM_BK);           // box 64 (M) x 64 (K)
+            tma_load_2d(sa + 8192, tmA, &full_bar[stage], m0 + 64, kb * GEMM_BK);
+          } else {
+            tma_load_2d(sa, tmA, &full_bar[stage], kb * GEMM_BK + (lo ? P.a_lo : 0), m0);   // box 64 (K) x 128 (M)
+          }
+          if (MODE == 0) {
+            tma_load_2d(sb, tmB, &full_bar[stage], kb * GEMM_BK + (lo ? P.b_lo : 0), n0);   // box 64 (K) x BN (N)
+          } else {
+            for (int i = 0; i < nb; ++i)
+              tma_load_2d(sb + i * 8192, tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);   // box 64 (N) x 64 (K)
+          }
         }
         if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -239,51 +248,45 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       const uint32_t ones_addr = smem_u32(smem + ONES_OFFSET);
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const int u0 = (split ? 2 : 1) * kb0, u1 = (split ? 2 : 1) * kb1;
+      for (int ug = u0; ug < u1; ug += GEMM_GROUP) {
+        const int cnt = min(GEMM_GROUP, u1 - ug);
+        mbar_wait(&full_bar[stage], phase);
+        if (ug == u0) VLA_STAMP(3);                                 // first operands landed
+        tc_fence_after();
         if (split) {
-          // two ring slots per k-block: slot s0 = (A_hi, B_hi), slot s1 = (A_lo, B_lo); three passes of four MMAs
-          const int s0 = stage;
-          mbar_wait(&full_bar[s0], phase);
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-          const int s1 = stage;
-          mbar_wait(&full_bar[s1], phase);
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-          if (kb == kb0) VLA_STAMP(3);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s0 * STAGE_BYTES), b_hi = a_hi + A_STAGE_BYTES;
-          const uint32_t a_lo = smem_u32(smem + s1 * STAGE_BYTES), b_lo = a_lo + A_STAGE_BYTES;
+          // the two slots of the stage = (A_hi, B_hi) and (A_lo, B_lo) of one k-block; three passes of four MMAs
+          const uint32_t a_hi = smem_u32(smem + (stage * GEMM_GROUP) * STAGE_BYTES), b_hi = a_hi + A_STAGE_BYTES;
+          const uint32_t a_lo = a_hi + STAGE_BYTES, b_lo = a_lo + A_STAGE_BYTES;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint32_t pa = pass == 1 ? a_lo : a_hi, pb = pass == 2 ? b_lo : b_hi;
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k)
               umma_bf16(tmem_base, make_smem_desc(pa + k * 32, 16, 1024), make_smem_desc(pb + k * 32, 16, 1024), idesc,
-                        (kb > kb0 || k > 0 || pass > 0) ? 1u : 0u);
+                        (ug > u0 || k > 0 || pass > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s0]);
-          umma_commit(&empty_bar[s1]);
-          continue;
-        }
-        mbar_wait(&full_bar[stage], phase);
-        if (kb == kb0) VLA_STAMP(3);                               // first operands landed
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        } else {
+          for (int j = 0; j < cnt; ++j) {
+            const uint32_t sa = smem_u32(smem + (stage * GEMM_GROUP + j) * STAGE_BYTES);
+            const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          uint64_t adesc, bdesc;
-          if (MODE == 1) adesc = make_smem_desc(sa + k * 2048, 8192, 1024);  // MN-major: +16 K-rows of 128 B
-          else           adesc = make_smem_desc(sa + k * 32, 16, 1024);       // K-major: +16 bf16 of K inside the swizzle atom
-          if (MODE == 0) bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-          else           bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
-          const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
-          if (bias_mma) {
-            const uint64_t odesc = make_smem_desc(ones_addr, 16, 1024);
-            umma_bf16(tmem_base + GEMM_BIAS_TMEM_COL, adesc, odesc, idesc_ones, acc);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              uint64_t adesc, bdesc;
+              if (MODE == 1) adesc = make_smem_desc(sa + k * 2048, 8192, 1024);  // MN-major: +16 K-rows of 128 B
+              else           adesc = make_smem_desc(sa + k * 32, 16, 1024);       // K-major: +16 bf16 of K inside the swizzle atom
+              if (MODE == 0) bdesc = make_smem_desc(sb + k * 32, 16, 1024);
+              else           bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
+              const uint32_t acc = (ug > u0 || j > 0 || k > 0) ? 1u : 0u;
+              umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
+              if (bias_mma) {
+                const uint64_t odesc = make_smem_desc(ones_addr, 16, 1024);
+                umma_bf16(tmem_base + GEMM_BIAS_TMEM_COL, adesc, odesc, idesc_ones, acc);
+              }
+            }
           }
         }
-        umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+        umma_commit(&empty_bar[stage]);   // frees the stage's slots when these MMAs retire
         if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(acc_bar);           // accumulator complete
@@ -311,8 +314,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       const bool ok = col < P.N;
       vec[i] = (ok && (P.flags & GF_BIAS)) ? P.bias[col] : 0.f;
       if (FEATS & GF_BNSTATS) {
-        vec[GEMM_BN_MAX_TN + i] = (ok && (P.flags & GF_BNSTATS)) ? __ldcg(P.mean + col) : 0.f;
-        vec[2 * GEMM_BN_MAX_TN + i] = (ok && (P.flags & GF_BNSTATS)) ? __ldcg(P.rstd + col) : 0.f;
+        vec[VEC_LD + i] = (ok && (P.flags & GF_BNSTATS)) ? __ldcg(P.mean + col) : 0.f;
+        vec[2 * VEC_LD + i] = (ok && (P.flags & GF_BNSTATS)) ? __ldcg(P.rstd + col) : 0.f;
       }
     }
     named_bar_sync(1, EPI_THREADS);
@@ -458,8 +461,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
         if (flags & GF_BNSTATS) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 mv = *reinterpret_cast<const float4*>(vec + GEMM_BN_MAX_TN + c * 32 + j);
-            const float4 rv = *reinterpret_cast<const float4*>(vec + 2 * GEMM_BN_MAX_TN + c * 32 + j);
+            const float4 mv = *reinterpret_cast<const float4*>(vec + VEC_LD + c * 32 + j);
+            const float4 rv = *reinterpret_cast<const float4*>(vec + 2 * VEC_LD + c * 32 + j);
             const float4 pv = pr[j >> 2];
             s2[j] = v[j] * (pv.x - mv.x) * rv.x;         s2[j + 1] = v[j + 1] * (pv.y - mv.y) * rv.y;
             s2[j + 2] = v[j + 2] * (pv.z - mv.z) * rv.z; s2[j + 3] = v[j + 3] * (pv.w - mv.w) * rv.w;
@@ -714,7 +717,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
 
   // ---- every thread: advance the ring position and the tile parity ----
   if (!(dbgf & 2)) {
-    const int s = ctx.stage + (split ? 2 : 1) * (kb1 - kb0);
+    const int units = (split ? 2 : 1) * (kb1 - kb0);
+    const int s = ctx.stage + (units + GEMM_GROUP - 1) / GEMM_GROUP;
     ctx.phase ^= static_cast<uint32_t>(s / GEMM_STAGES) & 1u;
     ctx.stage = s % GEMM_STAGES;
     ctx.tile_parity ^= 1u;

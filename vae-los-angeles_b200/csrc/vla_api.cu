@@ -667,7 +667,14 @@ int finalize_group(vla_model* m, GemmGroup& g, int mode) {
   for (int i = 0; i < n; ++i) {
     nc[i] = 0;
     if (g_pending[i].fixed) { cand[i][nc[i]++] = g.p[i].BN; }
-    else if (mode == 0) { for (int bn = 32; bn <= GEMM_BN_MAX_NT; bn += 32) cand[i][nc[i]++] = bn; }
+    else if (mode == 0) {
+      for (int bn = 32; bn <= GEMM_BN_MAX_NT; bn += 32) cand[i][nc[i]++] = bn;
+      // the widest tile (144 = 4.5 chunks) for problems whose epilogue does not need whole 32-column chunks
+      const GemmProblem& q = g.p[i];
+      const bool chunky = (q.flags & (GF_COLSTATS | GF_BNSTATS | GF_MASK)) != 0 || ((q.flags & GF_LOSS) && q.loss_kind == LOSS_CE) ||
+                          q.mask_bits_out != nullptr;
+      if (!chunky && GEMM_BN_MAX_NT % 32) cand[i][nc[i]++] = GEMM_BN_MAX_NT;
+    }
     else { for (int bn = 64; bn <= GEMM_BN_MAX_TN; bn += 64) cand[i][nc[i]++] = bn; }
     // a width beyond the padded N only wastes MMA columns
     int keep = 0;
@@ -938,7 +945,6 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.keep_mask = io.keep_masks ? io.keep_masks[e.first_drop + r] : nullptr;
       a.rows = B; a.n = bn.n; a.train = io.train; a.update_running = io.train; a.p_drop = 0.1f;
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
-      a.mask_bits = (bn.n % 64 == 0) ? reinterpret_cast<unsigned int*>(w.bits[r]) : nullptr;
       // train mode needs the statistics of the WHOLE batch: a grid-wide dependency, the stretch ends in front of it
       if (m->chain_on) { if ((rc = chain_add(m, st, CK_BN_ACT, -1, &a, sizeof(a), "bn_act", 0, 6.0 * B * bn.n, a.train != 0))) return rc; }
       else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
@@ -1284,7 +1290,6 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       const size_t tgt = r - 1;                       // gradient w.r.t. act[tgt]
       if ((rc = add_nn(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_MASK | GF_BNSTATS | GF_OUT_BF16, &p))) return rc;
       p->mask_src = w.act[tgt]; p->ld_mask = w.ld_act[tgt]; p->mask_scale = train ? 1.0f / 0.9f : 1.0f;
-      if (l.in % 64 == 0) p->mask_bits_in = reinterpret_cast<const unsigned int*>(w.bits[tgt]);
       p->pre = w.pre[tgt]; p->ld_pre = l.in; p->mean = w.mean[tgt]; p->rstd = w.rstd[tgt];
       p->stats = w.bstats[tgt];
       p->out_bf16 = w.gy[tgt]; p->ld_bf16 = l.in;
@@ -2219,6 +2224,7 @@ int vla_test_set_timeline(unsigned long long* dbg) { g_test_dbg = dbg; return VL
 
 int vla_test_gemm(int mode, const void* A, int lda, const void* B, int ldb, float* C, int M, int N, int K, int bn,
                   int k_splits, float* bias_grad, vla_stream_t stream) {
+  if (bn > (mode == 0 ? GEMM_BN_MAX_NT : GEMM_BN_MAX_TN)) return fail(VLA_ERR_INVALID, "vla_test_gemm: tile wider than the kernel's limit (144 NT, 128 TN / NN)");
   static vla_model scratch;   // only its tensor-map cache is used
   GemmGroup g; init_group(g);
   int rc;

@@ -34,9 +34,15 @@ enum LossKind : int { LOSS_NONE = 0, LOSS_MSE = 1, LOSS_BCE = 2, LOSS_CE = 3 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 5;
-constexpr int GEMM_BN_MAX_NT = 160;   // multiple of 16
-constexpr int GEMM_BN_MAX_TN = 192;   // multiple of 64
+// Pipeline: GEMM_STAGES hand-shakes in flight, each covering GEMM_GROUP consecutive 64-wide k-blocks (one shared-memory slot
+// per k-block).  A hand-shake (mbarrier wait -> expect_tx -> TMA issue | mbarrier wait -> MMA issue -> tcgen05.commit) costs
+// ~0.33 us whatever it carries (profiles/r2_rowchain_experiments.md); at one k-block per hand-shake the main loops ran at
+// 40 % tensor occupancy, so a stage carries two (split-bf16 operands: the hi and the lo copy of one k-block).
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_GROUP = 2;
+constexpr int GEMM_SLOTS = GEMM_STAGES * GEMM_GROUP;
+constexpr int GEMM_BN_MAX_NT = 144;   // multiple of 16
+constexpr int GEMM_BN_MAX_TN = 128;   // multiple of 64
 constexpr int GEMM_MAX_PROBLEMS = 16;
 constexpr int GEMM_THREADS = 320;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int GEMM_TMEM_COLS = 256;
@@ -192,8 +198,6 @@ struct BnActArgs {
   float p_drop;
   unsigned long long seed, offset;      // Philox stream for dropout when keep_mask == nullptr
   const struct DynParams* dyn;          // if set, the Philox offset also mixes in dyn->step
-  unsigned int* mask_bits;              // optional: (output > 0) per element as bits, [n / 32][rows] words (needs n % 64 == 0):
-                                        // what the backward's ReLU / dropout mask reads instead of the bf16 activation
 };
 cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s);
 
