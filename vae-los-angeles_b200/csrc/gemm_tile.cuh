@@ -373,10 +373,24 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
         if (nvalid > 0) {
           const float* tp = P.aux0 + (tgt_row0 + rbase) * P.N + col0 + lane;
           const uint32_t dst = smem_u32(tgt_patch + tgt_groups * (32 * PATCH_LD) + lane);
+          if ((P.N & 3) == 0 && (reinterpret_cast<uintptr_t>(P.aux0) & 15) == 0) {
+            // rows are 16-byte aligned: 16-byte copies, eight lanes per row, four rows per instruction (a quarter of the
+            // instructions of the 4-byte path; nvalid is then a multiple of 4)
+            const float* tp16 = P.aux0 + (tgt_row0 + rbase) * P.N + col0 + (lane & 7) * 4;
+            const uint32_t dst16 = smem_u32(tgt_patch + tgt_groups * (32 * PATCH_LD) + (lane >> 3) * PATCH_LD + (lane & 7) * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              const bool ok = rbase + rr < P.M && (lane & 7) * 4 < nvalid;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst16 + i * (4 * PATCH_LD * 4)),
+                           "l"(ok ? tp16 + static_cast<size_t>(rr) * P.N : P.aux0), "r"(ok ? 16 : 0) : "memory");
+            }
+          } else {
 #pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const bool ok = rbase + i < P.M && lane < nvalid;
-            cp_async4_zfill(dst + i * (PATCH_LD * 4), ok ? tp + static_cast<size_t>(i) * P.N : P.aux0, ok ? 4 : 0);
+            for (int i = 0; i < 32; ++i) {
+              const bool ok = rbase + i < P.M && lane < nvalid;
+              cp_async4_zfill(dst + i * (PATCH_LD * 4), ok ? tp + static_cast<size_t>(i) * P.N : P.aux0, ok ? 4 : 0);
+            }
           }
         }
         cp_async_commit();
