@@ -110,22 +110,28 @@ cudaError_t launch_ingest(const IngestArgs& a, cudaStream_t s) {
   return launch_pdl(ingest_kernel, dim3(grid_for(static_cast<long long>(a.rows) * 32, 256, 148 * 8)), dim3(256), 0, s, a);
 }
 
-int bn_rows_per_block(int rows, int m_tiles) {
-  int rpb = 32;
-  if (m_tiles > rpb) rpb = m_tiles;      // keep the per-block re-reduction of the tile partials below the tile's own traffic
-  return rpb;
+// Rows per block of the BatchNorm apply / backward kernels (a block = 64 columns x this many rows).  Every block re-reduces
+// the per-tile statistics of its 64 columns, and the kernels hold 76-112 registers (2-3 blocks of 256 threads per SM), so the
+// grid is sized to ONE wave of about two blocks per SM: wide layers (512 columns = 8 column blocks) get 128-row blocks.
+int bn_rows_per_block(int rows, int m_tiles, int n) {
+  const int col_blocks = (n + BN_COLS - 1) / BN_COLS;
+  long long rpb = (static_cast<long long>(rows) * col_blocks + 2 * 148 - 1) / (2 * 148);
+  rpb = (rpb + 31) / 32 * 32;
+  if (rpb < 32) rpb = 32;
+  if (m_tiles > rpb) rpb = (m_tiles + 31) / 32 * 32;      // keep the per-block re-reduction of the tile partials below the tile's own traffic
+  return static_cast<int>(rpb);
 }
 
 cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s) {
   if (a.n % 2) return cudaErrorInvalidValue;
-  const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0);
+  const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0, a.n);
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
   return launch_pdl(bn_act_kernel, grid, dim3(256), 0, s, a, rpb);
 }
 
 cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {
   if (a.n % 2) return cudaErrorInvalidValue;
-  const int rpb = bn_rows_per_block(a.rows, a.m_tiles);
+  const int rpb = bn_rows_per_block(a.rows, a.m_tiles, a.n);
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
   return launch_pdl(bn_bwd_kernel, grid, dim3(256), 0, s, a, rpb);
 }

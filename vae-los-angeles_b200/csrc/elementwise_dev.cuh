@@ -182,10 +182,10 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ stats,
   const int lane = tid & 31, ty = tid >> 5;
   double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
   if (col_ok) {
-    for (int tb = ty; tb < m_tiles; tb += 64) {       // batches of 8 tiles: 16 independent loads in flight per thread
-      float2 s0[8], s1[8];
+    for (int tb = ty; tb < m_tiles; tb += 32) {       // batches of 4 tiles: 8 independent loads in flight per thread
+      float2 s0[4], s1[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < 4; ++k) {
         const int t = tb + 8 * k;
         s0[k] = s1[k] = make_float2(0.f, 0.f);
         if (t < m_tiles) {
@@ -194,7 +194,7 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ stats,
         }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { a0 += s0[k].x; a1 += s0[k].y; b0 += s1[k].x; b1 += s1[k].y; }
+      for (int k = 0; k < 4; ++k) { a0 += s0[k].x; a1 += s0[k].y; b0 += s1[k].x; b1 += s1[k].y; }
     }
   }
   sh[ty][lane * 2][0] = a0; sh[ty][lane * 2 + 1][0] = a1;

@@ -438,7 +438,7 @@ size_t hb_smem_bytes(const HbArgs& a, bool backward);
 cudaError_t launch_head_block_fwd(const HbArgs& a, cudaStream_t s);
 cudaError_t launch_head_block_bwd(const HbArgs& a, cudaStream_t s);
 
-int bn_rows_per_block(int rows, int m_tiles);
+int bn_rows_per_block(int rows, int m_tiles, int n);
 
 // ---------------------------------------------------------------------------------------------
 // Data-parallel gradient exchange over NVLink peer memory (dp_exchange.cu)
