@@ -154,6 +154,12 @@ struct vla_model {
   int chain_clusters = 0;                 // 4-CTA clusters of the chain kernel the device runs at once
   int pinned = 0;                         // > 0: captured graphs reference the workspace / plans (vla_model_pin)
   bool hb_used = false;                   // the last forward ran the head-block kernel (the backward must mirror it)
+  // Side branch of a train step (single GPU): the decoder weight gradients and the decoder part of AdamW need nothing from
+  // the encoder backward; they run on a low-priority stream beside it (fork after the decoder data gradients, join at the
+  // end of the step; inside a capture the branch becomes a parallel arm of the graph).
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int dec_chunk0 = -1;                    // first AdamW chunk of the decoder parameters (arena order: encoders | decoders)
+  bool side_busy = false;                 // the branch is open: the caller must join it
 };
 
 // Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  Two allocations per rank:
@@ -387,6 +393,7 @@ int build_layout(vla_model* m) {
   // fused first decoder layers: one [sum of first hidden widths, L] matrix
   int cat_w = 0;
   for (const auto& s : ds) cat_w += s.type == 'A' ? 128 : (s.type == 'B' ? 256 : 64);
+  m->dec_chunk0 = static_cast<int>(m->chunks_h.size());     // every chunk from here on belongs to a decoder
   m->cat = ab.linear(cat_w, L, m->split);
   int off = 0;
   for (const auto& s : ds) {
@@ -1097,6 +1104,23 @@ int run_exchange(vla_model* m, vla_dp* dp, long long first2, long long end2, int
   return VLA_OK;
 }
 
+// Side stream of the model (lowest priority: its kernels fill the SMs the main chain leaves idle).  VLA_SIDE=0 turns it off.
+bool side_ready(vla_model* m) {
+  static const bool on = [] { const char* e = getenv("VLA_SIDE"); return !(e && e[0] == '0'); }();
+  if (!on) return false;
+  if (m->side) return true;
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  if (cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (m->side) { cudaStreamDestroy(m->side); m->side = nullptr; }
+    return false;
+  }
+  return true;
+}
+
 struct BwdIO {
   const float* params;
   const float* g_recon[3]; const float* recon_b;   // fp32 upstream gradients (autograd path), may be null
@@ -1106,6 +1130,7 @@ struct BwdIO {
   bool zero_grads;
   vla_dp* dp = nullptr;                            // data parallel: the decoder weight gradients are computed and sent early
   bool rc_suffix = false;                          // row-chain step: only BatchNorm backward of the first layers + weight gradients
+  bool side_dec = false;                           // single GPU engine step: decoder weight gradients on the model's side stream
 };
 
 int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
@@ -1173,7 +1198,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       else if (!active[i])
         CK(cudaMemset2DAsync(m->g_d0 + m->decs[i].cat_off, sizeof(bf16) * m->cat.out, 0, sizeof(bf16) * m->decs[i].cat_w, B, st));
   // Weight-gradient group over the encoder and / or decoder layers (dW = dY^T X, bias gradients by the ones-MMA).
-  auto emit_wgrad = [&](bool enc, bool dec, const char* name, cudaStream_t wst) -> int {
+  auto emit_wgrad = [&](bool enc, bool dec, const char* name, cudaStream_t wst, int max_ctas = 0) -> int {
     GemmGroup g; init_group(g);
     int rc2;
     if (enc) {
@@ -1213,14 +1238,28 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       }
     }
     if (!g.nprob) return VLA_OK;
-    finalize_tn(g, B);
+    int force = 0;
+    if (max_ctas > 0) {       // side branch: leave SMs to the main chain's launches
+      int base = 0;
+      for (int i = 0; i < g.nprob; ++i) base += g.p[i].m_tiles * g.p[i].n_tiles;
+      force = std::max(1, max_ctas / std::max(base, 1));
+    }
+    finalize_tn(g, B, force);
     return timed_gemm(m, g, 1, name, wst);
   };
   // Data parallel: the decoder weight gradients need nothing from the encoder backward.  Compute them now and send them
   // (with the loss scalars, which sit behind them in the flat buffer) on the side stream while the encoder backward runs.
   // (with the chain kernel the decoder data gradients sit in the middle of one launch: no fork point, no early exchange)
-  const bool early_dec = io.dp != nullptr && any_dec && !m->chain_on && dp_overlap(io.dp);
-  if (early_dec) {
+  const bool side_dec = io.dp == nullptr && io.side_dec && any_dec && !m->chain_on && !sfx && side_ready(m);
+  if (side_dec) {
+    CK(cudaEventRecord(m->ev_fork, st));
+    CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+    static const int side_ctas = [] { const char* e = getenv("VLA_SIDE_CTAS"); return e ? atoi(e) : 64; }();
+    if ((rc = emit_wgrad(false, true, "wgrad_dec", m->side, side_ctas))) return rc;
+    m->side_busy = true;
+  }
+  const bool early_dec = side_dec || (io.dp != nullptr && any_dec && !m->chain_on && dp_overlap(io.dp));
+  if (early_dec && !side_dec) {
     vla_dp* dp = io.dp;
     CK(cudaEventRecord(dp->ev_fork, st));
     CK(cudaStreamWaitEvent(dp->side, dp->ev_fork, 0));
@@ -1550,6 +1589,9 @@ void vla_model_destroy(vla_model_t* m) {
   if (m->layout_only) { delete m; return; }
   free_plans(m);
   cudaFree(m->rc_dbg); delete m->rc_last;
+  if (m->side) cudaStreamDestroy(m->side);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   cudaFree(m->shadow); cudaFree(m->chunks_d); cudaFree(m->dyn); cudaFree(m->loss_counter);
   cudaFree(m->ws);
   delete m;
@@ -1630,7 +1672,7 @@ int vla_loss(const vla_loss_args_t* a, vla_stream_t stream) {
 
 static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float* eas, float lr, float b1, float b2,
                      float eps, float wd, int step, bool dyn, bool zero_grad, cudaStream_t st, vla_dp* dp = nullptr,
-                     const DpArgs* fused = nullptr) {
+                     const DpArgs* fused = nullptr, int chunk0 = 0, int n_chunks = -1, const char* name = "adamw") {
   AdamArgs a{};
   a.p = p; a.g = const_cast<float*>(g); a.m = ea; a.v = eas; a.shadow = m->shadow;
   a.gclear = a.g;
@@ -1639,7 +1681,7 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
     a.tail2 = m->n_params / 2;
     a.sums_out = reinterpret_cast<float*>(dp->local + dp->off_sums);
   }
-  a.chunks = m->chunks_d; a.n_chunks = static_cast<int>(m->chunks_h.size());
+  a.chunks = m->chunks_d + chunk0; a.n_chunks = n_chunks >= 0 ? n_chunks : static_cast<int>(m->chunks_h.size()) - chunk0;
   a.lr = lr; a.beta1 = b1; a.beta2 = b2; a.eps = eps; a.weight_decay = wd;
   if (step > 0) {
     a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));
@@ -1651,7 +1693,9 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
     ProfScope ps(m, st, "dp_exchange_adamw", 0, 34.0 * m->n_params + dp_bytes(*fused)); CK(launch_dp_adamw(*fused, a, st));
     return VLA_OK;
   }
-  { ProfScope ps(m, st, "adamw", 0, 34.0 * m->n_params); CK(launch_adamw(a, st)); }
+  double n_el = 0;
+  for (int i = 0; i < a.n_chunks; ++i) n_el += m->chunks_h[chunk0 + i].n;
+  { ProfScope ps(m, st, name, 0, 34.0 * n_el); CK(launch_adamw(a, st)); }
   return VLA_OK;
 }
 
@@ -1940,8 +1984,28 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
-  bo.dp = dp;
+  bo.dp = dp; bo.side_dec = dp == nullptr && m->dec_chunk0 > 0;
   if ((rc = run_backward(m, bo, st))) return rc;
+  }
+  if (m->side_busy) {
+    // the side branch carries the decoder weight gradients; give it the decoder part of AdamW too, then join
+    m->side_busy = false;
+    static const bool side_adam = [] { const char* e = getenv("VLA_SIDE_ADAM"); return e && e[0] == '1'; }();
+    if (!side_adam) {
+      CK(cudaEventRecord(m->ev_join, m->side));
+      CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+      if (!do_opt) return VLA_OK;
+      return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
+                       true, st);
+    }
+    const int nd = static_cast<int>(m->chunks_h.size()) - m->dec_chunk0;
+    if (do_opt && (rc = run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0,
+                                  true, true, m->side, nullptr, nullptr, m->dec_chunk0, nd, "adamw_dec"))) return rc;
+    CK(cudaEventRecord(m->ev_join, m->side));
+    if (do_opt && (rc = run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0,
+                                  true, true, st, nullptr, nullptr, 0, m->dec_chunk0, "adamw_enc"))) return rc;
+    CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+    return VLA_OK;
   }
   if (!do_opt) return VLA_OK;
   if (dp) {
