@@ -203,6 +203,18 @@ int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, f
 /* Resets the device-side step counter (and beta1^t, beta2^t for the bias corrections) and the resident-batch index. */
 int vla_set_step(vla_model_t* m, int completed_steps, int batch_index, float beta1, float beta2, vla_stream_t stream);
 
+/* Lock-step train step of a POPULATION: n independent models of the same kind (any latent / embedding widths, batch sizes,
+ * datasets, hyper-parameters), each with its own vla_train_args_t exactly as for vla_train_step.  Launch j of the step is
+ * issued ONCE for all members (grouped GEMMs: every member's tiles in one grid; the element-wise launches likewise), so
+ * the population's step costs the launch latency of one model's.  Replaces the sequential trial / fold loops of the
+ * reference (optimize_hyperparameters.py:68-133 `objective` called per trial by study.optimize, :101-113 its batch loop;
+ * vae_cross_modality_cv.py:314-344 folds, :136-158 and :219-240 the batch loops of train_vae / train_ae).
+ * Results are bit-identical to n separate vla_train_step calls.  The merged launch tables are cached on models[0] (keyed
+ * by the argument image): the first call with a new combination must happen outside a stream capture.  dp must be NULL;
+ * phases as in vla_train_step. */
+int vla_train_step_group(vla_model_t* const* models, const vla_train_args_t* const* args, int n, vla_stream_t stream);
+int vla_group_cached_plans(vla_model_t* lead);
+
 
 /* Data-parallel gradient exchange over NVLink / NVSwitch peer memory (one process per GPU, one node).  The reference has
  * no distributed code; this replaces what DistributedDataParallel's all-reduce would do around

@@ -118,3 +118,95 @@ def test_population_epoch_with_ragged_tail_equals_solo_epochs():
                 assert float((got[k] - v).abs().max()) <= 2.1 * 5e-4 * 3 + 1e-6, k
         tr.close()
     pop.close()
+
+
+HETERO = [("multimodal", dict(A=782, B=572, S=24, L=10, E=16), 48), ("multimodal", dict(A=782, B=572, S=24, L=100, E=64), 48),
+          ("multimodal", dict(A=782, B=572, S=24, L=37, E=32), 48), ("multimodal", dict(A=782, B=572, S=24, L=64, E=16), 48)]
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_grouped_members_match_oracle(use_graph):
+    """Lock-step population step (vla_train_step_group: one merged launch per step of the sequence) with members of different
+    latent / embedding widths, injected eps and dropout masks: every member against the ORACLE trained alone
+    (optimize_hyperparameters.py:78-113 ranges: latent 10..100, embed 16 / 32 / 64)."""
+    from parity_util import TOL_BF16, assert_close, to_t
+    from vla_b200 import DeviceDataset, Population
+    n_steps, n_batches = 3, 2
+    specs, refs, noise = [], [], []
+    datasets = []
+    for i, (kind, dims, batch) in enumerate(HETERO):
+        state = vo.init_state(kind, dims, seed=60 + i)
+        tpm, beta_v, site = vo.synthetic_batch(batch * n_batches, dims, seed=60 + i)
+        eps, masks = vo.synthetic_noise(batch, dims, kind, seed=60 + i)
+        cw = vo.balanced_class_weights(site, dims["S"])
+        hyper = dict(lr=[1e-3, 3e-4, 5e-4, 2e-3][i], weight_decay=[1e-4, 1e-6, 1e-5, 0.0][i], beta_start=2e-3, gamma=[1.5, 0.7, 1.0, 2.0][i])
+        refs.append((state, _oracle_train_h(kind, dims, state, dict(a=tpm, b=beta_v, site=site), n_steps, batch, eps, masks,
+                                            hyper, cw)))
+        datasets.append(DeviceDataset(tpm, beta_v, site, "cuda"))
+        specs.append(dict(model=make_module(kind, dims, state, device="cpu"), class_weights=to_t(cw), **hyper))
+        noise.append((eps, masks))
+    pop = Population(specs, datasets, HETERO[0][2], use_graph=use_graph)
+    assert pop.grouped
+    for mem, (eps, masks) in zip(pop.members, noise):
+        mem.trainer.injected = dict(eps=to_t(eps), keep_masks=[to_t(v) for v in masks.values()])
+    pop.begin_epoch(50)           # beta = beta_start
+    got_losses = []
+    for _ in range(n_steps):
+        pop.step()
+        got_losses.append(pop.losses())
+    got_losses = np.array(got_losses)                       # [step, member, 4]
+    for i, (state, (ref_state, ref_losses)) in enumerate(refs):
+        np.testing.assert_allclose(got_losses[:, i, :], ref_losses, rtol=TOL_BF16)
+        sd = {k: v.detach().cpu().numpy() for k, v in pop.members[i].model.state_dict().items()}
+        lr = specs[i]["lr"]
+        for name, ref in ref_state.items():
+            got = sd[name]
+            if name.endswith("num_batches_tracked"):
+                assert int(got) == n_steps, name
+            elif name.endswith(("running_mean", "running_var")):
+                assert_close(name, got, ref, TOL_BF16, atol=4 * lr * n_steps * np.sqrt(ref.size))
+            elif is_pre_bn_bias(name):
+                assert np.abs(got - state[name]).max() <= 1.05 * lr * n_steps + 1e-7, name
+            else:
+                delta_ref = ref - state[name].astype(np.float64)
+                delta = got.astype(np.float64) - state[name].astype(np.float64)
+                assert rel_l2(delta, delta_ref) <= 0.2, (i, name, rel_l2(delta, delta_ref))
+    pop.close()
+
+
+def _oracle_train_h(kind, dims, state, data, n_steps, batch, eps, masks, hyper, cw):
+    from parity_util import MATCHED_Q
+    st = {k: (v.astype(np.float64) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
+    opt, step = vo.adamw_init(st)
+    losses = []
+    n_batches = len(data["site"]) // batch
+    for i in range(n_steps):
+        lo = (i % n_batches) * batch
+        b = {k: (v[lo:lo + batch].astype(np.float64) if v.dtype.kind == "f" else v[lo:lo + batch]) for k, v in data.items()}
+        scal, _, _, step = vo.train_step(kind, dims, st, opt, step, b, eps.astype(np.float64), masks, beta=hyper["beta_start"],
+                                         gamma=hyper["gamma"], class_weights=cw.astype(np.float64), q=MATCHED_Q,
+                                         lr=hyper["lr"], weight_decay=hyper["weight_decay"])
+        losses.append([scal["total"], scal["recon"], scal["cls"], scal["kld"]])
+    return st, np.array(losses)
+
+
+def test_grouped_step_bit_identical_to_separate_steps():
+    """vla_train_step_group issues the same tiles / blocks with the same arguments as n separate vla_train_step calls: with
+    injected noise and a single k-split per weight-gradient tile the results agree bit for bit; with split-K red.adds
+    (the normal case) up to summation order."""
+    from vla_b200 import DeviceDataset, Population
+    dims_list = [dict(A=782, B=572, S=24, L=20, E=32), dict(A=782, B=572, S=24, L=50, E=64)]
+    batch = 256
+    for kind in ("rna2dna", "dna2rna_ae"):
+        states = [vo.init_state(kind, d, seed=70 + i) for i, d in enumerate(dims_list)]
+        ds = DeviceDataset.synthetic(batch * 2, 782, 572, 24, "cuda", seed=9)
+        out = {}
+        for grouped in (True, False):
+            pop = Population([dict(model=make_module(kind, d, st, device="cpu"), seed=i) for i, (d, st) in enumerate(zip(dims_list, states))],
+                             ds, batch, grouped=grouped)
+            pop.step(3)
+            out[grouped] = (pop.losses(), [m.trainer.core.arena.clone() for m in pop.members])
+            pop.close()
+        np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-5)
+        for a, b in zip(out[True][1], out[False][1]):
+            assert float((a - b).abs().max()) <= 2.1 * 5e-4 * 3 + 1e-6

@@ -96,6 +96,113 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lock-step population step: the same bodies, one launch for every member (vla_internal.h, "Lock-step population step").
+// ---------------------------------------------------------------------------------------------
+struct MultiSel { int member; int local; int gx; int aux; };
+
+// Finds the member that owns this block and stages its argument structure in shared memory (the tables were written when
+// the plan was built, not by an earlier kernel of the stream: they may be read before griddepcontrol.wait).
+template <typename Args>
+__device__ __forceinline__ const Args& multi_select(const MultiHdr* __restrict__ hdr, const void* __restrict__ args, int stride,
+                                                    int n, MultiSel* sel, uint32_t* stage) {
+  __shared__ MultiSel s_sel;
+  const int bid = static_cast<int>(blockIdx.x);
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const MultiHdr h = hdr[t];
+    const int e = t + 1 < n ? hdr[t + 1].block_begin : 0x7fffffff;
+    if (bid >= h.block_begin && bid < e) { s_sel.member = t; s_sel.local = bid - h.block_begin; s_sel.gx = h.gx; s_sel.aux = h.aux; }
+  }
+  __syncthreads();
+  *sel = s_sel;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const char*>(args) + static_cast<size_t>(sel->member) * stride);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(Args) / 4); i += blockDim.x) stage[i] = src[i];
+  __syncthreads();
+  return *reinterpret_cast<const Args*>(stage);
+}
+#define MULTI_STAGE(Args) __shared__ __align__(16) uint32_t stage[(sizeof(Args) + 15) / 16 * 4]; static_assert(sizeof(Args) % 4 == 0, "argument structures are copied in words")
+
+__global__ void __launch_bounds__(256) ingest_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(IngestArgs);
+  MultiSel sel;
+  const IngestArgs& a = multi_select<IngestArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = sel.local * blockDim.x + threadIdx.x;
+  const int nthr = sel.gx * blockDim.x;                 // gx = blocks of this member
+  ingest_body(a, 0, a.rows, tid >> 5, nthr >> 5, threadIdx.x & 31, sel.local == 0 && threadIdx.x == 0);
+}
+
+__global__ void __launch_bounds__(256) bn_act_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(BnActArgs);
+  MultiSel sel;
+  const BnActArgs& a = multi_select<BnActArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[EW_SCRATCH_BYTES];
+  bn_act_body<false>(a, sel.aux, sel.local % sel.gx, sel.local / sel.gx, threadIdx.x, scratch);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(BnBwdArgs);
+  MultiSel sel;
+  const BnBwdArgs& a = multi_select<BnBwdArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[EW_SCRATCH_BYTES];
+  bn_bwd_body<false>(a, sel.aux, sel.local % sel.gx, sel.local / sel.gx, threadIdx.x, scratch);
+}
+
+__global__ void __launch_bounds__(256) latent_fwd_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(LatentFwdArgs);
+  MultiSel sel;
+  const LatentFwdArgs& a = multi_select<LatentFwdArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[256];
+  latent_fwd_body<false>(a, sel.local, threadIdx.x, scratch);
+}
+
+__global__ void __launch_bounds__(256) latent_bwd_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(LatentBwdArgs);
+  MultiSel sel;
+  const LatentBwdArgs& a = multi_select<LatentBwdArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  latent_bwd_body(a, sel.local, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) loss_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(LossArgs);
+  MultiSel sel;
+  const LossArgs& a = multi_select<LossArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[256 + LOSS_THREADS * 8];
+  loss_body<false>(a, sel.local, sel.gx, threadIdx.x, scratch);
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const MultiHdr* hdr, const void* args, int stride, int n) {
+  MULTI_STAGE(AdamArgs);
+  MultiSel sel;
+  const AdamArgs& a = multi_select<AdamArgs>(hdr, args, stride, n, &sel, stage);
+  pdl_wait();
+  pdl_launch_dependents();
+  adamw_body(a, sel.local, threadIdx.x);
+}
+
+// Appends a launch to the thread's recorder (vla_train_step_group) instead of issuing it.
+template <typename Args>
+bool record_launch(int kind, const Args& a, int blocks, int gx, int aux) {
+  Recorder* r = recorder();
+  if (!r) return false;
+  RecOp op;
+  op.kind = kind; op.blocks = blocks; op.gx = gx; op.aux = aux;
+  op.args.assign(reinterpret_cast<const char*>(&a), sizeof(Args));
+  r->ops.push_back(std::move(op));
+  return true;
+}
+
 inline int grid_for(long long work_items, int threads, int max_blocks) {
   long long b = (work_items + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -107,7 +214,9 @@ inline int grid_for(long long work_items, int threads, int max_blocks) {
 
 cudaError_t launch_ingest(const IngestArgs& a, cudaStream_t s) {
   // one warp per row, 8 warps per block
-  return launch_pdl(ingest_kernel, dim3(grid_for(static_cast<long long>(a.rows) * 32, 256, 148 * 8)), dim3(256), 0, s, a);
+  const int grid = grid_for(static_cast<long long>(a.rows) * 32, 256, 148 * 8);
+  if (record_launch(RK_INGEST, a, grid, grid, 0)) return cudaSuccess;
+  return launch_pdl(ingest_kernel, dim3(grid), dim3(256), 0, s, a);
 }
 
 // Rows per block of the BatchNorm apply / backward kernels (a block = 64 columns x this many rows).  Every block re-reduces
@@ -126,6 +235,7 @@ cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s) {
   if (a.n % 2) return cudaErrorInvalidValue;
   const int rpb = bn_rows_per_block(a.rows, a.train ? a.m_tiles : 0, a.n);
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
+  if (record_launch(RK_BN_ACT, a, grid.x * grid.y, grid.x, rpb)) return cudaSuccess;
   return launch_pdl(bn_act_kernel, grid, dim3(256), 0, s, a, rpb);
 }
 
@@ -133,6 +243,7 @@ cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {
   if (a.n % 2) return cudaErrorInvalidValue;
   const int rpb = bn_rows_per_block(a.rows, a.m_tiles, a.n);
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
+  if (record_launch(RK_BN_BWD, a, grid.x * grid.y, grid.x, rpb)) return cudaSuccess;
   return launch_pdl(bn_bwd_kernel, grid, dim3(256), 0, s, a, rpb);
 }
 
@@ -140,17 +251,21 @@ cudaError_t launch_latent_fwd(const LatentFwdArgs& a, int* grid_out, cudaStream_
   const long long total = static_cast<long long>(a.rows) * a.L;
   const int grid = static_cast<int>((total + 255) / 256);
   if (grid_out) *grid_out = grid;
+  if (record_launch(RK_LATENT_FWD, a, grid, grid, 0)) return cudaSuccess;
   return launch_pdl(latent_fwd_kernel, dim3(grid), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_latent_fwd_rows(const LatentFwdArgs& a, cudaStream_t s) {
   const int blocks = CHAIN_CLUSTER * ((a.rows + CHAIN_ROWS - 1) / CHAIN_ROWS);      // (slices past the last row write a zero partial)
+  if (recorder()) { recorder()->unsupported = true; return cudaErrorNotSupported; }
   return launch_pdl(latent_fwd_rows_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
   const long long total = static_cast<long long>(a.rows) * a.L;
-  return launch_pdl(latent_bwd_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, a);
+  const int grid = static_cast<int>((total + 255) / 256);
+  if (record_launch(RK_LATENT_BWD, a, grid, grid, 0)) return cudaSuccess;
+  return launch_pdl(latent_bwd_kernel, dim3(grid), dim3(256), 0, s, a);
 }
 
 int loss_grid_size(int rows, int width_a, int width_b, int n_sites) {
@@ -168,11 +283,13 @@ cudaError_t launch_loss(const LossArgs& a, cudaStream_t s) {
   const LossGrid g = loss_grid(a);
   int grid = g.nb_a + g.nb_b + g.nb_c + g.nb_k;
   if (grid == 0) grid = 1;   // KL-from-partials only: one block does the final reduction
+  if (record_launch(RK_LOSS, a, grid, grid, 0)) return cudaSuccess;
   return launch_pdl(loss_kernel, dim3(grid), dim3(LOSS_THREADS), 0, s, a);
 }
 
 cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
+  if (recorder()) { recorder()->unsupported = true; return cudaErrorNotSupported; }
   OutGradPack p{};
   p.n = n;
   long long work = 0;
@@ -182,7 +299,32 @@ cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s) {
 
 cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s) {
   if (a.n_chunks <= 0) return cudaSuccess;
+  if (a.gframed == nullptr && record_launch(RK_ADAMW, a, a.n_chunks, a.n_chunks, 0)) return cudaSuccess;
+  if (recorder()) { recorder()->unsupported = true; return cudaErrorNotSupported; }
   return launch_pdl(adamw_kernel, dim3(a.n_chunks), dim3(256), 0, s, a);
+}
+
+Recorder*& recorder() {
+  static thread_local Recorder* r = nullptr;
+  return r;
+}
+
+cudaError_t launch_multi(int kind, int variant, const MultiHdr* hdr, const void* args, int stride, int n, int total_blocks,
+                         cudaStream_t s) {
+  (void)variant;
+  if (n <= 0 || total_blocks <= 0) return cudaSuccess;
+  if (n > MULTI_MAX_MEMBERS) return cudaErrorInvalidValue;
+  const dim3 grid(total_blocks);
+  switch (kind) {
+    case RK_INGEST: return launch_pdl(ingest_multi_kernel, grid, dim3(256), 0, s, hdr, args, stride, n);
+    case RK_BN_ACT: return launch_pdl(bn_act_multi_kernel, grid, dim3(256), 0, s, hdr, args, stride, n);
+    case RK_BN_BWD: return launch_pdl(bn_bwd_multi_kernel, grid, dim3(256), 0, s, hdr, args, stride, n);
+    case RK_LATENT_FWD: return launch_pdl(latent_fwd_multi_kernel, grid, dim3(256), 0, s, hdr, args, stride, n);
+    case RK_LATENT_BWD: return launch_pdl(latent_bwd_multi_kernel, grid, dim3(256), 0, s, hdr, args, stride, n);
+    case RK_LOSS: return launch_pdl(loss_multi_kernel, grid, dim3(LOSS_THREADS), 0, s, hdr, args, stride, n);
+    case RK_ADAMW: return launch_pdl(adamw_multi_kernel, grid, dim3(256), 0, s, hdr, args, stride, n);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 namespace {

@@ -58,6 +58,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
 }
 
+// Lock-step population step: the same tile body, one launch for the groups of n members (tables in global memory).
+template <int MODE, int FEATS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_multi_kernel(const MultiHdr* __restrict__ hdr, const GemmGroup* __restrict__ groups, int n) {
+  __shared__ int s_sel[3];
+  const int bid = static_cast<int>(blockIdx.x);
+  for (int t = threadIdx.x; t < n; t += GEMM_THREADS) {
+    const int b = hdr[t].block_begin;
+    const int e = t + 1 < n ? hdr[t + 1].block_begin : 0x7fffffff;
+    if (bid >= b && bid < e) { s_sel[0] = t; s_sel[1] = bid - b; }
+  }
+  __syncthreads();
+  const GemmGroup& grp = groups[s_sel[0]];
+  const int tile = s_sel[1];
+  if (threadIdx.x < GEMM_MAX_PROBLEMS) {
+    const int i = threadIdx.x;
+    if (i < grp.nprob) {
+      const int b = grp.p[i].tile_begin;
+      const int e = i + 1 < grp.nprob ? grp.p[i + 1].tile_begin : 0x7fffffff;
+      if (tile >= b && tile < e) s_sel[2] = i;
+    }
+  }
+  __syncthreads();
+  const GemmProblem& P = grp.p[s_sel[2]];
+  if (threadIdx.x == 0) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
+  TileCtx ctx = tile_setup(true, true);
+  pdl_wait();
+  pdl_launch_dependents();
+  {
+    const int local = tile - P.tile_begin;
+    const int n_tile = local % P.n_tiles, rest = local / P.n_tiles;
+    gemm_tile<MODE, FEATS>(ctx, P, &P.tmA, &P.tmB, rest % P.m_tiles, n_tile, rest / P.m_tiles, &grp.tail);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    tmem_dealloc(ctx.tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 size_t gemm_smem_bytes() { return SMEM_BYTES; }
@@ -69,30 +109,73 @@ cudaError_t launch_one(const GemmGroup& g, cudaStream_t stream, size_t smem) {
   return launch_pdl(gemm_tc_kernel<MODE, FEATS>, dim3(g.total_tiles), dim3(GEMM_THREADS), smem, stream, g);
 }
 
-cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream) {
-  if (g.total_tiles <= 0) return cudaSuccess;
+template <int MODE, int FEATS>
+cudaError_t launch_one_multi(const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, cudaStream_t stream) {
+  static cudaError_t attr = cudaFuncSetAttribute(gemm_tc_multi_kernel<MODE, FEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (attr != cudaSuccess) return attr;
+  return launch_pdl(gemm_tc_multi_kernel<MODE, FEATS>, dim3(total_blocks), dim3(GEMM_THREADS), static_cast<size_t>(SMEM_BYTES), stream,
+                    hdr, groups, n);
+}
+
+// Which instantiation of the tile body a group runs: mode * 16 + {0 plain, 1 full, 2 loss (any mix), 3 BCE only, 4 MSE only}.
+int gemm_variant(const GemmGroup& g, int mode) {
   int used = 0;
   for (int i = 0; i < g.nprob; ++i) used |= g.p[i].flags;
-  size_t smem = SMEM_BYTES;
-  if (g.dbg_flags & 0xFFFF00) smem = static_cast<size_t>(g.dbg_flags >> 8);   // test hook (only valid with dbg_flags & 2)
   if (mode == 0) {
-    if (!(used & ~FEATS_FWD_PLAIN)) return launch_one<0, FEATS_FWD_PLAIN>(g, stream, smem);
+    if (!(used & ~FEATS_FWD_PLAIN)) return 0;
     if (used & GF_LOSS) {
-      if (used & ~FEATS_FWD_LOSS) return cudaErrorInvalidValue;
+      if (used & ~FEATS_FWD_LOSS) return -1;
       int kinds = 0;
       for (int i = 0; i < g.nprob; ++i) kinds |= (g.p[i].flags & GF_LOSS) ? 1 << g.p[i].loss_kind : 1 << LOSS_NONE;
       // uniform groups run the epilogue that contains only their loss kind (about half the code of the generic one)
-      if (kinds == 1 << LOSS_BCE && !(used & ~FEATS_FWD_LOSS_BCE)) return launch_one<0, FEATS_FWD_LOSS_BCE>(g, stream, smem);
-      if (kinds == 1 << LOSS_MSE && !(used & ~FEATS_FWD_LOSS_MSE)) return launch_one<0, FEATS_FWD_LOSS_MSE>(g, stream, smem);
-      return launch_one<0, FEATS_FWD_LOSS>(g, stream, smem);
+      if (kinds == 1 << LOSS_BCE && !(used & ~FEATS_FWD_LOSS_BCE)) return 3;
+      if (kinds == 1 << LOSS_MSE && !(used & ~FEATS_FWD_LOSS_MSE)) return 4;
+      return 2;
     }
-    return launch_one<0, FEATS_FWD_FULL>(g, stream, smem);
+    return 1;
   }
-  if (mode == 2) {
-    if (!(used & ~FEATS_DGRAD_PLAIN)) return launch_one<2, FEATS_DGRAD_PLAIN>(g, stream, smem);
-    return launch_one<2, FEATS_DGRAD_FULL>(g, stream, smem);
+  if (mode == 2) return 32 + ((used & ~FEATS_DGRAD_PLAIN) ? 1 : 0);
+  return 16;
+}
+
+#define VLA_GEMM_DISPATCH(variant, CALL)                                    \
+  switch (variant) {                                                        \
+    case 0: return CALL(0, FEATS_FWD_PLAIN);                                \
+    case 1: return CALL(0, FEATS_FWD_FULL);                                 \
+    case 2: return CALL(0, FEATS_FWD_LOSS);                                 \
+    case 3: return CALL(0, FEATS_FWD_LOSS_BCE);                             \
+    case 4: return CALL(0, FEATS_FWD_LOSS_MSE);                             \
+    case 16: return CALL(1, FEATS_WGRAD);                                   \
+    case 32: return CALL(2, FEATS_DGRAD_PLAIN);                             \
+    case 33: return CALL(2, FEATS_DGRAD_FULL);                              \
+    default: return cudaErrorInvalidValue;                                  \
   }
-  return launch_one<1, FEATS_WGRAD>(g, stream, smem);
+
+cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream) {
+  if (g.total_tiles <= 0) return cudaSuccess;
+  const int variant = gemm_variant(g, mode);
+  if (variant < 0) return cudaErrorInvalidValue;
+  if (Recorder* r = recorder()) {          // lock-step population step: collect, do not launch
+    if (g.dbg || g.dbg_flags) { r->unsupported = true; return cudaErrorNotSupported; }
+    RecOp op;
+    op.kind = RK_GEMM; op.variant = variant; op.blocks = g.total_tiles; op.gx = g.total_tiles;
+    op.args.assign(reinterpret_cast<const char*>(&g), sizeof(GemmGroup));
+    r->ops.push_back(std::move(op));
+    return cudaSuccess;
+  }
+  size_t smem = SMEM_BYTES;
+  if (g.dbg_flags & 0xFFFF00) smem = static_cast<size_t>(g.dbg_flags >> 8);   // test hook (only valid with dbg_flags & 2)
+#define VLA_CALL_ONE(M_, F_) launch_one<M_, F_>(g, stream, smem)
+  VLA_GEMM_DISPATCH(variant, VLA_CALL_ONE)
+#undef VLA_CALL_ONE
+}
+
+cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, cudaStream_t stream) {
+  if (n <= 0 || total_blocks <= 0) return cudaSuccess;
+  if (n > MULTI_MAX_MEMBERS) return cudaErrorInvalidValue;
+#define VLA_CALL_MULTI(M_, F_) launch_one_multi<M_, F_>(hdr, groups, n, total_blocks, stream)
+  VLA_GEMM_DISPATCH(variant, VLA_CALL_MULTI)
+#undef VLA_CALL_MULTI
 }
 
 // ---------------------------------------------------------------------------------------------

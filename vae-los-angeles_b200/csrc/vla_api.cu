@@ -108,6 +108,15 @@ struct ChainPlanCached {
   std::vector<std::string> phase_names;
 };
 
+// One cached lock-step step of a population: for launch j the table [MultiHdr n | argument structures n x stride].  Keyed
+// by the host image (a replayed or re-captured step presents the same image).  Never freed before the leading model.
+struct GroupPlanCached {
+  std::string key;
+  char* dev = nullptr;
+  struct Launch { int kind, variant, stride, n, total_blocks; size_t hdr_off, args_off; };
+  std::vector<Launch> launches;
+};
+
 struct vla_model {
   bool layout_only = false;
   bool prof_on = false;
@@ -160,6 +169,8 @@ struct vla_model {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int dec_chunk0 = -1;                    // first AdamW chunk of the decoder parameters (arena order: encoders | decoders)
   bool side_busy = false;                 // the branch is open: the caller must join it
+  // lock-step population steps led by this model (vla_train_step_group): device images of the merged launch tables
+  std::vector<struct GroupPlanCached*> group_plans;
 };
 
 // Peer-memory gradient exchange of one data-parallel trainer (dp_exchange.cu).  Two allocations per rank:
@@ -813,6 +824,7 @@ int run_shadow_refresh(vla_model* m, const float* params, cudaStream_t st) {
 // within the oracle tolerances (fp32 instead of split-bf16 for these layers), but 23 us + 21 us for the two launches against
 // ~30 us of step time for the seven launches they replace: the step takes 135 us instead of 122 us.
 bool headblock_enabled() {
+  if (recorder()) return false;         // lock-step population steps run the separate launches
   const char* e = getenv("VLA_HEADBLOCK");
   return e && e[0] == '1';
 }
@@ -1250,7 +1262,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   // Data parallel: the decoder weight gradients need nothing from the encoder backward.  Compute them now and send them
   // (with the loss scalars, which sit behind them in the flat buffer) on the side stream while the encoder backward runs.
   // (with the chain kernel the decoder data gradients sit in the middle of one launch: no fork point, no early exchange)
-  const bool side_dec = io.dp == nullptr && io.side_dec && any_dec && !m->chain_on && !sfx && side_ready(m);
+  const bool side_dec = io.dp == nullptr && io.side_dec && any_dec && !m->chain_on && !sfx && !recorder() && side_ready(m);
   if (side_dec) {
     CK(cudaEventRecord(m->ev_fork, st));
     CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
@@ -1588,6 +1600,7 @@ void vla_model_destroy(vla_model_t* m) {
   if (!m) return;
   if (m->layout_only) { delete m; return; }
   free_plans(m);
+  for (GroupPlanCached* g : m->group_plans) { cudaFree(g->dev); delete g; }
   cudaFree(m->rc_dbg); delete m->rc_last;
   if (m->side) cudaStreamDestroy(m->side);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -1915,7 +1928,7 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   io.tgt_a = a->x_a; io.tgt_b = a->x_b; io.tgt_site = a->site; io.class_w = a->class_weights; io.loss_out = a->loss_out;
   int rc;
   // ---- row-chain step: ingest + first encoder layer | the on-chip middle | BatchNorm backward + weight gradients | AdamW ----
-  const bool rowchain = rowchain_enabled() && io.fuse_loss && rowchain_fits(m, present_mask(m, io)) && !a->recon_a && !a->recon_b &&
+  const bool rowchain = !recorder() && rowchain_enabled() && io.fuse_loss && rowchain_fits(m, present_mask(m, io)) && !a->recon_a && !a->recon_b &&
                         !a->recon_c && !a->mu && !a->logvar && a->batch >= 2;
   if (rowchain) {
     io.rc_prefix = true;
@@ -2040,6 +2053,106 @@ int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t strea
   if (rc) return rc;
   return cs.finish(st);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Lock-step population step
+// ---------------------------------------------------------------------------------------------
+int vla_train_step_group(vla_model_t* const* ms, const vla_train_args_t* const* as, int n, vla_stream_t stream) {
+  if (!ms || !as || n <= 0) return fail(VLA_ERR_INVALID, "vla_train_step_group: null argument");
+  if (n > MULTI_MAX_MEMBERS) return fail(VLA_ERR_INVALID, "vla_train_step_group: at most " + std::to_string(MULTI_MAX_MEMBERS) + " members per call");
+  cudaStream_t st = as_stream(stream);
+  // ---- record every member's launches (nothing is issued) ----
+  std::vector<Recorder> recs(n);
+  for (int i = 0; i < n; ++i) {
+    vla_model_t* m = ms[i]; const vla_train_args_t* a = as[i];
+    if (!m || !a || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->buffers || !a->loss_out)
+      return fail(VLA_ERR_INVALID, "vla_train_step_group: null argument (member " + std::to_string(i) + ")");
+    if (a->dp) return fail(VLA_ERR_INVALID, "vla_train_step_group: members are independent models (no data-parallel exchange)");
+    if (m->prof_on) return fail(VLA_ERR_STATE, "vla_train_step_group: per-launch profiling is per model");
+    for (int j = 0; j < i; ++j) if (ms[j] == m) return fail(VLA_ERR_INVALID, "vla_train_step_group: a model appears twice");
+    const bool chain_prev = m->chain_on, hb_prev = m->hb_used;
+    m->chain_on = false;
+    recorder() = &recs[i];
+    const int rc = train_step_sequence(m, a, st);
+    recorder() = nullptr;
+    m->chain_on = chain_prev; (void)hb_prev;
+    if (recs[i].unsupported) return fail(VLA_ERR_STATE, "vla_train_step_group: this step contains a launch without a grouped form (member " + std::to_string(i) + ")");
+    if (rc) return rc;
+  }
+  // ---- zip: launch j of every member must be the same kernel ----
+  const size_t n_ops = recs[0].ops.size();
+  for (int i = 1; i < n; ++i) {
+    if (recs[i].ops.size() != n_ops) return fail(VLA_ERR_INVALID, "vla_train_step_group: members of different kinds (launch counts differ)");
+    for (size_t j = 0; j < n_ops; ++j)
+      if (recs[i].ops[j].kind != recs[0].ops[j].kind || recs[i].ops[j].variant != recs[0].ops[j].variant ||
+          recs[i].ops[j].args.size() != recs[0].ops[j].args.size())
+        return fail(VLA_ERR_INVALID, "vla_train_step_group: members of different kinds (launch " + std::to_string(j) + " differs)");
+  }
+  // ---- host image ----
+  std::string img;
+  std::vector<GroupPlanCached::Launch> launches(n_ops);
+  for (size_t j = 0; j < n_ops; ++j) {
+    GroupPlanCached::Launch& l = launches[j];
+    const RecOp& o0 = recs[0].ops[j];
+    l.kind = o0.kind; l.variant = o0.variant; l.n = n;
+    l.stride = static_cast<int>((o0.args.size() + 63) / 64 * 64);          // tensor maps inside a GemmGroup need 64-byte alignment
+    img.resize((img.size() + 255) / 256 * 256, '\0');
+    l.hdr_off = img.size();
+    int begin = 0;
+    for (int i = 0; i < n; ++i) {
+      const RecOp& o = recs[i].ops[j];
+      MultiHdr h{begin, o.gx, o.aux, 0};
+      img.append(reinterpret_cast<const char*>(&h), sizeof(h));
+      begin += o.blocks;
+    }
+    l.total_blocks = begin;
+    img.resize((img.size() + 255) / 256 * 256, '\0');
+    l.args_off = img.size();
+    for (int i = 0; i < n; ++i) {
+      img.append(recs[i].ops[j].args);
+      img.resize(l.args_off + static_cast<size_t>(i + 1) * l.stride, '\0');
+    }
+  }
+  // ---- cached device copy (keyed by the image) ----
+  vla_model_t* lead = ms[0];
+  GroupPlanCached* plan = nullptr;
+  for (GroupPlanCached* c : lead->group_plans) if (c->key == img) { plan = c; break; }
+  if (!plan) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(VLA_ERR_STATE, "vla_train_step_group: a new plan cannot be built inside a stream capture; make the same call once outside the capture");
+    if (lead->group_plans.size() >= 64) {
+      if (lead->pinned > 0) return fail(VLA_ERR_STATE, "vla_train_step_group: plan cache full while captured graphs are live");
+      cudaStreamSynchronize(st);
+      for (GroupPlanCached* g : lead->group_plans) { cudaFree(g->dev); delete g; }
+      lead->group_plans.clear();
+    }
+    plan = new GroupPlanCached();
+    if (cudaMalloc(&plan->dev, img.size()) != cudaSuccess) { delete plan; (void)cudaGetLastError(); return fail(VLA_ERR_CUDA, "vla_train_step_group: cudaMalloc"); }
+    if (cudaMemcpy(plan->dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(plan->dev); delete plan; (void)cudaGetLastError();
+      return fail(VLA_ERR_CUDA, "vla_train_step_group: copy of the launch tables");
+    }
+    plan->key = img; plan->launches = launches;
+    lead->group_plans.push_back(plan);
+  }
+  // ---- issue ----
+  for (const GroupPlanCached::Launch& l : plan->launches) {
+    const MultiHdr* hdr = reinterpret_cast<const MultiHdr*>(plan->dev + l.hdr_off);
+    const void* args = plan->dev + l.args_off;
+    cudaError_t e;
+    if (l.kind == RK_GEMM) {
+      if (l.stride != static_cast<int>(sizeof(GemmGroup))) return fail(VLA_ERR_STATE, "vla_train_step_group: GemmGroup stride");
+      e = launch_gemm_multi(l.variant, hdr, reinterpret_cast<const GemmGroup*>(args), l.n, l.total_blocks, st);
+    } else {
+      e = launch_multi(l.kind, l.variant, hdr, args, l.stride, l.n, l.total_blocks, st);
+    }
+    if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("vla_train_step_group: launch: ") + cudaGetErrorString(e));
+  }
+  return VLA_OK;
+}
+int vla_group_cached_plans(vla_model_t* lead) { return lead ? static_cast<int>(lead->group_plans.size()) : 0; }
 
 int vla_model_pin(vla_model_t* m, int delta) {
   if (!m) return fail(VLA_ERR_INVALID, "null model");

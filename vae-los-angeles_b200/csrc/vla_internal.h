@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 namespace vla {
 
@@ -480,5 +481,32 @@ cudaError_t launch_gather_rows(const GatherArgs& g, cudaStream_t s);
 struct ScaleArgs { float* x[8]; long long n[8]; int count; const float* scale; };
 cudaError_t launch_scale(const ScaleArgs& a, cudaStream_t s);
 cudaError_t launch_metrics(const MetricsArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// Lock-step population step (vla_train_step_group): n independent models of one kind take their train steps as ONE launch
+// per step of the sequence -- launch j covers launch j of every member.  The members' launches are recorded instead of
+// issued (the launch_* functions below append to the thread's Recorder when one is installed), zipped, and issued through
+// the *_multi kernels: block -> (member, block of the member's own grid) through a table in global memory; the member's
+// argument structure (the same one its stand-alone launch takes) is read from global memory too.
+// (optimize_hyperparameters.py:68-133 trials, vae_cross_modality_cv.py:113-283 folds: the reference runs them one by one.)
+// ---------------------------------------------------------------------------------------------
+enum RecKind : int { RK_GEMM = 0, RK_INGEST, RK_BN_ACT, RK_BN_BWD, RK_LATENT_FWD, RK_LATENT_BWD, RK_ADAMW, RK_LOSS, RK_COUNT };
+struct alignas(16) MultiHdr { int block_begin; int gx; int aux; int pad; };   // gx: width of a 2-D grid; aux: rows per block
+constexpr int MULTI_MAX_MEMBERS = 256;
+struct RecOp {
+  int kind = 0, variant = 0;       // RK_GEMM: variant = mode * 16 + instantiation
+  int blocks = 0, gx = 0, aux = 0;
+  std::string args;                // the launch's argument structure, byte for byte
+};
+struct Recorder {
+  std::vector<RecOp> ops;
+  bool unsupported = false;        // a launch that has no *_multi form was attempted
+};
+Recorder*& recorder();             // thread-local; nullptr = launch normally
+// One merged launch: hdr[n] and args[n] (stride bytes apart) in device memory.
+cudaError_t launch_multi(int kind, int variant, const MultiHdr* hdr, const void* args, int stride, int n, int total_blocks,
+                         cudaStream_t s);
+cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, cudaStream_t s);
+int gemm_variant(const GemmGroup& g, int mode);     // which instantiation launch_gemm_group picks (-1: invalid flags)
 
 }  // namespace vla

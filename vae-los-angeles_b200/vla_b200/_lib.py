@@ -99,6 +99,8 @@ EXPORTS = {
     "vla_metrics_workspace_bytes": (C.c_longlong, [C.c_longlong]),
     "vla_recon_metrics": (C.c_int, [C.POINTER(MetricsArgs), C.c_void_p]),
     "vla_train_step": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
+    "vla_train_step_group": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.POINTER(TrainArgs)), C.c_int, C.c_void_p]),
+    "vla_group_cached_plans": (C.c_int, [C.c_void_p]),
     "vla_set_hyper": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "vla_set_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "vla_dp_create": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)]),

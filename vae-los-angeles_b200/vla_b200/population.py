@@ -3,19 +3,26 @@
 The reference trains its hyper-parameter trials (`optimize_hyperparameters.py:68-133`) and cross-validation folds
 (`vae_cross_modality_cv.py:113-196, 198-283`) one after the other.  The models are independent -- no data-path
 exchange, "replicas only" -- and each one's train step is a chain of short dependent launches that leaves most SMs idle
-most of the time.  `Population` therefore gives every model its own fused `Trainer` (one CUDA graph
-each) on its own stream and steps them round-robin with no host synchronisation: the graphs of different models overlap on
-the device and fill each other's gaps.  Across GPUs the population is sharded by index (`models[rank::world]`), one
-process per GPU, no collective.
+most of the time.  `Population` steps its members in LOCK-STEP (`grouped=True`, the default): launch j of
+the train step is issued once for every live member (`vla_train_step_group`: grouped tcgen05 GEMMs whose grid holds all
+members' tiles, the element-wise launches likewise), captured as one CUDA graph per set of live members -- a population's
+step costs the launch latency of one model's.  `grouped=False` keeps the earlier scheme: one fused `Trainer` graph per model
+on its own stream, stepped round-robin, overlapping on the device.  Across GPUs the population is sharded by index
+(`models[rank::world]`), one process per GPU, no collective.
 
 The per-epoch control flow of the reference loops is restated on the host, per model, from ONE device->host read per epoch
 for the whole population: beta warm-up (`train_rna2dna.py:80`), `ReduceLROnPlateau` (torch's own scheduler object on a
 dummy optimizer, so the semantics are exactly the reference's, `vae_cross_modality_cv.py:127`), early stopping with a
 device-side snapshot of the best state (`vae_cross_modality_cv.py:129-196`).
 """
+import ctypes as C
+
 import torch
 
-from .engine import Trainer
+from . import _lib
+from .engine import Trainer, _stream
+
+GROUP_MAX = 256      # MULTI_MAX_MEMBERS of the library: members per merged launch
 
 
 class Member:
@@ -38,8 +45,11 @@ class Population:
     one per member (folds); every member trains at `batch_size`."""
 
     def __init__(self, specs, datasets, batch_size, device="cuda", beta_warmup_epochs=50, lr_factor=0.5, lr_patience=5,
-                 patience=15, use_graph=True):
+                 patience=15, use_graph=True, grouped=True):
         self.device = torch.device(device)
+        self.grouped = bool(grouped)
+        self.use_graph = use_graph
+        self._group_graphs = {}
         self.batch = int(batch_size)
         self.beta_warmup_epochs = beta_warmup_epochs
         self.patience = patience
@@ -51,8 +61,9 @@ class Population:
                          beta_start=spec.get("beta_start", 1e-3), gamma=spec.get("gamma", 1.0), seed=spec.get("seed", i))
             model = spec["model"].to(self.device).train()
             ds = datasets if shared else datasets[i]
-            stream = torch.cuda.Stream(device=self.device)
-            stream.wait_stream(main)
+            stream = main if self.grouped else torch.cuda.Stream(device=self.device)
+            if not self.grouped:
+                stream.wait_stream(main)
             with torch.cuda.stream(stream):
                 tr = Trainer(model, ds, self.batch, lr=hyper["lr"], weight_decay=hyper["weight_decay"],
                              beta_kl=hyper["beta_start"], gamma=hyper["gamma"], class_weights=spec.get("class_weights"),
@@ -65,10 +76,69 @@ class Population:
     def __len__(self):
         return len(self.members)
 
+    # -- lock-step stepping (vla_train_step_group) -----------------------------------------------------------------------
+    def _group_call(self, members, args_list):
+        L = _lib.lib()
+        for lo in range(0, len(members), GROUP_MAX):
+            ms, ar = members[lo:lo + GROUP_MAX], args_list[lo:lo + GROUP_MAX]
+            n = len(ms)
+            handles = (C.c_void_p * n)(*[getattr(m.trainer.core.handle, "value", m.trainer.core.handle) for m in ms])
+            ptrs = (C.POINTER(_lib.TrainArgs) * n)(*[C.pointer(a) for a in ar])
+            _lib.check(L.vla_train_step_group(handles, ptrs, n, _stream()), "vla_train_step_group")
+
+    def _group_step(self, members, tails=None):
+        """One optimizer step of every member of `members` as merged launches.  tails: per member (first_row, rows) of a
+        ragged last batch (eager call), else the next resident batch of each member's dataset (graph replay)."""
+        if not members:
+            return
+        with torch.cuda.device(self.device):
+            for mem in members:
+                mem.trainer._refresh_shadows_if_needed()
+            if tails is not None:
+                args = []
+                for mem, (first_row, rows) in zip(members, tails):
+                    if rows < 2:
+                        raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d): the last batch has one row")
+                    tr = mem.trainer
+                    ds = tr.datasets[0]
+                    a = tr._args(ds, 0)
+                    a.x_a = C.c_void_p(ds.tpm.data_ptr() + first_row * ds.tpm.shape[1] * 4)
+                    a.x_b = C.c_void_p(ds.beta.data_ptr() + first_row * ds.beta.shape[1] * 4)
+                    a.site = C.c_void_p(ds.site.data_ptr() + first_row * 8)
+                    a.batch = int(rows)
+                    a.dataset_rows = int(rows)
+                    args.append(a)
+                self._group_call(members, args)
+            else:
+                key = tuple(id(m) for m in members)
+                if not self.use_graph:
+                    self._group_call(members, [m.trainer._args(m.trainer.datasets[0], 0) for m in members])
+                elif key in self._group_graphs:
+                    self._group_graphs[key].replay()
+                else:
+                    # first step eagerly on a side stream (builds and caches the merged launch tables), then the capture
+                    s = torch.cuda.Stream(device=self.device)
+                    s.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(s):
+                        self._group_call(members, [m.trainer._args(m.trainer.datasets[0], 0) for m in members])
+                    torch.cuda.current_stream(self.device).wait_stream(s)
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._group_call(members, [m.trainer._args(m.trainer.datasets[0], 0) for m in members])
+                    self._group_graphs[key] = g
+        for mem in members:
+            mem.trainer.steps += 1
+            mem.trainer.core.generation += 1
+
     # -- stepping ----------------------------------------------------------------------------------------------------
     def step(self, n=1):
-        """`n` optimizer steps of every active member, round-robin over the members' streams; no host synchronisation."""
+        """`n` optimizer steps of every active member (lock-step merged launches, or round-robin over the members'
+        streams with grouped=False); no host synchronisation."""
         for _ in range(n):
+            if self.grouped:
+                self._group_step([m for m in self.members if not m.stopped])
+                continue
             for mem in self.members:
                 if not mem.stopped:
                     with torch.cuda.stream(mem.stream):
@@ -85,6 +155,12 @@ class Population:
             plan.append((mem, n_full, tail))
             with torch.cuda.stream(mem.stream):
                 mem.trainer.reset_counters(mem.trainer.steps, 0)
+        if self.grouped:
+            for i in range(max((n for _, n, _ in plan), default=0)):
+                self._group_step([mem for mem, n_full, _ in plan if i < n_full])
+            with_tail = [(mem, n_full, tail) for mem, n_full, tail in plan if tail]
+            self._group_step([mem for mem, _, _ in with_tail], tails=[(n_full * self.batch, tail) for _, n_full, tail in with_tail])
+            return
         for i in range(max((n for _, n, _ in plan), default=0)):
             for mem, n_full, _ in plan:
                 if i < n_full:
@@ -173,6 +249,7 @@ class Population:
 
     def close(self):
         self.synchronize()
+        self._group_graphs.clear()
         for mem in self.members:
             mem.trainer.close()
 
