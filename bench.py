@@ -313,61 +313,80 @@ def torch_eager_throughput(workload, B, dev, steps, warmup, mode):
     return out
 
 
-def population_throughput(dev, B, n_models, steps, warmup):
-    """BASELINE configs[4] on one GPU: `n_models` independent tri-modal VAEs with hyper-parameters drawn from the ranges of
-    optimize_hyperparameters.py:71-76 (latent 10..100, embed 16/32/64, lr, weight decay, beta, gamma), each with its own
-    fused step graph on its own stream (vla_b200.Population), against the same models stepped one after the other."""
+def population_specs(n_models, first=0):
+    """Members `first .. first + n_models` of the population: tri-modal VAEs with hyper-parameters drawn from the ranges of
+    optimize_hyperparameters.py:71-76 (latent 10..100, embed 16/32/64, lr, weight decay, beta, gamma); member i is the same
+    model whatever the sharding."""
     import numpy as np
     import torch
     from src.models import MultiModalVAE
+    out = []
+    for i in range(first, first + n_models):
+        torch.manual_seed(1000 + i)
+        r = np.random.default_rng(1000 + i)
+        L, E = int(r.integers(10, 101)), int(r.choice([16, 32, 64]))
+        out.append(dict(model=MultiModalVAE(DIMS["A"], DIMS["B"], DIMS["S"], L, embed_dim=E), seed=i,
+                        lr=float(10 ** r.uniform(-5, -2)), weight_decay=float(10 ** r.uniform(-6, -3)),
+                        beta_start=float(10 ** r.uniform(-4, -2)), gamma=float(r.uniform(0.5, 5.0))))
+    return out
+
+
+def population_throughput(dev, B, n_models, steps, warmup, compare=True, first=0, barrier=None):
+    """BASELINE configs[4] on one GPU: `n_models` independent tri-modal VAEs stepped in LOCK-STEP (vla_b200.Population,
+    grouped=True: every launch of the train step issued once for all members -- grouped GEMMs), against (compare=True) the same
+    models as one graph per model on its own stream, and one after the other."""
+    import torch
     from vla_b200 import DeviceDataset, Population
     ds = DeviceDataset.synthetic(B * 8, DIMS["A"], DIMS["B"], DIMS["S"], dev, seed=9)
 
-    def specs():
-        out = []
-        torch.manual_seed(0)
-        r = np.random.default_rng(1)
-        for i in range(n_models):
-            L, E = int(r.integers(10, 101)), int(r.choice([16, 32, 64]))
-            out.append(dict(model=MultiModalVAE(DIMS["A"], DIMS["B"], DIMS["S"], L, embed_dim=E), seed=i,
-                            lr=float(10 ** r.uniform(-5, -2)), weight_decay=float(10 ** r.uniform(-6, -3)),
-                            beta_start=float(10 ** r.uniform(-4, -2)), gamma=float(r.uniform(0.5, 5.0))))
-        return out
-
-    def timed(pop, fn):
+    def timed(pop, fn, k):
         for _ in range(warmup):
             fn()
         pop.synchronize()
+        if barrier:
+            barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(k):
             fn()
         for mem in pop.members:
-            torch.cuda.current_stream(dev).wait_stream(mem.stream)
+            if mem.stream != torch.cuda.current_stream(dev):
+                torch.cuda.current_stream(dev).wait_stream(mem.stream)
         e1.record()
         torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1)
+        return e0.elapsed_time(e1) / k
 
-    pop = Population(specs(), ds, B, device=dev)
-    ms_conc = timed(pop, lambda: pop.step(1))
-
-    def one_by_one():
-        for mem in pop.members:                       # same graphs, serialised: every member's step waits for the previous member's
-            with torch.cuda.stream(mem.stream):
-                mem.trainer.step()
-            torch.cuda.current_stream(dev).wait_stream(mem.stream)
-            for other in pop.members:
-                other.stream.wait_stream(torch.cuda.current_stream(dev))
-
-    ms_seq = timed(pop, one_by_one)
+    pop = Population(population_specs(n_models, first), ds, B, device=dev, grouped=True)
+    ms_group = timed(pop, lambda: pop.step(1), steps)
     losses = pop.losses()
     pop.close()
-    ok = all(all(x == x and abs(x) < 1e30 for x in l) for l in losses)
-    out = {"workload": f"population: {n_models} independent tri-modal VAEs (latent 10..100, embed 16/32/64), batch {B} each, one GPU",
-           "value": steps * B * n_models / (ms_conc * 1e-3), "unit": "samples/s (all members)",
-           "ms_per_round": ms_conc / steps, "one_after_the_other_samples_per_s": steps * B * n_models / (ms_seq * 1e-3),
-           "concurrency_gain": ms_seq / ms_conc, "losses_finite": ok}
+    del pop
     torch.cuda.empty_cache()
+    ok = all(all(x == x and abs(x) < 1e30 for x in l) for l in losses)
+    out = {"workload": f"population: {n_models} independent tri-modal VAEs (latent 10..100, embed 16/32/64), batch {B} each, one GPU, "
+                       "lock-step grouped launches (vla_train_step_group)",
+           "value": B * n_models / (ms_group * 1e-3), "unit": "samples/s (all members)", "ms_per_round": ms_group,
+           "us_per_model_step": 1e3 * ms_group / n_models, "losses_finite": ok}
+    if compare:
+        pop = Population(population_specs(n_models, first), ds, B, device=dev, grouped=False)
+        k = max(3, steps // 3)
+        ms_streams = timed(pop, lambda: pop.step(1), k)
+
+        def one_by_one():
+            for mem in pop.members:                   # same graphs, serialised: every member's step waits for the previous member's
+                with torch.cuda.stream(mem.stream):
+                    mem.trainer.step()
+                torch.cuda.current_stream(dev).wait_stream(mem.stream)
+                for other in pop.members:
+                    other.stream.wait_stream(torch.cuda.current_stream(dev))
+
+        ms_seq = timed(pop, one_by_one, k)
+        pop.close()
+        del pop
+        torch.cuda.empty_cache()
+        out.update({"one_graph_per_model_on_streams_samples_per_s": B * n_models / (ms_streams * 1e-3),
+                    "one_after_the_other_samples_per_s": B * n_models / (ms_seq * 1e-3),
+                    "gain_over_one_after_the_other": ms_seq / ms_group, "gain_over_streams": ms_streams / ms_group})
     return out
 
 
@@ -629,8 +648,9 @@ def run_gpu(args, rank, local_rank, world):
             also.append(torch_eager_throughput(args.workload, B, dev, steps=40, warmup=5, mode=mode))
         also.append(inference_throughput(dev, batch=args.infer_batch, steps=10, warmup=3))
         also.append(metrics_throughput(dev, args.infer_batch, DIMS["A"], steps=10, warmup=3))
-        also.append(population_throughput(dev, B, n_models=8, steps=30, warmup=3))
-        also.append(population_throughput(dev, 32, n_models=8, steps=100, warmup=5))       # the reference's default batch size
+        # BASELINE configs[4]: 40 models per GPU (320 = 64 trials x 5 folds over 8 GPUs)
+        also.append(population_throughput(dev, B, n_models=40, steps=12, warmup=3))
+        also.append(population_throughput(dev, 32, n_models=40, steps=60, warmup=5))       # the reference's default batch size
 
     # ---- data parallel: driver-visible parity of the replicas + BASELINE configs[2] (dna2rna, global batch = world x B) ----
     dp_check = None
@@ -669,6 +689,18 @@ def run_gpu(args, rank, local_rank, world):
                          "value": 100 * B * world / (float(tt.item()) * 1e-3), "unit": "samples/s", "ms_per_step": float(tt.item()) / 100,
                          "losses": t2.losses()})
             extra_trainers.append(t2)
+            # BASELINE configs[4]: the population sharded over the GPUs (members rank * 40 .. rank * 40 + 39 here; replicas
+            # only, no data-path collective), every shard in lock-step grouped launches
+            per_gpu = 40
+            pl = population_throughput(dev, 32, n_models=per_gpu, steps=40, warmup=5, compare=False, first=rank * per_gpu, barrier=barrier)
+            tp = torch.tensor([pl["ms_per_round"]], device=dev, dtype=torch.float64)
+            okf = torch.tensor([1.0 if pl["losses_finite"] else 0.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            also.append({"workload": f"population (BASELINE configs[4]): {per_gpu * world} independent tri-modal VAEs, {per_gpu} per GPU over {world} GPUs "
+                                     "(sharded by index, no collective), batch 32 each, lock-step grouped launches",
+                         "value": 32 * per_gpu * world / (float(tp.item()) * 1e-3), "unit": "samples/s (all members, all GPUs)",
+                         "ms_per_round_max_over_ranks": float(tp.item()), "losses_finite": bool(okf.item() > 0)})
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
