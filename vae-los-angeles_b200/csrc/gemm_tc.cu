@@ -98,6 +98,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_multi_kernel(const Mu
   }
 }
 
+// Persistent form for launches of more than one wave (large batches, lock-step populations): one CTA per SM walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; two accumulators in TMEM let the MMAs of tile i + 1 overlap the epilogue of tile i,
+// and the producer streams the next tile's operands meanwhile (gemm_tile<.., PERSIST = true>).  n == 0: the tiles of `one`
+// (kernel parameter); n > 0: the tiles of n members' groups (tables in global memory).
+template <int MODE, int FEATS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ GemmGroup one, const MultiHdr* __restrict__ hdr,
+                                                                          const GemmGroup* __restrict__ groups, int n, int total_tiles) {
+  TileCtx ctx = tile_setup(true, true, 2 * GEMM_TMEM_COLS);
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int t = static_cast<int>(blockIdx.x); t < total_tiles; t += static_cast<int>(gridDim.x)) {
+    const GemmGroup* grp = &one;
+    int tile = t;
+    if (n > 0) {
+      int lo = 0, hi = n - 1;                      // last member whose block_begin <= t
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (hdr[mid].block_begin <= t) lo = mid; else hi = mid - 1;
+      }
+      grp = groups + lo;
+      tile = t - hdr[lo].block_begin;
+    }
+    int pi = 0;
+    for (int i = 1; i < grp->nprob; ++i)
+      if (tile >= grp->p[i].tile_begin) pi = i;
+    const GemmProblem& P = grp->p[pi];
+    const int local = tile - P.tile_begin;
+    const int n_tile = local % P.n_tiles, rest = local / P.n_tiles;
+    gemm_tile<MODE, FEATS, true>(ctx, P, &P.tmA, &P.tmB, rest % P.m_tiles, n_tile, rest / P.m_tiles, &grp->tail);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    tmem_dealloc(ctx.tmem_base, 2 * GEMM_TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 size_t gemm_smem_bytes() { return SMEM_BYTES; }
@@ -115,6 +153,20 @@ cudaError_t launch_one_multi(const MultiHdr* hdr, const GemmGroup* groups, int n
   if (attr != cudaSuccess) return attr;
   return launch_pdl(gemm_tc_multi_kernel<MODE, FEATS>, dim3(total_blocks), dim3(GEMM_THREADS), static_cast<size_t>(SMEM_BYTES), stream,
                     hdr, groups, n);
+}
+
+template <int MODE, int FEATS>
+cudaError_t launch_one_persist(const GemmGroup& one, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_tiles, cudaStream_t stream) {
+  static cudaError_t attr = cudaFuncSetAttribute(gemm_tc_persist_kernel<MODE, FEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (attr != cudaSuccess) return attr;
+  static const int sms = [] { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v > 0 ? v : 148; }();
+  return launch_pdl(gemm_tc_persist_kernel<MODE, FEATS>, dim3(total_tiles < sms ? total_tiles : sms), dim3(GEMM_THREADS),
+                    static_cast<size_t>(SMEM_BYTES), stream, one, hdr, groups, n, total_tiles);
+}
+// More than this many tiles (one wave and a half) and no fused loss: the persistent form.  VLA_PERSIST=0 turns it off.
+bool use_persist(int variant, int total_tiles) {
+  static const int thr = [] { const char* e = getenv("VLA_PERSIST"); return e ? atoi(e) : 222; }();
+  return thr > 0 && total_tiles > thr && !(variant >= 2 && variant <= 4);
 }
 
 // Which instantiation of the tile body a group runs: mode * 16 + {0 plain, 1 full, 2 loss (any mix), 3 BCE only, 4 MSE only}.
@@ -163,6 +215,18 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
     r->ops.push_back(std::move(op));
     return cudaSuccess;
   }
+  if (!g.dbg && !g.dbg_flags && use_persist(variant, g.total_tiles)) {
+#define VLA_CALL_PERSIST(M_, F_) launch_one_persist<M_, F_>(g, nullptr, nullptr, 0, g.total_tiles, stream)
+    switch (variant) {
+      case 0: return VLA_CALL_PERSIST(0, FEATS_FWD_PLAIN);
+      case 1: return VLA_CALL_PERSIST(0, FEATS_FWD_FULL);
+      case 16: return VLA_CALL_PERSIST(1, FEATS_WGRAD);
+      case 32: return VLA_CALL_PERSIST(2, FEATS_DGRAD_PLAIN);
+      case 33: return VLA_CALL_PERSIST(2, FEATS_DGRAD_FULL);
+      default: return cudaErrorInvalidValue;
+    }
+#undef VLA_CALL_PERSIST
+  }
   size_t smem = SMEM_BYTES;
   if (g.dbg_flags & 0xFFFF00) smem = static_cast<size_t>(g.dbg_flags >> 8);   // test hook (only valid with dbg_flags & 2)
 #define VLA_CALL_ONE(M_, F_) launch_one<M_, F_>(g, stream, smem)
@@ -173,6 +237,19 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
 cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, cudaStream_t stream) {
   if (n <= 0 || total_blocks <= 0) return cudaSuccess;
   if (n > MULTI_MAX_MEMBERS) return cudaErrorInvalidValue;
+  if (use_persist(variant, total_blocks)) {
+    static GemmGroup none;      // unused kernel parameter of the multi form
+#define VLA_CALL_PERSIST(M_, F_) launch_one_persist<M_, F_>(none, hdr, groups, n, total_blocks, stream)
+    switch (variant) {
+      case 0: return VLA_CALL_PERSIST(0, FEATS_FWD_PLAIN);
+      case 1: return VLA_CALL_PERSIST(0, FEATS_FWD_FULL);
+      case 16: return VLA_CALL_PERSIST(1, FEATS_WGRAD);
+      case 32: return VLA_CALL_PERSIST(2, FEATS_DGRAD_PLAIN);
+      case 33: return VLA_CALL_PERSIST(2, FEATS_DGRAD_FULL);
+      default: return cudaErrorInvalidValue;
+    }
+#undef VLA_CALL_PERSIST
+  }
 #define VLA_CALL_MULTI(M_, F_) launch_one_multi<M_, F_>(hdr, groups, n, total_blocks, stream)
   VLA_GEMM_DISPATCH(variant, VLA_CALL_MULTI)
 #undef VLA_CALL_MULTI

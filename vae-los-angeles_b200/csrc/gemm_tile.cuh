@@ -48,7 +48,13 @@ static_assert((GEMM_BN_MAX_NT / 32 + 1 + 1) / 2 <= 3, "a warp stages the targets
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_BYTES % 1024 == 0 && A_STAGE_BYTES % 1024 == 0, "swizzle atoms need 1 KiB alignment");
 static_assert(GEMM_BN_MAX_NT % 16 == 0 && GEMM_BN_MAX_TN % 64 == 0, "tile limits");
-static_assert((2 * GEMM_STAGES + 3) * 8 + 4 <= 128, "barrier block");
+static_assert((2 * GEMM_STAGES + 5) * 8 + 4 <= 128, "barrier block");
+// Persistent form (gemm_tc_persist_kernel): a CTA walks a list of tiles with TWO accumulators in TMEM -- the MMA issuer fills
+// one while the epilogue warps drain the other -- and the producer runs ahead into the next tile's operands.  The ring then has
+// PERSIST_STAGES stages (slots 0..3); the epilogue's transpose patches move out of the ring into the space of slots 4..5.
+constexpr int PERSIST_STAGES = 2;
+constexpr int PERSIST_CHUNK_OFFSET = PERSIST_STAGES * GEMM_GROUP * STAGE_BYTES;
+static_assert(PERSIST_CHUNK_OFFSET + CHUNK_BYTES <= GEMM_SLOTS * STAGE_BYTES, "persistent form: patches must fit behind the ring");
 
 constexpr int FEATS_FWD_PLAIN = GF_BIAS | GF_RELU | GF_OUT_F32 | GF_OUT_BF16;                      // hidden decoder layers, heads
 constexpr int FEATS_FWD_FULL = FEATS_FWD_PLAIN | GF_SIGMOID | GF_COLSTATS;                         // + BatchNorm statistics / sigmoid
@@ -104,6 +110,7 @@ struct TileCtx {
   uint32_t tmem_base;
   int stage; uint32_t phase;  // position in the shared-memory ring (producer and MMA roles advance identically)
   uint32_t tile_parity;       // parity of acc_bar / dep_bar for the tile in flight
+  uint32_t tile_seq;          // tiles this CTA has processed (persistent form: accumulator = tile_seq & 1)
   uint32_t ew_parity;         // parity of the element-wise bulk-load barrier
   unsigned long long* dbg;    // optional [.][8] globaltimer stamps
   int dbg_row;
@@ -115,7 +122,8 @@ __device__ __forceinline__ uint64_t* tile_ew_bar(uint8_t* smem) { return tile_ba
 
 // One-time CTA setup shared by both kernels: barriers, bf16 ones for the bias-gradient MMA, TMEM.
 // Ends with a CTA-wide barrier; returns the context with the ring at its origin.
-__device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = true) {
+// Barrier block: full[S] | empty[S] | acc (persistent: acc_full[0]) | dep (acc_full[1]) | ew (acc_empty[0]) | acc_empty[1] | TMEM slot
+__device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = true, uint32_t tmem_cols = GEMM_TMEM_COLS) {
   TileCtx c;
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
@@ -123,9 +131,10 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
   uint64_t* acc_bar = empty_bar + GEMM_STAGES;
   uint64_t* dep_bar = acc_bar + 1;
   uint64_t* ew_bar = dep_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ew_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ew_bar + 2);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
+    mbar_init(ew_bar + 1, 1);
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -135,7 +144,7 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
     mbar_init(ew_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1 && alloc_tmem) tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  if (warp == 1 && alloc_tmem) tmem_alloc(tmem_slot, tmem_cols);
   if (warp >= 2 && fill_ones) {
     // 2 KiB of bf16 1.0: the B operand of the bias-gradient MMA (layout-invariant)
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem + ONES_OFFSET);
@@ -146,7 +155,7 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
   __syncthreads();
   tc_fence_after();
   c.tmem_base = alloc_tmem ? *tmem_slot : 0u;
-  c.stage = 0; c.phase = 0; c.tile_parity = 0; c.ew_parity = 0;
+  c.stage = 0; c.phase = 0; c.tile_parity = 0; c.ew_parity = 0; c.tile_seq = 0;
   c.dbg = nullptr; c.dbg_row = 0; c.dbg_flags = 0;
   return c;
 }
@@ -156,13 +165,18 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
 // FEATS: compile-time superset of the epilogue flags that may occur; everything else is compiled out (smaller code:
 // the epilogue is instruction-fetch sensitive).  All threads of the CTA call this; on return the tile's global writes
 // have been issued by the epilogue threads (the caller orders them: barrier + fence) and ctx has advanced.
-template <int MODE, int FEATS>
+template <int MODE, int FEATS, bool PERSIST = false>
 __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                           int m_tile, int n_tile, int k_split, const LossTail* tail_desc = nullptr) {
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* acc_bar = empty_bar + GEMM_STAGES;
+  static_assert(!PERSIST || !(FEATS & GF_LOSS), "the loss epilogue stages its targets in the ring's slots: not persistent");
+  constexpr int NS = PERSIST ? PERSIST_STAGES : GEMM_STAGES;          // ring stages in use
+  const uint32_t acc_buf = PERSIST ? (ctx.tile_seq & 1u) : 0u;        // which accumulator this tile uses
+  const uint32_t acc_par = PERSIST ? ((ctx.tile_seq >> 1) & 1u) : ctx.tile_parity;
+  uint64_t* acc_bar = empty_bar + GEMM_STAGES + acc_buf;              // accumulator complete (MMA -> epilogue)
+  uint64_t* acc_free = empty_bar + GEMM_STAGES + 2 + acc_buf;         // persistent: accumulator drained (epilogue -> MMA)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -200,7 +214,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
   const bool split = (MODE == 0) && P.a_lo > 0;
   const bool bias_mma = (MODE == 1) && (FEATS & GF_BIASGRAD) && (P.flags & GF_BIASGRAD) && n_tile == 0;
   const int dbgf = ctx.dbg_flags;                 // test hooks (0 outside vla_test_gemm)
-  const uint32_t tmem_base = ctx.tmem_base;
+  const uint32_t tmem_base = ctx.tmem_base + acc_buf * GEMM_TMEM_COLS;
 
   if (dbgf & 2) {
     // test hook: no main loop, no epilogue
@@ -237,7 +251,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
               tma_load_2d(sb + i * 8192, tmB, &full_bar[stage], n0 + i * 64, kb * GEMM_BK);   // box 64 (N) x 64 (K)
           }
         }
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -249,6 +263,10 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
       const int u0 = (split ? 2 : 1) * kb0, u1 = (split ? 2 : 1) * kb1;
+      if (PERSIST) {                     // the epilogue of the tile before last has drained this accumulator
+        mbar_wait(acc_free, acc_par ^ 1u);
+        tc_fence_after();
+      }
       for (int ug = u0; ug < u1; ug += GEMM_GROUP) {
         const int cnt = min(GEMM_GROUP, u1 - ug);
         mbar_wait(&full_bar[stage], phase);
@@ -287,7 +305,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
           }
         }
         umma_commit(&empty_bar[stage]);   // frees the stage's slots when these MMAs retire
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
       umma_commit(acc_bar);           // accumulator complete
       VLA_STAMP(4);                                                // all MMAs issued
@@ -348,13 +366,13 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       }
     }
 
-    mbar_wait(acc_bar, ctx.tile_parity);
+    mbar_wait(acc_bar, acc_par);
     tc_fence_after();
     if (et == 0) VLA_STAMP(5);                                     // accumulator ready
 
     // Per-warp transpose patch: global traffic of the epilogue is always issued with consecutive lanes on consecutive
     // addresses of one row (1 L1 wavefront per 128 bytes) instead of 32 rows per instruction.
-    float* patch = reinterpret_cast<float*>(smem + CHUNK_OFFSET) + (warp - 2) * (32 * PATCH_LD);
+    float* patch = reinterpret_cast<float*>(smem + (PERSIST ? PERSIST_CHUNK_OFFSET : CHUNK_OFFSET)) + (warp - 2) * (32 * PATCH_LD);
     const int rbase = m0 + q * 32;                      // first accumulator row of this warp
     const bool f32_vec = ((reinterpret_cast<uintptr_t>(P.out_f32) & 15) == 0) && ((P.ld_f32 & 3) == 0);
     const bool bf16_vec = ((reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0) && ((P.ld_bf16 & 7) == 0);
@@ -727,15 +745,23 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
         }
       }
     }
+    if (PERSIST) {
+      // every epilogue thread has read its accumulator rows and is done with this tile's column vectors / partials: hand
+      // the accumulator back to the MMA issuer; the next tile may overwrite vec / part
+      tc_fence_before();
+      named_bar_sync(2, EPI_THREADS);
+      if (et == 0) mbar_arrive(acc_free);
+    }
   }
 
   // ---- every thread: advance the ring position and the tile parity ----
   if (!(dbgf & 2)) {
     const int units = (split ? 2 : 1) * (kb1 - kb0);
     const int s = ctx.stage + (units + GEMM_GROUP - 1) / GEMM_GROUP;
-    ctx.phase ^= static_cast<uint32_t>(s / GEMM_STAGES) & 1u;
-    ctx.stage = s % GEMM_STAGES;
+    ctx.phase ^= static_cast<uint32_t>(s / NS) & 1u;
+    ctx.stage = s % NS;
     ctx.tile_parity ^= 1u;
+    ctx.tile_seq += 1u;
   }
 }
 
