@@ -53,6 +53,13 @@ def test_gemm_kernels_use_tcgen05_tma_tmem(sass):
         assert have["LDTM"] > 0, name             # tcgen05.ld (TMEM -> registers)
         assert have["UTCBAR"] > 0, name           # tcgen05.commit -> mbarrier
         assert not any(op.startswith(("HMMA", "WGMMA")) for op in ops), name      # no mma.sync / wgmma path
+    # the lock-step population form and the persistent form run the same tile body
+    for needle, at_least in (("gemm_tc_multi_kernel", 5), ("gemm_tc_persist_kernel", 4)):
+        more = _find(kernels, needle)
+        assert len(more) >= at_least, (needle, len(more))
+        for name, ops in more.items():
+            have = {op.split(".")[0] for op in ops}
+            assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= have, name
     rowchain = _find(kernels, "15rowchain_kernel")
     assert rowchain and all({"UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"} <= {op.split(".")[0] for op in ops} for ops in rowchain.values())
     chain = _find(kernels, "12chain_kernel")

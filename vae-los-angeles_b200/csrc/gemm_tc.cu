@@ -18,6 +18,7 @@
 // autograd backward.
 #include "gemm_tile.cuh"
 
+#include <algorithm>
 #include <mutex>
 
 namespace vla {
@@ -108,25 +109,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
   TileCtx ctx = tile_setup(true, true, 2 * GEMM_TMEM_COLS);
   pdl_wait();
   pdl_launch_dependents();
-  for (int t = static_cast<int>(blockIdx.x); t < total_tiles; t += static_cast<int>(gridDim.x)) {
-    const GemmGroup* grp = &one;
-    int tile = t;
-    if (n > 0) {
-      int lo = 0, hi = n - 1;                      // last member whose block_begin <= t
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (hdr[mid].block_begin <= t) lo = mid; else hi = mid - 1;
+  // A CTA takes a CONTIGUOUS range of tiles (n-tiles of one row block are neighbours: the row block's A operand is read from
+  // HBM once and re-read from L2 by the same SM); the (member, problem) lookup is repeated only when the range leaves a problem.
+  const int per = (total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int t0 = static_cast<int>(blockIdx.x) * per, t1 = min(total_tiles, t0 + per);
+  const GemmGroup* grp = &one;
+  const GemmProblem* Pp = nullptr;
+  int p_begin = 0, p_end = 0, p_nt = 1, p_mt = 1;       // tiles [p_begin, p_end) of the launch belong to *Pp
+  for (int t = t0; t < t1; ++t) {
+    if (t >= p_end) {
+      int base = 0;
+      if (n > 0) {
+        int lo = 0, hi = n - 1;                    // last member whose block_begin <= t
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (hdr[mid].block_begin <= t) lo = mid; else hi = mid - 1;
+        }
+        grp = groups + lo;
+        base = hdr[lo].block_begin;
       }
-      grp = groups + lo;
-      tile = t - hdr[lo].block_begin;
+      const int np = grp->nprob;
+      int pi = 0;
+      for (int i = 1; i < np; ++i)
+        if (t - base >= grp->p[i].tile_begin) pi = i;
+      Pp = &grp->p[pi];
+      p_nt = Pp->n_tiles; p_mt = Pp->m_tiles;
+      p_begin = base + Pp->tile_begin;
+      p_end = p_begin + p_mt * p_nt * Pp->k_splits;
     }
-    int pi = 0;
-    for (int i = 1; i < grp->nprob; ++i)
-      if (tile >= grp->p[i].tile_begin) pi = i;
-    const GemmProblem& P = grp->p[pi];
-    const int local = tile - P.tile_begin;
-    const int n_tile = local % P.n_tiles, rest = local / P.n_tiles;
-    gemm_tile<MODE, FEATS, true>(ctx, P, &P.tmA, &P.tmB, rest % P.m_tiles, n_tile, rest / P.m_tiles, &grp->tail);
+    const int local = t - p_begin;
+    const int n_tile = local % p_nt, rest = local / p_nt;
+    gemm_tile<MODE, FEATS, true>(ctx, *Pp, &Pp->tmA, &Pp->tmB, rest % p_mt, n_tile, rest / p_mt, &grp->tail);
   }
   tc_fence_before();
   __syncthreads();
@@ -166,8 +179,23 @@ cudaError_t launch_one_persist(const GemmGroup& one, const MultiHdr* hdr, const 
 // More than this many tiles (one wave and a half) and no fused loss: the persistent form.  VLA_PERSIST=0 turns it off.
 bool use_persist(int variant, int total_tiles) {
   static const int thr = [] { const char* e = getenv("VLA_PERSIST"); return e ? atoi(e) : 222; }();
-  return thr > 0 && total_tiles > thr && !(variant >= 2 && variant <= 4);
+  // not the loss epilogues (their target patches live in the ring), not the data gradients with BatchNorm-backward statistics
+  // (measured 1.3-1.4x slower in the persistent form: profiles/r2_population_profile.md)
+  return thr > 0 && total_tiles > thr && !(variant >= 2 && variant <= 4) && variant != 33;
 }
+// The persistent form runs a two-stage ring (its transpose patches need the other slots): it pays where the epilogue is the
+// larger part of a tile -- short main loops -- and loses where the main loop is (measured: lock-step populations at batch
+// 4096 slow down by 16 % when the K = 4096 weight-gradient tiles take it).  Longest main loop of a group, in ring slots:
+int gemm_max_units(const GemmGroup& g) {
+  int u = 0;
+  for (int i = 0; i < g.nprob; ++i) {
+    const GemmProblem& p = g.p[i];
+    const int kb = p.k_splits > 1 ? p.kb_per_split : (p.K + GEMM_BK - 1) / GEMM_BK;
+    u = std::max(u, kb * (p.a_lo > 0 ? 2 : 1));
+  }
+  return u;
+}
+constexpr int PERSIST_MAX_UNITS = 8;
 
 // Which instantiation of the tile body a group runs: mode * 16 + {0 plain, 1 full, 2 loss (any mix), 3 BCE only, 4 MSE only}.
 int gemm_variant(const GemmGroup& g, int mode) {
@@ -215,7 +243,7 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
     r->ops.push_back(std::move(op));
     return cudaSuccess;
   }
-  if (!g.dbg && !g.dbg_flags && use_persist(variant, g.total_tiles)) {
+  if (!g.dbg && !g.dbg_flags && use_persist(variant, g.total_tiles) && gemm_max_units(g) <= PERSIST_MAX_UNITS) {
 #define VLA_CALL_PERSIST(M_, F_) launch_one_persist<M_, F_>(g, nullptr, nullptr, 0, g.total_tiles, stream)
     switch (variant) {
       case 0: return VLA_CALL_PERSIST(0, FEATS_FWD_PLAIN);
@@ -234,10 +262,11 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
 #undef VLA_CALL_ONE
 }
 
-cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, cudaStream_t stream) {
+cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, int max_units,
+                              cudaStream_t stream) {
   if (n <= 0 || total_blocks <= 0) return cudaSuccess;
   if (n > MULTI_MAX_MEMBERS) return cudaErrorInvalidValue;
-  if (use_persist(variant, total_blocks)) {
+  if (use_persist(variant, total_blocks) && max_units <= PERSIST_MAX_UNITS) {
     static GemmGroup none;      // unused kernel parameter of the multi form
 #define VLA_CALL_PERSIST(M_, F_) launch_one_persist<M_, F_>(none, hdr, groups, n, total_blocks, stream)
     switch (variant) {

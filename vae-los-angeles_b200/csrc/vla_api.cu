@@ -113,7 +113,7 @@ struct ChainPlanCached {
 struct GroupPlanCached {
   std::string key;
   char* dev = nullptr;
-  struct Launch { int kind, variant, stride, n, total_blocks; size_t hdr_off, args_off; };
+  struct Launch { int kind, variant, stride, n, total_blocks, max_units; size_t hdr_off, args_off; };
   std::vector<Launch> launches;
 };
 
@@ -2094,7 +2094,10 @@ int vla_train_step_group(vla_model_t* const* ms, const vla_train_args_t* const* 
   for (size_t j = 0; j < n_ops; ++j) {
     GroupPlanCached::Launch& l = launches[j];
     const RecOp& o0 = recs[0].ops[j];
-    l.kind = o0.kind; l.variant = o0.variant; l.n = n;
+    l.kind = o0.kind; l.variant = o0.variant; l.n = n; l.max_units = 0;
+    if (l.kind == RK_GEMM)
+      for (int i = 0; i < n; ++i)
+        l.max_units = std::max(l.max_units, gemm_max_units(*reinterpret_cast<const GemmGroup*>(recs[i].ops[j].args.data())));
     l.stride = static_cast<int>((o0.args.size() + 63) / 64 * 64);          // tensor maps inside a GemmGroup need 64-byte alignment
     img.resize((img.size() + 255) / 256 * 256, '\0');
     l.hdr_off = img.size();
@@ -2138,17 +2141,41 @@ int vla_train_step_group(vla_model_t* const* ms, const vla_train_args_t* const* 
     lead->group_plans.push_back(plan);
   }
   // ---- issue ----
+  // VLA_GROUP_PROF=1 (diagnostic, eager calls only): an event pair around every merged launch, printed to stderr
+  static const bool gprof = [] { const char* e = getenv("VLA_GROUP_PROF"); return e && e[0] == '1'; }();
+  std::vector<cudaEvent_t> gev;
+  bool timing = false;
+  if (gprof) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    timing = cap == cudaStreamCaptureStatusNone;
+  }
+  auto stamp = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); gev.push_back(e); } };
+  stamp();
   for (const GroupPlanCached::Launch& l : plan->launches) {
     const MultiHdr* hdr = reinterpret_cast<const MultiHdr*>(plan->dev + l.hdr_off);
     const void* args = plan->dev + l.args_off;
     cudaError_t e;
     if (l.kind == RK_GEMM) {
       if (l.stride != static_cast<int>(sizeof(GemmGroup))) return fail(VLA_ERR_STATE, "vla_train_step_group: GemmGroup stride");
-      e = launch_gemm_multi(l.variant, hdr, reinterpret_cast<const GemmGroup*>(args), l.n, l.total_blocks, st);
+      e = launch_gemm_multi(l.variant, hdr, reinterpret_cast<const GemmGroup*>(args), l.n, l.total_blocks, l.max_units, st);
     } else {
       e = launch_multi(l.kind, l.variant, hdr, args, l.stride, l.n, l.total_blocks, st);
     }
     if (e != cudaSuccess) return fail(VLA_ERR_CUDA, std::string("vla_train_step_group: launch: ") + cudaGetErrorString(e));
+    stamp();
+  }
+  if (timing) {
+    static const char* kind_name[RK_COUNT] = {"gemm", "ingest", "bn_act", "bn_bwd", "latent_fwd", "latent_bwd", "adamw", "loss"};
+    cudaStreamSynchronize(st);
+    for (size_t j = 0; j + 1 < gev.size(); ++j) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, gev[j], gev[j + 1]);
+      const GroupPlanCached::Launch& l = plan->launches[j];
+      fprintf(stderr, "[group] %2zu %-10s variant %2d blocks %6d max_units %3d  %9.1f us\n", j, kind_name[l.kind], l.variant, l.total_blocks,
+              l.max_units, 1e3 * ms);
+    }
+    for (cudaEvent_t e : gev) cudaEventDestroy(e);
   }
   return VLA_OK;
 }

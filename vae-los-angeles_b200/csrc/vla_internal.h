@@ -506,7 +506,9 @@ Recorder*& recorder();             // thread-local; nullptr = launch normally
 // One merged launch: hdr[n] and args[n] (stride bytes apart) in device memory.
 cudaError_t launch_multi(int kind, int variant, const MultiHdr* hdr, const void* args, int stride, int n, int total_blocks,
                          cudaStream_t s);
-cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, cudaStream_t s);
+cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, int max_units,
+                              cudaStream_t s);
+int gemm_max_units(const GemmGroup& g);             // longest main loop of the group in ring slots (persistent-form heuristic)
 int gemm_variant(const GemmGroup& g, int mode);     // which instantiation launch_gemm_group picks (-1: invalid flags)
 
 }  // namespace vla
