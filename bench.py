@@ -746,8 +746,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    # stdout carries ONE line (the JSON result): NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) would precede it
+    # stdout carries ONE line (the JSON result).  NCCL prints its version banner with printf on file descriptor 1 whatever
+    # NCCL_DEBUG says on some boxes: point descriptor 1 at stderr for native code and keep the real stdout for Python's print.
     os.environ["NCCL_DEBUG"] = os.environ.get("VLA_NCCL_DEBUG", "WARN")
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w", buffering=1)
     if args.impl == "reference":
         reference_main(args, rank)
         return
