@@ -184,8 +184,9 @@ bool use_persist(int variant, int total_tiles) {
   return thr > 0 && total_tiles > thr && !(variant >= 2 && variant <= 4) && variant != 33;
 }
 // The persistent form runs a two-stage ring (its transpose patches need the other slots): it pays where the epilogue is the
-// larger part of a tile -- short main loops -- and loses where the main loop is (measured: lock-step populations at batch
-// 4096 slow down by 16 % when the K = 4096 weight-gradient tiles take it).  Longest main loop of a group, in ring slots:
+// larger part of a tile -- short main loops -- and loses where the main loop is (measured on the merged launches of 40 tri-modal
+// models at batch 4096, profiles/r2_population_profile.md: 9 / 13 slots 1.7x / 1.2x faster, 16 slots equal, 26 slots (split
+// operands, K = 782) 1.2x slower, the K = 4096 weight-gradient tiles 1.8x slower).  Longest main loop of a group, in ring slots:
 int gemm_max_units(const GemmGroup& g) {
   int u = 0;
   for (int i = 0; i < g.nprob; ++i) {
@@ -195,7 +196,7 @@ int gemm_max_units(const GemmGroup& g) {
   }
   return u;
 }
-constexpr int PERSIST_MAX_UNITS = 8;
+static const int PERSIST_MAX_UNITS = [] { const char* e = getenv("VLA_PERSIST_UNITS"); return e ? atoi(e) : 14; }();
 
 // Which instantiation of the tile body a group runs: mode * 16 + {0 plain, 1 full, 2 loss (any mix), 3 BCE only, 4 MSE only}.
 int gemm_variant(const GemmGroup& g, int mode) {
