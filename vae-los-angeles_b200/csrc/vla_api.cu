@@ -1262,11 +1262,12 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   // Data parallel: the decoder weight gradients need nothing from the encoder backward.  Compute them now and send them
   // (with the loss scalars, which sit behind them in the flat buffer) on the side stream while the encoder backward runs.
   // (with the chain kernel the decoder data gradients sit in the middle of one launch: no fork point, no early exchange)
+  // CTAs of a weight-gradient launch that runs beside the main chain (the rest of the SMs stay free for the chain's launches)
+  static const int side_ctas = [] { const char* e = getenv("VLA_SIDE_CTAS"); return e ? atoi(e) : 64; }();
   const bool side_dec = io.dp == nullptr && io.side_dec && any_dec && !m->chain_on && !sfx && !recorder() && side_ready(m);
   if (side_dec) {
     CK(cudaEventRecord(m->ev_fork, st));
     CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
-    static const int side_ctas = [] { const char* e = getenv("VLA_SIDE_CTAS"); return e ? atoi(e) : 64; }();
     if ((rc = emit_wgrad(false, true, "wgrad_dec", m->side, side_ctas))) return rc;
     m->side_busy = true;
   }
@@ -1275,7 +1276,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     vla_dp* dp = io.dp;
     CK(cudaEventRecord(dp->ev_fork, st));
     CK(cudaStreamWaitEvent(dp->side, dp->ev_fork, 0));
-    if ((rc = emit_wgrad(false, true, "wgrad_dec", dp->side))) return rc;
+    if ((rc = emit_wgrad(false, true, "wgrad_dec", dp->side, side_ctas))) return rc;
     if ((rc = run_exchange(m, dp, m->cat.w_off / 2, dp->n / 2, 1, dp->side, false))) return rc;
     CK(cudaEventRecord(dp->ev_join, dp->side));
   }
@@ -2211,7 +2212,11 @@ int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&d->local, d->local_bytes);
   if (e == cudaSuccess) e = cudaMemset(d->local, 0, d->local_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {      // lowest priority: the side branch fills the SMs the main chain leaves idle
+    int lo = 0, hi = 0;
+    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaFree(d->base); cudaFree(d->local); delete d; return fail(VLA_ERR_CUDA, std::string("vla_dp_create: ") + cudaGetErrorString(e)); }
