@@ -614,7 +614,7 @@ def run_gpu(args, rank, local_rank, world):
     else:
         ach, peak, unit = top["bytes"] / (top["avg_us"] * 1e-6) / 1e9, peaks["hbm_gbs"], "GB/s"
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath) and args.workload == "rna2dna" and B == 4096:
         with open(tpath) as f:
             traffic = json.load(f).get(top["name"])          # DRAM bytes per launch from the committed ncu --set full capture
