@@ -933,11 +933,14 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
         const int flags = GF_BIAS | GF_OUT_F32 | (io.train ? GF_COLSTATS : 0);
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, flags, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_f32 = w.pre[r]; p->ld_f32 = l.out; p->stats = w.stats[r];
-      } else if (r == e.fc.size() && !io.rc_prefix && !use_hb) {
+      } else if (r == std::max(e.fc.size(), std::min<size_t>(1, max_depth)) && !io.rc_prefix && !use_hb) {
+        // (an encoder without hidden layers -- the site encoder -- runs its heads in round 1 with the other heads, not beside
+        // the wide first layers: round 0 then fits one wave of 32-column tiles)
         const Lin& l = e.heads;
-        const bf16* A = r == 0 ? w.x : w.act[r - 1];
-        const int lda = r == 0 ? w.ldx : w.ld_act[r - 1];
-        const int a_lo = r == 0 ? w.x_lo : w.act_lo[r - 1];
+        const size_t d = e.fc.size();
+        const bf16* A = d == 0 ? w.x : w.act[d - 1];
+        const int lda = d == 0 ? w.ldx : w.ld_act[d - 1];
+        const int a_lo = d == 0 ? w.x_lo : w.act_lo[d - 1];
         if ((rc = add_nt(m, g, A, lda, SH + l.sh_off, l.sh_ld, B, l.out, l.in, GF_BIAS | GF_OUT_F32, &p, 0, a_lo, l.sh_lo))) return rc;
         p->bias = P + l.b_off; p->out_f32 = w.ml; p->ld_f32 = m->HW;
       }
