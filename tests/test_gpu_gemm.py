@@ -73,3 +73,36 @@ def test_gemm_nn_mixed_major(M, N, K, bn):
     ref = A.float() @ B.float()
     err = (out - ref).norm() / ref.norm()
     assert err < 2e-3, float(err)
+
+
+# Launches of more than 1.5 waves with short main loops take the PERSISTENT form (gemm_tc_persist_kernel: a CTA walks a
+# contiguous range of tiles, two TMEM accumulators, two-stage ring); same arithmetic, same tolerance.  Ragged M / N / K on purpose.
+@pytest.mark.parametrize("M,N,K,bn", [(40000, 572, 512, 144), (33001, 160, 200, 32), (70000, 40, 128, 64), (20011, 782, 128, 96)])
+def test_gemm_nt_persistent_form(M, N, K, bn):
+    Ab, A = _padded(M, K, 11)
+    Bb, B = _padded(N, K, 12)
+    out, _ = _run(0, Ab, Bb, M, N, K, bn, 1)
+    ref = A.float() @ B.float().t()
+    assert (out - ref).norm() / ref.norm() < 2e-3
+    assert (out - ref).abs().max() < 2e-3 * ref.abs().max() + 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(40000, 256, 512, 128), (25003, 128, 40, 64)])
+def test_gemm_nn_persistent_form(M, N, K, bn):
+    Ab, A = _padded(M, K, 13)
+    Bb, B = _padded(K, N, 14)
+    out, _ = _run(2, Ab, Bb, M, N, K, bn, 1)
+    ref = A.float() @ B.float()
+    assert (out - ref).norm() / ref.norm() < 2e-3
+
+
+def test_gemm_tn_persistent_form():
+    """Weight-gradient tiles with one k-block per split: 7 x 8 x 8 = 448 tiles, red.add partial sums."""
+    M, N, Kb, bn, splits = 782, 512, 512, 64, 8
+    Gb, G = _padded(Kb, M, 15)
+    Xb, X = _padded(Kb, N, 16)
+    out, bias = _run(1, Gb, Xb, M, N, Kb, bn, splits, want_bias=True)
+    ref = G.float().t() @ X.float()
+    assert (out - ref).norm() / ref.norm() < 2e-3
+    bref = G.float().sum(0)
+    assert (bias - bref).norm() / bref.norm() < 2e-3
