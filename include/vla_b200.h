@@ -197,6 +197,10 @@ typedef struct {
                                    gradients (and the 4 loss scalars behind them) are summed over the ranks through NVLink
                                    peer memory.  grads must be vla_dp_grads(dp), loss_out its last 4 floats; the summed
                                    losses land in vla_dp_losses(dp).  Every rank must call in lockstep. */
+  int sync_bn;                  /* with dp: 1 = BatchNorm statistics over the GLOBAL batch (forward mean / variance and the two
+                                   backward sums of every BatchNorm layer, encoders.py:14,32,36, are all-reduced over the ranks
+                                   through peer memory): the step then equals the reference on the concatenated batch.
+                                   0 = per-shard statistics (the DistributedDataParallel convention; default). */
 } vla_train_args_t;
 int vla_train_step(vla_model_t* m, const vla_train_args_t* a, vla_stream_t stream);
 int vla_set_hyper(vla_model_t* m, float lr, float weight_decay, float beta_kl, float gamma, vla_stream_t stream);

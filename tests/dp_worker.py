@@ -26,7 +26,8 @@ def main():
         raise SystemExit("dp_worker needs one GPU per rank")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    kind, dims, per_rank, steps = "rna2dna", dict(A=782, B=572, S=24, L=20, E=32), 64, 3
+    sync_bn = os.environ.get("DP_SYNCBN", "0") == "1"
+    kind, dims, per_rank, steps = os.environ.get("DP_KIND", "rna2dna"), dict(A=782, B=572, S=24, L=20, E=32), 64, 3
     state = vo.init_state(kind, dims, seed=31)
     tpm, beta, site = vo.synthetic_batch(per_rank * world, dims, seed=31)
     eps, masks = vo.synthetic_noise(per_rank * world, dims, kind, seed=31)
@@ -34,7 +35,7 @@ def main():
     m = make_module(kind, dims, state, device=f"cuda:{local}").train()
     ds = DeviceDataset(tpm[sl], beta[sl], site[sl], f"cuda:{local}")
     tr = Trainer(m, ds, per_rank, beta_kl=1e-3, process_group=dist.group.WORLD, use_graph=os.environ.get("DP_GRAPH", "1") == "1",
-                 exchange=exchange)
+                 exchange=exchange, sync_bn=sync_bn and os.environ.get("DP_SYNCBN_NEGATIVE_CONTROL") != "1")
     tr.injected = dict(eps=to_t(eps[sl], f"cuda:{local}"), keep_masks=[to_t(v[sl], f"cuda:{local}") for v in masks.values()])
     losses = []
     for _ in range(steps):
@@ -46,7 +47,36 @@ def main():
     ref = flat.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(flat, ref), "replicas diverged"
-    if rank == 0:
+    if rank == 0 and sync_bn:
+        # SyncBN oracle: the reference on the CONCATENATED batch (global BatchNorm statistics), one process
+        st = {k: (v.astype(np.float64) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
+        opt, step = vo.adamw_init(st)
+        ref_losses = []
+        full = dict(a=tpm.astype(np.float64), b=beta.astype(np.float64), site=site)
+        for _ in range(steps):
+            scal, _, _, step = vo.train_step(kind, dims, st, opt, step, full, eps.astype(np.float64), masks, beta=1e-3, gamma=1.0,
+                                             q=MATCHED_Q)
+            ref_losses.append([scal["total"], scal["recon"], scal["cls"], scal["kld"]])
+        got = np.array(losses)
+        np.testing.assert_allclose(got[:, 0], np.array(ref_losses)[:, 0], rtol=2e-2)
+        np.testing.assert_allclose(got[:, 3], np.array(ref_losses)[:, 3], rtol=2e-2)
+        sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        worst = 0.0
+        for name, refv in st.items():
+            if name.endswith("num_batches_tracked"):
+                assert int(sd[name]) == steps, name
+                continue
+            if vo.is_buffer(name):        # running statistics of the GLOBAL batch on every rank
+                np.testing.assert_allclose(sd[name], refv, rtol=2e-2, atol=4 * 5e-4 * steps * np.sqrt(refv.size), err_msg=name)
+                continue
+            if is_pre_bn_bias(name):
+                continue
+            d_ref = refv - state[name].astype(np.float64)
+            d_got = sd[name].astype(np.float64) - state[name].astype(np.float64)
+            worst = max(worst, rel_l2(d_got, d_ref))
+        assert worst <= 0.2, worst
+        print(f"DP_OK world={world} exchange={exchange} syncbn kind={kind} worst displacement rel err {worst:.3f} losses {got[-1].tolist()}", flush=True)
+    elif rank == 0:
         # oracle: every shard forward/backward separately (per-shard BatchNorm statistics), gradients summed, one AdamW
         st = {k: (v.astype(np.float64) if v.dtype.kind == "f" else v.copy()) for k, v in state.items()}
         opt, step = vo.adamw_init(st)

@@ -29,3 +29,13 @@ def test_two_rank_dp_matches_summed_shard_oracle(graph, exchange):
         pytest.skip("needs 2 GPUs")
     out = run_worker(dict(DP_GRAPH=graph, DP_EXCHANGE=exchange), 29617)
     assert f"exchange={exchange}" in out
+
+
+@pytest.mark.parametrize("kind", ["rna2dna", "dna2rna"])
+def test_two_rank_sync_bn_equals_reference_on_concatenated_batch(kind):
+    """Opt-in SyncBN: with the BatchNorm column sums all-reduced forward and backward, the 2-rank step
+    equals the reference run ONCE on the concatenated batch (encoders.py:14,32,36 see the global statistics)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = run_worker(dict(DP_GRAPH="1", DP_EXCHANGE="p2p", DP_SYNCBN="1", DP_KIND=kind), 29631)
+    assert f"syncbn kind={kind}" in out

@@ -126,7 +126,38 @@ __global__ void __launch_bounds__(DP_THREADS, 4) dp_adamw_kernel(const DpArgs x,
   }
 }
 
+// SyncBN: all-reduce(SUM) of one BatchNorm layer's column sums (vla_internal.h, DpSmallArgs).  Replaces what
+// torch.nn.SyncBatchNorm would do for encoders.py:14,32,36 under data parallelism.
+__global__ void __launch_bounds__(DP_THREADS) dp_small_allreduce_kernel(const DpSmallArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const unsigned int epoch = static_cast<unsigned int>(__ldcg(&a.dyn->dp_epoch));
+  const int W = a.world, me = a.rank, n = a.n;
+  // word i carries the flattened [2][n] values 2 i and 2 i + 1 (n is even)
+  for (int i = threadIdx.x; i < n; i += DP_THREADS) {
+    double s0 = 0, s1 = 0;
+    for (int t = 0; t < a.m_tiles; ++t) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(a.partials + static_cast<size_t>(t) * 2 * n) + i);
+      s0 += v.x; s1 += v.y;
+    }
+    const float f0 = static_cast<float>(s0), f1 = static_cast<float>(s1);
+    for (int d = 0; d < W; ++d) st_framed(a.slots[(me + d) % W] + static_cast<size_t>(me) * DP_SMALL_WORDS + i, f0, f1, epoch);
+    double t0 = 0, t1 = 0;
+    for (int r = 0; r < W; ++r) {                         // rank order: every rank computes bit-identical sums
+      const uint4* w = a.slots[me] + static_cast<size_t>(r) * DP_SMALL_WORDS + i;
+      const float2 v = r == me ? make_float2(f0, f1) : finish_framed(w, ld_framed(w), epoch);
+      t0 += v.x; t1 += v.y;
+    }
+    reinterpret_cast<float2*>(a.partials)[i] = make_float2(static_cast<float>(t0), static_cast<float>(t1));
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_dp_small_allreduce(const DpSmallArgs& a, cudaStream_t s) {
+  if (a.n <= 0 || (a.n & 1) || a.n > DP_SMALL_WORDS) return cudaErrorInvalidValue;
+  return launch_pdl(dp_small_allreduce_kernel, dim3(1), dim3(DP_THREADS), 0, s, a);
+}
 
 cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s, bool pdl) {
   if (a.n2 <= 0) return cudaSuccess;

@@ -245,9 +245,10 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
     double r[4];
     reduce_partials<MEGA>(a.stats, a.m_tiles, a.n, col, col_ok, sh, r, tid);
     if (ty == 0 && col_ok) {
+      const int srows = a.stat_rows > 0 ? a.stat_rows : a.rows;
       for (int j = 0; j < 2; ++j) {
-        const double mean = r[j] / a.rows;
-        double var = r[2 + j] / a.rows - mean * mean;
+        const double mean = r[j] / srows;
+        double var = r[2 + j] / srows - mean * mean;
         var = var < 0 ? 0 : var;
         const float rstd = rsqrtf(static_cast<float>(var) + 1e-5f);
         s_mean[lane * 2 + j] = static_cast<float>(mean);
@@ -258,7 +259,7 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
         }
         if (by == 0) {
           if (a.update_running) {
-            const double unbiased = a.rows > 1 ? var * a.rows / (a.rows - 1) : var;
+            const double unbiased = srows > 1 ? var * srows / (srows - 1) : var;
             a.running_mean[col + j] = 0.9f * a.running_mean[col + j] + 0.1f * static_cast<float>(mean);
             a.running_var[col + j] = 0.9f * a.running_var[col + j] + 0.1f * static_cast<float>(unbiased);
           }
@@ -344,15 +345,16 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdArgs& a, int rows_per_blo
         s_s1[lane * 2 + j] = static_cast<float>(r[j]);
         s_s2[lane * 2 + j] = static_cast<float>(r[2 + j]);
         if (by == 0) {
-          a.dbeta[col + j] = static_cast<float>(r[j]);
-          a.dgamma[col + j] = static_cast<float>(r[2 + j]);
+          const double gs = a.param_grad_scale > 0.f ? a.param_grad_scale : 1.0;
+          a.dbeta[col + j] = static_cast<float>(r[j] * gs);
+          a.dgamma[col + j] = static_cast<float>(r[2 + j] * gs);
         }
       }
     }
   }
   ew_sync<MEGA>();
   if (!col_ok) return;
-  const float inv_n = 1.0f / a.rows;
+  const float inv_n = 1.0f / (a.stat_rows > 0 ? a.stat_rows : a.rows);
   const float m0 = __ldcg(a.mean + col), m1 = __ldcg(a.mean + col + 1);
   const float rs0 = __ldcg(a.rstd + col), rs1 = __ldcg(a.rstd + col + 1);
   const float g0 = a.gamma[col] * rs0, g1 = a.gamma[col + 1] * rs1;

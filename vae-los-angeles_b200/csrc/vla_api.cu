@@ -182,7 +182,8 @@ struct vla_dp {
   long long per2 = 0;              // float2s per shard
   char* base = nullptr;            // exported allocation (RECV | RSUM)
   char* local = nullptr;           // private allocation (G | sums | trace)
-  size_t off_recv = 0, off_rsum = 0, off_sums = 0, off_trace = 0, bytes = 0, local_bytes = 0;
+  size_t off_recv = 0, off_rsum = 0, off_small = 0, off_sums = 0, off_trace = 0, bytes = 0, local_bytes = 0;
+  int small_next = 0;              // SyncBN: next (BatchNorm layer, direction) region of the step being issued
   char* peer[DP_MAX_WORLD] = {};   // every rank's allocation as mapped here (own: base)
   bool connected = false;
   cudaStream_t side = nullptr;     // the early (decoder) part of the exchange runs here, beside the encoder backward
@@ -226,6 +227,7 @@ int chain_flush(vla_model* m, cudaStream_t st);
 int chain_add(vla_model* m, cudaStream_t st, int kind, int gemm_mode, const void* args, size_t size, const char* name,
               double flops, double bytes, bool needs_all);
 int finalize_group(vla_model* m, GemmGroup& g, int mode);
+int run_stats_allreduce(vla_model* m, vla_dp* dp, float* partials, int m_tiles, int n, const char* name, cudaStream_t st);
 void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
   *flops = 0; *bytes = 0;
   for (int i = 0; i < g.nprob; ++i) {
@@ -795,6 +797,7 @@ struct FwdIO {
   const float* tgt_a = nullptr; const float* tgt_b = nullptr; const long long* tgt_site = nullptr;
   const float* class_w = nullptr; float* loss_out = nullptr;
   bool rc_prefix = false;   // row-chain step: only ingest + the first encoder layer (the row-chain kernel takes over behind it)
+  vla_dp* sync_dp = nullptr;   // opt-in SyncBN: BatchNorm statistics over the global batch (all-reduce of the column sums)
 };
 
 int present_mask(const vla_model* m, const FwdIO& io) {
@@ -959,6 +962,10 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       const Bn& bn = e.bn[r];
       BnActArgs a{};
       a.pre = w.pre[r]; a.ld_pre = bn.n; a.stats = w.stats[r]; a.m_tiles = mt;
+      if (io.sync_dp && io.train) {
+        if ((rc = run_stats_allreduce(m, io.sync_dp, w.stats[r], mt, bn.n, "syncbn_fwd", st))) return rc;
+        a.m_tiles = 1; a.stat_rows = B * io.sync_dp->world;
+      }
       a.gamma = P + bn.g_off; a.beta = P + bn.b_off;
       a.running_mean = io.buffers + bn.rm_off; a.running_var = io.buffers + bn.rv_off;
       a.num_batches_tracked = io.counters ? io.counters + bn.counter : nullptr;
@@ -1119,6 +1126,20 @@ int run_exchange(vla_model* m, vla_dp* dp, long long first2, long long end2, int
   return VLA_OK;
 }
 
+// SyncBN: sum a BatchNorm layer's per-tile column sums over the ranks, in place (tile 0 then holds the global sums).
+int run_stats_allreduce(vla_model* m, vla_dp* dp, float* partials, int m_tiles, int n, const char* name, cudaStream_t st) {
+  if (n > DP_SMALL_WORDS || (n & 1)) return fail(VLA_ERR_INVALID, "SyncBN: BatchNorm width must be even and at most 1024");
+  if (dp->small_next >= DP_SMALL_REGIONS) return fail(VLA_ERR_STATE, "SyncBN: more BatchNorm exchanges in one step than regions");
+  DpSmallArgs a{};
+  a.world = dp->world; a.rank = dp->rank; a.partials = partials; a.m_tiles = m_tiles; a.n = n; a.dyn = m->dyn;
+  const size_t region = static_cast<size_t>(dp->small_next++) * dp->world * DP_SMALL_WORDS;
+  for (int r = 0; r < dp->world; ++r) a.slots[r] = reinterpret_cast<uint4*>(dp->peer[r] + dp->off_small) + region;
+  { int rcf = chain_flush(m, st); if (rcf) return rcf; }
+  ProfScope ps(m, st, name, 0, 16.0 * n * dp->world);
+  CK(launch_dp_small_allreduce(a, st));
+  return VLA_OK;
+}
+
 // Side stream of the model (lowest priority: its kernels fill the SMs the main chain leaves idle).  VLA_SIDE=0 turns it off.
 bool side_ready(vla_model* m) {
   static const bool on = [] { const char* e = getenv("VLA_SIDE"); return !(e && e[0] == '0'); }();
@@ -1146,6 +1167,7 @@ struct BwdIO {
   vla_dp* dp = nullptr;                            // data parallel: the decoder weight gradients are computed and sent early
   bool rc_suffix = false;                          // row-chain step: only BatchNorm backward of the first layers + weight gradients
   bool side_dec = false;                           // single GPU engine step: decoder weight gradients on the model's side stream
+  bool sync_bn = false;                            // opt-in SyncBN (with dp): global BatchNorm-backward sums
 };
 
 int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
@@ -1357,6 +1379,10 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       a.gy = w.gy[it.second]; a.ld_gy = bn.n; a.pre = w.pre[it.second]; a.ld_pre = bn.n;
       // partial statistics per 128-row GEMM tile, or per 32-row block when the head block produced them
       a.stats = w.bstats[it.second]; a.m_tiles = (use_hb && it.second + 1 == e.fc.size()) ? ceil_div(B, HB_ROWS) : mt;
+      if (io.sync_bn && io.dp && train) {
+        if ((rc = run_stats_allreduce(m, io.dp, w.bstats[it.second], a.m_tiles, bn.n, "syncbn_bwd", st))) return rc;
+        a.m_tiles = 1; a.stat_rows = B * io.dp->world; a.param_grad_scale = 1.0f / io.dp->world;
+      }
       a.mean = w.mean[it.second]; a.rstd = w.rstd[it.second]; a.gamma = P + bn.g_off;
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
@@ -1910,7 +1936,14 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   if (a->batch <= 0) return fail(VLA_ERR_INVALID, "batch must be positive");
   const bool do_fb = a->phases != 2, do_opt = a->phases != 1;
   vla_dp* dp = reinterpret_cast<vla_dp*>(a->dp);
+  if (a->sync_bn && !dp) return fail(VLA_ERR_INVALID, "vla_train_step: sync_bn needs the data-parallel exchange (dp)");
   if (dp) {
+    dp->small_next = 0;
+    if (a->sync_bn) {
+      if (m->chain_on || rowchain_enabled() || headblock_enabled())
+        return fail(VLA_ERR_STATE, "vla_train_step: sync_bn runs the separate launches only (VLA_CHAIN / VLA_ROWCHAIN / VLA_HEADBLOCK off)");
+      io.sync_dp = dp;
+    }
     if (!do_fb || !do_opt) return fail(VLA_ERR_INVALID, "vla_train_step: the peer-memory exchange needs the whole step (phases 0 or 3)");
     if (!dp->connected) return fail(VLA_ERR_STATE, "vla_train_step: vla_dp_connect has not been called");
     if (dp->n != m->n_params + 4) return fail(VLA_ERR_INVALID, "vla_train_step: exchange buffer size != param_count + 4");
@@ -2001,7 +2034,7 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
-  bo.dp = dp; bo.side_dec = dp == nullptr && m->dec_chunk0 > 0;
+  bo.dp = dp; bo.side_dec = dp == nullptr && m->dec_chunk0 > 0; bo.sync_bn = dp != nullptr && a->sync_bn != 0;
   if ((rc = run_backward(m, bo, st))) return rc;
   }
   if (m->side_busy) {
@@ -2205,7 +2238,8 @@ int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out) {
   d->per2 = ((n2 + world - 1) / world + 1) & ~1LL;
   d->off_recv = 0;
   d->off_rsum = up(sizeof(uint4) * 2 * static_cast<size_t>(world) * d->per2);   // one RECV region per part
-  d->bytes = d->off_rsum + up(sizeof(uint4) * static_cast<size_t>(n2));
+  d->off_small = d->off_rsum + up(sizeof(uint4) * static_cast<size_t>(n2));       // SyncBN slot arrays [region][world][words]
+  d->bytes = d->off_small + up(sizeof(uint4) * static_cast<size_t>(DP_SMALL_REGIONS) * world * DP_SMALL_WORDS);
   d->off_sums = up(sizeof(float) * n_floats);
   d->off_trace = d->off_sums + 256;
   d->local_bytes = d->off_trace + 256;

@@ -194,6 +194,7 @@ struct BnActArgs {
   int out_lo;                           // > 0: lo copy of the activation out_lo elements further along the row
   const unsigned char* keep_mask;       // optional injected keep mask [rows, n]
   int rows, n;
+  int stat_rows;                        // > 0: rows behind the statistics (SyncBN: the global batch); 0 = rows
   int train;                            // batch statistics + dropout
   int update_running;
   float p_drop;
@@ -210,6 +211,9 @@ struct BnBwdArgs {
   float* dgamma; float* dbeta;
   bf16* gpre; int ld_gpre;
   int rows, n, train;
+  int stat_rows;                        // > 0: rows behind the statistics (SyncBN: the global batch); 0 = rows
+  float param_grad_scale;               // SyncBN: dgamma / dbeta come out of GLOBAL sums on every rank -> 1 / world, so that the
+                                        // step's all-reduce(SUM) of the gradient arena delivers them once; else 1
 };
 cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s);
 
@@ -457,6 +461,19 @@ struct DpArgs {
   unsigned long long* trace;            // optional [4] %globaltimer stamps of the last launch (block 0)
 };
 cudaError_t launch_dp_exchange(const DpArgs& a, cudaStream_t s, bool pdl);
+// Opt-in SyncBN: all-reduce(SUM) over the ranks of a BatchNorm layer's column sums.  One block:
+// reduces this rank's per-tile partials [m_tiles][2][n] (double), pushes the 2n sums framed into every rank's slot array,
+// polls the peers' pushes, adds in rank order (bit-identical on every rank) and writes [2][n] over tile 0 of `partials`
+// (each thread only touches its own columns).  The BatchNorm kernels then run with m_tiles = 1, stat_rows = world * rows.
+constexpr int DP_SMALL_WORDS = 1024;      // framed words per slot: up to 1024 columns
+constexpr int DP_SMALL_REGIONS = 8;       // (BatchNorm layer, direction) slots used within one step
+struct DpSmallArgs {
+  int world, rank;
+  float* partials; int m_tiles, n;
+  uint4* slots[DP_MAX_WORLD];           // every rank's slot array of this region: [world][DP_SMALL_WORDS]
+  const DynParams* dyn;
+};
+cudaError_t launch_dp_small_allreduce(const DpSmallArgs& a, cudaStream_t s);
 cudaError_t launch_dp_adamw(const DpArgs& x, const AdamArgs& a, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------

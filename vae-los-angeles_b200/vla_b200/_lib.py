@@ -63,7 +63,7 @@ class TrainArgs(C.Structure):
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("recon_a", C.c_void_p), ("recon_b", C.c_void_p), ("recon_c", C.c_void_p),
                 ("mu", C.c_void_p), ("logvar", C.c_void_p), ("loss_out", C.c_void_p), ("phases", C.c_int),
-                ("dp", C.c_void_p)]
+                ("dp", C.c_void_p), ("sync_bn", C.c_int)]
 
 
 class MetricsArgs(C.Structure):

@@ -134,8 +134,12 @@ class Trainer:
     torch.distributed only carries the 64-byte IPC handles once); exchange="nccl": torch.distributed.all_reduce."""
 
     def __init__(self, module, dataset, batch_size, lr=5e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8,
-                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True, process_group=None, exchange="p2p"):
+                 beta_kl=1e-3, gamma=1.0, class_weights=None, seed=0, use_graph=True, process_group=None, exchange="p2p",
+                 sync_bn=False):
         self.module = module
+        if sync_bn and (process_group is None or exchange != "p2p"):
+            raise ValueError("sync_bn=True needs process_group and the peer-memory exchange (exchange='p2p')")
+        self.sync_bn = bool(sync_bn)
         self.core = module._ensure_core()
         self.datasets = list(dataset) if isinstance(dataset, (list, tuple)) else [dataset]
         self.batch = int(batch_size)
@@ -229,7 +233,7 @@ class Trainer:
             batch=self.batch, dataset_rows=len(ds), eps=_ptr(eps), keep_masks=masks, seed=self.seed,
             beta1=self.betas[0], beta2=self.betas[1], adam_eps=self.eps,
             recon_a=None, recon_b=None, recon_c=None, mu=None, logvar=None, loss_out=_ptr(self._loss_local), phases=phases,
-            dp=self.dp)
+            dp=self.dp, sync_bn=1 if self.sync_bn else 0)
 
     def _call(self, ds, phases):
         args = self._args(ds, phases)
