@@ -1301,7 +1301,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     vla_dp* dp = io.dp;
     CK(cudaEventRecord(dp->ev_fork, st));
     CK(cudaStreamWaitEvent(dp->side, dp->ev_fork, 0));
-    if ((rc = emit_wgrad(false, true, "wgrad_dec", dp->side, side_ctas))) return rc;
+    if ((rc = emit_wgrad(false, true, "wgrad_dec", dp->side))) return rc;      // (full width: the exchange behind it is on the clock)
     if ((rc = run_exchange(m, dp, m->cat.w_off / 2, dp->n / 2, 1, dp->side, false))) return rc;
     CK(cudaEventRecord(dp->ev_join, dp->side));
   }
@@ -2249,11 +2249,7 @@ int vla_dp_create(int world, int rank, long long n_floats, vla_dp_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&d->local, d->local_bytes);
   if (e == cudaSuccess) e = cudaMemset(d->local, 0, d->local_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) {      // lowest priority: the side branch fills the SMs the main chain leaves idle
-    int lo = 0, hi = 0;
-    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo);
-  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaFree(d->base); cudaFree(d->local); delete d; return fail(VLA_ERR_CUDA, std::string("vla_dp_create: ") + cudaGetErrorString(e)); }
