@@ -1289,7 +1289,9 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
   // (with the chain kernel the decoder data gradients sit in the middle of one launch: no fork point, no early exchange)
   // CTAs of a weight-gradient launch that runs beside the main chain (the rest of the SMs stay free for the chain's launches)
   static const int side_ctas = [] { const char* e = getenv("VLA_SIDE_CTAS"); return e ? atoi(e) : 64; }();
-  const bool side_dec = io.dp == nullptr && io.side_dec && any_dec && !m->chain_on && !sfx && !recorder() && side_ready(m);
+  // (data parallel: only where the decoder gradients are not exchanged early -- that path has its own branch below)
+  const bool side_dec = (io.dp == nullptr || !dp_overlap(io.dp)) && io.side_dec && any_dec && !m->chain_on && !sfx && !recorder() &&
+                        side_ready(m);
   if (side_dec) {
     CK(cudaEventRecord(m->ev_fork, st));
     CK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
@@ -2034,19 +2036,17 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   }
   BwdIO bo{};
   bo.params = a->params; bo.grads = a->grads; bo.engine = true; bo.zero_grads = false;   // AdamW leaves grads zeroed
-  bo.dp = dp; bo.side_dec = dp == nullptr && m->dec_chunk0 > 0; bo.sync_bn = dp != nullptr && a->sync_bn != 0;
+  bo.dp = dp; bo.side_dec = m->dec_chunk0 > 0; bo.sync_bn = dp != nullptr && a->sync_bn != 0;
   if ((rc = run_backward(m, bo, st))) return rc;
   }
   if (m->side_busy) {
     // the side branch carries the decoder weight gradients; give it the decoder part of AdamW too, then join
     m->side_busy = false;
     static const bool side_adam = [] { const char* e = getenv("VLA_SIDE_ADAM"); return e && e[0] == '1'; }();
-    if (!side_adam) {
+    if (!side_adam || dp) {      // join, then the optimizer launch of the normal flow (plain AdamW, or exchange + AdamW)
       CK(cudaEventRecord(m->ev_join, m->side));
       CK(cudaStreamWaitEvent(st, m->ev_join, 0));
-      if (!do_opt) return VLA_OK;
-      return run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0, true,
-                       true, st);
+      goto side_joined;
     }
     const int nd = static_cast<int>(m->chunks_h.size()) - m->dec_chunk0;
     if (do_opt && (rc = run_adamw(m, a->params, a->grads, a->exp_avg, a->exp_avg_sq, 0.f, a->beta1, a->beta2, a->adam_eps, 0.f, 0,
@@ -2057,6 +2057,7 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
     CK(cudaStreamWaitEvent(st, m->ev_join, 0));
     return VLA_OK;
   }
+side_joined:
   if (!do_opt) return VLA_OK;
   if (dp) {
     // ---- the step's one collective, second part: the encoder gradients (the decoder part left from run_backward on the
