@@ -1106,14 +1106,15 @@ DpArgs make_dp_args(vla_model* m, vla_dp* dp, long long first2, long long end2, 
   x.trace = reinterpret_cast<unsigned long long*>(dp->local + dp->off_trace) + 4 * part;
   return x;
 }
-// Send the decoder gradients early, on the side stream, while the encoder backward runs?  Measured (rna2dna, batch 4096 per
-// GPU, profiles/r1_dp_exchange.md): neutral at 2 GPUs (129.0 vs 128.7 us / step), -4 us at 8 GPUs (130.1 vs 134.2) where
-// the pushes are 7/8 of the buffer; the split costs one more weight-gradient launch.  Default: on from 4 ranks.
-// VLA_DP_OVERLAP=0/1 overrides (every rank must use the same setting).
+// Send the decoder gradients early, on the side stream, while the encoder backward runs?  Round 1 (rna2dna, batch 4096 per
+// GPU, profiles/r1_dp_exchange.md): neutral at 2 GPUs, -4 us at 8 GPUs.  Round 2, with the decoder weight gradients on the
+// low-priority 64-CTA side branch instead (as on one GPU): 137.0 us without the early exchange vs 139.3 us with it at 8 GPUs
+// (profiles/r2_bench_n8*.json) -- the early exchange's polling blocks and its full-width weight-gradient launch hold SMs the
+// main chain's GEMM CTAs need (dgrad_enc_l1 13.7 vs 10.6 us).  Default: off.  VLA_DP_OVERLAP=1 turns it on (every rank alike).
 bool dp_overlap(const vla_dp* dp) {
+  (void)dp;
   const char* e = getenv("VLA_DP_OVERLAP");
-  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-  return dp->world >= 4;
+  return e && e[0] == '1';
 }
 // algorithmic bytes of an exchange: payload out + in over NVLink
 double dp_bytes(const DpArgs& x) { return 16.0 * x.n2 * (x.world - 1) / x.world; }
