@@ -741,12 +741,27 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
     const unsigned idx = static_cast<unsigned>(ch.first + e);                                // one tensor < 2^31 elements
     int r = static_cast<int>(idx / static_cast<unsigned>(ch.cols));
     int c = static_cast<int>(idx - static_cast<unsigned>(r) * ch.cols);
-    for (int k = 0; k < nv; ++k) {
-      const bf16 h = __float2bfloat16(p[k]);
-      bf16* dst = a.shadow + ch.shadow_off + static_cast<long long>(r) * ch.ld_shadow + c;
-      *dst = h;
-      if (ch.sh_lo > 0) dst[ch.sh_lo] = bf16_lo_of(p[k], h);
-      if (++c == ch.cols) { c = 0; ++r; }
+    if (nv == 4 && !(ch.cols & 1) && !(ch.shadow_off & 1) && !(ch.sh_lo & 1)) {
+      // even row width (idx is a multiple of 4, so c is even and a pair never straddles a row): two packed 4-byte stores per
+      // copy instead of four 2-byte ones (the row pitch and the lo offset are multiples of 8)
+#pragma unroll
+      for (int k = 0; k < 4; k += 2) {
+        uint32_t lo;
+        const uint32_t hi = pack_bf16x2_hi_lo(p[k], p[k + 1], lo);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(a.shadow + ch.shadow_off + static_cast<long long>(r) * ch.ld_shadow + c);
+        *dst = hi;
+        if (ch.sh_lo > 0) dst[ch.sh_lo >> 1] = lo;
+        c += 2;
+        if (c >= ch.cols) { c = 0; ++r; }
+      }
+    } else {
+      for (int k = 0; k < nv; ++k) {
+        const bf16 h = __float2bfloat16(p[k]);
+        bf16* dst = a.shadow + ch.shadow_off + static_cast<long long>(r) * ch.ld_shadow + c;
+        *dst = h;
+        if (ch.sh_lo > 0) dst[ch.sh_lo] = bf16_lo_of(p[k], h);
+        if (++c == ch.cols) { c = 0; ++r; }
+      }
     }
   }
 }
