@@ -149,6 +149,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_persist_kernel(const 
   }
 }
 
+// NT launches whose problems all have a multiple of GEMM_CLUSTER n-tiles per row block: 4-CTA clusters, the A tile of a row
+// block multicast across the cluster (gemm_tile<.., CL>).
+constexpr int GEMM_CLUSTER = 4;
+template <int FEATS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_cluster_kernel(const __grid_constant__ GemmGroup grp) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_PROBLEMS; ++i)
+    if (i < grp.nprob && static_cast<int>(blockIdx.x) >= grp.p[i].tile_begin) pi = i;
+  const GemmProblem& P = grp.p[pi];
+  if (threadIdx.x == 0) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
+  TileCtx ctx = tile_setup(true, false, GEMM_TMEM_COLS, GEMM_CLUSTER);
+  cluster_sync_all();              // every CTA's barriers exist before a peer's multicast can signal them
+  pdl_wait();
+  pdl_launch_dependents();
+  {
+    const int local = static_cast<int>(blockIdx.x) - P.tile_begin;
+    const int n_tile = local % P.n_tiles, rest = local / P.n_tiles;
+    gemm_tile<0, FEATS, false, GEMM_CLUSTER>(ctx, P, &P.tmA, &P.tmB, rest % P.m_tiles, n_tile, rest / P.m_tiles, &grp.tail);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // no CTA leaves while a peer may still write into its slots or arrive on its barriers
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    tmem_dealloc(ctx.tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 size_t gemm_smem_bytes() { return SMEM_BYTES; }
@@ -198,6 +227,41 @@ int gemm_max_units(const GemmGroup& g) {
 }
 static const int PERSIST_MAX_UNITS = [] { const char* e = getenv("VLA_PERSIST_UNITS"); return e ? atoi(e) : 14; }();
 
+template <int FEATS>
+cudaError_t launch_one_cluster(const GemmGroup& g, cudaStream_t stream) {
+  static cudaError_t attr = cudaFuncSetAttribute(gemm_tc_cluster_kernel<FEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (attr != cudaSuccess) return attr;
+  static const bool pdl_on = [] { const char* e = getenv("VLA_NO_PDL"); return !(e && e[0] == '1'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g.total_tiles); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = GEMM_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_on ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_cluster_kernel<FEATS>, g);
+}
+// How many 4-CTA clusters of the cluster kernel the device runs at once (0: clusters unavailable).
+int gemm_cluster_capacity() {
+  static const int cap = [] {
+    if (cudaFuncSetAttribute(gemm_tc_cluster_kernel<FEATS_FWD_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(GEMM_CLUSTER * 64); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = GEMM_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_cluster_kernel<FEATS_FWD_PLAIN>, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+  }();
+  return cap;
+}
+
 // Which instantiation of the tile body a group runs: mode * 16 + {0 plain, 1 full, 2 loss (any mix), 3 BCE only, 4 MSE only}.
 int gemm_variant(const GemmGroup& g, int mode) {
   int used = 0;
@@ -243,6 +307,16 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
     op.args.assign(reinterpret_cast<const char*>(&g), sizeof(GemmGroup));
     r->ops.push_back(std::move(op));
     return cudaSuccess;
+  }
+  if (mode == 0 && g.pad[0] == GEMM_CLUSTER && !g.dbg && !g.dbg_flags) {      // (finalize_group built the A maps for the multicast ring)
+    switch (variant) {
+      case 0: return launch_one_cluster<FEATS_FWD_PLAIN>(g, stream);
+      case 1: return launch_one_cluster<FEATS_FWD_FULL>(g, stream);
+      case 2: return launch_one_cluster<FEATS_FWD_LOSS>(g, stream);
+      case 3: return launch_one_cluster<FEATS_FWD_LOSS_BCE>(g, stream);
+      case 4: return launch_one_cluster<FEATS_FWD_LOSS_MSE>(g, stream);
+      default: return cudaErrorInvalidValue;
+    }
   }
   if (!g.dbg && !g.dbg_flags && use_persist(variant, g.total_tiles) && gemm_max_units(g) <= PERSIST_MAX_UNITS) {
 #define VLA_CALL_PERSIST(M_, F_) launch_one_persist<M_, F_>(g, nullptr, nullptr, 0, g.total_tiles, stream)

@@ -123,7 +123,8 @@ __device__ __forceinline__ uint64_t* tile_ew_bar(uint8_t* smem) { return tile_ba
 // One-time CTA setup shared by both kernels: barriers, bf16 ones for the bias-gradient MMA, TMEM.
 // Ends with a CTA-wide barrier; returns the context with the ring at its origin.
 // Barrier block: full[S] | empty[S] | acc (persistent: acc_full[0]) | dep (acc_full[1]) | ew (acc_empty[0]) | acc_empty[1] | TMEM slot
-__device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = true, uint32_t tmem_cols = GEMM_TMEM_COLS) {
+__device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = true, uint32_t tmem_cols = GEMM_TMEM_COLS,
+                                               uint32_t empty_count = 1) {
   TileCtx c;
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
@@ -137,7 +138,7 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
     mbar_init(ew_bar + 1, 1);
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], empty_count);      // (multicast ring: one release per CTA of the cluster)
     }
     mbar_init(acc_bar, 1);
     mbar_init(dep_bar, 1);
@@ -165,13 +166,18 @@ __device__ __forceinline__ TileCtx tile_setup(bool alloc_tmem, bool fill_ones = 
 // FEATS: compile-time superset of the epilogue flags that may occur; everything else is compiled out (smaller code:
 // the epilogue is instruction-fetch sensitive).  All threads of the CTA call this; on return the tile's global writes
 // have been issued by the epilogue threads (the caller orders them: barrier + fence) and ctx has advanced.
-template <int MODE, int FEATS, bool PERSIST = false>
+// CL > 1 (NT mode, gemm_tc_cluster_kernel): the CL CTAs of a cluster work on CL neighbouring n-tiles of ONE row block.  Each
+// loads 1 / CL of the A tile (GEMM_BM / CL rows) and MULTICASTS it into every CTA's slot, so an SM takes in A / CL + B per
+// k-block instead of A + B (the main loop is bound by the per-SM L2 -> shared-memory intake: profiles/r2_ring_depth_experiment.md).
+// A slot is reused only when all CL CTAs have consumed it: every MMA issuer's commit releases the stage in all CL CTAs.
+template <int MODE, int FEATS, bool PERSIST = false, int CL = 1>
 __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                           int m_tile, int n_tile, int k_split, const LossTail* tail_desc = nullptr) {
   uint8_t* smem = aligned_smem();
   uint64_t* full_bar = tile_bars(smem);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
   static_assert(!PERSIST || !(FEATS & GF_LOSS), "the loss epilogue stages its targets in the ring's slots: not persistent");
+  static_assert(CL == 1 || (MODE == 0 && !PERSIST && GEMM_BM % CL == 0), "multicast ring: NT mode, one tile per CTA");
   constexpr int NS = PERSIST ? PERSIST_STAGES : GEMM_STAGES;          // ring stages in use
   const uint32_t acc_buf = PERSIST ? (ctx.tile_seq & 1u) : 0u;        // which accumulator this tile uses
   const uint32_t acc_par = PERSIST ? ((ctx.tile_seq >> 1) & 1u) : ctx.tile_parity;
@@ -221,8 +227,8 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
   } else if (warp == 0) {
     // =========================== TMA producer ===========================
     // A load unit = one k-block of A and B (split operands: the hi or the lo copy of a k-block) = one shared-memory slot.
-    // GEMM_GROUP consecutive units share ONE full / empty barrier pair (one hand-shake).
-    if (lane == 0) {
+    // GEMM_GROUP consecutive units share ONE full / empty barrier pair (one hand-shake).  One elected thread (see the MMA issuer).
+    if (elect_one()) {
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
       const int u0 = (split ? 2 : 1) * kb0, u1 = (split ? 2 : 1) * kb1;
@@ -241,6 +247,11 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
           if (MODE == 1) {
             tma_load_2d(sa, tmA, &full_bar[stage], m0, kb * GEMM_BK);           // box 64 (M) x 64 (K)
             tma_load_2d(sa + 8192, tmA, &full_bar[stage], m0 + 64, kb * GEMM_BK);
+          } else if (CL > 1) {
+            // this CTA's share of the row block, to every CTA of the cluster (tmA's box is 64 (K) x GEMM_BM / CL rows)
+            const uint32_t rk = cluster_ctarank();
+            tma_load_2d_mc(sa + rk * (A_STAGE_BYTES / CL), tmA, &full_bar[stage], kb * GEMM_BK + (lo ? P.a_lo : 0),
+                           m0 + static_cast<int>(rk) * (GEMM_BM / CL), static_cast<uint16_t>((1u << CL) - 1u));
           } else {
             tma_load_2d(sa, tmA, &full_bar[stage], kb * GEMM_BK + (lo ? P.a_lo : 0), m0);   // box 64 (K) x 128 (M)
           }
@@ -256,10 +267,14 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // One ELECTED thread (elect.sync: the compiler then keeps the whole loop on the uniform datapath without a vote loop around
+    // every tcgen05.mma); operand descriptors are built once per slot and ADVANCED along K by adding to the start-address field
+    // (16-byte units, no carry: shared memory < 256 KB).  The issue loop used to cost ~116 cycles per MMA -- more than the MMA
+    // itself for tiles narrower than 224 columns -- and bounded every main loop (profiles/r2_mma_issue.md).
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MODE == 1 ? 1 : 0, MODE == 0 ? 0 : 1);
       const uint32_t idesc_ones = make_idesc_bf16(GEMM_BM, 16, 1, 0);
-      const uint32_t ones_addr = smem_u32(smem + ONES_OFFSET);
+      const uint64_t odesc = make_smem_desc(smem_u32(smem + ONES_OFFSET), 16, 1024);
       int stage = ctx.stage;
       uint32_t phase = ctx.phase;
       const int u0 = (split ? 2 : 1) * kb0, u1 = (split ? 2 : 1) * kb1;
@@ -274,37 +289,37 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
         tc_fence_after();
         if (split) {
           // the two slots of the stage = (A_hi, B_hi) and (A_lo, B_lo) of one k-block; three passes of four MMAs
-          const uint32_t a_hi = smem_u32(smem + (stage * GEMM_GROUP) * STAGE_BYTES), b_hi = a_hi + A_STAGE_BYTES;
-          const uint32_t a_lo = a_hi + STAGE_BYTES, b_lo = a_lo + A_STAGE_BYTES;
+          const uint32_t a_hi = smem_u32(smem + (stage * GEMM_GROUP) * STAGE_BYTES);
+          const uint64_t dah = make_smem_desc(a_hi, 16, 1024), dbh = make_smem_desc(a_hi + A_STAGE_BYTES, 16, 1024);
+          const uint64_t dal = dah + (STAGE_BYTES >> 4), dbl = dbh + (STAGE_BYTES >> 4);
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t pa = pass == 1 ? a_lo : a_hi, pb = pass == 2 ? b_lo : b_hi;
+            const uint64_t da = pass == 1 ? dal : dah, db = pass == 2 ? dbl : dbh;
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              umma_bf16(tmem_base, make_smem_desc(pa + k * 32, 16, 1024), make_smem_desc(pb + k * 32, 16, 1024), idesc,
-                        (ug > u0 || k > 0 || pass > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k)        // +16 bf16 of K inside the swizzle atom = +32 bytes = +2 units
+              umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (ug > u0 || k > 0 || pass > 0) ? 1u : 0u);
           }
         } else {
           for (int j = 0; j < cnt; ++j) {
             const uint32_t sa = smem_u32(smem + (stage * GEMM_GROUP + j) * STAGE_BYTES);
             const uint32_t sb = sa + A_STAGE_BYTES;
+            // MN-major: +16 K-rows of 128 B = +128 units per MMA; K-major: +16 bf16 of K inside the swizzle atom = +2 units
+            const uint64_t a0 = MODE == 1 ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
+            const uint64_t b0 = MODE == 0 ? make_smem_desc(sb, 16, 1024) : make_smem_desc(sb, 8192, 1024);
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) {
-              uint64_t adesc, bdesc;
-              if (MODE == 1) adesc = make_smem_desc(sa + k * 2048, 8192, 1024);  // MN-major: +16 K-rows of 128 B
-              else           adesc = make_smem_desc(sa + k * 32, 16, 1024);       // K-major: +16 bf16 of K inside the swizzle atom
-              if (MODE == 0) bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-              else           bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
+              const uint64_t adesc = a0 + (MODE == 1 ? 128 : 2) * k;
+              const uint64_t bdesc = b0 + (MODE == 0 ? 2 : 128) * k;
               const uint32_t acc = (ug > u0 || j > 0 || k > 0) ? 1u : 0u;
               umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
               if (bias_mma) {
-                const uint64_t odesc = make_smem_desc(ones_addr, 16, 1024);
                 umma_bf16(tmem_base + GEMM_BIAS_TMEM_COL, adesc, odesc, idesc_ones, acc);
               }
             }
           }
         }
-        umma_commit(&empty_bar[stage]);   // frees the stage's slots when these MMAs retire
+        if (CL > 1) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1u));
+        else umma_commit(&empty_bar[stage]);   // frees the stage's slots when these MMAs retire
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
       umma_commit(acc_bar);           // accumulator complete

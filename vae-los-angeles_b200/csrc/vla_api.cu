@@ -560,6 +560,9 @@ int choose_bn_tn(int N) {
 
 // Per-group list of the B operands whose tensor maps wait for the joint tile-width choice (finalize_group)
 thread_local PendingB g_pending[GEMM_MAX_PROBLEMS];
+// ... and the A operands of an NT group (the multicast kernel needs their maps with GEMM_BM / 4-row boxes)
+struct PendingA { const void* base; uint64_t inner, outer, pitch; };
+thread_local PendingA g_pending_a[GEMM_MAX_PROBLEMS];
 
 // C[M,N] = A[M,K] * W[N,K]^T ; A bf16 [M, lda], W bf16 [N, ldw]
 // a_lo / b_lo > 0 (both or neither): split-bf16 operands, the lo copies sit a_lo / b_lo elements further along each row
@@ -577,6 +580,7 @@ int add_nt(vla_model* m, GemmGroup& g, const bf16* A, int lda, const bf16* W, in
   p.a_lo = a_lo; p.b_lo = b_lo;
   int rc;
   if ((rc = get_tmap(m, &p.tmA, A, a_lo > 0 ? a_lo + K : K, M, static_cast<uint64_t>(lda) * 2, GEMM_BM))) return rc;
+  g_pending_a[g.nprob] = PendingA{A, static_cast<uint64_t>(a_lo > 0 ? a_lo + K : K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2};
   g_pending[g.nprob] = PendingB{W, static_cast<uint64_t>(b_lo > 0 ? b_lo + K : K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, 0, K, force_bn != 0};
   g.nprob++;
   *out = &p;
@@ -737,6 +741,22 @@ int finalize_group(vla_model* m, GemmGroup& g, int mode) {
     if ((rc = get_tmap(m, &p.tmB, b.base, b.inner, b.outer, b.pitch, mode == 0 ? static_cast<uint32_t>(p.BN) : 64u))) return rc;
     p.tile_begin = g.total_tiles;
     g.total_tiles += p.m_tiles * p.n_tiles;
+  }
+  // One wave of NT tiles whose row blocks all have a multiple of 4 n-tiles: 4-CTA clusters with the A tile multicast
+  // (gemm_tc_cluster_kernel; VLA_CLUSTER=0 turns it off).  The A maps are rebuilt with 32-row boxes.
+  g.pad[0] = 0;
+  static const bool cluster_on = [] { const char* e = getenv("VLA_CLUSTER"); return !(e && e[0] == '0'); }();
+  if (mode == 0 && cluster_on && !recorder() && g.total_tiles <= 148 && g.total_tiles / 4 <= gemm_cluster_capacity()) {
+    bool ok = n > 0;
+    for (int i = 0; i < n; ++i) ok = ok && (g.p[i].n_tiles % 4 == 0) && g.p[i].k_splits == 1;
+    if (ok) {
+      for (int i = 0; i < n; ++i) {
+        const PendingA& a = g_pending_a[i];
+        int rc;
+        if ((rc = get_tmap(m, &g.p[i].tmA, a.base, a.inner, a.outer, a.pitch, GEMM_BM / 4))) return rc;
+      }
+      g.pad[0] = 4;
+    }
   }
   return VLA_OK;
 }

@@ -119,7 +119,7 @@ struct GemmGroup {
   int dbg_flags;             // test hook: 1 = skip epilogue stores, 2 = skip main loop, 4 = skip TMEM alloc (with 2)
   int pad0;
   LossTail tail;             // used by problems with GF_LOSS
-  int pad[8];
+  int pad[8];                // pad[0] = 4: NT group laid out for the 4-CTA multicast kernel (A maps with 32-row boxes)
   GemmProblem p[GEMM_MAX_PROBLEMS];
 };
 static_assert(sizeof(LossTail) == 80, "LossTail layout");
@@ -526,6 +526,7 @@ cudaError_t launch_multi(int kind, int variant, const MultiHdr* hdr, const void*
 cudaError_t launch_gemm_multi(int variant, const MultiHdr* hdr, const GemmGroup* groups, int n, int total_blocks, int max_units,
                               cudaStream_t s);
 int gemm_max_units(const GemmGroup& g);             // longest main loop of the group in ring slots (persistent-form heuristic)
+int gemm_cluster_capacity();                         // 4-CTA clusters of the multicast GEMM kernel the device runs at once
 int gemm_variant(const GemmGroup& g, int mode);     // which instantiation launch_gemm_group picks (-1: invalid flags)
 
 }  // namespace vla
