@@ -308,7 +308,8 @@ cudaError_t launch_gemm_group(const GemmGroup& g, int mode, cudaStream_t stream)
     r->ops.push_back(std::move(op));
     return cudaSuccess;
   }
-  if (mode == 0 && g.pad[0] == GEMM_CLUSTER && !g.dbg && !g.dbg_flags) {      // (finalize_group built the A maps for the multicast ring)
+  if (g.pad[0] == GEMM_CLUSTER && (mode != 0 || g.dbg || g.dbg_flags)) return cudaErrorInvalidValue;   // A maps have 32-row boxes
+  if (mode == 0 && g.pad[0] == GEMM_CLUSTER) {      // (finalize_group built the A maps for the multicast ring)
     switch (variant) {
       case 0: return launch_one_cluster<FEATS_FWD_PLAIN>(g, stream);
       case 1: return launch_one_cluster<FEATS_FWD_FULL>(g, stream);

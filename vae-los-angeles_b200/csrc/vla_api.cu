@@ -746,7 +746,8 @@ int finalize_group(vla_model* m, GemmGroup& g, int mode) {
   // (gemm_tc_cluster_kernel; VLA_CLUSTER=0 turns it off).  The A maps are rebuilt with 32-row boxes.
   g.pad[0] = 0;
   static const bool cluster_on = [] { const char* e = getenv("VLA_CLUSTER"); return !(e && e[0] == '0'); }();
-  if (mode == 0 && cluster_on && !recorder() && g.total_tiles <= 148 && g.total_tiles / 4 <= gemm_cluster_capacity()) {
+  if (mode == 0 && cluster_on && !recorder() && !g.dbg && !g.dbg_flags && g.total_tiles <= 148 &&
+      g.total_tiles / 4 <= gemm_cluster_capacity()) {
     bool ok = n > 0;
     for (int i = 0; i < n; ++i) ok = ok && (g.p[i].n_tiles % 4 == 0) && g.p[i].k_splits == 1;
     if (ok) {
@@ -1979,7 +1980,8 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
   io.n_batches = a->dataset_rows > a->batch ? static_cast<int>(a->dataset_rows / a->batch) : 1;
   io.beta1 = a->beta1; io.beta2 = a->beta2;
   // loss fused into the last decoder layers' epilogues (the CE term needs the whole logit row in one 32-column chunk)
-  io.fuse_loss = m->S <= 32;
+  static const bool fuse_loss_on = [] { const char* e = getenv("VLA_FUSE_LOSS"); return !(e && e[0] == '0'); }();
+  io.fuse_loss = m->S <= 32 && fuse_loss_on;
   for (const Dec& d : m->decs) {
     if (d.type == 'A' && !a->x_a) return fail(VLA_ERR_INVALID, "x_a (target) missing");
     if (d.type == 'B' && !a->x_b) return fail(VLA_ERR_INVALID, "x_b (target) missing");
