@@ -60,6 +60,16 @@ def test_gemm_kernels_use_tcgen05_tma_tmem(sass):
         for name, ops in more.items():
             have = {op.split(".")[0] for op in ops}
             assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= have, name
+    # the 4-CTA cluster form: A tiles by multicast TMA, stage release by multicast tcgen05.commit, cluster barriers
+    cl = _find(kernels, "gemm_tc_cluster_kernel")
+    assert len(cl) >= 4, len(cl)
+    for name, ops in cl.items():
+        assert {"UTCHMMA", "UTMALDG.2D.MULTICAST", "UTCBAR.MULTICAST", "UCGABAR_ARV", "UCGABAR_WAIT"} <= set(ops) | {op.split(".")[0] for op in ops}, name
+    # the MMAs of a k-block issue back to back: no vote loop (ELECT ... BRA.U.ANY) around tcgen05.mma any more
+    for name, ops in gemms.items():
+        idx = [i for i, op in enumerate(ops) if op.startswith("UTCHMMA")]
+        gaps = [b - a for a, b in zip(idx, idx[1:])]
+        assert gaps and sorted(gaps)[len(gaps) // 2] <= 4, (name, sorted(gaps)[len(gaps) // 2])
     rowchain = _find(kernels, "15rowchain_kernel")
     assert rowchain and all({"UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"} <= {op.split(".")[0] for op in ops} for ops in rowchain.values())
     chain = _find(kernels, "12chain_kernel")
