@@ -91,28 +91,23 @@ __device__ __forceinline__ float block_sum(float v, float* sh, int tid) {
 // gradient.  One element per thread and iteration (site and table loads of different rows are independent).
 __device__ __forceinline__ void ingest_site(const IngestArgs& a, int r_begin, int r_end, int t, int nthreads, long long row0) {
   if (a.site == nullptr) return;
-  const int nrows = r_end - r_begin;
-  const int n_h = nrows * a.ld_hsite, n_o = nrows * a.ld_onehot;
-#pragma unroll 4
-  for (int i = t; i < n_h; i += nthreads) {
-    const int r = i / a.ld_hsite, c = i - r * a.ld_hsite;
-    const long long s = __ldg(a.site + row0 + r_begin + r);
+  // one warp per row, lane = column: one label load per row, no index division
+  const int lane = t & 31, gwarp = t >> 5, nwarps = nthreads >> 5;
+  for (int r = r_begin + gwarp; r < r_end; r += nwarps) {
+    const long long s = __ldg(a.site + row0 + r);
+    bf16* hrow = a.h_site + static_cast<size_t>(r) * a.ld_hsite;
     if (a.hsite_lo > 0) {                       // split layout: hi in [0, embed), lo in [hsite_lo, hsite_lo + embed), rest stays zero
-      const int cc = c >= a.hsite_lo ? c - a.hsite_lo : c;
-      if (cc < a.embed) {
-        const float x = a.emb[s * a.embed + cc];
+      for (int c = lane; c < a.embed; c += 32) {
+        const float x = __ldg(a.emb + s * a.embed + c);
         const bf16 h = __float2bfloat16(x);
-        a.h_site[static_cast<size_t>(r_begin + r) * a.ld_hsite + c] = c >= a.hsite_lo ? bf16_lo_of(x, h) : h;
+        hrow[c] = h;
+        hrow[a.hsite_lo + c] = bf16_lo_of(x, h);
       }
     } else {
-      a.h_site[static_cast<size_t>(r_begin + r) * a.ld_hsite + c] = __float2bfloat16(c < a.embed ? a.emb[s * a.embed + c] : 0.f);
+      for (int c = lane; c < a.ld_hsite; c += 32) hrow[c] = __float2bfloat16(c < a.embed ? __ldg(a.emb + s * a.embed + c) : 0.f);
     }
-  }
-#pragma unroll 4
-  for (int i = t; i < n_o; i += nthreads) {
-    const int r = i / a.ld_onehot, c = i - r * a.ld_onehot;
-    const long long s = __ldg(a.site + row0 + r_begin + r);
-    a.onehot[static_cast<size_t>(r_begin + r) * a.ld_onehot + c] = __float2bfloat16(s == c ? 1.f : 0.f);
+    bf16* orow = a.onehot + static_cast<size_t>(r) * a.ld_onehot;
+    for (int c = lane; c < a.ld_onehot; c += 32) orow[c] = __float2bfloat16(s == c ? 1.f : 0.f);
   }
 }
 
@@ -128,10 +123,35 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
   const long long row0 = a.n_batches > 1 ? static_cast<long long>(a.dyn->batch_index % a.n_batches) * a.rows : 0;
   for (int e = 0; e < a.n; ++e) {
     const int lo_off = a.lo_off[e];
-    // split layout [hi: 0 .. w | zeros | lo: lo_off .. lo_off + w | zeros]: only the quads that hold data are written
-    const int quads = lo_off > 0 ? (a.width[e] + 3) >> 2 : a.ld_dst[e] >> 2;   // ld_dst is a multiple of 8
     const float* __restrict__ src = a.src[e];
     const int w = a.width[e];
+    if ((w % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0) && lo_off > 0) {
+      // split layout [hi: 0 .. w | zeros | lo: lo_off .. lo_off + w | zeros], even width: one warp per row, lanes stride over
+      // 8-byte pairs (rows are 8-byte aligned), four pairs in flight per lane; 4-byte bf16x2 stores, 128 contiguous bytes per
+      // warp instruction.  Only the columns that hold data are written (the padding stays zero from the allocation).
+      const int pairs = w >> 1, lo_w = lo_off >> 1;
+      for (int r = r_begin + gwarp; r < r_end; r += nwarps) {
+        const float2* sp = reinterpret_cast<const float2*>(src + (row0 + r) * w);
+        uint32_t* dp = reinterpret_cast<uint32_t*>(a.dst[e] + static_cast<size_t>(r) * a.ld_dst[e]);
+        for (int p0 = lane; p0 < pairs; p0 += 128) {
+          float2 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = (p0 + 32 * k < pairs) ? __ldg(sp + p0 + 32 * k) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int p = p0 + 32 * k;
+            if (p < pairs) {
+              uint32_t lo;
+              dp[p] = pack_bf16x2_hi_lo(v[k].x, v[k].y, lo);
+              dp[lo_w + p] = lo;
+            }
+          }
+        }
+      }
+      continue;
+    }
+    // split layout [hi: 0 .. w | zeros | lo: lo_off .. lo_off + w | zeros]: only the quads that hold data are written
+    const int quads = lo_off > 0 ? (a.width[e] + 3) >> 2 : a.ld_dst[e] >> 2;   // ld_dst is a multiple of 8
     const bool vec_ok = (w % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
     for (int r = r_begin + gwarp; r < r_end; r += nwarps) {    // one warp per row: no index division
       const float* sp = src + (row0 + r) * w;

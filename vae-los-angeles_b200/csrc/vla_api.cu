@@ -2131,12 +2131,12 @@ int vla_train_step_group(vla_model_t* const* ms, const vla_train_args_t* const* 
     if (a->dp) return fail(VLA_ERR_INVALID, "vla_train_step_group: members are independent models (no data-parallel exchange)");
     if (m->prof_on) return fail(VLA_ERR_STATE, "vla_train_step_group: per-launch profiling is per model");
     for (int j = 0; j < i; ++j) if (ms[j] == m) return fail(VLA_ERR_INVALID, "vla_train_step_group: a model appears twice");
-    const bool chain_prev = m->chain_on, hb_prev = m->hb_used;
+    const bool chain_prev = m->chain_on;
     m->chain_on = false;
     recorder() = &recs[i];
     const int rc = train_step_sequence(m, a, st);
     recorder() = nullptr;
-    m->chain_on = chain_prev; (void)hb_prev;
+    m->chain_on = chain_prev;
     if (recs[i].unsupported) return fail(VLA_ERR_STATE, "vla_train_step_group: this step contains a launch without a grouped form (member " + std::to_string(i) + ")");
     if (rc) return rc;
   }
