@@ -127,18 +127,21 @@ __device__ __forceinline__ void ingest_body(const IngestArgs& a, int r_begin, in
     const int w = a.width[e];
     if ((w % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0) && lo_off > 0) {
       // split layout [hi: 0 .. w | zeros | lo: lo_off .. lo_off + w | zeros], even width: one warp per row, lanes stride over
-      // 8-byte pairs (rows are 8-byte aligned), four pairs in flight per lane; 4-byte bf16x2 stores, 128 contiguous bytes per
+      // 8-byte pairs (rows are 8-byte aligned); 4-byte bf16x2 stores, 128 contiguous bytes per
       // warp instruction.  Only the columns that hold data are written (the padding stays zero from the allocation).
       const int pairs = w >> 1, lo_w = lo_off >> 1;
       for (int r = r_begin + gwarp; r < r_end; r += nwarps) {
         const float2* sp = reinterpret_cast<const float2*>(src + (row0 + r) * w);
         uint32_t* dp = reinterpret_cast<uint32_t*>(a.dst[e] + static_cast<size_t>(r) * a.ld_dst[e]);
-        for (int p0 = lane; p0 < pairs; p0 += 128) {
-          float2 v[4];
+        // (up to 14 pairs = 896 columns per lane in flight at once: the whole row of either modality in ONE round of loads --
+        // the launch is a chain of dependent load rounds, not a bandwidth problem)
+        constexpr int INFLIGHT = 14;
+        for (int p0 = lane; p0 < pairs; p0 += 32 * INFLIGHT) {
+          float2 v[INFLIGHT];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = (p0 + 32 * k < pairs) ? __ldg(sp + p0 + 32 * k) : make_float2(0.f, 0.f);
+          for (int k = 0; k < INFLIGHT; ++k) v[k] = (p0 + 32 * k < pairs) ? __ldg(sp + p0 + 32 * k) : make_float2(0.f, 0.f);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < INFLIGHT; ++k) {
             const int p = p0 + 32 * k;
             if (p < pairs) {
               uint32_t lo;
