@@ -264,6 +264,11 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
     xpf[i] = (col_ok && row < row_end) ? __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col))
                                        : make_float2(0.f, 0.f);
   }
+  // ... and so are the affine parameters and the step counter: every load of the launch is issued in ONE round
+  const float2 gam = col_ok ? __ldg(reinterpret_cast<const float2*>(a.gamma + col)) : make_float2(0.f, 0.f);
+  const float2 bet = col_ok ? __ldg(reinterpret_cast<const float2*>(a.beta + col)) : make_float2(0.f, 0.f);
+  unsigned long long offset = a.offset;
+  if (a.dyn) offset += static_cast<unsigned long long>(__ldcg(&a.dyn->step)) << 20;   // bumped earlier in the same launch: bypass L1
   if (a.train) {
     double r[4];
     reduce_partials<MEGA>(a.stats, a.m_tiles, a.n, col, col_ok, sh, r, tid);
@@ -302,12 +307,10 @@ __device__ __forceinline__ void bn_act_body(const BnActArgs& a, int rows_per_blo
   ew_sync<MEGA>();
   if (!col_ok) return;
   const float m0 = s_mean[lane * 2], m1 = s_mean[lane * 2 + 1];
-  const float r0 = s_rstd[lane * 2] * a.gamma[col], r1 = s_rstd[lane * 2 + 1] * a.gamma[col + 1];
-  const float b0 = a.beta[col], b1 = a.beta[col + 1];
+  const float r0 = s_rstd[lane * 2] * gam.x, r1 = s_rstd[lane * 2 + 1] * gam.y;
+  const float b0 = bet.x, b1 = bet.y;
   const bool drop = a.train && a.p_drop > 0.f;
   const float keep_scale = drop ? 1.0f / (1.0f - a.p_drop) : 1.0f;
-  unsigned long long offset = a.offset;
-  if (a.dyn) offset += static_cast<unsigned long long>(__ldcg(&a.dyn->step)) << 20;   // bumped earlier in the same launch: bypass L1
   auto do_row = [&](int row, float2 x) {
     float y0 = fmaxf((x.x - m0) * r0 + b0, 0.f);
     float y1 = fmaxf((x.y - m1) * r1 + b1, 0.f);
@@ -360,6 +363,23 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdArgs& a, int rows_per_blo
   const int lane = tid & 31, ty = tid >> 5;
   const int col = bx * BN_COLS + lane * 2;
   const bool col_ok = col < a.n;
+  // everything that does not depend on the reduced statistics is loaded first (one round of loads for the launch): the saved
+  // mean / rstd, gamma, and this thread's first batch of rows
+  const float2 mean2 = col_ok ? __ldcg(reinterpret_cast<const float2*>(a.mean + col)) : make_float2(0.f, 0.f);
+  const float2 rstd2 = col_ok ? __ldcg(reinterpret_cast<const float2*>(a.rstd + col)) : make_float2(0.f, 0.f);
+  const float2 gam2 = col_ok ? __ldg(reinterpret_cast<const float2*>(a.gamma + col)) : make_float2(0.f, 0.f);
+  const int row_end = min(a.rows, (by + 1) * rows_per_block);
+  const int rb_first = by * rows_per_block + ty;
+  float2 gy0[4], x0[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = rb_first + 8 * k;
+    gy0[k] = x0[k] = make_float2(0.f, 0.f);
+    if (col_ok && row < row_end) {
+      gy0[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.gy + static_cast<size_t>(row) * a.ld_gy + col));
+      x0[k] = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
+    }
+  }
   {
     double r[4];
     reduce_partials<MEGA>(a.stats, a.m_tiles, a.n, col, col_ok, sh, r, tid);
@@ -378,19 +398,19 @@ __device__ __forceinline__ void bn_bwd_body(const BnBwdArgs& a, int rows_per_blo
   ew_sync<MEGA>();
   if (!col_ok) return;
   const float inv_n = 1.0f / (a.stat_rows > 0 ? a.stat_rows : a.rows);
-  const float m0 = __ldcg(a.mean + col), m1 = __ldcg(a.mean + col + 1);
-  const float rs0 = __ldcg(a.rstd + col), rs1 = __ldcg(a.rstd + col + 1);
-  const float g0 = a.gamma[col] * rs0, g1 = a.gamma[col + 1] * rs1;
+  const float m0 = mean2.x, m1 = mean2.y;
+  const float rs0 = rstd2.x, rs1 = rstd2.y;
+  const float g0 = gam2.x * rs0, g1 = gam2.y * rs1;
   const float c10 = a.train ? s_s1[lane * 2] * inv_n : 0.f, c11 = a.train ? s_s1[lane * 2 + 1] * inv_n : 0.f;
   const float c20 = a.train ? s_s2[lane * 2] * inv_n : 0.f, c21 = a.train ? s_s2[lane * 2 + 1] * inv_n : 0.f;
-  const int row_end = min(a.rows, (by + 1) * rows_per_block);
-  for (int rb = by * rows_per_block + ty; rb < row_end; rb += 32) {   // batches of four rows: all loads before the stores
+  for (int rb = rb_first; rb < row_end; rb += 32) {   // batches of four rows: all loads before the stores
     float2 gy[4], x[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int row = rb + 8 * k;
       gy[k] = x[k] = make_float2(0.f, 0.f);
-      if (row < row_end) {
+      if (rb == rb_first) { gy[k] = gy0[k]; x[k] = x0[k]; }       // (fetched before the reduction)
+      else if (row < row_end) {
         gy[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.gy + static_cast<size_t>(row) * a.ld_gy + col));
         x[k] = __ldg(reinterpret_cast<const float2*>(a.pre + static_cast<size_t>(row) * a.ld_pre + col));
       }
