@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   }
 }
 
+// The same with the chunk offsets as a kernel parameter (single model, no exchange): one round of loads.
+__global__ void __launch_bounds__(256) adamw_hinted_kernel(AdamArgs a, const __grid_constant__ AdamHints h) {
+  pdl_wait();
+  pdl_launch_dependents();
+  adamw_body(a, blockIdx.x, threadIdx.x, nullptr, static_cast<long long>(h.off4[blockIdx.x]) * 4, h.arena_elems);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Lock-step population step: the same bodies, one launch for every member (vla_internal.h, "Lock-step population step").
 // ---------------------------------------------------------------------------------------------
@@ -297,10 +304,12 @@ cudaError_t launch_out_grad(const OutGradArgs* a, int n, cudaStream_t s) {
   return launch_pdl(out_grad_kernel, dim3(grid_for(work, 256, 148 * 8)), dim3(256), 0, s, p);
 }
 
-cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s) {
+cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s, const AdamHints* hints) {
   if (a.n_chunks <= 0) return cudaSuccess;
   if (a.gframed == nullptr && record_launch(RK_ADAMW, a, a.n_chunks, a.n_chunks, 0)) return cudaSuccess;
   if (recorder()) { recorder()->unsupported = true; return cudaErrorNotSupported; }
+  if (hints && hints->n == a.n_chunks && a.gframed == nullptr && a.update)
+    return launch_pdl(adamw_hinted_kernel, dim3(a.n_chunks), dim3(256), 0, s, a, *hints);
   return launch_pdl(adamw_kernel, dim3(a.n_chunks), dim3(256), 0, s, a);
 }
 

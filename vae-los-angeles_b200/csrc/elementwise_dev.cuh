@@ -716,7 +716,18 @@ __device__ __forceinline__ void loss_body(const LossArgs& a, int block, int grid
 // (torch.optim.AdamW semantics; call sites train_rna2dna.py:94-96, 185-189)
 // ---------------------------------------------------------------------------------------------
 // g_given: the gradient of this thread's four elements when the caller already holds it (dp_adamw_kernel: shard owner).
-__device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid, const float4* g_given = nullptr) {
+__device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid, const float4* g_given = nullptr,
+                                           long long off_hint = -1, long long arena_elems = 0) {
+  // speculative loads at the hinted arena offset (AdamHints): in flight together with the chunk-table entry
+  const long long gi_spec = off_hint >= 0 ? off_hint + 4 * tid : -1;
+  const bool spec = gi_spec >= 0 && gi_spec + 4 <= arena_elems && a.update && a.gframed == nullptr && g_given == nullptr;
+  float4 sp_p = make_float4(0.f, 0.f, 0.f, 0.f), sp_g = sp_p, sp_m = sp_p, sp_v = sp_p;
+  if (spec) {
+    sp_p = *reinterpret_cast<const float4*>(a.p + gi_spec);
+    sp_g = *reinterpret_cast<const float4*>(a.g + gi_spec);
+    sp_m = *reinterpret_cast<const float4*>(a.m + gi_spec);
+    sp_v = *reinterpret_cast<const float4*>(a.v + gi_spec);
+  }
   const AdamChunk ch = a.chunks[chunk];
   const int e = 4 * tid;                               // element index inside the chunk
   if (e >= ch.n) return;
@@ -740,7 +751,10 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
     f0 = ld_framed(a.gframed + (gi >> 1));
     f1 = ld_framed(a.gframed + (gi >> 1) + 1);
   }
-  if (nv == 4) {
+  if (nv == 4 && spec && gi == gi_spec) {
+    *reinterpret_cast<float4*>(p) = sp_p; *reinterpret_cast<float4*>(g) = sp_g;
+    *reinterpret_cast<float4*>(m) = sp_m; *reinterpret_cast<float4*>(v) = sp_v;
+  } else if (nv == 4) {
     *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(a.p + gi);
     if (a.update) {
       if (!framed && !g_given) *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(a.g + gi);

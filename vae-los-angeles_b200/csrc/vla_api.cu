@@ -169,6 +169,7 @@ struct vla_model {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int dec_chunk0 = -1;                    // first AdamW chunk of the decoder parameters (arena order: encoders | decoders)
   bool side_busy = false;                 // the branch is open: the caller must join it
+  AdamHints* adam_hints = nullptr;        // chunk offsets as a kernel parameter (built on first use)
   // lock-step population steps led by this model (vla_train_step_group): device images of the merged launch tables
   std::vector<struct GroupPlanCached*> group_plans;
 };
@@ -1655,6 +1656,7 @@ void vla_model_destroy(vla_model_t* m) {
   if (m->layout_only) { delete m; return; }
   free_plans(m);
   for (GroupPlanCached* g : m->group_plans) { cudaFree(g->dev); delete g; }
+  delete m->adam_hints;
   cudaFree(m->rc_dbg); delete m->rc_last;
   if (m->side) cudaStreamDestroy(m->side);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -1762,7 +1764,19 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
   }
   double n_el = 0;
   for (int i = 0; i < a.n_chunks; ++i) n_el += m->chunks_h[chunk0 + i].n;
-  { ProfScope ps(m, st, name, 0, 34.0 * n_el); CK(launch_adamw(a, st)); }
+  // chunk offsets as a kernel parameter for the whole-arena launch of a single model (one round of loads in the kernel)
+  const AdamHints* hints = nullptr;
+  if (chunk0 == 0 && a.n_chunks == static_cast<int>(m->chunks_h.size()) && a.n_chunks <= ADAM_HINT_CHUNKS && !dp && a.update) {
+    if (!m->adam_hints) {
+      m->adam_hints = new AdamHints();
+      memset(m->adam_hints, 0, sizeof(AdamHints));
+      for (int i = 0; i < a.n_chunks; ++i) m->adam_hints->off4[i] = static_cast<unsigned int>(m->chunks_h[i].offset / 4);
+      m->adam_hints->n = a.n_chunks;
+      m->adam_hints->arena_elems = m->n_params;
+    }
+    hints = m->adam_hints;
+  }
+  { ProfScope ps(m, st, name, 0, 34.0 * n_el); CK(launch_adamw(a, st, hints)); }
   return VLA_OK;
 }
 

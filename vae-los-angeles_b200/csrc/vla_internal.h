@@ -312,7 +312,11 @@ struct AdamArgs {
   long long tail2;
   float* sums_out;
 };
-cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s);
+// Arena offsets of the chunks as a KERNEL PARAMETER (constant bank): a block can issue its p / g / m / v loads at once instead
+// of after the round trip for its chunk-table entry (the launch is a chain of dependent load rounds, not a bandwidth problem).
+constexpr int ADAM_HINT_CHUNKS = 2040;
+struct AdamHints { unsigned int off4[ADAM_HINT_CHUNKS]; int n; long long arena_elems; };   // offset / 4; n = 0: no hints
+cudaError_t launch_adamw(const AdamArgs& a, cudaStream_t s, const AdamHints* hints = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // Chain kernel (chain_kernel.cu): the ROW-LOCAL stretches of a step -- consecutive launches in which a 128-row block of
