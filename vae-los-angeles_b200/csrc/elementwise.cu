@@ -32,6 +32,25 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdArgs a, int rows_per_b
   bn_bwd_body<false>(a, rows_per_block, blockIdx.x, blockIdx.y, threadIdx.x, scratch);
 }
 
+// Two independent BatchNorm layers in one launch: blocks [0, nb0) work on the first, the rest on the second.
+__global__ void __launch_bounds__(256) bn_act_pair_kernel(BnActArgs a0, int rpb0, int gx0, int nb0, BnActArgs a1, int rpb1, int gx1) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[EW_SCRATCH_BYTES];
+  const int b = static_cast<int>(blockIdx.x);
+  if (b < nb0) bn_act_body<false>(a0, rpb0, b % gx0, b / gx0, threadIdx.x, scratch);
+  else bn_act_body<false>(a1, rpb1, (b - nb0) % gx1, (b - nb0) / gx1, threadIdx.x, scratch);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_pair_kernel(BnBwdArgs a0, int rpb0, int gx0, int nb0, BnBwdArgs a1, int rpb1, int gx1) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) unsigned char scratch[EW_SCRATCH_BYTES];
+  const int b = static_cast<int>(blockIdx.x);
+  if (b < nb0) bn_bwd_body<false>(a0, rpb0, b % gx0, b / gx0, threadIdx.x, scratch);
+  else bn_bwd_body<false>(a1, rpb1, (b - nb0) % gx1, (b - nb0) / gx1, threadIdx.x, scratch);
+}
+
 __global__ void __launch_bounds__(256) latent_fwd_kernel(LatentFwdArgs a) {
   pdl_wait();
   pdl_launch_dependents();
@@ -244,6 +263,25 @@ cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s) {
   dim3 grid((a.n + BN_COLS - 1) / BN_COLS, (a.rows + rpb - 1) / rpb);
   if (record_launch(RK_BN_ACT, a, grid.x * grid.y, grid.x, rpb)) return cudaSuccess;
   return launch_pdl(bn_act_kernel, grid, dim3(256), 0, s, a, rpb);
+}
+
+cudaError_t launch_bn_act_pair(const BnActArgs& a0, const BnActArgs& a1, cudaStream_t s) {
+  if ((a0.n % 2) || (a1.n % 2)) return cudaErrorInvalidValue;
+  // (the pair shares one wave: size each layer's blocks as if the other's elements were its own)
+  const int rpb0 = bn_rows_per_block(a0.rows, a0.train ? a0.m_tiles : 0, a0.n + a1.n);
+  const int rpb1 = bn_rows_per_block(a1.rows, a1.train ? a1.m_tiles : 0, a0.n + a1.n);
+  const int gx0 = (a0.n + BN_COLS - 1) / BN_COLS, gy0 = (a0.rows + rpb0 - 1) / rpb0;
+  const int gx1 = (a1.n + BN_COLS - 1) / BN_COLS, gy1 = (a1.rows + rpb1 - 1) / rpb1;
+  return launch_pdl(bn_act_pair_kernel, dim3(gx0 * gy0 + gx1 * gy1), dim3(256), 0, s, a0, rpb0, gx0, gx0 * gy0, a1, rpb1, gx1);
+}
+
+cudaError_t launch_bn_bwd_pair(const BnBwdArgs& a0, const BnBwdArgs& a1, cudaStream_t s) {
+  if ((a0.n % 2) || (a1.n % 2)) return cudaErrorInvalidValue;
+  const int rpb0 = bn_rows_per_block(a0.rows, a0.m_tiles, a0.n + a1.n);
+  const int rpb1 = bn_rows_per_block(a1.rows, a1.m_tiles, a0.n + a1.n);
+  const int gx0 = (a0.n + BN_COLS - 1) / BN_COLS, gy0 = (a0.rows + rpb0 - 1) / rpb0;
+  const int gx1 = (a1.n + BN_COLS - 1) / BN_COLS, gy1 = (a1.rows + rpb1 - 1) / rpb1;
+  return launch_pdl(bn_bwd_pair_kernel, dim3(gx0 * gy0 + gx1 * gy1), dim3(256), 0, s, a0, rpb0, gx0, gx0 * gy0, a1, rpb1, gx1);
 }
 
 cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {

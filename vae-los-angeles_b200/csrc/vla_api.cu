@@ -976,6 +976,7 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       m->generation++;
       return VLA_OK;
     }
+    std::vector<BnActArgs> round_bn;                     // BatchNorm applies of this round: independent of one another
     for (size_t i = 0; i < m->encs.size(); ++i) {
       if (!(present >> i & 1)) continue;
       const Enc& e = m->encs[i]; EncWS& w = m->ews[i];
@@ -998,7 +999,14 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
       a.seed = io.seed; a.offset = io.offset * 16 + 1 + e.first_drop + r; a.dyn = io.engine ? m->dyn : nullptr;
       // train mode needs the statistics of the WHOLE batch: a grid-wide dependency, the stretch ends in front of it
       if (m->chain_on) { if ((rc = chain_add(m, st, CK_BN_ACT, -1, &a, sizeof(a), "bn_act", 0, 6.0 * B * bn.n, a.train != 0))) return rc; }
-      else { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * bn.n); CK(launch_bn_act(a, st)); }
+      else round_bn.push_back(a);
+    }
+    // two BatchNorm layers in one round (both dense encoders): ONE launch for the pair -- a launch less on the chain
+    if (round_bn.size() == 2 && !recorder()) {
+      ProfScope ps(m, st, "bn_act", 0, 6.0 * B * (round_bn[0].n + round_bn[1].n));
+      CK(launch_bn_act_pair(round_bn[0], round_bn[1], st));
+    } else {
+      for (const BnActArgs& a : round_bn) { ProfScope ps(m, st, "bn_act", 0, 6.0 * B * a.n); CK(launch_bn_act(a, st)); }
     }
   }
   // ---- latent ----
@@ -1398,6 +1406,7 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       bn_todo.emplace_back(i, tgt);
     }
     if (g.nprob && !sfx && (rc = timed_gemm(m, g, 2, r == 1 ? "dgrad_enc_l1" : "dgrad_enc_l2", st))) return rc;
+    std::vector<BnBwdArgs> round_bb;
     for (auto& it : bn_todo) {
       const Enc& e = m->encs[it.first]; EncWS& w = m->ews[it.first]; const Bn& bn = e.bn[it.second];
       BnBwdArgs a{};
@@ -1412,7 +1421,13 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
       a.dgamma = G + bn.g_off; a.dbeta = G + bn.b_off;
       a.gpre = w.gpre[it.second]; a.ld_gpre = bn.n; a.rows = B; a.n = bn.n; a.train = train;
       if (m->chain_on) { if ((rc = chain_add(m, st, CK_BN_BWD, -1, &a, sizeof(a), "bn_bwd", 0, 8.0 * B * bn.n, train != 0))) return rc; }
-      else { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * bn.n); CK(launch_bn_bwd(a, st)); }
+      else round_bb.push_back(a);
+    }
+    if (round_bb.size() == 2 && !recorder()) {
+      ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * (round_bb[0].n + round_bb[1].n));
+      CK(launch_bn_bwd_pair(round_bb[0], round_bb[1], st));
+    } else {
+      for (const BnBwdArgs& a : round_bb) { ProfScope ps(m, st, "bn_bwd", 0, 8.0 * B * a.n); CK(launch_bn_bwd(a, st)); }
     }
   }
   if (!site_done && !sfx && !use_hb) {

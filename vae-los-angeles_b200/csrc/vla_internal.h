@@ -202,6 +202,8 @@ struct BnActArgs {
   const struct DynParams* dyn;          // if set, the Philox offset also mixes in dyn->step
 };
 cudaError_t launch_bn_act(const BnActArgs& a, cudaStream_t s);
+// Two independent BatchNorm layers (the two dense encoders' layers of one round) as ONE launch.
+cudaError_t launch_bn_act_pair(const BnActArgs& a0, const BnActArgs& a1, cudaStream_t s);
 
 struct BnBwdArgs {
   const bf16* gy; int ld_gy;            // dL/dy (already through dropout and ReLU), [rows, n]
@@ -216,6 +218,7 @@ struct BnBwdArgs {
                                         // step's all-reduce(SUM) of the gradient arena delivers them once; else 1
 };
 cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s);
+cudaError_t launch_bn_bwd_pair(const BnBwdArgs& a0, const BnBwdArgs& a1, cudaStream_t s);
 
 struct LatentFwdArgs {
   const float* ml[3]; int ld_ml[3]; int n_enc;    // present encoders' heads output [rows, 2L]
