@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
   pdl_wait();
   pdl_launch_dependents();
   adamw_body(a, blockIdx.x, threadIdx.x);
+  if (a.has_tail && blockIdx.x == 0) {
+    __shared__ double dsh[32];
+    loss_tail_reduce(a.tail, threadIdx.x, dsh);
+  }
   if (a.gframed && a.sums_out && blockIdx.x == 0 && threadIdx.x < 2) {
     // data parallel: the summed loss scalars travel behind the gradients (vla_b200.h, vla_dp_losses)
     const unsigned int epoch = static_cast<unsigned int>(__ldcg(&a.dyn->dp_epoch));
@@ -120,6 +124,10 @@ __global__ void __launch_bounds__(256) adamw_hinted_kernel(AdamArgs a, const __g
   pdl_wait();
   pdl_launch_dependents();
   adamw_body(a, blockIdx.x, threadIdx.x, nullptr, static_cast<long long>(h.off4[blockIdx.x]) * 4, h.arena_elems);
+  if (a.has_tail && blockIdx.x == 0) {
+    __shared__ double dsh[32];
+    loss_tail_reduce(a.tail, threadIdx.x, dsh);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

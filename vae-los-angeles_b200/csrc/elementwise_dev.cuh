@@ -823,4 +823,35 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
   }
 }
 
+// Final reduction of the fused loss by block 0 of the step's AdamW launch (LossTail with counter == nullptr): the same fixed
+// order as the in-tile reduction of gemm_tile.cuh (every thread a strided share of each partial array, one shuffle butterfly
+// per term, thread 0 adds the eight warp results in order).  256 threads.
+static __device__ __noinline__ void loss_tail_reduce(const LossTail& T, int tid, double* dsh /* [8 * 4] shared */) {
+  const int starts[4] = {0, T.n_mse, T.n_mse + T.n_bce, T.n_mse + T.n_bce + T.n_ce};
+  double acc4[4] = {0, 0, 0, 0};                             // mse, bce, ce, kl
+  for (int role = 0; role < 3; ++role)
+    for (int i = starts[role] + tid; i < starts[role + 1]; i += 256) acc4[role] += __ldcg(T.partials + i);
+  for (int i = tid; i < T.n_kl; i += 256) acc4[3] += __ldcg(T.kl_partials + i);
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int role = 0; role < 4; ++role) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc4[role] += __shfl_xor_sync(0xffffffffu, acc4[role], o);
+    if (lane == 0) dsh[warp * 4 + role] = acc4[role];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double sums[4] = {0, 0, 0, 0};
+    for (int w = 0; w < 8; ++w)
+      for (int role = 0; role < 4; ++role) sums[role] += dsh[w * 4 + role];
+    const double beta = T.dyn->beta_kl, gamma = T.dyn->gamma;
+    const double recon = sums[0] + sums[1];
+    T.out[0] = static_cast<float>(recon + gamma * sums[2] + beta * sums[3]);
+    T.out[1] = static_cast<float>(recon);
+    T.out[2] = static_cast<float>(sums[2]);
+    T.out[3] = static_cast<float>(sums[3]);
+    if (T.dyn_bump) T.dyn_bump->batch_index += 1;
+  }
+}
+
 }  // namespace vla

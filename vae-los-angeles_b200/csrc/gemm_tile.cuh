@@ -700,8 +700,9 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       if (lane == 0) P.aux_partials[static_cast<size_t>(local) * 8 + (warp - 2)] = loss_acc;
       int* s_flag = reinterpret_cast<int*>(part);                  // column-stat scratch is unused by loss tiles
       double* dsh = reinterpret_cast<double*>(part + 8);
-      named_bar_sync(3, EPI_THREADS);
       const LossTail T = *tail_desc;
+      if (T.counter != nullptr) {          // (nullptr: the step's AdamW launch sums the partials -- nothing more to do here)
+      named_bar_sync(3, EPI_THREADS);
       if (et == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(T.counter, 1u);
@@ -739,6 +740,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
           *T.counter = 0u;                                         // re-arm for the next step (graph replays)
           if (T.dyn_bump) T.dyn_bump->batch_index += 1;
         }
+      }
       }
     }
     if (et == 0) VLA_STAMP(6);                                     // this thread's chunks are done

@@ -170,6 +170,7 @@ struct vla_model {
   int dec_chunk0 = -1;                    // first AdamW chunk of the decoder parameters (arena order: encoders | decoders)
   bool side_busy = false;                 // the branch is open: the caller must join it
   AdamHints* adam_hints = nullptr;        // chunk offsets as a kernel parameter (built on first use)
+  LossTail deferred_tail{}; bool deferred_tail_valid = false;   // final loss reduction handed to the step's AdamW launch
   // lock-step population steps led by this model (vla_train_step_group): device images of the merged launch tables
   std::vector<struct GroupPlanCached*> group_plans;
 };
@@ -819,6 +820,7 @@ struct FwdIO {
   const float* tgt_a = nullptr; const float* tgt_b = nullptr; const long long* tgt_site = nullptr;
   const float* class_w = nullptr; float* loss_out = nullptr;
   bool rc_prefix = false;   // row-chain step: only ingest + the first encoder layer (the row-chain kernel takes over behind it)
+  bool defer_loss_sum = false; // single-GPU whole step: the loss tiles only write partials, AdamW's block 0 does the final sum
   vla_dp* sync_dp = nullptr;   // opt-in SyncBN: BatchNorm statistics over the global batch (all-reduce of the column sums)
 };
 
@@ -1107,6 +1109,8 @@ int run_forward(vla_model* m, const FwdIO& io, cudaStream_t st) {
     T.n_mse = 8 * tiles[LOSS_MSE]; T.n_bce = 8 * tiles[LOSS_BCE]; T.n_ce = 8 * tiles[LOSS_CE];
     T.partials = m->eloss_partials; T.kl_partials = m->kl_partials; T.n_kl = m->kl_grid;
     T.out = io.loss_out; T.dyn = m->dyn; T.dyn_bump = m->dyn;
+    m->deferred_tail_valid = false;
+    if (io.defer_loss_sum) { T.counter = nullptr; m->deferred_tail = T; m->deferred_tail_valid = true; }
     const int base[4] = {0, 0, T.n_mse, T.n_mse + T.n_bce};
     for (GemmGroup& g : dec_groups) {
       g.tail = T;
@@ -1772,6 +1776,11 @@ static int run_adamw(vla_model_t* m, float* p, const float* g, float* ea, float*
     a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), step)));
   }
   a.dyn = dyn ? m->dyn : nullptr; a.update = 1; a.zero_grad = zero_grad ? 1 : 0;
+  if (m->deferred_tail_valid && chunk0 == 0) {        // (the launch that holds block 0 of the step's optimizer)
+    if (dp || fused) return fail(VLA_ERR_STATE, "deferred loss reduction under data parallelism");
+    a.tail = m->deferred_tail; a.has_tail = 1;
+    m->deferred_tail_valid = false;
+  }
   { int rcf = chain_flush(m, st); if (rcf) return rcf; }
   if (fused) {      // exchange of `fused`'s range + AdamW as one launch (dp_exchange.cu)
     ProfScope ps(m, st, "dp_exchange_adamw", 0, 34.0 * m->n_params + dp_bytes(*fused)); CK(launch_dp_adamw(*fused, a, st));
@@ -2017,6 +2026,10 @@ static int train_step_sequence(vla_model_t* m, const vla_train_args_t* a, cudaSt
     if (d.type == 'C' && !a->site) return fail(VLA_ERR_INVALID, "site (target) missing");
   }
   io.tgt_a = a->x_a; io.tgt_b = a->x_b; io.tgt_site = a->site; io.class_w = a->class_weights; io.loss_out = a->loss_out;
+  {
+    static const bool defer_on = [] { const char* e = getenv("VLA_DEFER_LOSS"); return !(e && e[0] == '0'); }();
+    io.defer_loss_sum = defer_on && do_opt && dp == nullptr && !recorder();
+  }
   int rc;
   // ---- row-chain step: ingest + first encoder layer | the on-chip middle | BatchNorm backward + weight gradients | AdamW ----
   const bool rowchain = !recorder() && rowchain_enabled() && io.fuse_loss && rowchain_fits(m, present_mask(m, io)) && !a->recon_a && !a->recon_b &&

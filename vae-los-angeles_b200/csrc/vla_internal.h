@@ -101,7 +101,8 @@ struct alignas(64) GemmProblem : GemmScalars {
 // Final reduction of the fused loss: the epilogue of the tile that takes the last ticket sums every partial in a fixed
 // order (deterministic) and writes out[4] = {total, recon, class, kld} (losses.py:27-46).
 struct LossTail {
-  unsigned int* counter;       // zero between steps (re-armed by the last tile)
+  unsigned int* counter;       // zero between steps (re-armed by the last tile); nullptr: the tiles only write their partials and
+                               // the step's AdamW launch does the final reduction (AdamArgs::tail) -- no ticket on the chain
   int total_tickets;           // loss tiles of the whole step (possibly spread over several launches)
   int n_mse, n_bce, n_ce;      // partial floats per term, contiguous in `partials` in this order
   const float* partials;
@@ -314,6 +315,9 @@ struct AdamArgs {
   const uint4* gframed;
   long long tail2;
   float* sums_out;
+  // deferred final reduction of the fused loss (single-GPU whole step): block 0 sums the loss tiles' partials in the fixed
+  // order of the in-tile reduction, writes out[4] and advances the batch index
+  LossTail tail; int has_tail; int pad_tail;
 };
 // Arena offsets of the chunks as a KERNEL PARAMETER (constant bank): a block can issue its p / g / m / v loads at once instead
 // of after the round trip for its chunk-table entry (the launch is a chain of dependent load rounds, not a bandwidth problem).
