@@ -826,7 +826,7 @@ __device__ __forceinline__ void adamw_body(const AdamArgs& a, int chunk, int tid
 // Final reduction of the fused loss by block 0 of the step's AdamW launch (LossTail with counter == nullptr): the same fixed
 // order as the in-tile reduction of gemm_tile.cuh (every thread a strided share of each partial array, one shuffle butterfly
 // per term, thread 0 adds the eight warp results in order).  256 threads.
-static __device__ __noinline__ void loss_tail_reduce(const LossTail& T, int tid, double* dsh /* [8 * 4] shared */) {
+__device__ __forceinline__ void loss_tail_reduce(const LossTail& T, int tid, double* dsh /* [8 * 4] shared */) {
   const int starts[4] = {0, T.n_mse, T.n_mse + T.n_bce, T.n_mse + T.n_bce + T.n_ce};
   double acc4[4] = {0, 0, 0, 0};                             // mse, bce, ce, kl
   for (int role = 0; role < 3; ++role)
