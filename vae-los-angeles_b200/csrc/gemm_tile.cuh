@@ -381,6 +381,16 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
       }
     }
 
+    // GF_BNSTATS: the fp32 pre-activations this warp will read (32 rows x 128 bytes per chunk, L2-resident) are pulled into
+    // L1 while the main loop runs -- no registers held (holding them across the wait spills: profiles/r2_mma_issue.md)
+    if ((FEATS & GF_BNSTATS) && (P.flags & GF_BNSTATS) && !(dbgf & 1)) {
+      const int prow = m0 + q * 32 + lane;
+      if (prow < P.M)
+        for (int c = half; c < n_chunks; c += 2)
+          if (n0 + c * 32 < P.N)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.pre + static_cast<size_t>(prow) * P.ld_pre + n0 + c * 32));
+    }
+
     mbar_wait(acc_bar, acc_par);
     tc_fence_after();
     if (et == 0) VLA_STAMP(5);                                     // accumulator ready
