@@ -96,6 +96,43 @@ def test_head_block_train_steps_match_oracle(kind, dims, batch, monkeypatch):
     tr.close()
 
 
+@pytest.mark.parametrize("kind,dims,batch", [("rna2dna", FULL, 200), ("multimodal", FULL, 136), ("dna2rna_ae", SMALL, 40),
+                                             ("multimodal", dict(A=50, B=36, S=5, L=100, E=16), 70)])
+def test_latent_backward_in_gemm_epilogue(kind, dims, batch, monkeypatch):
+    """The latent backward (reparameterisation + KL backward, /reference/src/models/vae.py:11-15, src/utils/losses.py:44) runs
+    in the epilogue of the GEMM that produces dL/dz: no latent_bwd launch in the step, and the same parameters after three
+    steps as with the separate launch (VLA_FUSE_LATBWD=0) -- ragged row blocks, latent widths 10 / 20 / 100 (four column
+    chunks), one and several modalities, autoencoder mode."""
+    from vla_b200 import DeviceDataset, Trainer
+    state = vo.init_state(kind, dims, seed=9)
+    tpm, beta_v, site = vo.synthetic_batch(batch * 2, dims, seed=9)
+    eps, masks = vo.synthetic_noise(batch, dims, kind, seed=9)
+    out = {}
+    for fused in (True, False):
+        monkeypatch.setenv("VLA_FUSE_LATBWD", "1" if fused else "0")
+        m = make_module(kind, dims, state).train()
+        ds = DeviceDataset(tpm, beta_v, site, "cuda")
+        tr = Trainer(m, ds, batch, lr=5e-4, weight_decay=1e-5, beta_kl=3e-2, gamma=1.5, use_graph=True)
+        tr.injected = dict(eps=to_t(eps), keep_masks=[to_t(v) for v in masks.values()])
+        for _ in range(3):
+            tr.step()
+        names = [name for name, ms, fl, by in tr.profile(1)]
+        assert ("latent_bwd" in names) == (not fused), names
+        assert "dgrad_dec_l0" in names
+        out[fused] = ({k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}, np.array(tr.losses()))
+        tr.close()
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-5)
+    for name, ref in out[False][0].items():
+        if ref.dtype.kind == "f" and not is_pre_bn_bias(name) and not name.endswith(("running_mean", "running_var")):
+            # same arithmetic on the same fp32 dL/dz; the weight gradients' split-K red.add order is the only free variable
+            # (it can flip Adam's first +-lr steps of an element whose gradient is rounding noise: compare displacements)
+            d_ref = ref.astype(np.float64) - state[name].astype(np.float64)
+            d_got = out[True][0][name].astype(np.float64) - state[name].astype(np.float64)
+            if np.linalg.norm(d_ref) > 0:
+                assert rel_l2(d_got, d_ref) <= 0.02, (name, rel_l2(d_got, d_ref))
+            assert_close(name, out[True][0][name], ref, 2e-3, atol=1e-6)
+
+
 def test_adamw_kernel_fp32():
     """vla_adamw alone (fp32 arithmetic) against the oracle's AdamW: 1e-5 relative on p, and on m, v."""
     from vla_b200 import _lib

@@ -210,7 +210,7 @@ bool use_persist(int variant, int total_tiles) {
   static const int thr = [] { const char* e = getenv("VLA_PERSIST"); return e ? atoi(e) : 222; }();
   // not the loss epilogues (their target patches live in the ring), not the data gradients with BatchNorm-backward statistics
   // (measured 1.3-1.4x slower in the persistent form: profiles/r2_population_profile.md)
-  return thr > 0 && total_tiles > thr && !(variant >= 2 && variant <= 4) && variant != 33;
+  return thr > 0 && total_tiles > thr && !(variant >= 2 && variant <= 4) && variant != 33 && variant != 34;
 }
 // The persistent form runs a two-stage ring (its transpose patches need the other slots): it pays where the epilogue is the
 // larger part of a tile -- short main loops -- and loses where the main loop is (measured on the merged launches of 40 tri-modal
@@ -279,7 +279,13 @@ int gemm_variant(const GemmGroup& g, int mode) {
     }
     return 1;
   }
-  if (mode == 2) return 32 + ((used & ~FEATS_DGRAD_PLAIN) ? 1 : 0);
+  if (mode == 2) {
+    if (used & GF_LATBWD) {                // the latent-backward epilogue has its own (small) instantiation: uniform groups only
+      for (int i = 0; i < g.nprob; ++i) if (g.p[i].flags != GF_LATBWD) return -1;
+      return 34;
+    }
+    return 32 + ((used & ~FEATS_DGRAD_PLAIN) ? 1 : 0);
+  }
   return 16;
 }
 
@@ -293,6 +299,7 @@ int gemm_variant(const GemmGroup& g, int mode) {
     case 16: return CALL(1, FEATS_WGRAD);                                   \
     case 32: return CALL(2, FEATS_DGRAD_PLAIN);                             \
     case 33: return CALL(2, FEATS_DGRAD_FULL);                              \
+    case 34: return CALL(2, FEATS_DGRAD_LAT);                               \
     default: return cudaErrorInvalidValue;                                  \
   }
 

@@ -66,6 +66,7 @@ constexpr int FEATS_FWD_LOSS_BCE = GF_BIAS | GF_SIGMOID | GF_OUT_BF16 | GF_LOSS 
 constexpr int FEATS_FWD_LOSS_MSE = GF_BIAS | GF_OUT_BF16 | GF_LOSS | GF_LK_MSE;
 constexpr int FEATS_DGRAD_PLAIN = GF_MASK | GF_OUT_F32 | GF_OUT_BF16;                              // decoder data gradients
 constexpr int FEATS_DGRAD_FULL = FEATS_DGRAD_PLAIN | GF_BNSTATS;                                   // + BatchNorm backward statistics
+constexpr int FEATS_DGRAD_LAT = GF_LATBWD;                                                         // dL/dz -> d(mu | logvar) in the epilogue
 constexpr int FEATS_WGRAD = GF_RED | GF_BIASGRAD;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -204,7 +205,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
   P.a_lo = (MODE == 0) ? Pd.a_lo : 0; P.b_lo = (MODE == 0) ? Pd.b_lo : 0; P.out_lo = (MODE == 0) ? Pd.out_lo : 0;
   P.mask_bits_out = Pd.mask_bits_out; P.mask_bits_in = Pd.mask_bits_in;
   P.mask_src = Pd.mask_src; P.pre = Pd.pre; P.mean = Pd.mean; P.rstd = Pd.rstd; P.stats = Pd.stats; P.bias_grad = Pd.bias_grad;
-  if (FEATS & GF_LOSS) {
+  if (FEATS & (GF_LOSS | GF_LATBWD)) {
     P.aux0 = Pd.aux0; P.aux1 = Pd.aux1; P.aux_site = Pd.aux_site; P.aux_partials = Pd.aux_partials; P.dyn = Pd.dyn;
     P.aux_n = Pd.aux_n; P.loss_kind = Pd.loss_kind; P.aux_scale = Pd.aux_scale;
   }
@@ -391,6 +392,36 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
             asm volatile("prefetch.global.L1 [%0];" ::"l"(P.pre + static_cast<size_t>(prow) * P.ld_pre + n0 + c * 32));
     }
 
+    // GF_LATBWD: d(mu) = dz + ca, d(logvar) = dz * cb + cc with ca = beta mu, cb = eps exp(logvar / 2) / 2,
+    // cc = beta (exp(logvar) - 1) / 2 (latent_bwd_elem).  The two warps of a lane quarter SHARE every 32-column chunk: each reads
+    // the whole accumulator chunk but works on 16 of its 32 rows, lane = column (every global access is a contiguous piece of
+    // one row).  The coefficients of the first chunk are loaded and computed here, before the accumulator wait -- 48 registers
+    // per thread, all the exponentials off the critical path; later chunks (latent widths above 32) do it inside the loop.
+    constexpr bool LAT = (FEATS & GF_LATBWD) != 0;
+    float lat_a[16], lat_b[16], lat_c[16];
+    auto lat_load = [&](int c) {
+      const int col0 = n0 + c * 32;
+      const int nvalid = min(32, min(P.N, n0 + BN) - col0);
+      if (nvalid <= 0 || P.loss_kind != 0) return;                   // (warp-uniform; autoencoder: no coefficients)
+      // no predicates: rows past M and lanes past the chunk read a valid neighbour and are ignored later
+      const int cc = col0 + min(lane, nvalid - 1);
+      const int rb = m0 + q * 32 + 16 * half;
+      const float beta = P.dyn ? P.dyn->beta_kl : P.aux_scale;
+      float mu[16], lv[16], ep[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const unsigned off = static_cast<unsigned>(min(rb + i, P.M - 1)) * static_cast<unsigned>(P.N) + cc;
+        mu[i] = __ldg(P.aux0 + off); lv[i] = __ldg(P.aux1 + off); ep[i] = __ldg(P.pre + off);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        lat_a[i] = beta * mu[i];
+        lat_b[i] = ep[i] * 0.5f * expf(0.5f * lv[i]);
+        lat_c[i] = beta * 0.5f * (expf(lv[i]) - 1.0f);
+      }
+    };
+    if (LAT && (P.flags & GF_LATBWD)) lat_load(0);
+
     mbar_wait(acc_bar, acc_par);
     tc_fence_after();
     if (et == 0) VLA_STAMP(5);                                     // accumulator ready
@@ -441,7 +472,7 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
     }
     int tgt_k = 0;                                       // index of the chunk in flight among this warp's chunks
 
-    for (int c = half; c < ((dbgf & 1) ? 0 : n_chunks); c += 2) {
+    for (int c = LAT ? 0 : half; c < ((dbgf & 1) ? 0 : n_chunks); c += LAT ? 1 : 2) {
       const int my_k = tgt_k++;                         // which of this warp's staged target patches belongs to this chunk
       const int col0 = n0 + c * 32;
       const int nvalid = min(32, min(P.N, n0 + BN) - col0);   // <= 0: nothing to store (tile padding); a tile never touches
@@ -497,6 +528,44 @@ __device__ __forceinline__ void gemm_tile(TileCtx& ctx, const GemmScalars& Pd, c
         const float4 bv = *reinterpret_cast<const float4*>(vec + c * 32 + j);
         v[j] = __uint_as_float(r[j]) + bv.x;         v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
         v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+      }
+      if ((FEATS & GF_LATBWD) && (flags & GF_LATBWD)) {
+        // v = dL/dz of this row chunk.  Backward of z = mu + eps * exp(logvar / 2) and of the KL term, then of the mean over
+        // the modalities (vae.py:11-15, 60-66; losses.py:44; directional_vae.py:47-52) -- the arithmetic of latent_bwd_elem.
+        // The row goes through the warp's transpose patch; then lane = column, this warp's 16 rows (coefficients: lat_load).
+        if (my_k > 0) lat_load(c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(patch + lane * PATCH_LD + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        __syncwarp();
+        if (lane < nvalid) {
+          const bool ae = P.loss_kind != 0;
+          const float nmod = static_cast<float>(P.aux_n);
+          const int r16 = rbase + 16 * half;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (r16 + i < P.M) {
+              const size_t idx = static_cast<size_t>(r16 + i) * P.N + col0 + lane;
+              bf16* gp = P.out_bf16 + static_cast<size_t>(r16 + i) * P.ld_bf16 + col0 + lane;
+              const float gz = patch[(16 * half + i) * PATCH_LD + lane];
+              if (ae) {
+                float g = gz + (P.mean ? __ldg(P.mean + idx) : 0.f);
+                if (P.aux_n > 1) g /= nmod;
+                *gp = __float2bfloat16(g);
+              } else {
+                float gmu = gz + lat_a[i];
+                float glv = gz * lat_b[i] + lat_c[i];
+                if (P.mean) gmu += __ldg(P.mean + idx);
+                if (P.rstd) glv += __ldg(P.rstd + idx);
+                if (P.aux_n > 1) { gmu /= nmod; glv /= nmod; }
+                gp[0] = __float2bfloat16(gmu);
+                gp[P.N] = __float2bfloat16(glv);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        continue;
       }
       if (bit_mask) {                                  // ReLU / dropout backward from the forward's (activation > 0) bits
         const float sc = P.mask_scale;

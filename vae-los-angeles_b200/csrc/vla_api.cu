@@ -242,6 +242,7 @@ void gemm_work(const GemmGroup& g, double* flops, double* bytes) {
     *bytes += opw * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K) +
               (out_b + tgt_b + ((p.flags & GF_OUT_BF16) ? (p.out_lo > 0 ? 4.0 : 2.0) : 0.0)) * p.M * p.N;
     if (p.a_lo > 0) *flops += 4.0 * p.M * p.N * p.K;      // three MMA passes
+    if (p.flags & GF_LATBWD) *bytes += (p.loss_kind ? 2.0 : 16.0) * p.M * p.N;   // mu, logvar, eps in; d(mu | logvar) bf16 out
   }
 }
 int timed_gemm(vla_model* m, GemmGroup& g, int mode, const char* name, cudaStream_t st, bool finalized = false) {
@@ -1357,15 +1358,29 @@ int run_backward(vla_model* m, const BwdIO& io, cudaStream_t st) {
     for (int e = 0; e < hb.n_enc; ++e) fl += 2.0 * B * hb.enc[e].in_dim * m->HW;
     { ProfScope ps(m, st, "head_block_bwd", fl, static_cast<double>(B) * (m->cat.out * 2.0 + m->L * 12.0)); CK(launch_head_block_bwd(hb, st)); }
   }
+  // The latent backward is row-local arithmetic on dL/dz: with VLA_FUSE_LATBWD=1 it runs in the epilogue of the GEMM that
+  // produces dL/dz (GF_LATBWD, one launch less).  OPT-IN: measured slower at batch 4096 (profiles/r2_latbwd_fusion.md: rna2dna
+  // 100.6 -> 111.9 us with the side branch, 102.6 -> 105.0 us without) -- the epilogue's operand loads and exponentials do not
+  // hide behind a two-k-block main loop, and the next GEMM then competes for SMs with the side branch's weight gradients.
+  const bool fuse_latbwd_on = [] { const char* e = getenv("VLA_FUSE_LATBWD"); return e && e[0] == '1'; }();   // (read per call: a
+                                                                  // graph step issues its launches once, at capture)
+  const bool fuse_latbwd = fuse_latbwd_on && any_dec && !sfx && !use_hb && !m->chain_on;
   if (any_dec && !sfx && !use_hb) {
     GemmGroup g; init_group(g); GemmProblem* p;
     const Lin& l = m->cat;
-    if ((rc = add_nn(m, g, m->g_d0, l.out, SH + l.sh_off, l.sh_ld, B, l.in, l.out, GF_OUT_F32, &p))) return rc;
-    p->out_f32 = m->gz; p->ld_f32 = L;
+    if ((rc = add_nn(m, g, m->g_d0, l.out, SH + l.sh_off, l.sh_ld, B, l.in, l.out, fuse_latbwd ? GF_LATBWD : GF_OUT_F32, &p))) return rc;
+    if (fuse_latbwd) {
+      p->aux0 = m->mu; p->aux1 = m->logvar; p->pre = m->eps; p->mean = io.g_mu; p->rstd = io.g_logvar;
+      p->out_bf16 = m->gml; p->ld_bf16 = m->ldgml;
+      p->aux_n = n_present; p->loss_kind = m->ae ? 1 : 0;
+      p->dyn = io.engine ? m->dyn : nullptr; p->aux_scale = 0.f;
+    } else {
+      p->out_f32 = m->gz; p->ld_f32 = L;
+    }
     if ((rc = timed_gemm(m, g, 2, "dgrad_dec_l0", st))) return rc;
   }
   // ---- latent ----
-  if (!sfx && !use_hb) {
+  if (!sfx && !use_hb && !fuse_latbwd) {
     LatentBwdArgs a{};
     a.gz = any_dec ? m->gz : nullptr; a.ld_gz = L;
     a.gmu_in = io.g_mu; a.glv_in = io.g_logvar;

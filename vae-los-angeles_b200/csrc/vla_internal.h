@@ -30,6 +30,9 @@ enum GemmFlags : int {
   GF_LOSS = 1 << 11,      // NT mode, last decoder layer: loss value partials + dL/d(pre-activation) as bf16 (loss_kind)
   // compile-time only (never set in GemmProblem::flags): which loss kinds an instantiation of the loss epilogue contains
   GF_LK_MSE = 1 << 12, GF_LK_BCE = 1 << 13, GF_LK_CE = 1 << 14,
+  GF_LATBWD = 1 << 15,    // NN mode, data gradient of the fused first decoder layer: the tile's result is dL/dz; the epilogue
+                          // turns it into d(mu | logvar) (reparameterisation + KL backward, divided by the number of
+                          // modalities) and stores the bf16 operand of the heads' backward -- no separate latent_bwd launch
 };
 enum LossKind : int { LOSS_NONE = 0, LOSS_MSE = 1, LOSS_BCE = 2, LOSS_CE = 3 };
 
@@ -78,6 +81,10 @@ struct GemmScalars {
   const struct DynParams* dyn;
   int aux_n, loss_kind;
   float aux_scale;                   // CE: gamma when dyn == nullptr
+  // GF_LATBWD:     aux0 = mu, aux1 = logvar, pre = eps (fp32 [rows, N], N = latent width), mean / rstd = incoming d(mu) /
+  //                d(logvar) of the autograd path or nullptr, out_bf16 / ld_bf16 = the [mu | logvar] gradient rows,
+  //                aux_n = modalities averaged by the forward, loss_kind != 0: autoencoder (no logvar half),
+  //                beta = dyn->beta_kl or aux_scale.
   // ---- split-bf16 operands (NT mode) ----
   // a_lo > 0: both operands carry a second bf16 copy ("lo" = bf16(x - bf16(x))) a_lo / b_lo elements further along K in the
   // same rows; the tile then accumulates A_hi B_hi + A_lo B_hi + A_hi B_lo, i.e. operands of ~16 mantissa bits.  Used by
