@@ -92,3 +92,16 @@ def test_kernel_code_size_budget(sass, needle, limit_kb):
     for name, ops in found.items():
         kb = len(ops) * 16 / 1024
         assert kb <= limit_kb, f"{name}: {kb:.1f} KB of SASS > {limit_kb} KB"
+
+
+def test_latent_backward_epilogue_is_compiled_in(sass):
+    """The opt-in GF_LATBWD instantiation really contains its epilogue (exponentials, 16-bit stores): the tile body works on a
+    local snapshot of the problem descriptor, and a field the snapshot does not copy is undefined -- the compiler then drops
+    the whole epilogue without a warning (this happened once while the path was written)."""
+    _, kernels = sass
+    found = _find(kernels, "gemm_tc_kernelILi2ELi32768")
+    assert found
+    for name, ops in found.items():
+        assert sum(op.startswith("MUFU.EX2") for op in ops) >= 8, name
+        assert sum(op.startswith("STG.E.U16") for op in ops) >= 8, name
+        assert any(op.startswith("LDTM") for op in ops) and any(op.startswith("UTCHMMA") for op in ops), name
